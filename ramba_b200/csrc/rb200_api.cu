@@ -1,0 +1,243 @@
+// rb200_api.cu — the C-ABI declared in include/ramba_b200.h (host side) and small helper kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <string>
+
+#include "rb200_launch.h"
+
+namespace rb200 {
+template <class T> __device__ __forceinline__ T red_combine(int op, T a, T b) {
+  switch (op) {
+    case RB200_RED_ADD: return a + b;
+    case RB200_RED_MUL: return a * b;
+    case RB200_RED_MIN: return (b < a) ? b : a;
+    default: return (b > a) ? b : a;
+  }
+}
+// stage 2 helper: out[j] = reduce_k part[k*stride_k + j]
+template <class T> __global__ void reduce_partials_kernel(T* out, const T* part, long long n, long long k, long long stride_k, int op) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    T v = part[j];
+    for (long long q = 1; q < k; ++q) v = red_combine<T>(op, v, part[q * stride_k + j]);
+    out[j] = v;
+  }
+}
+
+}  // namespace rb200
+
+// =============================================================================================
+// host side: C-ABI
+// =============================================================================================
+using namespace rb200;
+
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+static int fail_cuda(const char* what, cudaError_t e) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+
+static int dtype_size(int dt) {
+  switch (dt) {
+    case RB200_F64:
+    case RB200_I64: return 8;
+    case RB200_F32:
+    case RB200_I32:
+    case RB200_U32: return 4;
+    case RB200_I16:
+    case RB200_U16: return 2;
+    case RB200_BOOL:
+    case RB200_U8:
+    case RB200_I8: return 1;
+    default: return 0;
+  }
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count > 0) return g_sm_count;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  g_sm_count = n;
+  return n;
+}
+
+constexpr int kRedScratchPartials = 4096;  // max grid size of a launch with global reductions
+
+extern "C" {
+
+const char* rb200_last_error(void) { return g_last_error.c_str(); }
+int rb200_abi_version(void) { return RB200_ABI_VERSION; }
+int64_t rb200_launch_count(void) { return (int64_t)g_launches.load(); }
+void rb200_reset_launch_count(void) { g_launches.store(0); }
+int rb200_device_sm_count(void) { return sm_count(); }
+int64_t rb200_red_scratch_bytes(void) { return (int64_t)(256 + 8 * RB200_MAX_REDS * kRedScratchPartials); }
+
+int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
+  if (!op) return fail("null fused op");
+  if (op->abi_version != RB200_ABI_VERSION) return fail("ABI version mismatch between caller and libramba_b200");
+  if (op->ndim < 1 || op->ndim > RB200_MAX_DIMS) return fail("ndim out of range");
+  if (op->n_views < 0 || op->n_views > RB200_MAX_VIEWS) return fail("too many views");
+  if (op->n_scalars < 0 || op->n_scalars > RB200_MAX_SCALARS) return fail("too many scalars");
+  if (op->n_insns < 0 || op->n_insns > RB200_MAX_INSNS) return fail("too many instructions");
+  if (op->n_regs < 0 || op->n_regs > RB200_MAX_REGS) return fail("too many spill registers");
+  if (op->n_reds < 0 || op->n_reds > RB200_MAX_REDS) return fail("too many reductions");
+  const int sms = sm_count();
+  if (sms <= 0) return fail("no usable CUDA device (libramba_b200 has no CPU path)");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+
+  constexpr int V = 4;
+  KParams P;
+  memset(&P, 0, sizeof(P));
+  P.ndim = op->ndim;
+  P.n_insns = op->n_insns;
+  P.n_views = op->n_views;
+  P.n_regs = op->n_regs;
+  P.n_reds = op->n_reds;
+  long long total = 1;
+  for (int d = 0; d < op->ndim; ++d) {
+    if (op->itershape[d] < 0) return fail("negative itershape");
+    P.shape[d] = op->itershape[d];
+    P.gstart[d] = op->global_start[d];
+    total *= op->itershape[d];
+  }
+  if (total == 0 || op->n_insns == 0) return 0;  // empty range: nothing to do
+  const long long inner = P.shape[op->ndim - 1];
+  P.n_chunks = (inner + V - 1) / V;
+
+  for (int i = 0; i < op->n_insns; ++i) {
+    const rb200_insn& I = op->insns[i];
+    if (I.op >= RB200_NUM_OPS) return fail("bad opcode");
+    if (I.ctype > RB200_T_I64) return fail("bad compute class");
+    const uint8_t kinds[3] = {I.a_kind, I.b_kind, I.c_kind};
+    const uint8_t idxs[3] = {I.a_idx, I.b_idx, I.c_idx};
+    for (int q = 0; q < 3; ++q) {
+      if (I.op == RB200_OP_RED && q == 1) continue;  // b_idx is the slot
+      switch (kinds[q]) {
+        case RB200_K_NONE:
+        case RB200_K_ACC: break;
+        case RB200_K_REG: if (idxs[q] >= op->n_regs) return fail("register index out of range"); break;
+        case RB200_K_VIEW: if (idxs[q] >= op->n_views) return fail("view index out of range"); break;
+        case RB200_K_SCAL: if (idxs[q] >= op->n_scalars) return fail("scalar index out of range"); break;
+        case RB200_K_IOTA: if (idxs[q] >= op->ndim) return fail("iota dim out of range"); break;
+        default: return fail("bad operand kind");
+      }
+    }
+    if (I.st_reg != RB200_NOSTORE && I.st_reg >= op->n_regs) return fail("st_reg out of range");
+    if (I.st_view != RB200_NOSTORE && I.st_view >= op->n_views) return fail("st_view out of range");
+    if (I.mask_reg != RB200_NOSTORE && I.mask_reg >= op->n_regs) return fail("mask_reg out of range");
+    if (I.op == RB200_OP_SINCOS && I.st2 >= op->n_regs) return fail("sincos st2 out of range");
+    if (I.op == RB200_OP_RED && I.b_idx >= op->n_reds) return fail("reduction slot out of range");
+    P.insns[i] = I;
+  }
+  for (int i = 0; i < op->n_scalars; ++i) P.scalars[i] = op->scalars[i];
+
+  for (int i = 0; i < op->n_views; ++i) {
+    const rb200_view& v = op->views[i];
+    const int es = dtype_size(v.dtype);
+    if (es == 0) return fail("bad view dtype");
+    if (!v.base) return fail("null view base pointer");
+    KView& k = P.views[i];
+    k.base = (char*)v.base;
+    k.dtype = v.dtype;
+    for (int d = 0; d < op->ndim; ++d) k.stride[d] = v.stride[d];
+    // vector path: innermost stride 1, base and every outer stride aligned to min(16, V*es)
+    const long long align = (V * es >= 16) ? 16 : V * es;
+    bool vec = (v.stride[op->ndim - 1] == 1) && (((uintptr_t)v.base) % align == 0);
+    for (int d = 0; d < op->ndim - 1 && vec; ++d)
+      if (op->itershape[d] > 1 && ((v.stride[d] * es) % align) != 0) vec = false;
+    k.vec = vec ? 1 : 0;
+  }
+
+  const size_t smem = (size_t)op->n_regs * V * kThreads * sizeof(unsigned long long);
+  cudaError_t e;
+
+  if (op->n_axis_red_dims != 0) {
+    // axis mode: the first n_axis_red_dims dims are the reduced ones (host permutes)
+    const int nred = op->n_axis_red_dims;
+    if (nred >= op->ndim) return fail("axis reduction needs at least one kept dim");
+    if (op->n_reds < 1) return fail("axis reduction without reduction slots");
+    if (!op->red_scratch) return fail("axis reduction needs a partial buffer");
+    P.red_ndim = nred;
+    long long red_len = 1, kept_rows = 1;
+    for (int d = 0; d < nred; ++d) red_len *= P.shape[d];
+    for (int d = nred; d < op->ndim - 1; ++d) kept_rows *= P.shape[d];
+    const long long kept_work = kept_rows * P.n_chunks;
+    int n_split = op->axis_nsplit;
+    if (n_split < 1) n_split = 1;
+    if ((long long)n_split > red_len) n_split = (int)red_len;
+    P.red_len = red_len;
+    P.n_split = n_split;
+    P.red_split = (red_len + n_split - 1) / n_split;
+    P.total_work = kept_work * n_split;
+    P.red_partials = (unsigned long long*)op->red_scratch;
+    for (int s = 0; s < op->n_reds; ++s) {
+      P.reds[s].op = op->reds[s].op;
+      P.reds[s].ctype = op->reds[s].ctype;
+    }
+    long long blocks = (P.total_work + kThreads - 1) / kThreads;
+    long long cap = (long long)sms * 8;
+    if (blocks > cap) blocks = cap;
+    e = launch_vm_axis_reduce(P, (unsigned)blocks, smem, stream);
+    if (e != cudaSuccess) return fail_cuda("vm_axis_reduce_kernel launch", e);
+    g_launches.fetch_add(1);
+    return 0;
+  }
+
+  long long rows = total / inner;
+  P.total_work = rows * P.n_chunks;
+  long long blocks = (P.total_work + kThreads - 1) / kThreads;
+  // persistent-style grid: a multiple of the SM count, capped; grid-stride covers the rest
+  long long cap = (long long)sms * 8;
+  if (op->n_reds > 0 && cap > kRedScratchPartials) cap = kRedScratchPartials;
+  if (blocks > cap) blocks = cap;
+  if (op->n_reds > 0) {
+    if (!op->red_scratch) return fail("global reduction needs red_scratch");
+    P.red_counter = (unsigned int*)op->red_scratch;
+    P.red_partials = (unsigned long long*)((char*)op->red_scratch + 256);
+    for (int s = 0; s < op->n_reds; ++s) {
+      if (!op->reds[s].out) return fail("null reduction output");
+      if (dtype_size(op->reds[s].out_dtype) == 0) return fail("bad reduction output dtype");
+      if (op->reds[s].ctype != RB200_T_F64 && op->reds[s].ctype != RB200_T_I64) return fail("reduction class must be F64 or I64");
+      P.reds[s].op = op->reds[s].op;
+      P.reds[s].ctype = op->reds[s].ctype;
+      P.reds[s].out = op->reds[s].out;
+      P.reds[s].out_dtype = op->reds[s].out_dtype;
+    }
+  }
+  e = launch_vm_elementwise(P, (unsigned)blocks, smem, stream);
+  if (e != cudaSuccess) return fail_cuda("vm_elementwise_kernel launch", e);
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+int rb200_reduce_partials(void* out, const void* partials, int64_t n, int64_t k, int64_t stride_k, int32_t dtype,
+                          int32_t redop, void* stream_v) {
+  if (!out || !partials) return fail("null pointer");
+  if (n <= 0 || k <= 0) return 0;
+  if (sm_count() <= 0) return fail("no usable CUDA device (libramba_b200 has no CPU path)");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dtype == RB200_F64)
+    reduce_partials_kernel<double><<<(unsigned)blocks, 256, 0, stream>>>((double*)out, (const double*)partials, n, k, stride_k, redop);
+  else if (dtype == RB200_I64)
+    reduce_partials_kernel<long long><<<(unsigned)blocks, 256, 0, stream>>>((long long*)out, (const long long*)partials, n, k, stride_k, redop);
+  else
+    return fail("reduce_partials: dtype must be F64 or I64 (accumulator classes)");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda("reduce_partials_kernel launch", e);
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+}  // extern "C"

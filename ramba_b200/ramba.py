@@ -1,0 +1,1695 @@
+"""ramba_b200.ramba — array handles, operator tables and the deferred-op fuser.
+
+Drop-in for the part of `ramba.ramba` that lies on the fused elementwise / reduction /
+shifted-slice path:
+
+  bdarray / ndarray        ramba/ramba.py:1049-1158, 5409-6901
+  op tables + make_method  ramba/ramba.py:7842-7993
+  deferred_op              ramba/ramba.py:8039-8533  (add_op / do_ops / execute keep their call shape;
+                           the alternating "code string, operand" oplist becomes [dst, expression])
+  creation / sync          ramba/ramba.py:8563-8991, 9843-9849
+
+API calls append statements to the current fused op; nothing runs until a flush (sync(),
+asarray(), a scalar read, or an incompatible op).  At flush, arrays whose Python handle is dead
+never touch HBM (they are register temporaries), live ones are read/written in place
+(ramba/ramba.py:8123-8127).  Execution is SPMD: every rank runs this driver code and executes its
+own division on its own GPU through ramba_b200.runtime.
+"""
+import builtins
+import numbers
+import weakref
+
+import numpy as np
+
+from . import _cabi as cabi
+from . import common
+from . import shardview
+from .common import dprint, timer, add_time
+from .program import E, Iota, Lowering, ProgramError, TempVar, dtype_class, rb_dtype
+from .runtime import RT, torch_dtype
+
+int64 = np.int64
+float64 = np.float64
+float32 = np.float32
+
+_gid_counter = [0]
+
+
+def _new_gid():
+    """Deterministic ids so that all SPMD ranks agree (ramba/ramba_uuid.py:15-31)."""
+    _gid_counter[0] += 1
+    return _gid_counter[0]
+
+
+def shapeToInt(shape):
+    if isinstance(shape, numbers.Integral):
+        return (int(shape),)
+    return tuple(int(x) if isinstance(x, numbers.Integral) else x for x in shape)
+
+
+# =============================================================================================
+# bdarray: the physical distributed buffer
+# =============================================================================================
+class bdarray:
+    gid_map = weakref.WeakValueDictionary()
+    __slots__ = ("shape", "gid", "pad", "distribution", "nrefs", "remote_constructed", "flex_dist", "dtype", "__weakref__")
+
+    def __init__(self, shape, distribution, gid, pad, fdist, dtype):
+        self.shape = shape
+        self.gid = gid
+        self.pad = pad
+        self.distribution = distribution
+        self.nrefs = 0
+        self.remote_constructed = False
+        self.flex_dist = fdist
+        self.dtype = np.dtype(dtype)
+        bdarray.gid_map[gid] = self
+
+    def ndarray_del_callback(self):
+        self.nrefs -= 1
+        if self.nrefs < 1:
+            deferred_op.del_remote_array(self.gid)
+
+    @classmethod
+    def assign_bdarray(cls, nd, shape, gid=None, distribution=None, pad=0, flexible_dist=False, dtype=None, **kwargs):
+        if gid is None:
+            gid = _new_gid()
+        bd = cls.gid_map.get(gid)
+        if bd is None:
+            if dtype is None:
+                dtype = np.float64
+            if shape == ():
+                distribution = np.zeros((), dtype=dtype)
+            elif distribution is None:
+                distribution = shardview.default_distribution(shape, **kwargs)
+            else:
+                # a new array: same boxes, fresh buffer coordinates
+                distribution = [shardview.clean_range(s) for s in distribution]
+            bd = cls(shape, distribution, gid, pad, flexible_dist, dtype)
+        bd.nrefs += 1
+        return bd
+
+    @classmethod
+    def get_by_gid(cls, gid):
+        return cls.gid_map[gid]
+
+    @classmethod
+    def valid_gid(cls, gid):
+        return gid in cls.gid_map
+
+
+class ndarray_details:
+    __slots__ = ("shape", "distribution", "dtype", "local_border")
+
+    def __init__(self, nd):
+        self.shape = nd.shape
+        self.distribution = nd.distribution
+        self.dtype = nd.dtype
+        self.local_border = nd.local_border
+
+
+# =============================================================================================
+# the fuser
+# =============================================================================================
+class ArrRef:
+    """What a statement remembers about an array operand.  Statements must not keep the Python
+    handle alive: whether a temporary is materialised depends on its handle being dead at flush
+    time (ramba/ramba.py:8123-8127; the reference keeps only variable names + the bdarray)."""
+
+    __slots__ = ("gid", "distribution", "shape", "dtype", "local_border", "bd", "value")
+
+    def __init__(self, nd):
+        self.gid = nd.gid
+        self.distribution = nd.distribution
+        self.shape = nd.shape
+        self.dtype = nd.dtype
+        self.local_border = nd.local_border
+        self.bd = nd.bdarray
+        self.value = nd.distribution.item() if nd.shape == () else None
+
+
+def _detach(x):
+    if isinstance(x, ndarray):
+        return ArrRef(x)
+    if isinstance(x, E):
+        return E(x.op, *[_detach(a) for a in x.args], imm=x.imm)
+    return x
+
+
+def _walk_operands(x, out):
+    if isinstance(x, E):
+        for a in x.args:
+            _walk_operands(a, out)
+    else:
+        out.append(x)
+    return out
+
+
+class deferred_op:
+    ramba_deferred_ops = None
+    count = 0
+    max_statements = 40
+
+    class temp_var(TempVar):
+        pass
+
+    def __init__(self, shape, distribution, fdist):
+        self.shape = shape
+        self.distribution = distribution
+        self.flex_dist = fdist
+        self.delete_gids = []
+        self.read_arrs = []
+        self.write_arrs = []
+        self.use_gids = {}  # gid -> ([(view index within gid, details)], bd_shape, bd_distribution, pad, flex)
+        self.preconstructed_gids = {}
+        self.statements = []
+        self.axis_reductions = []
+        self.keepalives = set()
+        self.uuid = "ramba_def_ops_%05d" % deferred_op.count
+        deferred_op.count += 1
+
+    @classmethod
+    def get_temp_var(cls):
+        return cls.temp_var()
+
+    def add_gid(self, nd):
+        gid = nd.gid
+        bd = nd.bdarray
+        if gid not in self.use_gids:
+            self.use_gids[gid] = ([], bd.shape, bd.distribution, bd.pad, bd.flex_dist and not bd.remote_constructed)
+            self.keepalives.add(bd)
+        for det in self.use_gids[gid][0]:
+            if det.distribution is nd.distribution or shardview.dist_is_eq(det.distribution, nd.distribution):
+                return
+        self.use_gids[gid][0].append(ArrRef(nd))
+        if bd.remote_constructed:
+            self.preconstructed_gids[gid] = True
+
+    # ---- adding statements --------------------------------------------------------------
+    @classmethod
+    def add_op(cls, oplist, write_array, imports=(), axis_reduce=None, precode=(), postcode=()):
+        """oplist = [dst, expr]: `dst = expr` for every index of the iteration space.  dst is an
+        ndarray or a temp_var; expr is an E tree over ndarrays, scalars, temp_vars and Iota.
+        Global reductions pass precode=[tmp, init] and postcode=[red_array_view, redop-name]
+        (ramba/ramba.py:5798-5807); axis reductions pass axis_reduce=(axes, red_view)
+        (ramba/ramba.py:5809-5814)."""
+        t0 = timer()
+        dst, expr = oplist[0], oplist[1]
+        operands = ([dst] if isinstance(dst, ndarray) else []) + [o for o in _walk_operands(expr, []) if isinstance(o, ndarray)]
+        arr = write_array if write_array is not None else next((o for o in operands if isinstance(o, ndarray)), None)
+        assert arr is not None, "Deferred op with no ndarray parameter"
+        shape, distribution = arr.shape, arr.distribution
+        cur = cls.ramba_deferred_ops
+        if cur is not None and (
+            cur.shape != shape
+            or (
+                not shardview.compatible_distributions(cur.distribution, distribution)
+                and (arr.bdarray.remote_constructed or not arr.bdarray.flex_dist)
+                and not cur.flex_dist
+            )
+            or len(cur.statements) >= cls.max_statements
+        ):
+            cls.do_ops()
+        cur = cls.ramba_deferred_ops
+        # reductions on an axis must agree (ramba/ramba.py:8425-8432)
+        if cur is not None and axis_reduce is not None and cur.axis_reductions and cur.axis_reductions[0][0] != list(axis_reduce[0]):
+            cls.do_ops()
+        if cur is not None and axis_reduce is None and cur.axis_reductions:
+            # a plain statement after an axis reduction would run once per reduced element
+            cls.do_ops()
+        cur = cls.ramba_deferred_ops
+        # alias check 1: reads/writes a shifted version of an array written earlier in this op
+        if cur is not None and builtins.any(
+            o.gid == wgid and wdist is not None and not shardview.dist_is_eq(wdist, o.distribution)
+            for o in operands for (wgid, wdist) in cur.write_arrs
+        ):
+            cls.do_ops()
+        cur = cls.ramba_deferred_ops
+        # alias check 2: writes an array that is also read through a different view
+        if write_array is not None and isinstance(dst, ndarray) and (
+            builtins.any(o is not dst and o.gid == write_array.gid and not shardview.dist_is_eq(o.distribution, write_array.distribution)
+                         for o in operands)
+            or (cur is not None and builtins.any(
+                rgid == write_array.gid and rdist is not None and not shardview.dist_is_eq(rdist, write_array.distribution)
+                for (rgid, rdist) in cur.read_arrs))
+        ):
+            tmp_array = empty_like(write_array)
+            cls.add_op([tmp_array, expr], tmp_array, imports)
+            cls.do_ops()
+            cls.add_op([write_array, tmp_array], write_array)
+            return
+        if cls.ramba_deferred_ops is None:
+            cls.ramba_deferred_ops = cls(shape, distribution, arr.bdarray.flex_dist)
+        cur = cls.ramba_deferred_ops
+        if not arr.bdarray.flex_dist:
+            cur.distribution = distribution
+            cur.flex_dist = False
+        mask = None
+        if write_array is not None and isinstance(dst, ndarray) and write_array.maskarray is not None:
+            mask = write_array.maskarray
+            operands = [mask] + operands
+        if write_array is not None and isinstance(dst, ndarray):
+            cur.write_arrs.append((write_array.gid, None if write_array.bdarray.flex_dist else write_array.distribution))
+        for x in operands:
+            if x.shape == ():
+                continue
+            cur.read_arrs.append((x.gid, None if x.bdarray.flex_dist else x.distribution))
+            cur.add_gid(x)
+        expr = _detach(expr)
+        if axis_reduce is not None:
+            axes, red_view = axis_reduce
+            cur.add_gid(red_view)
+            cur.axis_reductions.append((list(axes), ArrRef(red_view)))
+            cur.statements.append(("ared", postcode[1], expr, ArrRef(red_view)))
+        elif precode:
+            red_view = postcode[0]
+            cur.add_gid(red_view)
+            cur.statements.append(("gred", postcode[1], expr, ArrRef(red_view)))
+        else:
+            cur.statements.append(("assign", _detach(dst), expr, _detach(mask) if mask is not None else None))
+        add_time("deferred_ops::add_op", timer() - t0)
+
+    @classmethod
+    def del_remote_array(cls, gid):
+        if cls.ramba_deferred_ops is None:
+            RT.destroy_array(gid)
+        else:
+            cls.ramba_deferred_ops.delete_gids.append(gid)
+
+    @classmethod
+    def do_ops(cls):
+        if cls.ramba_deferred_ops is not None:
+            cur = cls.ramba_deferred_ops
+            cls.ramba_deferred_ops = None
+            cur.execute()
+
+    # ---- flush ---------------------------------------------------------------------------
+    def execute(self):
+        t0 = timer()
+        live_gids = {
+            k: v for (k, v) in self.use_gids.items()
+            if (bdarray.valid_gid(k) and k not in self.delete_gids) or k in self.preconstructed_gids
+        }
+        # pin flexible distributions to the op's distribution (ramba/ramba.py:8130-8136)
+        for (_, (_, s, d, _, flex)) in live_gids.items():
+            if flex and self.shape == s:
+                d[:] = shardview.clean_dist(self.distribution)
+        # view table
+        views = []  # (gid, details)
+        vindex = {}
+
+        def view_of(nd):
+            key = nd.gid
+            lst = vindex.setdefault(key, [])
+            for (dist, idx) in lst:
+                if dist is nd.distribution or shardview.dist_is_eq(dist, nd.distribution):
+                    return idx
+            idx = len(views)
+            views.append((nd.gid, nd))
+            lst.append((nd.distribution, idx))
+            return idx
+
+        # count reads per view for CSE; register views in first-use order
+        reads = {}
+
+        def count_reads(x):
+            for o in _walk_operands(x, []):
+                if isinstance(o, ArrRef) and o.shape != () and o.gid in live_gids:
+                    i = view_of(o)
+                    reads[i] = reads.get(i, 0) + 1
+
+        for st in self.statements:
+            if st[0] == "assign":
+                count_reads(st[2])
+                if st[3] is not None:
+                    count_reads(st[3])
+                if isinstance(st[1], ArrRef) and st[1].gid in live_gids:
+                    view_of(st[1])
+            else:
+                count_reads(st[2])
+                view_of(st[3])
+        if len(views) > cabi.MAX_VIEWS:
+            raise ProgramError("fused op touches %d array views (max %d)" % (len(views), cabi.MAX_VIEWS))
+        if not views or not self.statements:
+            self._finish(live_gids)
+            return
+
+        lw = Lowering([rb_dtype(det.dtype) for (_, det) in views])
+        lw.note_view_reads(reads)
+        temps = {}
+        dead_values = {}
+
+        def resolve(o):
+            if isinstance(o, ArrRef):
+                if o.shape == ():
+                    return lw.scalar(o.value)
+                if o.gid in live_gids:
+                    return lw.read_view(view_of(o))
+                if o.gid in dead_values:
+                    return dead_values[o.gid]
+                return lw.scalar(0)  # read of an uninitialised, already dead array
+            if isinstance(o, TempVar):
+                return temps[o]
+            if isinstance(o, np.ndarray) and o.shape == ():
+                return lw.scalar(o.item())
+            return lw.scalar(o)
+
+        gred = []  # (slot, red_view)
+        ared = []
+        for st in self.statements:
+            if st[0] == "assign":
+                _, dst, expr, mask = st
+                tv = lw.build(expr, resolve)
+                if isinstance(dst, TempVar):
+                    temps[dst] = tv
+                elif dst.gid in live_gids:
+                    m = resolve(mask) if mask is not None else None
+                    lw.store(view_of(dst), tv, m)
+                else:
+                    dead_values[dst.gid] = tv
+            elif st[0] == "gred":
+                _, redop, expr, red_view = st
+                slot = lw.reduce(redop, lw.build(expr, resolve))
+                gred.append((slot, red_view))
+            else:
+                _, redop, expr, red_view = st
+                slot = lw.reduce(redop, lw.build(expr, resolve))
+                ared.append((slot, red_view, redop))
+        prog = lw.finish()
+        if common.debug_showcode and common.worker_num == 0:
+            print(format_program(prog, views, self.shape))
+        t1 = timer()
+        run_deferred_ops(self.uuid, views, prog, self.distribution, gred, ared,
+                         self.axis_reductions[0][0] if self.axis_reductions else None)
+        self._finish(live_gids)
+        add_time("driver_deferred_op", t1 - t0)
+        add_time("run_deferred_ops", timer() - t1)
+
+    def _finish(self, live_gids):
+        for g in self.delete_gids:
+            RT.destroy_array(g)
+        for k in live_gids.keys():
+            if k not in self.delete_gids and bdarray.valid_gid(k):
+                bd = bdarray.get_by_gid(k)
+                bd.remote_constructed = True
+                bd.flex_dist = False
+
+
+def format_program(prog, views, shape):
+    """RAMBA_SHOW_CODE: print the op list (the reference prints the generated Python,
+    ramba/ramba.py:8266-8284)."""
+    kinds = ["-", "acc", "r", "v", "s", "iota"]
+    cls = ["f64", "f32", "i64"]
+    lines = ["fused op over %s: %d insns, %d regs, %d views" % (shape, len(prog.insns), prog.n_regs, len(views))]
+    for i, f in enumerate(prog.insns):
+        def opnd(p):
+            k = f[p + "_kind"]
+            if k == 0:
+                return ""
+            return kinds[k] + (str(f[p + "_idx"]) if k != 1 else "")
+        extra = ""
+        if f["st_reg"] != cabi.NOSTORE:
+            extra += " ->r%d" % f["st_reg"]
+        if f["st_view"] != cabi.NOSTORE:
+            extra += " ->v%d" % f["st_view"]
+        lines.append("  %2d: %-8s %s %s %s %s%s" % (i, cabi.OPS[f["op"]], cls[f["ctype"]], opnd("a"), opnd("b"), opnd("c"), extra))
+    for i, (gid, det) in enumerate(views):
+        lines.append("  v%d: gid %s %s %s" % (i, gid, det.shape, det.dtype))
+    return "\n".join(lines)
+
+
+# =============================================================================================
+# executing a flush on this worker
+# =============================================================================================
+_pack_programs = {}
+
+
+def _pack_program(src_code, dst_code):
+    key = (src_code, dst_code)
+    if key not in _pack_programs:
+        lw = Lowering([src_code, dst_code])
+        lw.store(1, lw.read_view(0))
+        _pack_programs[key] = lw.finish()
+    return _pack_programs[key]
+
+
+_combine_programs = {}
+
+
+def _combine_program(red_code, acc_code, redop):
+    """red_view = red_view (op) partial  — applies stage-1 axis partials to the partial array."""
+    key = (red_code, acc_code, redop)
+    if key not in _combine_programs:
+        lw = Lowering([red_code, acc_code])
+        name = {cabi.RED_ADD: "add", cabi.RED_MUL: "mul", cabi.RED_MIN: "min", cabi.RED_MAX: "max"}[redop]
+        tv = lw.build(E(name, lw.read_view(0), lw.read_view(1)), None)
+        lw.store(0, tv)
+        _combine_programs[key] = lw.finish()
+    return _combine_programs[key]
+
+
+def _local_shape(bd_dist, w):
+    sv = bd_dist[w]
+    return tuple(int(x) for x in sv.size)
+
+
+def _contig_strides(shape, bcast):
+    st = [0] * len(shape)
+    acc = 1
+    for d in reversed(range(len(shape))):
+        if bcast[d]:
+            st[d] = 0
+        else:
+            st[d] = acc
+            acc *= int(shape[d])
+    return st, acc
+
+
+def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
+    """This worker's share of one flush (RemoteState.run_deferred_ops, ramba/ramba.py:3493-3819)."""
+    import torch
+
+    w, W = common.worker_num, common.num_workers
+    subspace = shardview.clean_range(exec_dist[w])
+    # allocate shards on first touch
+    shards = []
+    for (gid, det) in views:
+        bd = bdarray.get_by_gid(gid)
+        sh = RT.shards.get(gid)
+        if sh is None:
+            sh = RT.create_array(gid, _local_shape(bd.distribution, w), bd.dtype)
+        shards.append(sh)
+    nviews = len(views)
+    vdist = [det.distribution for (_, det) in views]
+    vcode = [rb_dtype(det.dtype) for (_, det) in views]
+    written = [bool(prog.view_written.get(i)) for i in range(nviews)]
+    ared_views = set()
+    # which views are aligned with the iteration box on every worker?
+    local_everywhere = []
+    for i in range(nviews):
+        ok = True
+        for j in range(W):
+            ss = shardview.clean_range(exec_dist[j])
+            if shardview.is_empty(ss):
+                continue
+            if not shardview.is_compat(ss, vdist[i][j]):
+                ok = False
+                break
+        local_everywhere.append(ok)
+    # parts[i] = list of (box, data_ptr, elem_strides or None(shard-addressed), sv)
+    parts = [[] for _ in range(nviews)]
+    recv_bufs = []
+    if W > 1 and not builtins.all(local_everywhere):
+        RT.ensure_process_group()
+        import torch.distributed as dist
+
+        ops = []
+        sends_keep = []
+        for i in range(nviews):
+            if local_everywhere[i]:
+                continue
+            if written[i]:
+                raise ProgramError("fused op writes a view that is not aligned with its iteration space")
+            bc = [int(a) < 0 for a in vdist[i][0].axis_map]
+            for peer in range(W):
+                if peer == w:
+                    continue
+                # what `peer` needs from me
+                pe = shardview.clean_range(exec_dist[peer])
+                if not shardview.is_empty(pe) and not shardview.is_compat(pe, vdist[i][peer]):
+                    part = shardview.intersect(vdist[i][w], exec_dist[peer])
+                    if not shardview.is_empty(part):
+                        shp = [1 if bc[d] else int(part.size[d]) for d in range(len(bc))]
+                        cst, n = _contig_strides(shp, bc)
+                        buf = torch.empty(max(n, 1), dtype=torch_dtype(views[i][1].dtype), device=RT.device)
+                        off, st = RT.bind_view(vdist[i][w], shards[i].strides, part)
+                        src_ptr = shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize
+                        RT.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
+                                  [(src_ptr, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
+                                   (buf.data_ptr(), cst, vcode[i])])
+                        ops.append(dist.P2POp(dist.isend, buf, peer))
+                        sends_keep.append(buf)
+                        RT.bytes_sent += buf.numel() * buf.element_size()
+                # what I need from `peer`
+                if not shardview.is_empty(subspace) and not shardview.is_compat(subspace, vdist[i][w]):
+                    part = shardview.intersect(vdist[i][peer], exec_dist[w])
+                    if not shardview.is_empty(part):
+                        shp = [1 if bc[d] else int(part.size[d]) for d in range(len(bc))]
+                        cst, n = _contig_strides(shp, bc)
+                        buf = torch.empty(max(n, 1), dtype=torch_dtype(views[i][1].dtype), device=RT.device)
+                        ops.append(dist.P2POp(dist.irecv, buf, peer))
+                        recv_bufs.append(buf)
+                        parts[i].append((shardview.clean_range(part), buf.data_ptr(), cst, None))
+        if ops:
+            if not RT.test_mode:
+                # the pack kernels run on the current stream; NCCL orders after them
+                pass
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+    if shardview.is_empty(subspace):
+        return
+    # local parts
+    for i in range(nviews):
+        sv = vdist[i][w]
+        if shardview.is_compat(subspace, sv):
+            parts[i].append((subspace, None, None, sv))
+        else:
+            part = shardview.intersect(sv, exec_dist[w])
+            if not shardview.is_empty(part):
+                parts[i].append((shardview.clean_range(part), None, None, shardview.mapslice_keep(sv, part.start, part.start + part.size)))
+    # ranges: every operand has one source inside a range
+    if builtins.all(len(p) == 1 and p[0][3] is not None and shardview.is_compat(p[0][0], subspace) for p in parts):
+        ranges = [subspace]
+    else:
+        ranges = shardview.get_range_splits_list([shardview.clean_range(subspace)] + [p[0] for pl in parts for p in pl])
+        ranges = [r for r in ranges if not shardview.is_empty(r) and shardview.contains(subspace, r)]
+    k = len(subspace.size)
+    red_axes = list(red_axes) if red_axes else []
+    order = red_axes + [d for d in range(k) if d not in red_axes]
+    gred_out = None
+    if gred:
+        gred_out = [None] * len(prog.reds)
+        for (slot, red_view) in gred:
+            i = [j for j, (g, det) in enumerate(views) if g == red_view.gid and shardview.dist_is_eq(det.distribution, red_view.distribution)][0]
+            # this worker's element of the partial array: the first element of its (size-1) block
+            off, _ = RT.bind_view(vdist[i][w], shards[i].strides, shardview.clean_range(vdist[i][w]))
+            gred_out[slot] = (shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize, vcode[i])
+    for r in ranges:
+        bound = []
+        ok = True
+        for i in range(nviews):
+            src = None
+            for (box, ptr, cst, sv) in parts[i]:
+                if shardview.contains(box, r):
+                    src = (box, ptr, cst, sv)
+                    break
+            if src is None:
+                if ared and builtins.any(views[i][0] == rv.gid for (_, rv, _) in ared):
+                    src = None
+                ok = ok and (src is not None)
+                bound.append(None)
+                continue
+            box, ptr, cst, sv = src
+            if sv is not None:
+                off, st = RT.bind_view(sv, shards[i].strides, r)
+                bound.append((shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize, st, vcode[i]))
+            else:
+                off = 0
+                for d in range(k):
+                    off += int(r.start[d] - box.start[d]) * cst[d]
+                bound.append((ptr + off * np.dtype(views[i][1].dtype).itemsize, list(cst), vcode[i]))
+        if not ok:
+            raise ProgramError("internal: an operand has no source for range %r" % (r,))
+        shape_r = [int(x) for x in r.size]
+        gs = [int(x) for x in r.start]
+        if not ared:
+            RT.launch(prog, shape_r, gs, bound, reds=gred_out, worker_num=w, num_workers=W)
+            continue
+        # ---- axis reduction: stage 1 into per-split partials, then fold into the partial array
+        shape_p = [shape_r[d] for d in order]
+        gs_p = [gs[d] for d in order]
+        bound_p = [(b[0], [b[1][d] for d in order], b[2]) for b in bound]
+        nred = len(red_axes)
+        kept_elems = 1
+        for d in range(nred, k):
+            kept_elems *= shape_p[d]
+        red_len = 1
+        for d in range(nred):
+            red_len *= shape_p[d]
+        kept_work = max(1, kept_elems // 4)
+        target = 148 * 2048
+        nsplit = 1 if kept_work >= target else builtins.min(builtins.max(1, red_len // 8), -(-target // kept_work))
+        nslots = len(prog.reds)
+        partials = torch.empty(nslots * nsplit * kept_elems + 1, dtype=torch.float64, device=RT.device)
+        prog_p = _remap_iota(prog, order)
+        RT.launch(prog_p, shape_p, gs_p, bound_p, n_axis_red=nred, axis_nsplit=nsplit,
+                  axis_partials=partials.data_ptr(), worker_num=w, num_workers=W)
+        for (slot, red_view, redop) in ared:
+            rop, rct = prog.reds[slot]
+            acc_code = cabi.F64 if rct == cabi.T_F64 else cabi.I64
+            base = partials.data_ptr() + slot * nsplit * kept_elems * 8
+            tot_ptr = base
+            if nsplit > 1:
+                tot = torch.empty(kept_elems + 1, dtype=torch.float64, device=RT.device)
+                RT._reduce_partials(tot.data_ptr(), base, kept_elems, nsplit, kept_elems, acc_code, rop, RT.stream_handle())
+                tot_ptr = tot.data_ptr()
+                recv_bufs.append(tot)
+            i = [j for j, (g, det) in enumerate(views) if g == red_view.gid and shardview.dist_is_eq(det.distribution, red_view.distribution)][0]
+            kept_shape = shape_p[nred:]
+            cst, _ = _contig_strides(kept_shape, [False] * len(kept_shape))
+            rb = bound_p[i]
+            RT.launch(_combine_program(vcode[i], acc_code, rop), kept_shape, gs_p[nred:],
+                      [(rb[0], rb[1][nred:], rb[2]), (tot_ptr, cst, acc_code)])
+        recv_bufs.append(partials)
+    if recv_bufs and not RT.test_mode:
+        # staging buffers must outlive the kernels that read them
+        torch.cuda.current_stream(RT.device).synchronize()
+
+
+def _remap_iota(prog, order):
+    """Iteration dims were permuted to `order`: point IOTA operands at the new positions."""
+    if not prog.uses_iota:
+        return prog
+    import copy
+
+    p = copy.copy(prog)
+    inv = {d: i for i, d in enumerate(order)}
+    p.insns = []
+    for f in prog.insns:
+        g = dict(f)
+        for nm in ("a", "b", "c"):
+            if g[nm + "_kind"] == cabi.K_IOTA:
+                g[nm + "_idx"] = inv[g[nm + "_idx"]]
+        p.insns.append(g)
+    p.uses_iota = {inv[d] for d in prog.uses_iota}
+    return p
+
+
+# =============================================================================================
+# ndarray
+# =============================================================================================
+def unify_args(lhs, rhs, dtype):
+    """Result dtype of a binary op (ramba/ramba.py:4170-4191)."""
+    rhs_dtype = rhs.dtype if hasattr(rhs, "dtype") else None
+    if dtype is not None:
+        if dtype == "float":
+            if rhs_dtype is None:
+                try:
+                    rhs_dtype = np.dtype(type(rhs))
+                except Exception:
+                    rhs_dtype = None
+            dtype = np.float32 if (rhs_dtype == np.float32 and lhs == np.float32) else np.float64
+        return np.dtype(dtype)
+    try:
+        return np.result_type(lhs, rhs)
+    except Exception:
+        return np.result_type(lhs, rhs_dtype)
+
+
+def numpy_broadcast_shape(a, b):
+    def shp(x):
+        if isinstance(x, tuple):
+            return x
+        if isinstance(x, (ndarray, np.ndarray)):
+            return x.shape
+        if isinstance(x, numbers.Number):
+            return ()
+        return (1,)
+
+    sa, sb = shp(a), shp(b)
+    if (isinstance(a, numbers.Number) or sa == ()) and (isinstance(b, numbers.Number) or sb == ()):
+        return None
+    return tuple(np.broadcast_shapes(sa, sb))
+
+
+def canonical_dim(dim, dim_size, end=False, neg_slice=False, checkbounds=False, axis=0):
+    if not isinstance(dim, (numbers.Integral, type(None))):
+        raise TypeError("indices must be integer or None")
+    if dim is None:
+        dim = dim_size if end != neg_slice else 0
+        dim -= 1 if neg_slice else 0
+        return dim
+    if dim < -dim_size:
+        if checkbounds:
+            raise IndexError(f"index {dim} out of bounds for axis {axis} with size {dim_size}")
+        return -1 if neg_slice else 0
+    elif dim < 0:
+        return dim + dim_size
+    elif dim < dim_size:
+        return dim
+    else:
+        if checkbounds:
+            raise IndexError(f"index {dim} out of bounds for axis {axis} with size {dim_size}")
+        return dim_size - 1 if neg_slice else dim_size
+
+
+def canonical_slice(sl, dim_size):
+    s = 1 if sl.step is None else sl.step
+    if not isinstance(s, numbers.Integral):
+        raise TypeError("step must be integer or None")
+    if s == 0:
+        raise TypeError("step cannot be zero")
+    return slice(canonical_dim(sl.start, dim_size, neg_slice=(s < 0)),
+                 canonical_dim(sl.stop, dim_size, end=True, neg_slice=(s < 0)), int(s))
+
+
+def canonical_index(index, shape):
+    if not isinstance(index, tuple):
+        index = (index,)
+    if len(index) > len(shape):
+        raise IndexError(f"too many indices for array: array is {len(shape)}-dimensional, but {len(index)} were indexed")
+    out = []
+    for i in range(len(shape)):
+        if i >= len(index):
+            out.append(slice(0, shape[i], 1))
+            continue
+        ti = index[i]
+        if isinstance(ti, numbers.Integral):
+            ni = canonical_dim(ti, shape[i], checkbounds=True, axis=i)
+            out.append(slice(ni, ni + 1, 1))
+        elif isinstance(ti, slice):
+            out.append(canonical_slice(ti, shape[i]))
+        else:
+            raise IndexError("unsupported index term %r on the fused path" % (ti,))
+    return tuple(out)
+
+
+def _slice_len(s):
+    if s.step > 0:
+        return builtins.max(0, -(-(s.stop - s.start) // s.step))
+    return builtins.max(0, -(-(s.start - s.stop) // (-s.step)))
+
+
+class ndarray:
+    __slots__ = ("base", "bdarray", "shape", "distribution", "local_border", "readonly", "maskarray", "__weakref__")
+    __array_priority__ = 20.0
+
+    def __init__(self, shape, dtype=None, *, base=None, distribution=None, local_border=0, flex_dist=True,
+                 readonly=False, maskarray=None, **kwargs):
+        if isinstance(shape, ndarray):  # copy constructor
+            o = shape
+            base, distribution, local_border, dtype = o.base if o.base is not None else o, o.distribution, o.local_border, o.dtype
+            flex_dist, readonly, maskarray, shape = o.bdarray.flex_dist, o.readonly, o.maskarray, o.shape
+        self.base = base
+        gid = None
+        if base is not None:
+            gid = base.gid
+            if base.readonly:
+                readonly = True
+        shape = shapeToInt(shape)
+        self.bdarray = bdarray.assign_bdarray(self, shape, gid, distribution, local_border, flex_dist, dtype, **kwargs)
+        self.shape = shape
+        self.distribution = distribution if (distribution is not None and gid is not None) else self.bdarray.distribution
+        self.local_border = local_border
+        self.readonly = readonly
+        self.maskarray = maskarray
+
+    def __del__(self):
+        try:
+            self.bdarray.ndarray_del_callback()
+        except Exception:
+            pass
+
+    # ---- properties
+    @property
+    def gid(self):
+        return self.bdarray.gid
+
+    @property
+    def dtype(self):
+        return self.bdarray.dtype
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape)) if self.shape else 1
+
+    def __len__(self):
+        return self.shape[0]
+
+    @property
+    def T(self):
+        return self.transpose()
+
+    def get_details(self):
+        return ndarray_details(self)
+
+    def instantiate(self):
+        deferred_op.do_ops()
+        return self
+
+    # ---- host round trip (ramba/ramba.py:5735-5765)
+    def asarray(self, out=None):
+        """NumPy copy of the whole array on every rank.  `out` (optional, ramba_b200 extension):
+        a preallocated C-contiguous host array (e.g. a view of pinned memory) to fill."""
+        if self.shape == ():
+            return self.distribution
+        deferred_op.do_ops()
+        return gather_to_host(self, out=out)
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.asarray()
+        return a if dtype is None else a.astype(dtype)
+
+    def item(self):
+        a = self.asarray()
+        return a.item()
+
+    def __float__(self):
+        return float(self.item())
+
+    def __int__(self):
+        return int(self.item())
+
+    def __bool__(self):
+        return bool(self.item())
+
+    def __index__(self):
+        return int(self.item())
+
+    def __repr__(self):
+        return "ramba_b200.ndarray(" + repr(self.asarray()) + ")"
+
+    def copy(self):
+        return copy(self)
+
+    # ---- elementwise machinery (ramba/ramba.py:5768-5786, 6055-6139)
+    @classmethod
+    def broadcast(cls, a, b):
+        new_shape = numpy_broadcast_shape(a, b)
+
+        def view(x):
+            if isinstance(x, ndarray) and x.shape == ():
+                return x.distribution
+            if not isinstance(x, ndarray) or new_shape == x.shape:
+                return x
+            return x.broadcast_to(new_shape)
+
+        return new_shape, view(a), view(b)
+
+    def broadcast_to(self, shape):
+        shape = shapeToInt(shape)
+        new_dims = len(shape) - len(self.shape)
+        if new_dims < 0 or builtins.any(a > 1 and b > 1 and a != b for a, b in zip(shape[new_dims:], self.shape)) or \
+                builtins.any(b != 1 and a != b for a, b in zip(shape[new_dims:], self.shape)):
+            raise ValueError("Non-broadcastable.")
+        bd = [i < new_dims or (shape[i] != 1 and self.shape[i - new_dims] == 1) for i in range(len(shape))]
+        if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
+            deferred_op.do_ops()
+        return ndarray(shape, base=self, distribution=shardview.broadcast(self.distribution, bd, shape),
+                       local_border=0, readonly=True)
+
+    def broadcastable_to(self, shape):
+        new_dims = len(shape) - len(self.shape)
+        if new_dims < 0:
+            return False
+        return not builtins.any(a > 1 and b > 1 and a != b for a, b in zip(shape[new_dims:], self.shape))
+
+    def array_unaryop(self, op, optext, reduction=False, dtype=None, axis=None, keepdims=False, redop=None, initval=0,
+                      asarray=False):
+        if dtype is None:
+            dtype = self.dtype
+        elif isinstance(dtype, str) and dtype == "float":
+            dtype = np.float32 if self.dtype == np.float32 else np.float64
+        dtype = np.dtype(dtype)
+        if not reduction:
+            new = create_array_with_divisions(self.shape, self.distribution, dtype=dtype)
+            deferred_op.add_op([new, E(optext, self)], new)
+            return new
+        return self._reduction(op, redop, dtype, axis, keepdims, initval, asarray)
+
+    def array_binop(self, rhs, op, optext, inplace=False, reverse=False, dtype=None):
+        if isinstance(rhs, np.ndarray):
+            rhs = fromarray(rhs) if rhs.shape != () else rhs.item()
+        if isinstance(rhs, (list, tuple)):
+            rhs = fromarray(np.array(rhs))
+        if not isinstance(rhs, (ndarray, numbers.Number, np.generic, bool)):
+            return NotImplemented
+        new_dtype = unify_args(self.dtype, rhs, dtype)
+        if op == "__truediv__":
+            # division becomes multiplication by the reciprocal (ramba/ramba.py:6121-6126)
+            optext = "mul"
+            rhs = 1.0 / rhs
+        elif op == "__itruediv__":
+            optext = "mul"
+            rhs = 1.0 / rhs
+        new_shape, selfview, rhsview = ndarray.broadcast(self, rhs)
+        if new_shape is None:  # 0-d with scalar: compute on the host
+            a = self.distribution if isinstance(self, ndarray) else self
+            b = rhs.distribution if isinstance(rhs, ndarray) else rhs
+            res = getattr(np.asarray(a), op)(b) if not reverse else getattr(np.asarray(a), op)(b)
+            return array(res)
+        if inplace:
+            if self.readonly:
+                raise ValueError("assignment destination is read-only")
+            assert self.shape == new_shape, "non-broadcastable output operand"
+            deferred_op.add_op([self, E(optext, self, rhsview)], self)
+            return self
+        new = empty(new_shape, dtype=new_dtype)
+        if reverse:
+            deferred_op.add_op([new, E(optext, rhsview, selfview)], new)
+        else:
+            deferred_op.add_op([new, E(optext, selfview, rhsview)], new)
+        return new
+
+    # ---- reductions (ramba/ramba.py:5789-5937)
+    def _reduction(self, op, redop, dtype, axis, keepdims, initval, asarray):
+        if axis is not None:
+            if isinstance(axis, numbers.Number):
+                axis = [axis]
+            axis = sorted(a % self.ndim if -self.ndim <= a < self.ndim else _raise_axis(a, self.ndim) for a in axis)
+            if len(axis) == self.ndim:
+                axis = None
+        if isinstance(initval, numbers.Integral) and not isinstance(initval, bool):
+            if initval < 0:
+                initval = getminmax(dtype)[0]
+            elif initval > 1:
+                initval = getminmax(dtype)[1]
+        if self.maskarray is not None:
+            axis = None
+        if axis is None or (axis == [0] and self.ndim == 1):
+            dsz, dist, bdist = shardview.reduce_all_axes(self.shape, self.distribution)
+            red_arr = full(dsz, initval, dtype=dtype, distribution=dist, no_defer=True)
+            red_bcast = ndarray(self.shape, base=red_arr, distribution=bdist, local_border=0, readonly=False)
+            tmp = deferred_op.get_temp_var()
+            src = self
+            deferred_op.add_op([tmp, self if self.maskarray is None else E("where", self.maskarray, self, _identity_scalar(redop, dtype))],
+                               red_bcast, precode=[tmp, initval], postcode=[red_bcast, redop])
+            return _reduction2b(red_arr, op, dtype, asarray)
+        dsz, dist, bdist = shardview.reduce_axes(self.shape, self.distribution, axis)
+        red_arr = full(dsz, initval, dtype=dtype, distribution=dist, no_defer=True)
+        red_bcast = ndarray(self.shape, base=red_arr, distribution=bdist, local_border=0, readonly=False)
+        deferred_op.add_op([red_bcast, self], red_bcast, axis_reduce=(axis, red_bcast), postcode=[red_bcast, redop])
+        return _reduction2(red_arr, op, redop, dtype, axis, keepdims is True)
+
+    def mean(self, axis=None, dtype=None, **kwargs):
+        n = self.size if axis is None else int(np.prod([self.shape[a] for a in ([axis] if isinstance(axis, numbers.Number) else axis)]))
+        s = self.sum(axis=axis, **kwargs)
+        if dtype is None:
+            dtype = np.float64 if self.dtype.kind in "iub" else self.dtype
+        if isinstance(s, ndarray):
+            return (s * (1.0 / n)).astype(dtype) if np.dtype(dtype) != np.result_type(s.dtype, 1.0) else s * (1.0 / n)
+        return np.dtype(dtype).type(s / n)
+
+    # ---- views
+    def __getitem__(self, index):
+        if isinstance(index, ndarray) and index.dtype == np.bool_:
+            if not index.broadcastable_to(self.shape):
+                raise IndexError("Mask index shape does not match array shape")
+            m = index if index.shape == self.shape else index.broadcast_to(self.shape)
+            return ndarray(self.shape, base=self, distribution=self.distribution, local_border=0,
+                           readonly=self.readonly, maskarray=m)
+        if not isinstance(index, tuple):
+            index = (index,)
+        if builtins.any(i is Ellipsis for i in index):
+            pos = [j for j, i in enumerate(index) if i is Ellipsis][0]
+            fill = self.ndim - (len(index) - 1)
+            index = index[:pos] + (slice(None),) * fill + index[pos + 1:]
+        if builtins.all(isinstance(i, numbers.Integral) for i in index) and len(index) == self.ndim:
+            cindex = canonical_index(index, self.shape)
+            deferred_op.do_ops()
+            return getitem_global(self, tuple(s.start for s in cindex))
+        cindex = canonical_index(index, self.shape)
+        if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
+            deferred_op.do_ops()
+        dim_shapes = tuple(_slice_len(x) for x in cindex)
+        sdist = shardview.slice_distribution(cindex, self.distribution)
+        axismap = [i for i in range(len(dim_shapes)) if i >= len(index) or isinstance(index[i], slice)]
+        if len(axismap) < len(dim_shapes):
+            dim_shapes, sdist = shardview.remap_axis(dim_shapes, sdist, axismap)
+        return ndarray(dim_shapes, base=self, distribution=sdist, local_border=0, readonly=self.readonly)
+
+    def __setitem__(self, index, value):
+        if self.readonly:
+            raise ValueError("assignment destination is read-only")
+        if isinstance(value, (list, tuple)):
+            value = np.array(value)
+        view = self[index]
+        if not isinstance(view, ndarray):  # single element
+            cindex = canonical_index(index, self.shape)
+            view = self[tuple(slice(s.start, s.start + 1) for s in cindex)]
+        if isinstance(value, (numbers.Number, np.generic)) or (isinstance(value, np.ndarray) and value.shape == ()):
+            deferred_op.add_op([view, value if not isinstance(value, np.ndarray) else value.item()], view)
+            return
+        if isinstance(value, np.ndarray):
+            value = fromarray(value)
+        if value.shape == ():
+            deferred_op.add_op([view, value.distribution.item()], view)
+            return
+        if not value.broadcastable_to(view.shape):
+            raise ValueError("could not broadcast input array from shape %s into shape %s" % (value.shape, view.shape))
+        if value.shape != view.shape:
+            value = value.broadcast_to(view.shape)
+        if not (view.gid == value.gid and shardview.dist_is_eq(view.distribution, value.distribution)):
+            deferred_op.add_op([view, value], view)
+
+    def remapped_axis(self, newmap):
+        if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
+            deferred_op.do_ops()
+        newshape, newdist = shardview.remap_axis(self.shape, self.distribution, newmap)
+        return ndarray(newshape, base=self, distribution=newdist, local_border=0, readonly=self.readonly)
+
+    def transpose(self, *args):
+        nd = self.ndim
+        if len(args) == 0 or (len(args) == 1 and args[0] is None):
+            return self.remapped_axis(list(range(nd - 1, -1, -1)))
+        if len(args) == 1 and isinstance(args[0], (tuple, list)):
+            args = tuple(args[0])
+        axes = [a % nd for a in args]
+        if sorted(axes) != list(range(nd)):
+            raise ValueError("axes don't match array")
+        return self.remapped_axis(axes)
+
+    def swapaxes(self, a1, a2):
+        axes = list(range(self.ndim))
+        axes[a1], axes[a2] = axes[a2], axes[a1]
+        return self.remapped_axis(axes)
+
+    def moveaxis(self, source, destination):
+        src = [s % self.ndim for s in ([source] if isinstance(source, numbers.Integral) else list(source))]
+        dst = [d % self.ndim for d in ([destination] if isinstance(destination, numbers.Integral) else list(destination))]
+        order = [n for n in range(self.ndim) if n not in src]
+        for d, s in sorted(zip(dst, src)):
+            order.insert(d, s)
+        return self.remapped_axis(order)
+
+    def astype(self, dtype, copy=True):
+        dtype = np.dtype(dtype)
+        if dtype == self.dtype:
+            return globals()["copy"](self) if copy else self
+        new = create_array_with_divisions(self.shape, self.distribution, dtype=dtype)
+        deferred_op.add_op([new, self], new)
+        return new
+
+    def clip(self, a_min, a_max, out=None):
+        new = out if out is not None else create_array_with_divisions(self.shape, self.distribution, dtype=self.dtype)
+        deferred_op.add_op([new, E("min", a_max, E("max", self, a_min))], new)
+        return new
+
+    def allclose(self, other, rtol=1e-5, atol=1e-8, equal_nan=False):
+        return bool(isclose(self, other, rtol=rtol, atol=atol, equal_nan=equal_nan).all())
+
+    # ---- NumPy protocol hooks (ramba/ramba.py:6825-6894)
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        if method != "__call__" or kwargs.get("out") is not None:
+            return NotImplemented
+        name = ufunc.__name__
+        alias = {"multiply": "mul", "subtract": "sub", "divide": "truediv", "true_divide": "truediv",
+                 "floor_divide": "floordiv", "add": "add", "power": "pow", "remainder": "mod", "mod": "mod",
+                 "absolute": "abs", "negative": "neg", "greater": "gt", "less": "lt", "greater_equal": "ge",
+                 "less_equal": "le", "equal": "eq", "not_equal": "ne", "bitwise_and": "and", "bitwise_or": "or",
+                 "bitwise_xor": "xor", "left_shift": "lshift", "right_shift": "rshift", "invert": "invert"}
+        name = alias.get(name, name)
+        if len(inputs) == 1:
+            f = getattr(self, name, None) or getattr(self, "__" + name + "__", None)
+            return f() if f is not None else NotImplemented
+        a, b = inputs
+        if a is self:
+            f = getattr(self, "__" + name + "__", None) or getattr(self, name, None)
+            return f(b) if f is not None else NotImplemented
+        f = getattr(self, "__r" + name + "__", None)
+        if f is not None:
+            return f(a)
+        if name in ("gt", "lt", "ge", "le", "eq", "ne"):
+            swap = {"gt": "lt", "lt": "gt", "ge": "le", "le": "ge", "eq": "eq", "ne": "ne"}[name]
+            return getattr(self, "__" + swap + "__")(a)
+        f = getattr(self, name, None)  # commutative named ops (minimum, maximum, logical_*)
+        return f(a) if f is not None else NotImplemented
+
+    def __array_function__(self, func, types, args, kwargs):
+        f = HANDLED_FUNCTIONS.get(func.__name__)
+        if f is None:
+            return NotImplemented
+        return f(*args, **kwargs)
+
+
+def _raise_axis(a, nd):
+    raise np.exceptions.AxisError(a, nd)
+
+
+def getminmax(dtype):
+    dtype = np.dtype(dtype)
+    if dtype.kind == "f":
+        return (-np.inf, np.inf)
+    if dtype.kind == "b":
+        return (False, True)
+    i = np.iinfo(dtype)
+    return (i.min, i.max)
+
+
+def _identity_scalar(redop, dtype):
+    if redop == cabi.RED_ADD:
+        return 0
+    if redop == cabi.RED_MUL:
+        return 1
+    mm = getminmax(dtype)
+    return mm[1] if redop == cabi.RED_MIN else mm[0]
+
+
+def _np_reduce(op):
+    return {"sum": np.sum, "prod": np.prod, "min": np.min, "max": np.max, "all": np.all, "any": np.any}[op]
+
+
+def _reduction2b(red_arr, op, dtype, asarray):
+    """Stage 2 of a global reduction: gather one partial per worker and reduce on the host
+    (ramba/ramba.py:5852-5863)."""
+    if builtins.all(i == 1 for i in red_arr.shape):
+        sl = (0,) * red_arr.ndim if not asarray else (slice(0, 1),) + (0,) * (red_arr.ndim - 1)
+        return red_arr[sl]
+    local = np.array(red_arr.asarray())
+    val = _np_reduce(op)(local)
+    if not asarray:
+        return np.sum(val, dtype=dtype)
+    return full((1,), val, dtype=dtype)
+
+
+def _reduction2(red_arr, op, redop, dtype, axis, keepdims):
+    """Stage 2 of an axis reduction: fold the per-division partial slices
+    (ramba/ramba.py:5818-5849)."""
+    nd = red_arr.ndim
+    if keepdims:
+        sl1 = tuple(slice(None) for _ in range(nd))
+    else:
+        sl1 = tuple(0 if i in axis else slice(None) for i in range(nd))
+    sl2 = tuple(slice(0, 1) if i in axis else slice(None) for i in range(nd))
+    k = [red_arr.shape[a] for a in axis]
+    if builtins.all(x == 1 for x in k):
+        return red_arr if keepdims else red_arr[sl1]
+    arr = empty_like(red_arr[sl2])
+    name = {cabi.RED_ADD: "add", cabi.RED_MUL: "mul", cabi.RED_MIN: "min", cabi.RED_MAX: "max"}[redop]
+    expr = None
+    for j in np.ndindex(tuple(k)):
+        sl = []
+        ii = 0
+        for i in range(nd):
+            if i in axis:
+                sl.append(slice(j[ii], j[ii] + 1))
+                ii += 1
+            else:
+                sl.append(slice(None))
+        piece = red_arr[tuple(sl)]
+        expr = piece if expr is None else E(name, expr, piece)
+    deferred_op.add_op([arr, expr], arr)
+    return arr[sl1]
+
+
+# ---- operator tables (ramba/ramba.py:7893-7993) ------------------------------------------------
+def _make_binop(name, optext, dtype=None, inplace=False, reverse=False):
+    def _method(self, rhs):
+        return self.array_binop(rhs, name, optext, inplace=inplace, reverse=reverse, dtype=dtype)
+
+    _method.__name__ = name
+    return _method
+
+
+array_binop_funcs = {
+    "__add__": ("add", None), "__mul__": ("mul", None), "__sub__": ("sub", None), "__floordiv__": ("floordiv", None),
+    "__truediv__": ("div", "float"), "__mod__": ("mod", None), "__pow__": ("pow", None),
+    "minimum": ("min", None), "maximum": ("max", None),
+    "__gt__": ("gt", np.bool_), "__lt__": ("lt", np.bool_), "__ge__": ("ge", np.bool_), "__le__": ("le", np.bool_),
+    "__eq__": ("eq", np.bool_), "__ne__": ("ne", np.bool_),
+    "logical_and": ("land", np.bool_), "logical_or": ("lor", np.bool_), "logical_xor": ("lxor", np.bool_),
+    "__and__": ("band", None), "__xor__": ("bxor", None), "__or__": ("bor", None),
+    "__lshift__": ("shl", None), "__rshift__": ("shr", None),
+}
+for _n, (_t, _d) in array_binop_funcs.items():
+    setattr(ndarray, _n, _make_binop(_n, _t, dtype=_d))
+array_binop_rfuncs = {
+    "__radd__": ("add", None), "__rmul__": ("mul", None), "__rsub__": ("sub", None), "__rtruediv__": ("div", "float"),
+    "__rfloordiv__": ("floordiv", None), "__rmod__": ("mod", None), "__rpow__": ("pow", None),
+    "__rand__": ("band", None), "__rxor__": ("bxor", None), "__ror__": ("bor", None),
+}
+for _n, (_t, _d) in array_binop_rfuncs.items():
+    setattr(ndarray, _n, _make_binop(_n, _t, dtype=_d, reverse=True))
+array_inplace_binop_funcs = {
+    "__iadd__": "add", "__isub__": "sub", "__imul__": "mul", "__itruediv__": "div", "__ifloordiv__": "floordiv",
+    "__imod__": "mod", "__ipow__": "pow",
+}
+for _n, _t in array_inplace_binop_funcs.items():
+    setattr(ndarray, _n, _make_binop(_n, _t, inplace=True))
+ndarray.__hash__ = None
+
+
+def _make_unop(name, optext, dtype=None):
+    def _method(self, **kwargs):
+        if "dtype" not in kwargs:
+            kwargs["dtype"] = dtype
+        return self.array_unaryop(name, optext, **kwargs)
+
+    _method.__name__ = name
+    return _method
+
+
+array_unaryop_funcs = {
+    "__abs__": ("abs", None), "abs": ("abs", None), "square": ("square", None), "sqrt": ("sqrt", "float"),
+    "sin": ("sin", "float"), "cos": ("cos", "float"), "tan": ("tan", "float"), "sinh": ("sinh", "float"),
+    "cosh": ("cosh", "float"), "tanh": ("tanh", "float"), "arcsin": ("asin", "float"), "arccos": ("acos", "float"),
+    "arctan": ("atan", "float"), "__neg__": ("neg", None), "exp": ("exp", "float"), "log": ("log", "float"),
+    "cbrt": ("cbrt", "float"),
+    "isfinite": ("isfinite", np.bool_), "isinf": ("isinf", np.bool_), "isnan": ("isnan", np.bool_),
+    "isneginf": ("isneginf", np.bool_), "isposinf": ("isposinf", np.bool_), "logical_not": ("lnot", np.bool_),
+    "__invert__": ("invert", None),
+}
+for _n, (_t, _d) in array_unaryop_funcs.items():
+    setattr(ndarray, _n, _make_unop(_n, _t, dtype=_d))
+
+
+def _make_reduction(name, redop, init, dtype=None):
+    def _method(self, axis=None, dtype=dtype, keepdims=False, asarray=False, **kwargs):
+        return self.array_unaryop(name, None, reduction=True, dtype=dtype, axis=axis, keepdims=keepdims, redop=redop,
+                                  initval=init, asarray=asarray)
+
+    _method.__name__ = name
+    return _method
+
+
+array_simple_reductions = {
+    "sum": (cabi.RED_ADD, 0, None), "prod": (cabi.RED_MUL, 1, None), "min": (cabi.RED_MIN, 2, None),
+    "max": (cabi.RED_MAX, -2, None), "all": (cabi.RED_MUL, True, np.bool_), "any": (cabi.RED_ADD, False, np.bool_),
+}
+for _n, (_r, _i, _d) in array_simple_reductions.items():
+    setattr(ndarray, _n, _make_reduction(_n, _r, _i, _d))
+
+
+# =============================================================================================
+# host <-> device edges
+# =============================================================================================
+def _shard_view_tensor(nd, w):
+    """torch view (this worker's part of `nd`, in view coordinates) of its shard."""
+    sv = nd.distribution[w]
+    sh = RT.shards[nd.gid]
+    box = shardview.clean_range(sv)
+    off, st = RT.bind_view(sv, sh.strides, box)
+    return sh.buf.as_strided([int(x) for x in sv.size], st, off) if builtins.min(st + [0]) >= 0 else None, off, st
+
+
+def _is_whole_shard(sv, sh):
+    k = len(sv.size)
+    return (k == len(sh.shape) and builtins.all(int(sv.axis_map[d]) == d and int(sv.steps[d]) == 1 and int(sv.base_offset[d]) == 0
+                                                and int(sv.size[d]) == sh.shape[d] for d in range(k)))
+
+
+def _part_to_host(nd, w, out=None):
+    """This worker's part of view `nd` as a contiguous host array (get_view, ramba/ramba.py:2160-2176)."""
+    import torch
+
+    sv = nd.distribution[w]
+    if shardview.is_empty(sv):
+        return np.zeros([0] * nd.ndim, dtype=nd.dtype)
+    if nd.gid not in RT.shards:
+        bd = nd.bdarray
+        RT.create_array(nd.gid, _local_shape(bd.distribution, w), bd.dtype)
+    sh = RT.shards[nd.gid]
+    shape = [int(x) for x in sv.size]
+    if _is_whole_shard(sv, sh) and nd.dtype != np.bool_:
+        n = int(np.prod(shape))
+        if out is not None and out.flags.c_contiguous and out.dtype == nd.dtype and out.size == n:
+            torch.from_numpy(out.reshape(-1)).copy_(sh.buf[:n])  # straight DMA (pinned `out`: full PCIe rate)
+            return out.reshape(shape)
+        return sh.buf[:n].cpu().numpy().reshape(shape)
+    bc = [int(a) < 0 for a in sv.axis_map]
+    cst, n = _contig_strides(shape, [False] * len(shape))
+    buf = torch.empty(max(n, 1), dtype=torch_dtype(nd.dtype), device=RT.device)
+    off, st = RT.bind_view(sv, sh.strides, shardview.clean_range(sv))
+    code = rb_dtype(nd.dtype)
+    RT.launch(_pack_program(code, code), shape, [0] * len(shape),
+              [(sh.buf.data_ptr() + off * sh.dtype.itemsize, st, code), (buf.data_ptr(), cst, code)])
+    RT.synchronize()
+    host = buf[:n].cpu().numpy().reshape(shape)
+    if nd.dtype == np.bool_:
+        host = host.astype(np.bool_)
+    return host
+
+
+def gather_to_host(nd, out=None):
+    """Full NumPy copy of a distributed view on every rank (asarray, ramba/ramba.py:5735-5765)."""
+    import torch
+
+    w, W = common.worker_num, common.num_workers
+    if W == 1:
+        sv = nd.distribution[0]
+        if shardview.is_empty(sv):
+            return np.empty(nd.shape, dtype=nd.dtype) if out is None else out
+        mine = _part_to_host(nd, w, out=out)
+        if tuple(mine.shape) == tuple(nd.shape):
+            return mine
+        ret = np.empty(nd.shape, dtype=nd.dtype) if out is None else out
+        ret[shardview.to_slice(sv)] = mine
+        return ret
+    ret = np.empty(nd.shape, dtype=nd.dtype) if out is None else out
+    mine = _part_to_host(nd, w)
+    RT.ensure_process_group()
+    import torch.distributed as dist
+
+    for i in range(W):
+        sv = nd.distribution[i]
+        if shardview.is_empty(sv):
+            continue
+        shape = [int(x) for x in sv.size]
+        if i == w:
+            t = torch.from_numpy(np.ascontiguousarray(mine.astype(np.uint8) if nd.dtype == np.bool_ else mine))
+        else:
+            t = torch.empty(shape, dtype=torch_dtype(nd.dtype))
+        if not RT.test_mode:
+            t = t.to(RT.device)
+        dist.broadcast(t, src=i)
+        part = t.cpu().numpy()
+        if nd.dtype == np.bool_:
+            part = part.astype(np.bool_)
+        ret[shardview.to_slice(sv)] = part
+    return ret
+
+
+def getitem_global(nd, index):
+    """One element as a NumPy scalar (getitem_global, ramba/ramba.py:2183-2189)."""
+    sl = tuple(slice(i, i + 1) for i in index)
+    v = nd[sl]
+    return gather_to_host(v).reshape(-1)[0]
+
+
+def fromarray(x, local_border=0, dtype=None, **kwargs):
+    """Distribute a NumPy array: every rank uploads its own block (ramba/ramba.py:8785-8850)."""
+    import torch
+
+    if isinstance(x, numbers.Number):
+        return array(x)
+    x = np.asarray(x)
+    if dtype is None:
+        dtype = x.dtype
+    if x.shape == ():
+        return array(x.astype(dtype))
+    new = ndarray(x.shape, dtype=dtype, flex_dist=False, **kwargs)
+    deferred_op.do_ops()
+    w = common.worker_num
+    sv = new.distribution[w]
+    sh = RT.create_array(new.gid, _local_shape(new.bdarray.distribution, w), new.dtype)
+    if not shardview.is_empty(sv):
+        blk = x[shardview.to_slice(sv)]
+        if blk.dtype != new.dtype:
+            blk = blk.astype(new.dtype)
+        if not blk.flags.c_contiguous:
+            blk = np.ascontiguousarray(blk)
+        if new.dtype == np.bool_:
+            blk = blk.astype(np.uint8)
+        t = torch.from_numpy(blk.reshape(-1))  # a view when x is contiguous: pinned x -> straight DMA
+        sh.buf[: t.numel()].copy_(t, non_blocking=True)
+    new.bdarray.remote_constructed = True
+    new.bdarray.flex_dist = False
+    return new
+
+
+def array(x, dtype=None, copy=True, **kwargs):
+    if isinstance(x, ndarray):
+        return x.copy() if copy else x
+    a = np.array(x, dtype=dtype)
+    if a.shape == ():
+        nd = ndarray((), dtype=a.dtype)
+        nd.distribution = a
+        nd.bdarray.distribution = a
+        return nd
+    return fromarray(a, **kwargs)
+
+
+def asarray(x, dtype=None, **kwargs):
+    if isinstance(x, ndarray):
+        return x if dtype is None or np.dtype(dtype) == x.dtype else x.astype(dtype)
+    return array(x, dtype=dtype)
+
+
+# =============================================================================================
+# creation (ramba/ramba.py:8563-8991)
+# =============================================================================================
+def create_array_with_divisions(shape, divisions, local_border=0, dtype=None):
+    new = ndarray(shape, dtype=dtype, distribution=None, local_border=local_border, flex_dist=False)
+    new.bdarray.distribution[:] = shardview.clean_dist(divisions)
+    return new
+
+
+def create_array(shape, filler, local_border=0, dtype=None, distribution=None, no_defer=False, **kwargs):
+    shape = shapeToInt(shape)
+    if dtype is None:
+        dtype = np.float64
+    new = ndarray(shape, dtype=dtype, distribution=distribution, local_border=local_border,
+                  flex_dist=(distribution is None), **kwargs)
+    if shape == ():
+        new.distribution = np.array(0 if filler is None else filler, dtype=dtype)
+        new.bdarray.distribution = new.distribution
+        return new
+    if filler is None:
+        return new  # allocation is lazy; nothing to run (empty)
+    deferred_op.add_op([new, filler], new)
+    if no_defer:
+        deferred_op.do_ops()
+    return new
+
+
+def init_array(shape, filler, local_border=0, dtype=None, distribution=None, **kwargs):
+    if callable(filler):
+        return fromfunction(filler, shape, dtype=dtype)
+    return create_array(shape, filler, local_border=local_border, dtype=dtype, distribution=distribution, **kwargs)
+
+
+def empty(shape, dtype=None, order="C", local_border=0, distribution=None, **kwargs):
+    return create_array(shape, None, local_border=local_border, dtype=dtype, distribution=distribution, **kwargs)
+
+
+def empty_like(other, dtype=None, **kwargs):
+    return empty(other.shape, dtype=other.dtype if dtype is None else dtype, **kwargs)
+
+
+def zeros(shape, dtype=None, order="C", local_border=0, distribution=None, **kwargs):
+    return create_array(shape, 0, local_border=local_border, dtype=dtype, distribution=distribution, **kwargs)
+
+
+def zeros_like(other, dtype=None, shape=None, **kwargs):
+    return zeros(other.shape if shape is None else shape, dtype=other.dtype if dtype is None else dtype)
+
+
+def ones(shape, dtype=None, order="C", local_border=0, distribution=None, **kwargs):
+    return create_array(shape, 1, local_border=local_border, dtype=dtype, distribution=distribution, **kwargs)
+
+
+def ones_like(other, dtype=None, shape=None, **kwargs):
+    return ones(other.shape if shape is None else shape, dtype=other.dtype if dtype is None else dtype)
+
+
+def full(shape, v, dtype=None, local_border=0, **kwargs):
+    if dtype is None:
+        dtype = np.asarray(v).dtype
+    return create_array(shape, v, local_border=local_border, dtype=dtype, **kwargs)
+
+
+def full_like(other, v, dtype=None, **kwargs):
+    return full(other.shape, v, dtype=other.dtype if dtype is None else dtype)
+
+
+def copy(arr, local_border=0):
+    new = create_array_with_divisions(arr.shape, arr.distribution, dtype=arr.dtype)
+    deferred_op.add_op([new, arr], new)
+    return new
+
+
+def arange(start, stop=None, step=None, dtype=None, *, like=None, local_border=0):
+    """index[0] + global_start[0] as a fused op (ramba/ramba.py:8952-8972)."""
+    if stop is None:
+        size = start
+    elif step is None:
+        size = stop - start
+    else:
+        size = (stop - start + step - 1) // step
+    res = empty((builtins.max(0, int(size)),), dtype=np.int64 if dtype is None else dtype, local_border=local_border)
+    if stop is None:
+        expr = Iota(0)
+    elif step is None:
+        expr = E("add", start, Iota(0))
+    else:
+        expr = E("add", start, E("mul", step, Iota(0)))
+    deferred_op.add_op([res, expr], res)
+    return res
+
+
+def linspace(start, stop, num=50, endpoint=True, retstep=False, dtype=None):
+    assert num > 0
+    length = stop - start
+    step = length / (num - 1) if endpoint else length / num
+    res = arange(num) * step + start
+    if dtype is not None:
+        res = res.astype(dtype)
+    return (res, step) if retstep else res
+
+
+def fromfunction(function, shape, dtype=None, **kwargs):
+    """Index-driven filler.  The reference compiles `function` with Numba per element
+    (ramba/ramba.py:1535-1595, 8904-8905); here it is evaluated ONCE on lazy index arrays
+    (iota operands), so it must be built from array operators / ramba functions."""
+    shape = shapeToInt(shape)
+    idx = []
+    for d in range(len(shape)):
+        a = empty(shape, dtype=np.int64)
+        deferred_op.add_op([a, Iota(d)], a)
+        idx.append(a)
+    out = function(*idx)
+    if not isinstance(out, ndarray):
+        out = full(shape, out)
+    if dtype is not None and np.dtype(dtype) != out.dtype:
+        out = out.astype(dtype)
+    return out
+
+
+def eye(N, M=None, k=0, dtype=float64, **kwargs):
+    M = N if M is None else M
+    return fromfunction(lambda i, j: (i + k) == j, (N, M)).astype(dtype)
+
+
+def identity(n, dtype=float64):
+    return eye(n, dtype=dtype)
+
+
+# =============================================================================================
+# module-level functions
+# =============================================================================================
+HANDLED_FUNCTIONS = {}
+
+
+def _as_nd(x):
+    if isinstance(x, ndarray):
+        return x
+    if isinstance(x, np.ndarray):
+        return fromarray(x)
+    return x
+
+
+def _unary_fn(name):
+    def f(x, *args, **kwargs):
+        x = _as_nd(x)
+        if not isinstance(x, ndarray):
+            return getattr(np, name)(x, *args, **kwargs)
+        return getattr(x, name)(*args, **kwargs)
+
+    f.__name__ = name
+    HANDLED_FUNCTIONS[name] = f
+    return f
+
+
+# names that shadow Python builtins live in `api` and are exported by the package __init__ only
+api = {}
+for _n in ("abs", "square", "sqrt", "sin", "cos", "tan", "sinh", "cosh", "tanh", "arcsin", "arccos", "arctan", "exp",
+           "log", "cbrt", "isfinite", "isinf", "isnan", "isneginf", "isposinf", "logical_not", "sum", "prod", "min",
+           "max", "all", "any", "mean"):
+    api[_n] = _unary_fn(_n)
+    if _n not in ("abs", "sum", "min", "max", "all", "any"):
+        globals()[_n] = api[_n]
+absolute = api["abs"]
+HANDLED_FUNCTIONS["absolute"] = absolute
+amin, amax = api["min"], api["max"]
+
+
+def _binary_fn(name, method, rmethod=None):
+    def f(a, b, **kwargs):
+        a, b = _as_nd(a), _as_nd(b)
+        if isinstance(a, ndarray):
+            return getattr(a, method)(b)
+        if isinstance(b, ndarray):
+            return getattr(b, rmethod or method)(a)
+        return getattr(np, name)(a, b)
+
+    f.__name__ = name
+    HANDLED_FUNCTIONS[name] = f
+    return f
+
+
+minimum = _binary_fn("minimum", "minimum")
+maximum = _binary_fn("maximum", "maximum")
+logical_and = _binary_fn("logical_and", "logical_and")
+logical_or = _binary_fn("logical_or", "logical_or")
+logical_xor = _binary_fn("logical_xor", "logical_xor")
+power = _binary_fn("power", "__pow__", "__rpow__")
+add = _binary_fn("add", "__add__", "__radd__")
+subtract = _binary_fn("subtract", "__sub__", "__rsub__")
+multiply = _binary_fn("multiply", "__mul__", "__rmul__")
+divide = _binary_fn("divide", "__truediv__", "__rtruediv__")
+true_divide = divide
+floor_divide = _binary_fn("floor_divide", "__floordiv__", "__rfloordiv__")
+mod = _binary_fn("mod", "__mod__", "__rmod__")
+
+
+def isclose(a, b, rtol=1e-5, atol=1e-8, equal_nan=False):
+    """ramba.internal_isclose (ramba/ramba.py:7834-7839) spelled with fused ops."""
+    a = _as_nd(a)
+    b = _as_nd(b)
+    if not isinstance(a, ndarray):
+        a, b = b, a
+        diff = absolute(b - a) if isinstance(b, ndarray) else absolute(a - b)
+    else:
+        diff = absolute(a - b)
+    bb = absolute(b) if isinstance(b, ndarray) else builtins.abs(b)
+    tol = bb * rtol + atol
+    res = logical_and(isfinite(a), diff <= tol)  # noqa: F821
+    res = logical_or(res, logical_and(isinf(a), a == b))  # noqa: F821
+    if equal_nan:
+        nb = isnan(b) if isinstance(b, ndarray) else bool(np.isnan(b))  # noqa: F821
+        res = logical_or(res, logical_and(isnan(a), nb))  # noqa: F821
+    return res
+
+
+def allclose(a, b, rtol=1e-5, atol=1e-8, equal_nan=False):
+    return bool(isclose(a, b, rtol=rtol, atol=atol, equal_nan=equal_nan).all())
+
+
+def where(cond, a=None, b=None):
+    """`a if cond else b` as one fused statement (ramba/ramba.py:9755-9799)."""
+    cond, a, b = _as_nd(cond), _as_nd(a), _as_nd(b)
+    shape = cond.shape
+    for x in (a, b):
+        if isinstance(x, ndarray):
+            shape = tuple(np.broadcast_shapes(shape, x.shape))
+
+    def view(x):
+        if isinstance(x, ndarray) and x.shape != () and x.shape != shape:
+            return x.broadcast_to(shape)
+        return x
+
+    adt = a.dtype if isinstance(a, ndarray) else np.asarray(a).dtype
+    new = empty(shape, dtype=adt)
+    deferred_op.add_op([new, E("where", view(cond), view(a), view(b))], new)
+    return new
+
+
+def clip(a, a_min, a_max, out=None):
+    return a.clip(a_min, a_max, out=out)
+
+
+def transpose(a, *args):
+    return a.transpose(*args)
+
+
+def swapaxes(a, a1, a2):
+    return a.swapaxes(a1, a2)
+
+
+def moveaxis(a, s, d):
+    return a.moveaxis(s, d)
+
+
+def broadcast_to(a, shape):
+    return a.broadcast_to(shape)
+
+
+def ndim(a):
+    return a.ndim if hasattr(a, "ndim") else np.ndim(a)
+
+
+def result_type(*args):
+    return np.result_type(*[a.dtype if isinstance(a, ndarray) else a for a in args])
+
+
+def isscalar(x):
+    return np.isscalar(x)
+
+
+for _n in ("where", "clip", "transpose", "swapaxes", "moveaxis", "broadcast_to", "ndim", "result_type", "allclose",
+           "isclose", "empty_like", "zeros_like", "ones_like", "full_like", "copy", "array"):
+    HANDLED_FUNCTIONS[_n] = globals()[_n]
+
+
+def sync():
+    """Flush pending fused ops and wait for this rank's GPU (ramba/ramba.py:9843-9849)."""
+    t0 = timer()
+    deferred_op.do_ops()
+    RT.synchronize()
+    add_time("sync", timer() - t0)
+
+
+def get_timing(details=False):
+    return common.get_timing(details)
+
+
+def get_timing_str(details=False):
+    return common.get_timing_str(details)
+
+
+def reset_timing():
+    common.reset_timing()

@@ -1,0 +1,280 @@
+"""Worker runtime: this rank's shards in HBM and the execution of fused ops on them.
+
+Stands where RemoteState does in the reference (ramba/ramba.py:1880-3971), for ONE worker — the
+process's own GPU.  The driver/worker RPC layer (ramba/ramba.py:3985-4104) disappears: under SPMD
+every rank runs the driver and calls its own runtime directly.
+
+  * shards: one flat torch tensor per (gid) holding this worker's block, allocated lazily at the
+    first flush that touches it (ramba/ramba.py:3506-3523, 1947-2005) and freed when the last
+    handle dies (destroy_array, ramba/ramba.py:1943-1945);
+  * run_deferred_ops: classifies every operand view as local / partly remote (is_compat /
+    get_overlaps / intersect, ramba/ramba.py:3558-3644), exchanges the pieces that cross GPUs
+    with grouped NCCL send/recv instead of pickled mailbox messages (ramba/ramba.py:3646-3693),
+    cuts the iteration box into ranges in which every operand has exactly one source
+    (get_range_splits_list, ramba/ramba.py:3698-3706) and launches the op list once per range
+    through the C-ABI (ramba/ramba.py:3758-3780).
+
+PyTorch is used for device memory, streams and torch.distributed only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi as cabi
+from . import common
+from . import shardview
+from .program import np_dtype, rb_dtype
+
+_TORCH_DTYPE = {
+    np.dtype(np.float64): torch.float64,
+    np.dtype(np.float32): torch.float32,
+    np.dtype(np.int64): torch.int64,
+    np.dtype(np.int32): torch.int32,
+    np.dtype(np.bool_): torch.uint8,  # stored as bytes 0/1
+    np.dtype(np.uint8): torch.uint8,
+    np.dtype(np.int8): torch.int8,
+    np.dtype(np.int16): torch.int16,
+    np.dtype(np.uint16): torch.uint16,
+    np.dtype(np.uint32): torch.uint32,
+}
+
+
+def torch_dtype(dt):
+    return _TORCH_DTYPE[np.dtype(dt)]
+
+
+class Shard:
+    """This worker's block of one bdarray (LocalNdarray, ramba/ramba.py:1169-1357, without
+    borders)."""
+
+    __slots__ = ("buf", "shape", "dtype", "strides")
+
+    def __init__(self, buf, shape, dtype):
+        self.buf = buf
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        st = []
+        acc = 1
+        for s in reversed(self.shape):
+            st.append(acc)
+            acc *= max(1, s)
+        self.strides = tuple(reversed(st))  # elements, C order
+
+
+class Runtime:
+    def __init__(self):
+        self.shards = {}
+        self._device = None
+        self._executor = None
+        self._reduce_partials = None
+        self._red_scratch = None
+        self._pg_ready = False
+        self.test_mode = False
+        self.launches = 0
+        self.bytes_sent = 0
+        self.profile_events = None  # list -> (start, end, n_insns) CUDA events around every launch
+
+    # ---- device / process group ---------------------------------------------------------
+    @property
+    def device(self):
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError(
+                    "ramba_b200 needs a CUDA device (B200, sm_100a): torch.cuda.is_available() is False and "
+                    "there is no CPU execution path")
+            self._device = torch.device("cuda", common.local_rank)
+            torch.cuda.set_device(self._device)
+        return self._device
+
+    def set_test_executor(self, executor, reduce_partials, device="cpu"):
+        """TEST SEAM ONLY: run op lists through a checker (the oracle) on host buffers so that the
+        host logic can be exercised without a GPU.  Never used by the product path."""
+        self._executor = executor
+        self._reduce_partials = reduce_partials
+        self._device = torch.device(device)
+        self.test_mode = True
+
+    def reset(self):
+        """Forget every shard and go back to the product configuration (CUDA executor)."""
+        self.shards.clear()
+        self._device = None
+        self._executor = None
+        self._reduce_partials = None
+        self._red_scratch = None
+        self.test_mode = False
+
+    def executor(self):
+        if self._executor is None:
+            cabi.load()  # raises if the library is missing
+            self._executor = cabi.run_deferred_ops
+            self._reduce_partials = cabi.reduce_partials
+        return self._executor
+
+    def stream_handle(self):
+        if self.test_mode:
+            return None
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def ensure_process_group(self):
+        if common.num_workers <= 1 or self._pg_ready:
+            return
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            backend = "gloo" if self.test_mode else "nccl"
+            if backend == "nccl":
+                dist.init_process_group(backend, device_id=self.device)
+            else:
+                dist.init_process_group(backend)
+        self._pg_ready = True
+
+    # ---- shard storage --------------------------------------------------------------------
+    def create_array(self, gid, local_shape, dtype):
+        """Allocate this worker's block (uninitialised, like np.empty at ramba/ramba.py:1208-1214)."""
+        if gid in self.shards:
+            return self.shards[gid]
+        n = 1
+        for s in local_shape:
+            n *= int(s)
+        buf = torch.empty(max(n, 1), dtype=torch_dtype(dtype), device=self.device)
+        sh = Shard(buf, local_shape, dtype)
+        self.shards[gid] = sh
+        return sh
+
+    def destroy_array(self, gid):
+        self.shards.pop(gid, None)
+
+    def red_scratch(self):
+        if self._red_scratch is None:
+            nbytes = 256 + 8 * cabi.MAX_REDS * 4096 if self.test_mode else cabi.red_scratch_bytes()
+            self._red_scratch = torch.zeros(nbytes // 8 + 1, dtype=torch.int64, device=self.device)
+        return self._red_scratch
+
+    # ---- view binding -----------------------------------------------------------------------
+    @staticmethod
+    def bind_view(sv, local_strides, rng):
+        """(element offset, per-iteration-dim element strides) of view part `sv` (this worker's
+        shardview of the view) for iteration range `rng` (clean box inside sv's box), given the
+        C-order strides of the local buffer."""
+        k = len(sv.size)
+        off = 0
+        used = set()
+        strides = [0] * k
+        for d in range(k):
+            a = int(sv.axis_map[d])
+            if a < 0:
+                continue
+            used.add(a)
+            i0 = int(rng.start[d] - sv.start[d])
+            st = int(sv.steps[d])
+            if st > 0:
+                coord = int(sv.base_offset[a]) + i0 * st
+            else:
+                coord = int(sv.base_offset[a]) + (int(sv.size[d]) - 1 - i0) * (-st)
+            off += coord * local_strides[a]
+            strides[d] = st * local_strides[a]
+        for a in range(len(sv.base_offset)):
+            if a not in used:
+                off += int(sv.base_offset[a]) * local_strides[a]
+        return off, strides
+
+    # ---- launching ----------------------------------------------------------------------------
+    def launch(self, program, rng_shape, gstart, bound_views, reds=None, n_axis_red=0, axis_nsplit=1,
+               axis_partials=None, worker_num=0, num_workers=1):
+        """Bind `program` to one range and call the C-ABI.
+        bound_views: list of (data_ptr, elem strides per iteration dim, rb dtype)."""
+        ndim = len(rng_shape)
+        dims = list(range(ndim))
+        shape = [int(s) for s in rng_shape]
+        strides = [list(bv[1]) for bv in bound_views]
+        gs = [int(g) for g in gstart]
+        iota_dims = set(program.uses_iota)
+        # --- collapse: drop extent-1 dims, merge dims that are contiguous for every view
+        red_dims = set(range(n_axis_red))
+        keep = [d for d in dims if shape[d] != 1 or d in iota_dims]
+        if n_axis_red and not any(d in red_dims for d in keep):
+            keep = [0] + keep
+        if not any(d not in red_dims for d in keep):
+            keep = keep + [ndim - 1]
+        merged = []  # list of (shape, gstart, [strides per view], orig_dim or None, is_red)
+        for d in keep:
+            cur = [shape[d], gs[d], [s[d] for s in strides], d, d in red_dims]
+            if merged:
+                p = merged[-1]
+                can = (p[3] not in iota_dims) and (d not in iota_dims) and (p[4] == cur[4])
+                if can and all(p[2][v] == cur[2][v] * cur[0] for v in range(len(strides))):
+                    p[0] *= cur[0]
+                    p[2] = cur[2]
+                    p[3] = None
+                    continue
+            merged.append(cur)
+        if len(merged) > cabi.MAX_DIMS:
+            raise cabi.CabiError("fused op iterates over %d non-mergeable dims (max %d)" % (len(merged), cabi.MAX_DIMS))
+        fop = cabi.FusedOp()
+        fop.abi_version = cabi.ABI_VERSION
+        fop.ndim = len(merged)
+        iota_remap = {}
+        for i, m in enumerate(merged):
+            fop.itershape[i] = m[0]
+            fop.global_start[i] = m[1]
+            if m[3] is not None:
+                iota_remap[m[3]] = i
+        fop.worker_num = worker_num
+        fop.num_workers = num_workers
+        fop.n_views = len(bound_views)
+        for v, bv in enumerate(bound_views):
+            fop.views[v].base = bv[0]
+            for i, m in enumerate(merged):
+                fop.views[v].stride[i] = m[2][v]
+            fop.views[v].dtype = bv[2]
+            fop.views[v].flags = 1 if program.view_written.get(v) else 0
+        fop.n_scalars = len(program.scalars)
+        for i, bits in enumerate(program.scalars):
+            fop.scalars[i] = bits
+        fop.n_insns = len(program.insns)
+        for i, f in enumerate(program.insns):
+            ins = fop.insns[i]
+            for k_, v_ in f.items():
+                setattr(ins, k_, v_)
+            for nm in ("a", "b", "c"):
+                if getattr(ins, nm + "_kind") == cabi.K_IOTA:
+                    od = getattr(ins, nm + "_idx")
+                    if od not in iota_remap:
+                        # extent-1 dim was dropped: its index is the constant global_start
+                        raise cabi.CabiError("internal: iota over a collapsed dim")
+                    setattr(ins, nm + "_idx", iota_remap[od])
+        fop.n_regs = program.n_regs
+        fop.n_reds = len(program.reds)
+        fop.n_axis_red_dims = sum(1 for m in merged if m[4])
+        fop.axis_nsplit = axis_nsplit
+        if program.reds:
+            for s, (rop, rct) in enumerate(program.reds):
+                fop.reds[s].op = rop
+                fop.reds[s].ctype = rct
+                if reds is not None:
+                    fop.reds[s].out = reds[s][0]
+                    fop.reds[s].out_dtype = reds[s][1]
+            if n_axis_red:
+                fop.red_scratch = axis_partials
+            else:
+                fop.red_scratch = self.red_scratch().data_ptr()
+        ex = self.executor()
+        if self.profile_events is not None and not self.test_mode:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ex(fop, self.stream_handle())
+            e1.record()
+            self.profile_events.append((e0, e1, fop.n_insns))
+        else:
+            ex(fop, self.stream_handle())
+        self.launches += 1
+        return fop
+
+    def synchronize(self):
+        if not self.test_mode and self._device is not None:
+            torch.cuda.synchronize(self._device)
+
+
+RT = Runtime()

@@ -1,0 +1,41 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture
+def oracle_engine():
+    """Engine whose op lists are evaluated by the NumPy oracle on host buffers (no GPU)."""
+    import _oracle_backend
+    from ramba_b200 import ramba
+    from ramba_b200.runtime import RT
+
+    ramba.deferred_op.ramba_deferred_ops = None
+    RT.reset()
+    _oracle_backend.install()
+    yield
+    ramba.deferred_op.ramba_deferred_ops = None
+    RT.reset()
+
+
+@pytest.fixture
+def gpu_engine():
+    """Product configuration: op lists go through libramba_b200.so on cuda:0."""
+    from ramba_b200 import ramba
+    from ramba_b200.runtime import RT
+
+    ramba.deferred_op.ramba_deferred_ops = None
+    RT.reset()
+    yield
+    ramba.deferred_op.do_ops()
+    RT.synchronize()
+    RT.reset()

@@ -1,0 +1,62 @@
+"""-m gpu: the CUDA path (through the C-ABI) against the oracle on the same seeded programs."""
+import numpy as onp
+import pytest
+
+import _programs
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_oracle(prog):
+    import _oracle_backend
+    import ramba_b200 as rb
+    from ramba_b200 import ramba
+    from ramba_b200.runtime import RT
+
+    ramba.deferred_op.ramba_deferred_ops = None
+    RT.reset()
+    _oracle_backend.install()
+    try:
+        return prog(rb)
+    finally:
+        ramba.deferred_op.ramba_deferred_ops = None
+        RT.reset()
+
+
+@pytest.mark.parametrize("prog", _programs.ALL, ids=lambda p: p.__name__)
+def test_cuda_matches_oracle(gpu_engine, prog):
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    got = prog(rb)
+    assert not RT.test_mode and _cabi.launch_count() > before, "the CUDA library did not run"
+    exp = _run_oracle(prog)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        g, e = onp.asarray(g), onp.asarray(e)
+        assert g.shape == e.shape and g.dtype == e.dtype
+        if e.dtype.kind == "f" and prog.__name__ in ("chain",):
+            # fp64 transcendentals: CUDA libdevice vs glibc, stated tolerance
+            assert onp.allclose(g, e, rtol=1e-13, atol=1e-15), "%s[%d]" % (prog.__name__, i)
+        elif e.dtype.kind == "f" and prog.__name__ == "arith_float":
+            assert onp.allclose(g, e, rtol=1e-15, atol=0), "%s[%d]" % (prog.__name__, i)
+        else:
+            assert onp.array_equal(g, e), "%s[%d]" % (prog.__name__, i)
+
+
+def test_chain_large(gpu_engine):
+    """config-2 program at 2^26 elements: size-independent properties."""
+    import ramba_b200 as rb
+
+    N = 1 << 26
+    A = rb.arange(N) / 1000.0
+    B = rb.sin(A)
+    C = rb.cos(A)
+    D = B * B + C ** 2
+    a, d = A.asarray(), D.asarray()
+    assert onp.array_equal(a, onp.arange(N) * 0.001)
+    assert onp.max(onp.abs(d - 1.0)) <= 4 * onp.finfo(onp.float64).eps
+    b = B.asarray()
+    idx = onp.arange(0, N, 4099)
+    assert onp.allclose(b[idx], onp.sin(a[idx]), rtol=1e-13, atol=1e-15)

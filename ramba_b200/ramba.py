@@ -1506,6 +1506,8 @@ def fromfunction(function, shape, dtype=None, **kwargs):
     (ramba/ramba.py:1535-1595, 8904-8905); here it is evaluated ONCE on lazy index arrays
     (iota operands), so it must be built from array operators / ramba functions."""
     shape = shapeToInt(shape)
+    if dtype is None:
+        dtype = np.float64  # the reference's default array dtype (bdarray.assign_bdarray, ramba/ramba.py:1125-1126)
     idx = []
     for d in range(len(shape)):
         a = empty(shape, dtype=np.int64)
@@ -1514,7 +1516,7 @@ def fromfunction(function, shape, dtype=None, **kwargs):
     out = function(*idx)
     if not isinstance(out, ndarray):
         out = full(shape, out)
-    if dtype is not None and np.dtype(dtype) != out.dtype:
+    if np.dtype(dtype) != out.dtype:
         out = out.astype(dtype)
     return out
 

@@ -1,0 +1,46 @@
+"""Worker process of the multi-rank CPU tests: RANK/WORLD_SIZE come from the environment (the same
+variables torchrun sets); collectives run over gloo, op lists through the oracle."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, HERE)
+
+import numpy as onp  # noqa: E402
+
+import _oracle_backend  # noqa: E402
+
+_oracle_backend.install()
+
+import _programs  # noqa: E402
+import ramba_b200 as rb  # noqa: E402
+from ramba_b200 import common  # noqa: E402
+from ramba_b200.runtime import RT  # noqa: E402
+
+
+def main():
+    names = sys.argv[1].split(",")
+    RT.ensure_process_group()
+    failures = []
+    for prog in _programs.ALL:
+        if prog.__name__ not in names and names != ["all"]:
+            continue
+        got = prog(rb)
+        exp = prog(onp)
+        for i, (g, e) in enumerate(zip(got, exp)):
+            g, e = onp.asarray(g), onp.asarray(e)
+            ok = g.shape == e.shape and (onp.allclose(g, e, rtol=1e-13, atol=1e-15) if e.dtype.kind == "f" else onp.array_equal(g, e))
+            if not ok:
+                failures.append("%s[%d]" % (prog.__name__, i))
+    print("RANK %d/%d launches=%d bytes_sent=%d failures=%s" % (common.worker_num, common.num_workers, RT.launches, RT.bytes_sent, failures))
+    sys.stdout.flush()
+    import torch.distributed as dist
+
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()

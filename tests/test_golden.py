@@ -1,0 +1,58 @@
+"""Pins the oracle (and, through it, the lowering) against the REAL reference: the fixtures in
+tests/golden/ were produced by tests/golden/make_golden.py running Python-for-HPC/ramba itself."""
+import json
+import os
+
+import numpy as onp
+import pytest
+
+import _programs
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def golden_programs():
+    z = onp.load(os.path.join(GOLD, "programs_golden.npz"))
+    status = json.loads(str(z["__status__"]))
+    return z, status
+
+
+def compare_to_golden(name, got, z, transcendental_tol=False):
+    for i, g in enumerate(got):
+        e = z["%s__%d" % (name, i)]
+        g = onp.asarray(g)
+        assert g.shape == e.shape, "%s[%d]: shape %s vs reference %s" % (name, i, g.shape, e.shape)
+        assert g.dtype == e.dtype, "%s[%d]: dtype %s vs reference %s" % (name, i, g.dtype, e.dtype)
+        if e.dtype.kind == "f" and transcendental_tol:
+            # fp64 sin/cos chain: stated tolerance (Numba/libm under fastmath vs NumPy/CUDA libm)
+            assert onp.allclose(g, e, rtol=1e-13, atol=1e-15), "%s[%d]" % (name, i)
+        elif e.dtype.kind == "f":
+            assert onp.allclose(g, e, rtol=4e-16, atol=0), "%s[%d]" % (name, i)
+        else:
+            assert onp.array_equal(g, e), "%s[%d]" % (name, i)
+
+
+@pytest.mark.parametrize("prog", [p for p in _programs.ALL if p.__name__ not in _programs.NOT_IN_REFERENCE], ids=lambda p: p.__name__)
+def test_oracle_engine_matches_reference(oracle_engine, golden_programs, prog):
+    import ramba_b200 as rb
+
+    z, status = golden_programs
+    assert status[prog.__name__] == "ok"
+    compare_to_golden(prog.__name__, prog(rb), z, transcendental_tol=(prog.__name__ == "chain"))
+
+
+def test_c_oracle_chain_matches_reference(golden_programs):
+    """oracle/fused_chain.c (the CPU baseline) against the reference's own A, B, C, D."""
+    from oracle import chain
+
+    z, _ = golden_programs
+    A = onp.ascontiguousarray(z["chain__0"])
+    B = onp.empty_like(A); C = onp.empty_like(A); D = onp.empty_like(A)
+    chain.chain_f64(A, B, C, D)
+    assert onp.allclose(B, z["chain__1"], rtol=1e-13, atol=1e-15)
+    assert onp.allclose(C, z["chain__2"], rtol=1e-13, atol=1e-15)
+    assert onp.max(onp.abs(D - z["chain__3"])) <= 4 * onp.finfo(onp.float64).eps
+    A2 = onp.empty_like(A)
+    chain.chain_f64(A2, B, C, D, global_start=0, make_A=True)
+    assert onp.array_equal(A2, A), "arange * 0.001 must be bit-identical to the reference"

@@ -8,14 +8,6 @@
 #include "rb200_launch.h"
 
 namespace rb200 {
-template <class T> __device__ __forceinline__ T red_combine(int op, T a, T b) {
-  switch (op) {
-    case RB200_RED_ADD: return a + b;
-    case RB200_RED_MUL: return a * b;
-    case RB200_RED_MIN: return (b < a) ? b : a;
-    default: return (b > a) ? b : a;
-  }
-}
 // stage 2 helper: out[j] = reduce_k part[k*stride_k + j]
 template <class T> __global__ void reduce_partials_kernel(T* out, const T* part, long long n, long long k, long long stride_k, int op) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
@@ -95,7 +87,8 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   if (sms <= 0) return fail("no usable CUDA device (libramba_b200 has no CPU path)");
   cudaStream_t stream = (cudaStream_t)stream_v;
 
-  constexpr int V = 4;
+  constexpr int V = kV;
+  constexpr long long TILE = (long long)kThreads * V;
   KParams P;
   memset(&P, 0, sizeof(P));
   P.ndim = op->ndim;
@@ -106,14 +99,14 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   long long total = 1;
   for (int d = 0; d < op->ndim; ++d) {
     if (op->itershape[d] < 0) return fail("negative itershape");
+    if (op->ndim > 1 && op->itershape[d] >= (1ll << 31)) return fail("N-d iteration dims must be < 2^31");
     P.shape[d] = op->itershape[d];
     P.gstart[d] = op->global_start[d];
     total *= op->itershape[d];
   }
   if (total == 0 || op->n_insns == 0) return 0;  // empty range: nothing to do
-  const long long inner = P.shape[op->ndim - 1];
-  P.n_chunks = (inner + V - 1) / V;
 
+  bool view_read[RB200_MAX_VIEWS] = {false}, view_masked[RB200_MAX_VIEWS] = {false};
   for (int i = 0; i < op->n_insns; ++i) {
     const rb200_insn& I = op->insns[i];
     if (I.op >= RB200_NUM_OPS) return fail("bad opcode");
@@ -126,7 +119,10 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
         case RB200_K_NONE:
         case RB200_K_ACC: break;
         case RB200_K_REG: if (idxs[q] >= op->n_regs) return fail("register index out of range"); break;
-        case RB200_K_VIEW: if (idxs[q] >= op->n_views) return fail("view index out of range"); break;
+        case RB200_K_VIEW:
+          if (idxs[q] >= op->n_views) return fail("view index out of range");
+          view_read[idxs[q]] = true;
+          break;
         case RB200_K_SCAL: if (idxs[q] >= op->n_scalars) return fail("scalar index out of range"); break;
         case RB200_K_IOTA: if (idxs[q] >= op->ndim) return fail("iota dim out of range"); break;
         default: return fail("bad operand kind");
@@ -135,6 +131,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     if (I.st_reg != RB200_NOSTORE && I.st_reg >= op->n_regs) return fail("st_reg out of range");
     if (I.st_view != RB200_NOSTORE && I.st_view >= op->n_views) return fail("st_view out of range");
     if (I.mask_reg != RB200_NOSTORE && I.mask_reg >= op->n_regs) return fail("mask_reg out of range");
+    if (I.st_view != RB200_NOSTORE && I.mask_reg != RB200_NOSTORE) view_masked[I.st_view] = true;
     if (I.op == RB200_OP_SINCOS && I.st2 >= op->n_regs) return fail("sincos st2 out of range");
     if (I.op == RB200_OP_RED && I.b_idx >= op->n_reds) return fail("reduction slot out of range");
     P.insns[i] = I;
@@ -149,17 +146,11 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     KView& k = P.views[i];
     k.base = (char*)v.base;
     k.dtype = v.dtype;
+    k.pf_slot = -1;
     for (int d = 0; d < op->ndim; ++d) k.stride[d] = v.stride[d];
-    // vector path: innermost stride 1, base and every outer stride aligned to min(16, V*es)
-    const long long align = (V * es >= 16) ? 16 : V * es;
-    bool vec = (v.stride[op->ndim - 1] == 1) && (((uintptr_t)v.base) % align == 0);
-    for (int d = 0; d < op->ndim - 1 && vec; ++d)
-      if (op->itershape[d] > 1 && ((v.stride[d] * es) % align) != 0) vec = false;
-    k.vec = vec ? 1 : 0;
   }
-
-  const size_t smem = (size_t)op->n_regs * V * kThreads * sizeof(unsigned long long);
   cudaError_t e;
+  const size_t reg_bytes = (size_t)op->n_regs * V * kThreads * 8;
 
   if (op->n_axis_red_dims != 0) {
     // axis mode: the first n_axis_red_dims dims are the reduced ones (host permutes)
@@ -168,42 +159,53 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     if (op->n_reds < 1) return fail("axis reduction without reduction slots");
     if (!op->red_scratch) return fail("axis reduction needs a partial buffer");
     P.red_ndim = nred;
-    long long red_len = 1, kept_rows = 1;
+    long long red_len = 1, kept = 1;
     for (int d = 0; d < nred; ++d) red_len *= P.shape[d];
-    for (int d = nred; d < op->ndim - 1; ++d) kept_rows *= P.shape[d];
-    const long long kept_work = kept_rows * P.n_chunks;
+    for (int d = nred; d < op->ndim; ++d) kept *= P.shape[d];
     int n_split = op->axis_nsplit;
     if (n_split < 1) n_split = 1;
     if ((long long)n_split > red_len) n_split = (int)red_len;
     P.red_len = red_len;
     P.n_split = n_split;
     P.red_split = (red_len + n_split - 1) / n_split;
-    P.total_work = kept_work * n_split;
-    P.red_partials = (unsigned long long*)op->red_scratch;
+    P.total = kept;
+    P.n_tiles = ((kept + TILE - 1) / TILE) * n_split;
+    P.red_partials = (u64*)op->red_scratch;
     for (int s = 0; s < op->n_reds; ++s) {
       P.reds[s].op = op->reds[s].op;
       P.reds[s].ctype = op->reds[s].ctype;
     }
-    long long blocks = (P.total_work + kThreads - 1) / kThreads;
-    long long cap = (long long)sms * 8;
+    long long blocks = P.n_tiles;
+    long long cap = (long long)sms * 4;
     if (blocks > cap) blocks = cap;
-    e = launch_vm_axis_reduce(P, (unsigned)blocks, smem, stream);
+    e = launch_vm_axis_reduce(P, (unsigned)blocks, reg_bytes, stream);
     if (e != cudaSuccess) return fail_cuda("vm_axis_reduce_kernel launch", e);
     g_launches.fetch_add(1);
     return 0;
   }
 
-  long long rows = total / inner;
-  P.total_work = rows * P.n_chunks;
-  long long blocks = (P.total_work + kThreads - 1) / kThreads;
-  // persistent-style grid: a multiple of the SM count, capped; grid-stride covers the rest
-  long long cap = (long long)sms * 8;
-  if (op->n_reds > 0 && cap > kRedScratchPartials) cap = kRedScratchPartials;
-  if (blocks > cap) blocks = cap;
+  P.total = total;
+  P.n_tiles = (total + TILE - 1) / TILE;
+  P.wide = (total >= (1ll << 31)) ? 1 : 0;
+  // stage read-only 4/8-byte input views of 1-D ops one tile ahead through shared memory
+  size_t pf_bytes = 0;
+  if (op->ndim == 1) {
+    for (int i = 0; i < op->n_views && P.n_pf < kMaxPf; ++i) {
+      const int dt = op->views[i].dtype;
+      const bool wide_ok = (dt == RB200_F64 || dt == RB200_F32 || dt == RB200_I64 || dt == RB200_I32);
+      if (view_read[i] && !view_masked[i] && wide_ok && reg_bytes + (size_t)(P.n_pf + 1) * 2 * V * kThreads * 8 <= 96 * 1024) {
+        P.views[i].pf_slot = P.n_pf;
+        P.pf_view[P.n_pf] = i;
+        P.n_pf++;
+      }
+    }
+    pf_bytes = (size_t)P.n_pf * 2 * V * kThreads * 8;
+  }
+  const size_t smem = reg_bytes + pf_bytes;
   if (op->n_reds > 0) {
     if (!op->red_scratch) return fail("global reduction needs red_scratch");
     P.red_counter = (unsigned int*)op->red_scratch;
-    P.red_partials = (unsigned long long*)((char*)op->red_scratch + 256);
+    P.red_partials = (u64*)((char*)op->red_scratch + 256);
     for (int s = 0; s < op->n_reds; ++s) {
       if (!op->reds[s].out) return fail("null reduction output");
       if (dtype_size(op->reds[s].out_dtype) == 0) return fail("bad reduction output dtype");
@@ -214,7 +216,24 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
       P.reds[s].out_dtype = op->reds[s].out_dtype;
     }
   }
-  e = launch_vm_elementwise(P, (unsigned)blocks, smem, stream);
+  // persistent-style grid: SM count x resident CTAs per SM (smem / register limited), capped by
+  // the number of tiles; every CTA walks tiles b, b+grid, ...
+  int per_sm = (op->ndim == 1) ? 3 : 2;
+  if (smem > 0) {
+    int by_smem = (int)((220 * 1024) / (smem + 1024));
+    if (by_smem < 1) by_smem = 1;
+    if (per_sm > by_smem) per_sm = by_smem;
+  }
+  long long blocks = P.n_tiles;
+  long long cap = (long long)sms * per_sm;
+  if (op->n_reds > 0 && cap > kRedScratchPartials) cap = kRedScratchPartials;
+  if (blocks > cap) blocks = cap;
+  switch (op->ndim) {
+    case 1: e = launch_vm_elementwise_nd1(P, (unsigned)blocks, smem, stream); break;
+    case 2: e = launch_vm_elementwise_nd2(P, (unsigned)blocks, smem, stream); break;
+    case 3: e = launch_vm_elementwise_nd3(P, (unsigned)blocks, smem, stream); break;
+    default: e = launch_vm_elementwise_nd5(P, (unsigned)blocks, smem, stream); break;
+  }
   if (e != cudaSuccess) return fail_cuda("vm_elementwise_kernel launch", e);
   g_launches.fetch_add(1);
   return 0;

@@ -1,0 +1,8 @@
+// rb200_elementwise_nd3.cu — instantiation of the fused elementwise kernel for iteration rank 3
+// (one translation unit per rank so that they compile in parallel).
+#include "rb200_elementwise.cuh"
+namespace rb200 {
+cudaError_t launch_vm_elementwise_nd3(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
+  return launch_vm_elementwise_nd<kV, 3>(P, blocks, smem, stream);
+}
+}  // namespace rb200

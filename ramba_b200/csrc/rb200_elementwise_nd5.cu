@@ -1,0 +1,8 @@
+// rb200_elementwise_nd5.cu — instantiation of the fused elementwise kernel for iteration rank 5
+// (one translation unit per rank so that they compile in parallel).
+#include "rb200_elementwise.cuh"
+namespace rb200 {
+cudaError_t launch_vm_elementwise_nd5(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
+  return launch_vm_elementwise_nd<kV, 5>(P, blocks, smem, stream);
+}
+}  // namespace rb200

@@ -1,71 +1,47 @@
 #pragma once
 // rb200_interp.cuh — the op-list interpreter shared by the elementwise and axis-reduction kernels.
 //
-// Reference behaviour restated (not translated): the generated Numba loop of
+// Reference behaviour restated (not translated): the generated Numba loop body of
 // ramba/ramba.py:8247-8265 executed by RemoteState.run_deferred_ops (ramba/ramba.py:3758-3780).
 #include <cuda_runtime.h>
 #include <math.h>
-#include <stdio.h>
-#include <string.h>
-#include <atomic>
-#include <string>
 
 #include "rb200_vm.cuh"
 
 namespace rb200 {
 
 // ---------------------------------------------------------------------------------------------
-// reduction combine in the accumulator class
-template <class T> __device__ __forceinline__ T red_combine(int op, T a, T b) {
-  switch (op) {
-    case RB200_RED_ADD: return a + b;
-    case RB200_RED_MUL: return a * b;
-    case RB200_RED_MIN: return (b < a) ? b : a;
-    default: return (b > a) ? b : a;
-  }
-}
-__device__ __forceinline__ Val red_combine_val(int op, int ctype, Val a, Val b) {
-  Val r;
-  if (ctype == RB200_T_F64) r.d = red_combine<double>(op, a.d, b.d);
-  else r.i = red_combine<long long>(op, a.i, b.i);
-  return r;
-}
-__device__ __forceinline__ Val red_identity(int op, int ctype) {
-  Val r;
-  if (ctype == RB200_T_F64) {
-    r.d = (op == RB200_RED_ADD) ? 0.0 : (op == RB200_RED_MUL) ? 1.0 : (op == RB200_RED_MIN) ? INFINITY : -INFINITY;
-  } else {
-    r.i = (op == RB200_RED_ADD) ? 0ll : (op == RB200_RED_MUL) ? 1ll : (op == RB200_RED_MIN) ? 0x7fffffffffffffffll
-                                                                                             : (long long)0x8000000000000000ull;
-  }
-  return r;
-}
+// per-thread interpreter state.  ND = number of iteration dims this instantiation handles
+// (ND == 1: collapsed 1-D op, the hot path; element k of the thread is e0 + k*256).
+template <int V, int ND> struct Ctx {
+  const KParams& P;      // the __grid_constant__ kernel parameter: constant-bank (LDC) accesses
+  unsigned regfile_s;    // shared-window byte address of this thread's column of the register file
+  unsigned pf_s;         // shared-window byte address of this thread's column of the current prefetch stage
+  long long e0;          // ND == 1: index of element 0 of this thread in the tile
+  long long idx[V][ND];  // ND  > 1: N-d index of every element
+  unsigned valid;        // bit k: element k exists
+  u64 acc[V];
 
-// ---------------------------------------------------------------------------------------------
-// per-thread interpreter state
-template <int V> struct Ctx {
-  const KParams& P;
-  unsigned long long* regfile;  // [reg][k][thread]
-  long long idx[kMaxD];         // current index (innermost = first element of this thread's chunk)
-  int nvalid;
-  Val acc[V];
-  int tid;
-  __device__ __forceinline__ Ctx(const KParams& p, unsigned long long* rf) : P(p), regfile(rf) { tid = threadIdx.x; }
+  __device__ __forceinline__ Ctx(const KParams& p) : P(p) {}
 
-  __device__ __forceinline__ long long view_off(const KView& vw) const {
-    long long off = 0;
+  // element offsets (in elements) of the thread's V elements inside view `vw`
+  __device__ __forceinline__ void offsets(const KView& vw, long long (&off)[V]) const {
+    if constexpr (ND == 1) {
+      const long long s = vw.stride[0];
 #pragma unroll
-    for (int d = 0; d < kMaxD; ++d)
-      if (d < P.ndim) off += idx[d] * vw.stride[d];
-    return off;
-  }
-  __device__ __forceinline__ long long inner_stride(const KView& vw) const {
-    long long s = 0;
+      for (int k = 0; k < V; ++k) off[k] = (e0 + (long long)k * kThreads) * s;
+    } else {
 #pragma unroll
-    for (int d = 0; d < kMaxD; ++d)
-      if (d == P.ndim - 1) s = vw.stride[d];
-    return s;
+      for (int k = 0; k < V; ++k) {
+        long long o = 0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) o += idx[k][d] * vw.stride[d];
+        off[k] = o;
+      }
+    }
   }
+
+  __device__ __forceinline__ unsigned reg_addr(int r, int k) const { return regfile_s + (unsigned)((r * V + k) * kThreads * 8); }
 
   template <class T> __device__ __forceinline__ void fetch(int kind, int i, T (&out)[V]) {
     switch (kind) {
@@ -75,29 +51,45 @@ template <int V> struct Ctx {
         break;
       case RB200_K_REG:
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          Val v;
-          v.u = regfile[(i * V + k) * kThreads + tid];
-          out[k] = CT<T>::get(v);
-        }
+        for (int k = 0; k < V; ++k) out[k] = CT<T>::get(lds64(reg_addr(i, k)));
         break;
       case RB200_K_VIEW: {
         const KView& vw = P.views[i];
-        load_view<T, V>(vw, view_off(vw), inner_stride(vw), nvalid, out);
+        const int slot = vw.pf_slot;
+        const int dt = vw.dtype;
+        if (slot >= 0) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) out[k] = from_raw<T>(lds64(pf_s + (unsigned)((slot * V + k) * kThreads * 8)), dt);
+        } else {
+          long long off[V];
+          offsets(vw, off);
+          load_view<T, V>(vw.base, dt, off, valid, out);
+        }
       } break;
       case RB200_K_SCAL: {
-        T s = CT<T>::scal(P.scalars[i]);
+        T s = CT<T>::get(P.scalars[i]);
 #pragma unroll
         for (int k = 0; k < V; ++k) out[k] = s;
       } break;
       case RB200_K_IOTA: {
-        long long base = 0;
-        bool inner = (i == P.ndim - 1);
+        if constexpr (ND == 1) {
+          long long base = e0 + P.gstart[0];
 #pragma unroll
-        for (int d = 0; d < kMaxD; ++d)
-          if (d == i) base = idx[d] + P.gstart[d];
+          for (int k = 0; k < V; ++k) out[k] = (T)(base + (long long)k * kThreads);
+        } else {
+          long long g = 0;
 #pragma unroll
-        for (int k = 0; k < V; ++k) out[k] = (T)(base + (inner ? k : 0));
+          for (int d = 0; d < ND; ++d)
+            if (d == i) g = P.gstart[d];
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            long long x = 0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+              if (d == i) x = idx[k][d];
+            out[k] = (T)(x + g);
+          }
+        }
       } break;
       default:
 #pragma unroll
@@ -105,100 +97,129 @@ template <int V> struct Ctx {
     }
   }
 
-  __device__ __forceinline__ unsigned store_mask(const rb200_insn& I) const {
-    if (I.mask_reg == RB200_NOSTORE) return (1u << V) - 1u;
-    unsigned m = 0;
-#pragma unroll
-    for (int k = 0; k < V; ++k)
-      if (regfile[(I.mask_reg * V + k) * kThreads + tid] != 0ull) m |= (1u << k);
-    return m;
-  }
-
   template <class R> __device__ __forceinline__ void finish(const rb200_insn& I, const R (&r)[V]) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) CT<R>::set(acc[k], r[k]);
+    for (int k = 0; k < V; ++k) acc[k] = CT<R>::bits(r[k]);
     if (I.st_reg != RB200_NOSTORE) {
 #pragma unroll
-      for (int k = 0; k < V; ++k) regfile[(I.st_reg * V + k) * kThreads + tid] = acc[k].u;
+      for (int k = 0; k < V; ++k) sts64(reg_addr(I.st_reg, k), acc[k]);
     }
     if (I.st_view != RB200_NOSTORE) {
       const KView& vw = P.views[I.st_view];
-      store_view<R, V>(vw, view_off(vw), inner_stride(vw), nvalid, r, store_mask(I));
+      unsigned m = valid;
+      if (I.mask_reg != RB200_NOSTORE) {
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if (lds64(reg_addr(I.mask_reg, k)) == 0ull) m &= ~(1u << k);
+      }
+      long long off[V];
+      offsets(vw, off);
+      if (vw.dtype == RB200_BOOL) {
+        long long b[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
+        store_view<long long, V>(vw.base, RB200_U8, off, m, b);
+      } else {
+        store_view<R, V>(vw.base, vw.dtype, off, m, r);
+      }
     }
   }
 };
 
 // ---------------------------------------------------------------------------------------------
 // floating-point instruction set (F = double | float)
-template <class F, int V, class C> __device__ __forceinline__ bool exec_float(C& cx, const rb200_insn& I) {
-  F a[V], b[V], c[V], r[V];
+template <class F, int V, class C> __device__ __forceinline__ void exec_float(C& cx, const rb200_insn& I) {
+  F a[V], b[V], r[V];
   long long p[V];
   const int op = I.op;
-  // operands are fetched once, up front (three inlined fetch sites per compute class)
   cx.template fetch<F>(I.a_kind, I.a_idx, a);
   if (I.b_kind != RB200_K_NONE && op != RB200_OP_POWI) cx.template fetch<F>(I.b_kind, I.b_idx, b);
-  if (I.c_kind != RB200_K_NONE) cx.template fetch<F>(I.c_kind, I.c_idx, c);
   switch (op) {
-    // ---- binary arithmetic
+    // ---- binary arithmetic.  __d*/__f*_rn: no FMA contraction across op-list instructions, every
+    // op rounds once like the reference's separate scalar statements
     case RB200_OP_ADD:
-    case RB200_OP_SUB:
-    case RB200_OP_MUL:
-    case RB200_OP_DIV:
-    case RB200_OP_MIN:
-    case RB200_OP_MAX: {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        F x = a[k], y = b[k];
-        // __d/f*_rn intrinsics: no FMA contraction across op-list instructions, every op rounds
-        // once like the reference's un-fused scalar statements
-        if constexpr (sizeof(F) == 8) {
-          r[k] = op == RB200_OP_ADD   ? __dadd_rn(x, y)
-                 : op == RB200_OP_SUB ? __dsub_rn(x, y)
-                 : op == RB200_OP_MUL ? __dmul_rn(x, y)
-                 : op == RB200_OP_DIV ? __ddiv_rn(x, y)
-                 : op == RB200_OP_MIN ? ((y < x) ? y : x)
-                                      : ((y > x) ? y : x);
-        } else {
-          r[k] = op == RB200_OP_ADD   ? __fadd_rn(x, y)
-                 : op == RB200_OP_SUB ? __fsub_rn(x, y)
-                 : op == RB200_OP_MUL ? __fmul_rn(x, y)
-                 : op == RB200_OP_DIV ? __fdiv_rn(x, y)
-                 : op == RB200_OP_MIN ? ((y < x) ? y : x)
-                                      : ((y > x) ? y : x);
-        }
+        if constexpr (sizeof(F) == 8) r[k] = __dadd_rn(a[k], b[k]);
+        else r[k] = __fadd_rn(a[k], b[k]);
       }
       cx.template finish<F>(I, r);
-      return true;
-    }
-    case RB200_OP_FLOORDIV:
-    case RB200_OP_MOD:
-    case RB200_OP_POW: {
+      return;
+    case RB200_OP_SUB:
 #pragma unroll
-      for (int k = 0; k < V; ++k)
-        r[k] = op == RB200_OP_FLOORDIV ? py_ffloordiv<F>(a[k], b[k]) : op == RB200_OP_MOD ? py_fmod<F>(a[k], b[k]) : (F)pow(a[k], b[k]);
+      for (int k = 0; k < V; ++k) {
+        if constexpr (sizeof(F) == 8) r[k] = __dsub_rn(a[k], b[k]);
+        else r[k] = __fsub_rn(a[k], b[k]);
+      }
       cx.template finish<F>(I, r);
-      return true;
-    }
+      return;
+    case RB200_OP_MUL:
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if constexpr (sizeof(F) == 8) r[k] = __dmul_rn(a[k], b[k]);
+        else r[k] = __fmul_rn(a[k], b[k]);
+      }
+      cx.template finish<F>(I, r);
+      return;
+    case RB200_OP_DIV:
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if constexpr (sizeof(F) == 8) r[k] = __ddiv_rn(a[k], b[k]);
+        else r[k] = __fdiv_rn(a[k], b[k]);
+      }
+      cx.template finish<F>(I, r);
+      return;
+    case RB200_OP_MIN:
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = (b[k] < a[k]) ? b[k] : a[k];
+      cx.template finish<F>(I, r);
+      return;
+    case RB200_OP_MAX:
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = (b[k] > a[k]) ? b[k] : a[k];
+      cx.template finish<F>(I, r);
+      return;
+    case RB200_OP_FLOORDIV:
+#pragma unroll 1
+      for (int k = 0; k < V; ++k) r[k] = py_ffloordiv<F>(a[k], b[k]);
+      cx.template finish<F>(I, r);
+      return;
+    case RB200_OP_MOD:
+#pragma unroll 1
+      for (int k = 0; k < V; ++k) r[k] = py_fmod<F>(a[k], b[k]);
+      cx.template finish<F>(I, r);
+      return;
+    case RB200_OP_POW:
+#pragma unroll 1
+      for (int k = 0; k < V; ++k) r[k] = (F)pow(a[k], b[k]);
+      cx.template finish<F>(I, r);
+      return;
     case RB200_OP_POWI: {
       long long e[V];
       cx.template fetch<long long>(I.b_kind, I.b_idx, e);
-      if (e[0] == 2) {  // uniform scalar exponent in practice; x**2 == x*x exactly (int_power)
+      bool sq = true;
 #pragma unroll
-        for (int k = 0; k < V; ++k) r[k] = (e[k] == 2) ? a[k] * a[k] : powi<F>(a[k], e[k]);
+      for (int k = 0; k < V; ++k) sq = sq && (e[k] == 2);
+      if (sq) {  // x**2 == x*x exactly (int_power: r = 1*x*x)
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          if constexpr (sizeof(F) == 8) r[k] = __dmul_rn(a[k], a[k]);
+          else r[k] = __fmul_rn(a[k], a[k]);
+        }
       } else {
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < V; ++k) r[k] = powi<F>(a[k], e[k]);
       }
       cx.template finish<F>(I, r);
-      return true;
+      return;
     }
-    // ---- comparisons -> bool (I64 class 0/1)
+    // ---- comparisons / logic -> bool (I64 class 0/1)
     case RB200_OP_GT:
     case RB200_OP_LT:
     case RB200_OP_GE:
     case RB200_OP_LE:
     case RB200_OP_EQ:
-    case RB200_OP_NE: {
+    case RB200_OP_NE:
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         F x = a[k], y = b[k];
@@ -206,25 +227,23 @@ template <class F, int V, class C> __device__ __forceinline__ bool exec_float(C&
         p[k] = t ? 1 : 0;
       }
       cx.template finish<long long>(I, p);
-      return true;
-    }
+      return;
     case RB200_OP_LAND:
     case RB200_OP_LOR:
-    case RB200_OP_LXOR: {
+    case RB200_OP_LXOR:
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         bool x = a[k] != F(0), y = b[k] != F(0);
         p[k] = (op == RB200_OP_LAND ? (x && y) : op == RB200_OP_LOR ? (x || y) : (x != y)) ? 1 : 0;
       }
       cx.template finish<long long>(I, p);
-      return true;
-    }
+      return;
     case RB200_OP_ISFINITE:
     case RB200_OP_ISINF:
     case RB200_OP_ISNAN:
     case RB200_OP_ISNEGINF:
     case RB200_OP_ISPOSINF:
-    case RB200_OP_LNOT: {
+    case RB200_OP_LNOT:
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         F x = a[k];
@@ -237,60 +256,56 @@ template <class F, int V, class C> __device__ __forceinline__ bool exec_float(C&
         p[k] = t ? 1 : 0;
       }
       cx.template finish<long long>(I, p);
-      return true;
-    }
+      return;
     // ---- unary
     case RB200_OP_MOV:
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = a[k];
       cx.template finish<F>(I, r);
-      return true;
+      return;
     case RB200_OP_ABS:
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = fabs(a[k]);
       cx.template finish<F>(I, r);
-      return true;
+      return;
     case RB200_OP_NEG:
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = -a[k];
       cx.template finish<F>(I, r);
-      return true;
+      return;
     case RB200_OP_SQUARE:
 #pragma unroll
-      for (int k = 0; k < V; ++k) r[k] = a[k] * a[k];
+      for (int k = 0; k < V; ++k) {
+        if constexpr (sizeof(F) == 8) r[k] = __dmul_rn(a[k], a[k]);
+        else r[k] = __fmul_rn(a[k], a[k]);
+      }
       cx.template finish<F>(I, r);
-      return true;
+      return;
     case RB200_OP_SQRT:
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = sqrt(a[k]);
       cx.template finish<F>(I, r);
-      return true;
+      return;
     case RB200_OP_SIN:
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = sin(a[k]);
       cx.template finish<F>(I, r);
-      return true;
+      return;
     case RB200_OP_COS:
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = cos(a[k]);
       cx.template finish<F>(I, r);
-      return true;
+      return;
     case RB200_OP_SINCOS: {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         F sn, cs;
         sincos(a[k], &sn, &cs);
         r[k] = I.imm ? cs : sn;  // imm 1: accumulator half is cos, parked half is sin
-        c[k] = I.imm ? sn : cs;
-      }
-#pragma unroll
-      for (int k = 0; k < V; ++k) {
-        Val v;
-        CT<F>::set(v, c[k]);
-        cx.regfile[(I.st2 * V + k) * kThreads + cx.tid] = v.u;
+        sts64(cx.reg_addr(I.st2, k), CT<F>::bits(I.imm ? sn : cs));
       }
       cx.template finish<F>(I, r);
-      return true;
+      return;
     }
     case RB200_OP_TAN:
     case RB200_OP_SINH:
@@ -301,8 +316,9 @@ template <class F, int V, class C> __device__ __forceinline__ bool exec_float(C&
     case RB200_OP_ATAN:
     case RB200_OP_EXP:
     case RB200_OP_LOG:
-    case RB200_OP_CBRT: {
+    case RB200_OP_CBRT:
       // rarely on the hot path: one element at a time keeps the code small
+#pragma unroll 1
       for (int k = 0; k < V; ++k) {
         F x = a[k];
         r[k] = op == RB200_OP_TAN    ? tan(x)
@@ -317,25 +333,25 @@ template <class F, int V, class C> __device__ __forceinline__ bool exec_float(C&
                                      : cbrt(x);
       }
       cx.template finish<F>(I, r);
-      return true;
-    }
+      return;
     case RB200_OP_WHERE: {
+      F c[V];
+      cx.template fetch<F>(I.c_kind, I.c_idx, c);
       // condition arrives in `a`, already converted to the compute class (non-zero = true)
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = (a[k] != F(0)) ? b[k] : c[k];
       cx.template finish<F>(I, r);
-      return true;
+      return;
     }
-    default: return false;
+    default: return;
   }
 }
 
 // integer instruction set (all integer arithmetic is int64, like Numba's intp promotion)
-template <int V, class C> __device__ __forceinline__ bool exec_int(C& cx, const rb200_insn& I) {
-  long long a[V], b[V], c[V], r[V];
+template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const rb200_insn& I) {
+  long long a[V], b[V], r[V];
   cx.template fetch<long long>(I.a_kind, I.a_idx, a);
   if (I.b_kind != RB200_K_NONE) cx.template fetch<long long>(I.b_kind, I.b_idx, b);
-  if (I.c_kind != RB200_K_NONE) cx.template fetch<long long>(I.c_kind, I.c_idx, c);
   const int op = I.op;
   switch (op) {
     case RB200_OP_MOV:
@@ -343,8 +359,17 @@ template <int V, class C> __device__ __forceinline__ bool exec_int(C& cx, const 
       for (int k = 0; k < V; ++k) r[k] = a[k];
       break;
     case RB200_OP_ADD:
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = a[k] + b[k];
+      break;
     case RB200_OP_SUB:
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = a[k] - b[k];
+      break;
     case RB200_OP_MUL:
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = a[k] * b[k];
+      break;
     case RB200_OP_MIN:
     case RB200_OP_MAX:
     case RB200_OP_BAND:
@@ -355,26 +380,26 @@ template <int V, class C> __device__ __forceinline__ bool exec_int(C& cx, const 
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         long long x = a[k], y = b[k];
-        r[k] = op == RB200_OP_ADD   ? x + y
-               : op == RB200_OP_SUB ? x - y
-               : op == RB200_OP_MUL ? x * y
-               : op == RB200_OP_MIN ? ((y < x) ? y : x)
+        r[k] = op == RB200_OP_MIN ? ((y < x) ? y : x)
                : op == RB200_OP_MAX ? ((y > x) ? y : x)
                : op == RB200_OP_BAND ? (x & y)
                : op == RB200_OP_BOR  ? (x | y)
                : op == RB200_OP_BXOR ? (x ^ y)
-               : op == RB200_OP_SHL  ? (long long)((unsigned long long)x << (y & 63))
+               : op == RB200_OP_SHL  ? (long long)((u64)x << (y & 63))
                                      : (x >> (y & 63));
       }
       break;
     case RB200_OP_FLOORDIV:
+#pragma unroll 1
       for (int k = 0; k < V; ++k) r[k] = py_floordiv(a[k], b[k]);
       break;
     case RB200_OP_MOD:
+#pragma unroll 1
       for (int k = 0; k < V; ++k) r[k] = py_mod(a[k], b[k]);
       break;
     case RB200_OP_POWI:
     case RB200_OP_POW:
+#pragma unroll 1
       for (int k = 0; k < V; ++k) r[k] = ipowi(a[k], b[k]);
       break;
     case RB200_OP_GT:
@@ -432,14 +457,15 @@ template <int V, class C> __device__ __forceinline__ bool exec_int(C& cx, const 
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = 0;
       break;
-    case RB200_OP_WHERE:
+    case RB200_OP_WHERE: {
+      long long c[V];
+      cx.template fetch<long long>(I.c_kind, I.c_idx, c);
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = (a[k] != 0) ? b[k] : c[k];
-      break;
-    default: return false;
+    } break;
+    default: return;
   }
   cx.template finish<long long>(I, r);
-  return true;
 }
 
 // value a store + reload through storage dtype `dt` would give (narrowing round / wrap)
@@ -489,11 +515,13 @@ template <class S, int V, class C> __device__ __forceinline__ void exec_cvt_from
   }
 }
 
-// one interpreter pass over the op list for the current V elements.
-// RACC: reduction accumulators, [slot] (global mode, AX=false) or [slot][k] (axis mode)
-template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C& cx, Val (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
+// one interpreter pass over the op list for the thread's V elements.
+// racc: reduction accumulators (raw bits), [slot][0] (global mode, AX=false) or [slot][k] (axis mode)
+template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C& cx, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
   const KParams& P = cx.P;
-  for (int pc = 0; pc < P.n_insns; ++pc) {
+  const int n = P.n_insns;
+#pragma unroll 1
+  for (int pc = 0; pc < n; ++pc) {
     const rb200_insn I = P.insns[pc];
     if (I.op == RB200_OP_CVT) {
       switch (I.imm & 0xff) {
@@ -514,9 +542,9 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
           if (s == slot) {
 #pragma unroll
             for (int k = 0; k < V; ++k)
-              if (k < cx.nvalid) {
-                Val& t = racc[s][AX ? k : 0];
-                t.d = red_combine<double>(rop, t.d, a[k]);
+              if ((cx.valid >> k) & 1u) {
+                u64& t = racc[s][AX ? k : 0];
+                t = CT<double>::bits(red_combine<double>(rop, CT<double>::get(t), a[k]));
               }
           }
       } else {
@@ -527,9 +555,9 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
           if (s == slot) {
 #pragma unroll
             for (int k = 0; k < V; ++k)
-              if (k < cx.nvalid) {
-                Val& t = racc[s][AX ? k : 0];
-                t.i = red_combine<long long>(rop, t.i, a[k]);
+              if ((cx.valid >> k) & 1u) {
+                u64& t = racc[s][AX ? k : 0];
+                t = (u64)red_combine<long long>(rop, (long long)t, a[k]);
               }
           }
       }
@@ -539,6 +567,28 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
       case RB200_T_F64: exec_float<double, V>(cx, I); break;
       case RB200_T_F32: exec_float<float, V>(cx, I); break;
       default: exec_int<V>(cx, I);
+    }
+  }
+}
+
+// decode a flat (row-major) element index into the N-d index, dims d0..ND-1 (d0 = first kept dim)
+template <int ND> __device__ __forceinline__ void decode_index(const KParams& P, long long e, int d0, long long (&idx)[ND]) {
+#pragma unroll
+  for (int d = ND - 1; d >= 0; --d) {
+    if (d >= P.ndim || d < d0) {
+      if (d < d0) continue;
+      idx[d] = 0;
+      continue;
+    }
+    if (d == d0) {
+      idx[d] = e;
+    } else {
+      const long long sd = P.shape[d];
+      long long q;
+      if (((e | sd) >> 31) == 0) q = (long long)((unsigned)e / (unsigned)sd);
+      else q = e / sd;
+      idx[d] = e - q * sd;
+      e = q;
     }
   }
 }

@@ -2,7 +2,11 @@
 #include "rb200_vm.cuh"
 
 namespace rb200 {
-// launchers (one translation unit per kernel so that they compile in parallel)
-cudaError_t launch_vm_elementwise(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
+constexpr int kV = 4;  // elements per thread per tile
+// launchers (one translation unit per kernel instantiation so that they compile in parallel)
+cudaError_t launch_vm_elementwise_nd1(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
+cudaError_t launch_vm_elementwise_nd2(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
+cudaError_t launch_vm_elementwise_nd3(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
+cudaError_t launch_vm_elementwise_nd5(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_vm_axis_reduce(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 }  // namespace rb200

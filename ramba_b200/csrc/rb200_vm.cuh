@@ -1,12 +1,17 @@
-// rb200_vm.cuh — device side of the op-list accumulator machine (sm_100a).
+// rb200_vm.cuh — device side of the op-list accumulator machine (sm_100a): data layout, loads,
+// stores and scalar op semantics.
 //
-// The reference's worker executes Python source generated per fused op and JIT-compiled by
-// Numba (ramba/ramba.py:8247-8265, 3758-3780).  Here the same loop body is an op list that a
-// hand-written CUDA kernel walks: every thread owns V consecutive elements of the innermost
-// iteration dim, keeps the running value in registers (the accumulator), spills to a shared
-// memory register file only when the host-side allocator says a value is needed later, and
-// touches HBM only for live array views (16-byte vector loads/stores when the view is
-// contiguous and aligned).
+// The reference's worker executes Python source generated per fused op and JIT-compiled by Numba
+// (ramba/ramba.py:8247-8265, 3758-3780).  Here the same loop body is an op list that a hand-written
+// CUDA kernel walks.  Work decomposition: a CTA of 256 threads owns one tile of 256*V consecutive
+// elements of the (row-major, collapsed) iteration space at a time; thread t owns elements
+// t, 256+t, 512+t, ... of the tile ("strided-V"), so every per-k access of a warp covers 32
+// consecutive elements: fully coalesced requests for any contiguous view, with no alignment
+// requirement on the view's base (slices starting at odd offsets run at the same speed).  The
+// running value stays in registers (the accumulator); values needed later go to a shared-memory
+// register file; read-only input views of 1-D (collapsed) ops are staged one tile ahead into shared
+// memory with per-thread cp.async (LDGSTS) so that HBM latency overlaps the interpretation of the
+// current tile.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,14 +19,17 @@
 
 namespace rb200 {
 
+typedef unsigned long long u64;
+
 constexpr int kThreads = 256;
 constexpr int kMaxD = RB200_MAX_DIMS;
+constexpr int kMaxPf = 4;  // input views staged through shared memory
 
 struct KView {
   char* base;
   long long stride[kMaxD];  // elements
   int dtype;
-  int vec;  // 1: innermost stride 1 and base/rows 16B aligned -> vector path
+  int pf_slot;  // >= 0: staged by cp.async into prefetch slot pf_slot; -1: read directly
 };
 
 struct KRed {
@@ -32,228 +40,170 @@ struct KRed {
 };
 
 struct KParams {
-  int ndim, n_insns, n_views, n_regs, n_reds, axis_mode;
+  int ndim, n_insns, n_views, n_regs, n_reds, n_pf;
+  int pf_view[kMaxPf];
+  int wide;  // 1: element indices need 64 bits
+  int pad0;
   long long shape[kMaxD];
   long long gstart[kMaxD];
-  long long n_chunks;     // chunks of V along the innermost dim
-  long long total_work;   // rows * n_chunks
-  // axis reduction (column form): kept work items x splits of the reduced range
-  long long red_len;      // product of reduced dims (walked sequentially)
-  long long red_split;    // elements of the reduced range per split
+  long long total;    // elements of the (kept) iteration space
+  long long n_tiles;  // ceil(total / (kThreads*V))
+  // axis reduction (column form): leading red_ndim dims are walked sequentially
+  long long red_len;
+  long long red_split;
   int n_split;
-  int red_ndim;           // number of leading reduced dims folded into red_len
-  long long red_shape[kMaxD];
+  int red_ndim;
   KView views[RB200_MAX_VIEWS];
-  unsigned long long scalars[RB200_MAX_SCALARS];
+  u64 scalars[RB200_MAX_SCALARS];
   rb200_insn insns[RB200_MAX_INSNS];
   KRed reds[RB200_MAX_REDS];
-  unsigned long long* red_partials;  // [n_reds][grid]
+  u64* red_partials;
   unsigned int* red_counter;
 };
 
-union Val {
-  double d;
-  float f;
-  long long i;
-  unsigned long long u;
-};
-
 // ---------------------------------------------------------------------------------------------
-// type traits for the three compute classes
+// raw 64-bit machine values <-> the three compute classes (register moves, never memory)
 template <class T> struct CT;
 template <> struct CT<double> {
-  static __device__ __forceinline__ double get(const Val& v) { return v.d; }
-  static __device__ __forceinline__ void set(Val& v, double x) { v.d = x; }
-  static __device__ __forceinline__ double scal(unsigned long long u) { return __longlong_as_double((long long)u); }
+  static __device__ __forceinline__ double get(u64 v) { return __longlong_as_double((long long)v); }
+  static __device__ __forceinline__ u64 bits(double x) { return (u64)__double_as_longlong(x); }
 };
 template <> struct CT<float> {
-  static __device__ __forceinline__ float get(const Val& v) { return v.f; }
-  static __device__ __forceinline__ void set(Val& v, float x) { v.u = 0; v.f = x; }
-  static __device__ __forceinline__ float scal(unsigned long long u) { return __uint_as_float((unsigned)u); }
+  static __device__ __forceinline__ float get(u64 v) { return __uint_as_float((unsigned)v); }
+  static __device__ __forceinline__ u64 bits(float x) { return (u64)__float_as_uint(x); }
 };
 template <> struct CT<long long> {
-  static __device__ __forceinline__ long long get(const Val& v) { return v.i; }
-  static __device__ __forceinline__ void set(Val& v, long long x) { v.i = x; }
-  static __device__ __forceinline__ long long scal(unsigned long long u) { return (long long)u; }
+  static __device__ __forceinline__ long long get(u64 v) { return (long long)v; }
+  static __device__ __forceinline__ u64 bits(long long x) { return (u64)x; }
 };
 
-// conversions between storage values and compute classes (C semantics == Numba/LLVM casts:
-// float->int truncates toward zero (fptosi), int->float rounds to nearest, f64->f32 rn)
-template <class T, class S> __device__ __forceinline__ T cvt(S x) { return (T)x; }
+// ---------------------------------------------------------------------------------------------
+// shared memory by 32-bit shared-window address (guarantees LDS/STS, never generic LD/ST)
+__device__ __forceinline__ u64 lds64(unsigned addr) {
+  u64 v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
+
+// cp.async (LDGSTS): per-thread asynchronous global -> shared copy, zero-filled when !valid
+__device__ __forceinline__ void cp_async8(unsigned sdst, const void* gsrc, bool valid) {
+  int n = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sdst), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned sdst, const void* gsrc, bool valid) {
+  int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdst), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------
-// global loads / stores. Streams are touched once per launch: bypass L1 allocation for the
-// vector path (ld.global.nc / st.global with L1::no_allocate), default caching for scalar
-// (possibly re-used: broadcast, shifted stencil) accesses.
-__device__ __forceinline__ int4 ldg_stream16(const void* p) {
-  int4 r;
-  asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
+// element loads / stores through explicit global-space instructions.
+// C cast semantics == Numba/LLVM casts (float->int truncates, int->float rn, f64->f32 rn).
+template <class S> __device__ __forceinline__ S ldg(const S* p) { return *p; }
+template <> __device__ __forceinline__ double ldg<double>(const double* p) {
+  double v;
+  asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
 }
-__device__ __forceinline__ void stg_stream16(void* p, int4 v) {
-  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
-               "r"(v.w)
-               : "memory");
+template <> __device__ __forceinline__ float ldg<float>(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+template <> __device__ __forceinline__ long long ldg<long long>(const long long* p) {
+  long long v;
+  asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+template <> __device__ __forceinline__ int ldg<int>(const int* p) {
+  int v;
+  asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+template <class S> __device__ __forceinline__ void stg(S* p, S v) { *p = v; }
+template <> __device__ __forceinline__ void stg<double>(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+template <> __device__ __forceinline__ void stg<float>(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+template <> __device__ __forceinline__ void stg<long long>(long long* p, long long v) { asm volatile("st.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+template <> __device__ __forceinline__ void stg<int>(int* p, int v) { asm volatile("st.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+template <class T, class S, int V>
+__device__ __forceinline__ void load_direct(const char* base, const long long (&off)[V], unsigned valid, T (&out)[V]) {
+  const S* p = reinterpret_cast<const S*>(base);
+  S tmp[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) tmp[k] = ((valid >> k) & 1u) ? ldg<S>(p + off[k]) : S(0);
+#pragma unroll
+  for (int k = 0; k < V; ++k) out[k] = (T)tmp[k];
+}
+
+template <class T> __device__ __noinline__ T load_narrow_one(const char* base, int dtype, long long off) {
+  switch (dtype) {
+    case RB200_BOOL:
+    case RB200_U8: return (T) reinterpret_cast<const unsigned char*>(base)[off];
+    case RB200_I8: return (T) reinterpret_cast<const signed char*>(base)[off];
+    case RB200_I16: return (T) reinterpret_cast<const short*>(base)[off];
+    case RB200_U16: return (T) reinterpret_cast<const unsigned short*>(base)[off];
+    case RB200_U32: return (T) reinterpret_cast<const unsigned int*>(base)[off];
+    default: return T(0);
+  }
+}
+
+template <class T, int V>
+__device__ __forceinline__ void load_view(const char* base, int dtype, const long long (&off)[V], unsigned valid, T (&out)[V]) {
+  switch (dtype) {
+    case RB200_F64: load_direct<T, double, V>(base, off, valid, out); break;
+    case RB200_F32: load_direct<T, float, V>(base, off, valid, out); break;
+    case RB200_I64: load_direct<T, long long, V>(base, off, valid, out); break;
+    case RB200_I32: load_direct<T, int, V>(base, off, valid, out); break;
+    default:  // narrow integer dtypes: off the hot path, out of line
+#pragma unroll 1
+      for (int k = 0; k < V; ++k) out[k] = ((valid >> k) & 1u) ? load_narrow_one<T>(base, dtype, off[k]) : T(0);
+  }
+}
+
+// raw staged value (cp.async slot) -> compute class
+template <class T> __device__ __forceinline__ T from_raw(u64 raw, int dtype) {
+  switch (dtype) {
+    case RB200_F64: return (T)__longlong_as_double((long long)raw);
+    case RB200_F32: return (T)__uint_as_float((unsigned)raw);
+    case RB200_I64: return (T)(long long)raw;
+    default: return (T)(int)(unsigned)raw;  // RB200_I32
+  }
 }
 
 template <class T, class S, int V>
-__device__ __forceinline__ void load_typed(const KView& vw, long long off, long long istride, int nvalid, bool vec,
-                                           T (&out)[V]) {
-  const S* p = reinterpret_cast<const S*>(vw.base) + off;
-  if (vec && nvalid == V) {
-    constexpr int BYTES = V * (int)sizeof(S);
-    if constexpr (BYTES % 16 == 0) {
-      S tmp[V];
-#pragma unroll
-      for (int k = 0; k < BYTES / 16; ++k) reinterpret_cast<int4*>(tmp)[k] = ldg_stream16(reinterpret_cast<const int4*>(p) + k);
-#pragma unroll
-      for (int k = 0; k < V; ++k) out[k] = cvt<T, S>(tmp[k]);
-      return;
-    } else if constexpr (BYTES == 8) {
-      S tmp[V];
-      *reinterpret_cast<int2*>(tmp) = *reinterpret_cast<const int2*>(p);
-#pragma unroll
-      for (int k = 0; k < V; ++k) out[k] = cvt<T, S>(tmp[k]);
-      return;
-    } else if constexpr (BYTES == 4) {
-      S tmp[V];
-      *reinterpret_cast<int*>(tmp) = *reinterpret_cast<const int*>(p);
-#pragma unroll
-      for (int k = 0; k < V; ++k) out[k] = cvt<T, S>(tmp[k]);
-      return;
-    }
-  }
-  if (istride == 0) {
-    T x = cvt<T, S>(*p);
-#pragma unroll
-    for (int k = 0; k < V; ++k) out[k] = x;
-    return;
-  }
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    if (k < nvalid) out[k] = cvt<T, S>(p[(long long)k * istride]);
-    else out[k] = T(0);
-  }
-}
-
-// narrow integer dtypes are off the hot path: one out-of-line copy per compute class
-template <class T, int V> struct Pack { T v[V]; };
-template <class T, int V>
-__device__ __noinline__ Pack<T, V> load_view_narrow(const KView& vw, long long off, long long istride, int nvalid);
-
-template <class T, int V>
-__device__ __forceinline__ void load_view(const KView& vw, long long off, long long istride, int nvalid, T (&out)[V]) {
-  const bool vec = vw.vec != 0;
-  switch (vw.dtype) {
-    case RB200_F64: load_typed<T, double, V>(vw, off, istride, nvalid, vec, out); break;
-    case RB200_F32: load_typed<T, float, V>(vw, off, istride, nvalid, vec, out); break;
-    case RB200_I64: load_typed<T, long long, V>(vw, off, istride, nvalid, vec, out); break;
-    case RB200_I32: load_typed<T, int, V>(vw, off, istride, nvalid, vec, out); break;
-    default: {
-      Pack<T, V> p = load_view_narrow<T, V>(vw, off, istride, nvalid);
-#pragma unroll
-      for (int k = 0; k < V; ++k) out[k] = p.v[k];
-    }
-  }
-}
-
-template <class T, int V>
-__device__ __noinline__ Pack<T, V> load_view_narrow(const KView& vw, long long off, long long istride, int nvalid) {
-  const bool vec = vw.vec != 0;
-  Pack<T, V> pk;
-  T (&out)[V] = pk.v;
-  switch (vw.dtype) {
-    case RB200_BOOL:
-    case RB200_U8: load_typed<T, unsigned char, V>(vw, off, istride, nvalid, vec, out); break;
-    case RB200_I8: load_typed<T, signed char, V>(vw, off, istride, nvalid, vec, out); break;
-    case RB200_I16: load_typed<T, short, V>(vw, off, istride, nvalid, vec, out); break;
-    case RB200_U16: load_typed<T, unsigned short, V>(vw, off, istride, nvalid, vec, out); break;
-    case RB200_U32: load_typed<T, unsigned int, V>(vw, off, istride, nvalid, vec, out); break;
-    default:
-#pragma unroll
-      for (int k = 0; k < V; ++k) out[k] = T(0);
-  }
-  return pk;
-}
-
-template <class T, class S> __device__ __forceinline__ S store_cvt(T x) { return (S)x; }
-// bool stores: any non-zero -> 1 (numpy bool_ cast)
-template <class T> __device__ __forceinline__ unsigned char store_bool(T x) { return x != T(0) ? 1 : 0; }
-
-template <class T, class S, int V, bool IS_BOOL>
-__device__ __forceinline__ void store_typed(const KView& vw, long long off, long long istride, int nvalid,
-                                            const T (&val)[V], unsigned mask) {
-  S* p = reinterpret_cast<S*>(vw.base) + off;
-  S tmp[V];
-#pragma unroll
-  for (int k = 0; k < V; ++k) {
-    if constexpr (IS_BOOL) tmp[k] = (S)store_bool<T>(val[k]);
-    else tmp[k] = store_cvt<T, S>(val[k]);
-  }
-  constexpr int BYTES = V * (int)sizeof(S);
-  constexpr unsigned FULL = (1u << V) - 1u;
-  if (vw.vec != 0 && nvalid == V && mask == FULL) {
-    if constexpr (BYTES % 16 == 0) {
-#pragma unroll
-      for (int k = 0; k < BYTES / 16; ++k) stg_stream16(reinterpret_cast<int4*>(p) + k, reinterpret_cast<int4*>(tmp)[k]);
-      return;
-    } else if constexpr (BYTES == 8) {
-      *reinterpret_cast<int2*>(p) = *reinterpret_cast<int2*>(tmp);
-      return;
-    } else if constexpr (BYTES == 4) {
-      *reinterpret_cast<int*>(p) = *reinterpret_cast<int*>(tmp);
-      return;
-    }
-  }
-  if (istride == 0) {
-    // broadcast target (reduction accumulators written through a stride-0 view): last valid wins
-    int last = -1;
-#pragma unroll
-    for (int k = 0; k < V; ++k)
-      if (k < nvalid && ((mask >> k) & 1u)) last = k;
-    if (last >= 0) *p = tmp[last];
-    return;
-  }
+__device__ __forceinline__ void store_direct(char* base, const long long (&off)[V], unsigned mask, const T (&val)[V]) {
+  S* p = reinterpret_cast<S*>(base);
 #pragma unroll
   for (int k = 0; k < V; ++k)
-    if (k < nvalid && ((mask >> k) & 1u)) p[(long long)k * istride] = tmp[k];
+    if ((mask >> k) & 1u) stg<S>(p + off[k], (S)val[k]);
 }
 
-template <class T, int V>
-__device__ __noinline__ void store_view_narrow(const KView& vw, long long off, long long istride, int nvalid,
-                                               Pack<T, V> pk, unsigned mask);
-
-template <class T, int V>
-__device__ __forceinline__ void store_view(const KView& vw, long long off, long long istride, int nvalid,
-                                           const T (&val)[V], unsigned mask) {
-  switch (vw.dtype) {
-    case RB200_F64: store_typed<T, double, V, false>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_F32: store_typed<T, float, V, false>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_I64: store_typed<T, long long, V, false>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_I32: store_typed<T, int, V, false>(vw, off, istride, nvalid, val, mask); break;
-    default: {
-      Pack<T, V> pk;
-#pragma unroll
-      for (int k = 0; k < V; ++k) pk.v[k] = val[k];
-      store_view_narrow<T, V>(vw, off, istride, nvalid, pk, mask);
-    }
+template <class T> __device__ __noinline__ void store_narrow_one(char* base, int dtype, long long off, T x) {
+  switch (dtype) {
+    case RB200_BOOL: reinterpret_cast<unsigned char*>(base)[off] = (x != T(0)) ? 1 : 0; break;
+    case RB200_U8: reinterpret_cast<unsigned char*>(base)[off] = (unsigned char)(long long)x; break;
+    case RB200_I8: reinterpret_cast<signed char*>(base)[off] = (signed char)(long long)x; break;
+    case RB200_I16: reinterpret_cast<short*>(base)[off] = (short)(long long)x; break;
+    case RB200_U16: reinterpret_cast<unsigned short*>(base)[off] = (unsigned short)(long long)x; break;
+    case RB200_U32: reinterpret_cast<unsigned int*>(base)[off] = (unsigned int)(long long)x; break;
+    default: break;
   }
 }
 
 template <class T, int V>
-__device__ __noinline__ void store_view_narrow(const KView& vw, long long off, long long istride, int nvalid,
-                                               Pack<T, V> pk, unsigned mask) {
-  const T (&val)[V] = pk.v;
-  switch (vw.dtype) {
-    case RB200_BOOL: store_typed<T, unsigned char, V, true>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_U8: store_typed<T, unsigned char, V, false>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_I8: store_typed<T, signed char, V, false>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_I16: store_typed<T, short, V, false>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_U16: store_typed<T, unsigned short, V, false>(vw, off, istride, nvalid, val, mask); break;
-    case RB200_U32: store_typed<T, unsigned int, V, false>(vw, off, istride, nvalid, val, mask); break;
-    default: break;
+__device__ __forceinline__ void store_view(char* base, int dtype, const long long (&off)[V], unsigned mask, const T (&val)[V]) {
+  switch (dtype) {
+    case RB200_F64: store_direct<T, double, V>(base, off, mask, val); break;
+    case RB200_F32: store_direct<T, float, V>(base, off, mask, val); break;
+    case RB200_I64: store_direct<T, long long, V>(base, off, mask, val); break;
+    case RB200_I32: store_direct<T, int, V>(base, off, mask, val); break;
+    default:
+#pragma unroll 1
+      for (int k = 0; k < V; ++k)
+        if ((mask >> k) & 1u) store_narrow_one<T>(base, dtype, off[k], val[k]);
   }
 }
 
@@ -298,7 +248,7 @@ template <class F> __device__ __forceinline__ F py_ffloordiv(F a, F b) {
 // x ** n for integer n: Numba's int_power_impl (exponentiation by squaring, r starts at 1)
 template <class F> __device__ __forceinline__ F powi(F a, long long b) {
   bool invert = b < 0;
-  unsigned long long e = invert ? (unsigned long long)(-b) : (unsigned long long)b;
+  u64 e = invert ? (u64)(-b) : (u64)b;
   if (e > 0x10000ull) return (F)pow((double)a, (double)b);
   F r = F(1);
   while (e != 0) {
@@ -311,13 +261,35 @@ template <class F> __device__ __forceinline__ F powi(F a, long long b) {
 __device__ __forceinline__ long long ipowi(long long a, long long b) {
   if (b < 0) return (a == 1) ? 1 : ((a == -1) ? ((b & 1) ? -1 : 1) : 0);
   long long r = 1;
-  unsigned long long e = (unsigned long long)b;
+  u64 e = (u64)b;
   while (e != 0) {
     if (e & 1ull) r *= a;
     e >>= 1;
     a *= a;
   }
   return r;
+}
+
+// reduction combine in the accumulator class (raw bits)
+template <class T> __device__ __forceinline__ T red_combine(int op, T a, T b) {
+  switch (op) {
+    case RB200_RED_ADD: return a + b;
+    case RB200_RED_MUL: return a * b;
+    case RB200_RED_MIN: return (b < a) ? b : a;
+    default: return (b > a) ? b : a;
+  }
+}
+__device__ __forceinline__ u64 red_combine_bits(int op, int ctype, u64 a, u64 b) {
+  if (ctype == RB200_T_F64) return CT<double>::bits(red_combine<double>(op, CT<double>::get(a), CT<double>::get(b)));
+  return CT<long long>::bits(red_combine<long long>(op, (long long)a, (long long)b));
+}
+__device__ __forceinline__ u64 red_identity_bits(int op, int ctype) {
+  if (ctype == RB200_T_F64) {
+    double d = (op == RB200_RED_ADD) ? 0.0 : (op == RB200_RED_MUL) ? 1.0 : (op == RB200_RED_MIN) ? INFINITY : -INFINITY;
+    return CT<double>::bits(d);
+  }
+  long long i = (op == RB200_RED_ADD) ? 0ll : (op == RB200_RED_MUL) ? 1ll : (op == RB200_RED_MIN) ? 0x7fffffffffffffffll : (long long)0x8000000000000000ull;
+  return (u64)i;
 }
 
 }  // namespace rb200

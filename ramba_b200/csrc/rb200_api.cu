@@ -6,6 +6,7 @@
 #include <string>
 
 #include "rb200_launch.h"
+#include "rb200_handlers.h"
 
 namespace rb200 {
 // stage 2 helper: out[j] = reduce_k part[k*stride_k + j]
@@ -64,6 +65,57 @@ static int sm_count() {
 }
 
 constexpr int kRedScratchPartials = 4096;  // max grid size of a launch with global reductions
+
+// static operand kind of an op-list operand for the specialised handlers (-1: needs the generic path);
+// staged views are addressed by their prefetch slot (*idx is rewritten)
+static int static_kind(const KParams& P, int kind, int* idx, int ctype) {
+  switch (kind) {
+    case RB200_K_ACC: return S_ACC;
+    case RB200_K_REG: return S_REG;
+    case RB200_K_SCAL: return S_SCAL;
+    case RB200_K_VIEW: {
+      const KView& v = P.views[*idx];
+      if (v.pf_slot < 0) return -1;
+      const int own = ctype == RB200_T_F64 ? RB200_F64 : ctype == RB200_T_F32 ? RB200_F32 : RB200_I64;
+      if (v.dtype == own) {
+        *idx = v.pf_slot;
+        return S_PFV;
+      }
+      if (ctype == RB200_T_F64 && v.dtype == RB200_F32) {
+        *idx = v.pf_slot;
+        return S_PFV32;
+      }
+      return -1;
+    }
+    default: return -1;
+  }
+}
+
+static void assign_handlers(KParams& P, const rb200_fused_op* op) {
+  for (int i = 0; i < P.n_insns; ++i) {
+    rb200_insn I = P.insns[i];
+    int h = H_GENERIC;
+    int ai = I.a_idx, bi = I.b_idx;
+    const int ak = static_kind(P, I.a_kind, &ai, I.ctype);
+    if (I.op == RB200_OP_ADD || I.op == RB200_OP_SUB || I.op == RB200_OP_MUL) {
+      const int bk = static_kind(P, I.b_kind, &bi, I.ctype);
+      h = handler_bin(I.op, I.ctype, ak, bk);
+    } else if (I.op == RB200_OP_RED) {
+      h = handler_red(I.ctype, ak);
+    } else if (I.op == RB200_OP_POWI) {
+      // only x ** 2 with a scalar exponent (Numba int_power gives exactly x*x)
+      if (I.b_kind == RB200_K_SCAL && (long long)op->scalars[I.b_idx] == 2) h = handler_un(I.op, I.ctype, ak);
+    } else if (I.c_kind == RB200_K_NONE && I.b_kind == RB200_K_NONE) {
+      h = handler_un(I.op, I.ctype, ak);
+    }
+    if (h != H_GENERIC) {
+      I.a_idx = (uint8_t)ai;
+      if (I.op != RB200_OP_RED) I.b_idx = (uint8_t)bi;
+      P.insns[i] = I;
+    }
+    P.handler[i] = (unsigned short)h;
+  }
+}
 
 extern "C" {
 
@@ -178,6 +230,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     long long blocks = P.n_tiles;
     long long cap = (long long)sms * 4;
     if (blocks > cap) blocks = cap;
+    assign_handlers(P, op);
     e = launch_vm_axis_reduce(P, (unsigned)blocks, reg_bytes, stream);
     if (e != cudaSuccess) return fail_cuda("vm_axis_reduce_kernel launch", e);
     g_launches.fetch_add(1);
@@ -200,8 +253,15 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
       }
     }
     pf_bytes = (size_t)P.n_pf * 2 * V * kThreads * 8;
+    // whole-tile bulk copies need contiguous, 16-byte aligned sources
+    P.bulk = P.n_pf > 0 ? 1 : 0;
+    for (int j = 0; j < P.n_pf; ++j) {
+      const rb200_view& v = op->views[P.pf_view[j]];
+      if (v.stride[0] != 1 || (((uintptr_t)v.base) & 15u) != 0) P.bulk = 0;
+    }
   }
   const size_t smem = reg_bytes + pf_bytes;
+  if (op->ndim == 1) assign_handlers(P, op);  // N-d instantiations are generic-only
   if (op->n_reds > 0) {
     if (!op->red_scratch) return fail("global reduction needs red_scratch");
     P.red_counter = (unsigned int*)op->red_scratch;
@@ -234,7 +294,12 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     case 3: e = launch_vm_elementwise_nd3(P, (unsigned)blocks, smem, stream); break;
     default: e = launch_vm_elementwise_nd5(P, (unsigned)blocks, smem, stream); break;
   }
-  if (e != cudaSuccess) return fail_cuda("vm_elementwise_kernel launch", e);
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "vm_elementwise_kernel launch (ndim=%d blocks=%lld smem=%zu n_regs=%d n_pf=%d n_insns=%d)", op->ndim, blocks, smem,
+             op->n_regs, P.n_pf, op->n_insns);
+    return fail_cuda(buf, e);
+  }
   g_launches.fetch_add(1);
   return 0;
 }

@@ -17,6 +17,7 @@ template <int V> __global__ void __launch_bounds__(kThreads, 2) vm_axis_reduce_k
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
   cx.regfile_s = smem_s + threadIdx.x * 8u;
   cx.pf_s = 0;
+  cx.tid = threadIdx.x;
   const int nk0 = P.red_ndim;       // first kept dim
   const long long kept = P.total;   // kept elements
   const long long tiles_per_split = (kept + TILE - 1) / TILE;
@@ -80,7 +81,7 @@ template <int V> __global__ void __launch_bounds__(kThreads, 2) vm_axis_reduce_k
 }
 
 cudaError_t launch_vm_axis_reduce(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
-  if (smem > 48 * 1024) {
+  if (smem + 2048 > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(vm_axis_reduce_kernel<kV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }

@@ -7,55 +7,111 @@
 namespace rb200 {
 
 // Persistent-style grid (a multiple of the SM count): CTA b walks tiles b, b+grid, ...
-// Shared memory layout (dynamic): [register file: n_regs*V*256*8 B][prefetch: 2 stages * n_pf*V*256*8 B]
+// Shared memory layout (dynamic): [prefetch: 2 stages * n_pf * V*256*8 B][register file: n_regs*V*256*8 B]
 template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1) ? 3 : 2) vm_elementwise_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) u64 mbar_store[2];
   constexpr int TILE = kThreads * V;
+  constexpr unsigned SLOT = (unsigned)(TILE * 8);  // bytes reserved per staged view per stage
   Ctx<V, ND> cx(P);
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
-  cx.regfile_s = smem_s + threadIdx.x * 8u;
-  const unsigned pf_base = smem_s + (unsigned)(P.n_regs * V * kThreads * 8) + threadIdx.x * 8u;
-  const unsigned pf_stage_bytes = (unsigned)(P.n_pf * V * kThreads * 8);
+  cx.tid = threadIdx.x;
+  const int n_pf = (ND == 1) ? P.n_pf : 0;
+  // layout: [prefetch stage 0][prefetch stage 1][register file]  (stages first: 128-byte aligned)
+  const unsigned pf_base = smem_s;
+  const unsigned pf_stage_bytes = (unsigned)n_pf * SLOT;
+  cx.regfile_s = smem_s + 2u * pf_stage_bytes + threadIdx.x * 8u;
   cx.pf_s = pf_base;
+  const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&mbar_store[0]);
+  const bool bulk = (ND == 1) && n_pf > 0 && P.bulk;
+  if (bulk) {
+    if (threadIdx.x == 0) {
+      mbar_init(mbar0, 1);
+      mbar_init(mbar0 + 8u, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
 
   u64 racc[RB200_MAX_REDS][1];
 #pragma unroll
   for (int s = 0; s < RB200_MAX_REDS; ++s) racc[s][0] = red_identity_bits(s < P.n_reds ? P.reds[s].op : 0, s < P.n_reds ? P.reds[s].ctype : 0);
 
-  const int n_pf = (ND == 1) ? P.n_pf : 0;
-  // stage the inputs of tile `t` (ND == 1 only): one cp.async per element per staged view
-  auto issue_prefetch = [&](long long t, unsigned stage_s) {
-    const long long e0 = t * TILE + threadIdx.x;
+  // --- staging of the read-only inputs of tile t into stage `st` (ND == 1 only) --------------
+  // full tiles of contiguous, 16-byte aligned views: ONE bulk async copy per view by one thread
+  auto issue_bulk = [&](long long t, unsigned st) {
+    const unsigned mb = mbar0 + st * 8u;
+    unsigned bytes = 0;
+#pragma unroll 1
+    for (int j = 0; j < n_pf; ++j) {
+      const int dt = P.views[P.pf_view[j]].dtype;
+      bytes += (unsigned)TILE * ((dt == RB200_F64 || dt == RB200_I64) ? 8u : 4u);
+    }
+    mbar_expect_tx(mb, bytes);
 #pragma unroll 1
     for (int j = 0; j < n_pf; ++j) {
       const KView& vw = P.views[P.pf_view[j]];
-      const long long s = vw.stride[0];
+      const unsigned es = (vw.dtype == RB200_F64 || vw.dtype == RB200_I64) ? 8u : 4u;
+      bulk_g2s(pf_base + st * pf_stage_bytes + (unsigned)j * SLOT, vw.base + t * (long long)TILE * es, (unsigned)TILE * es, mb);
+    }
+  };
+  // ragged / strided / unaligned tiles: one cp.async per element, zero-filled past the end
+  auto issue_ldgsts = [&](long long t, unsigned st) {
+    const long long e0 = t * TILE + threadIdx.x;
+    const long long left = P.total - e0;  // element k exists iff k*256 < left
+#pragma unroll 1
+    for (int j = 0; j < n_pf; ++j) {
+      const KView& vw = P.views[P.pf_view[j]];
       const int es = (vw.dtype == RB200_F64 || vw.dtype == RB200_I64) ? 8 : 4;
+      const long long sb = vw.stride[0] * es;  // byte stride per element (uniform)
+      const long long step = sb * kThreads;
+      const char* src = vw.base + e0 * sb;
+      unsigned dst = pf_base + st * pf_stage_bytes + (unsigned)j * SLOT + threadIdx.x * (unsigned)es;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
-        const long long e = e0 + (long long)k * kThreads;
-        const bool ok = e < P.total;
-        const char* src = vw.base + (ok ? e * s * es : 0);
-        const unsigned dst = stage_s + (unsigned)((j * V + k) * kThreads * 8);
-        if (es == 8) cp_async8(dst, src, ok);
-        else cp_async4(dst, src, ok);
+        const bool ok = (long long)k * kThreads < left;
+        if (es == 8) cp_async8(dst, ok ? src : vw.base, ok);
+        else cp_async4(dst, ok ? src : vw.base, ok);
+        src += step;
+        dst += (unsigned)(kThreads * es);
       }
     }
   };
+  auto tile_is_bulk = [&](long long t) { return bulk && (t + 1) * TILE <= P.total; };
 
   long long tile = blockIdx.x;
-  unsigned stage = 0;
-  if (n_pf > 0) {
-    if (tile < P.n_tiles) issue_prefetch(tile, pf_base);
-    cp_async_commit();
+  unsigned stage = 0, phase0 = 0, phase1 = 0;
+  if (n_pf > 0 && tile < P.n_tiles) {
+    if (bulk) {
+      if (tile_is_bulk(tile) && threadIdx.x == 0) issue_bulk(tile, 0);
+    } else {
+      issue_ldgsts(tile, 0);
+      cp_async_commit();
+    }
   }
 #pragma unroll 1
   for (; tile < P.n_tiles; tile += gridDim.x) {
     if (n_pf > 0) {
       const long long nxt = tile + gridDim.x;
-      if (nxt < P.n_tiles) issue_prefetch(nxt, pf_base + (stage ^ 1u) * pf_stage_bytes);
-      cp_async_commit();
-      cp_async_wait<1>();  // everything but the group just committed has landed: this tile's inputs
+      if (bulk) {
+        // everybody is done reading the other stage (previous iteration) before it is refilled
+        __syncthreads();
+        if (nxt < P.n_tiles && tile_is_bulk(nxt) && threadIdx.x == 0) issue_bulk(nxt, stage ^ 1u);
+        if (tile_is_bulk(tile)) {
+          mbar_wait(mbar0 + stage * 8u, stage ? phase1 : phase0);
+          if (stage) phase1 ^= 1u;
+          else phase0 ^= 1u;
+        } else {  // the ragged last tile
+          issue_ldgsts(tile, stage);
+          cp_async_commit();
+          cp_async_wait<0>();
+        }
+      } else {
+        // per-thread pipeline (each thread re-reads only what it copied itself: no barrier)
+        if (nxt < P.n_tiles) issue_ldgsts(nxt, stage ^ 1u);
+        cp_async_commit();
+        cp_async_wait<1>();
+      }
       cx.pf_s = pf_base + stage * pf_stage_bytes;
       stage ^= 1u;
     }
@@ -82,7 +138,7 @@ template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1) ?
     cx.valid = valid;
     run_program<V, false>(cx, racc);
   }
-  if (n_pf > 0) cp_async_wait<0>();
+  if (n_pf > 0 && !bulk) cp_async_wait<0>();
 
   // ---- global reductions: thread -> warp shuffle -> block -> per-block partial -> last block
   if (P.n_reds > 0) {
@@ -153,7 +209,7 @@ template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1) ?
 }
 
 template <int V, int ND> cudaError_t launch_vm_elementwise_nd(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
-  if (smem > 48 * 1024) {
+  if (smem + 2048 > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(vm_elementwise_kernel<V, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }

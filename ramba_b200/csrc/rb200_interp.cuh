@@ -5,8 +5,10 @@
 // ramba/ramba.py:8247-8265 executed by RemoteState.run_deferred_ops (ramba/ramba.py:3758-3780).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <type_traits>
 
 #include "rb200_vm.cuh"
+#include "rb200_handlers.h"
 
 namespace rb200 {
 
@@ -16,7 +18,8 @@ namespace rb200 {
 template <int V, int ND> struct Ctx {
   const KParams& P;      // the __grid_constant__ kernel parameter: constant-bank (LDC) accesses
   unsigned regfile_s;    // shared-window byte address of this thread's column of the register file
-  unsigned pf_s;         // shared-window byte address of this thread's column of the current prefetch stage
+  unsigned pf_s;         // shared-window byte address of the current prefetch stage (element e of slot j at pf_s + j*V*2048 + e*itemsize)
+  unsigned tid;
   long long e0;          // ND == 1: index of element 0 of this thread in the tile
   long long idx[V][ND];  // ND  > 1: N-d index of every element
   unsigned valid;        // bit k: element k exists
@@ -28,8 +31,13 @@ template <int V, int ND> struct Ctx {
   __device__ __forceinline__ void offsets(const KView& vw, long long (&off)[V]) const {
     if constexpr (ND == 1) {
       const long long s = vw.stride[0];
+      const long long step = s * kThreads;  // uniform
+      long long o = e0 * s;
 #pragma unroll
-      for (int k = 0; k < V; ++k) off[k] = (e0 + (long long)k * kThreads) * s;
+      for (int k = 0; k < V; ++k) {
+        off[k] = o;
+        o += step;
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
@@ -58,8 +66,9 @@ template <int V, int ND> struct Ctx {
         const int slot = vw.pf_slot;
         const int dt = vw.dtype;
         if (slot >= 0) {
+          const unsigned slot_s = pf_s + (unsigned)(slot * V * kThreads * 8);
 #pragma unroll
-          for (int k = 0; k < V; ++k) out[k] = from_raw<T>(lds64(pf_s + (unsigned)((slot * V + k) * kThreads * 8)), dt);
+          for (int k = 0; k < V; ++k) out[k] = staged_load<T>(slot_s, k * kThreads + (int)tid, dt);
         } else {
           long long off[V];
           offsets(vw, off);
@@ -114,7 +123,10 @@ template <int V, int ND> struct Ctx {
       }
       long long off[V];
       offsets(vw, off);
-      if (vw.dtype == RB200_BOOL) {
+      constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+      if (vw.dtype == own) {
+        store_direct<R, R, V>(vw.base, off, m, r);
+      } else if (vw.dtype == RB200_BOOL) {
         long long b[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
@@ -125,6 +137,28 @@ template <int V, int ND> struct Ctx {
     }
   }
 };
+
+// rare ops: one out-of-line scalar routine each, called with static element indices so that the
+// operand arrays never need dynamic indexing (which would push them to local memory)
+template <class F> __device__ __noinline__ F rare_float_binary(int op, F a, F b) {
+  return op == RB200_OP_FLOORDIV ? py_ffloordiv<F>(a, b) : op == RB200_OP_MOD ? py_fmod<F>(a, b) : (F)pow(a, b);
+}
+template <class F> __device__ __noinline__ F rare_powi(F a, long long e) { return powi<F>(a, e); }
+template <class F> __device__ __noinline__ F rare_float_unary(int op, F x) {
+  return op == RB200_OP_TAN    ? tan(x)
+         : op == RB200_OP_SINH ? sinh(x)
+         : op == RB200_OP_COSH ? cosh(x)
+         : op == RB200_OP_TANH ? tanh(x)
+         : op == RB200_OP_ASIN ? asin(x)
+         : op == RB200_OP_ACOS ? acos(x)
+         : op == RB200_OP_ATAN ? atan(x)
+         : op == RB200_OP_EXP  ? exp(x)
+         : op == RB200_OP_LOG  ? log(x)
+                               : cbrt(x);
+}
+static __device__ __noinline__ long long rare_int_binary(int op, long long a, long long b) {
+  return op == RB200_OP_FLOORDIV ? py_floordiv(a, b) : op == RB200_OP_MOD ? py_mod(a, b) : ipowi(a, b);
+}
 
 // ---------------------------------------------------------------------------------------------
 // floating-point instruction set (F = double | float)
@@ -180,18 +214,10 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
       cx.template finish<F>(I, r);
       return;
     case RB200_OP_FLOORDIV:
-#pragma unroll 1
-      for (int k = 0; k < V; ++k) r[k] = py_ffloordiv<F>(a[k], b[k]);
-      cx.template finish<F>(I, r);
-      return;
     case RB200_OP_MOD:
-#pragma unroll 1
-      for (int k = 0; k < V; ++k) r[k] = py_fmod<F>(a[k], b[k]);
-      cx.template finish<F>(I, r);
-      return;
     case RB200_OP_POW:
-#pragma unroll 1
-      for (int k = 0; k < V; ++k) r[k] = (F)pow(a[k], b[k]);
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = rare_float_binary<F>(op, a[k], b[k]);
       cx.template finish<F>(I, r);
       return;
     case RB200_OP_POWI: {
@@ -207,8 +233,8 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
           else r[k] = __fmul_rn(a[k], a[k]);
         }
       } else {
-#pragma unroll 1
-        for (int k = 0; k < V; ++k) r[k] = powi<F>(a[k], e[k]);
+#pragma unroll
+        for (int k = 0; k < V; ++k) r[k] = rare_powi<F>(a[k], e[k]);
       }
       cx.template finish<F>(I, r);
       return;
@@ -287,22 +313,16 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
       cx.template finish<F>(I, r);
       return;
     case RB200_OP_SIN:
-#pragma unroll
-      for (int k = 0; k < V; ++k) r[k] = sin(a[k]);
-      cx.template finish<F>(I, r);
-      return;
     case RB200_OP_COS:
-#pragma unroll
-      for (int k = 0; k < V; ++k) r[k] = cos(a[k]);
-      cx.template finish<F>(I, r);
-      return;
     case RB200_OP_SINCOS: {
+      F sn[V], cs[V];
+      sincos_v<V>(a, sn, cs);
+      const bool want_cos = (op == RB200_OP_COS) || (op == RB200_OP_SINCOS && I.imm);  // imm 1: accumulator half is cos
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        F sn, cs;
-        sincos(a[k], &sn, &cs);
-        r[k] = I.imm ? cs : sn;  // imm 1: accumulator half is cos, parked half is sin
-        sts64(cx.reg_addr(I.st2, k), CT<F>::bits(I.imm ? sn : cs));
+      for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
+      if (op == RB200_OP_SINCOS) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) sts64(cx.reg_addr(I.st2, k), CT<F>::bits(want_cos ? sn[k] : cs[k]));
       }
       cx.template finish<F>(I, r);
       return;
@@ -317,21 +337,8 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
     case RB200_OP_EXP:
     case RB200_OP_LOG:
     case RB200_OP_CBRT:
-      // rarely on the hot path: one element at a time keeps the code small
-#pragma unroll 1
-      for (int k = 0; k < V; ++k) {
-        F x = a[k];
-        r[k] = op == RB200_OP_TAN    ? tan(x)
-               : op == RB200_OP_SINH ? sinh(x)
-               : op == RB200_OP_COSH ? cosh(x)
-               : op == RB200_OP_TANH ? tanh(x)
-               : op == RB200_OP_ASIN ? asin(x)
-               : op == RB200_OP_ACOS ? acos(x)
-               : op == RB200_OP_ATAN ? atan(x)
-               : op == RB200_OP_EXP  ? exp(x)
-               : op == RB200_OP_LOG  ? log(x)
-                                     : cbrt(x);
-      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = rare_float_unary<F>(op, a[k]);
       cx.template finish<F>(I, r);
       return;
     case RB200_OP_WHERE: {
@@ -390,17 +397,11 @@ template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const 
       }
       break;
     case RB200_OP_FLOORDIV:
-#pragma unroll 1
-      for (int k = 0; k < V; ++k) r[k] = py_floordiv(a[k], b[k]);
-      break;
     case RB200_OP_MOD:
-#pragma unroll 1
-      for (int k = 0; k < V; ++k) r[k] = py_mod(a[k], b[k]);
-      break;
     case RB200_OP_POWI:
     case RB200_OP_POW:
-#pragma unroll 1
-      for (int k = 0; k < V; ++k) r[k] = ipowi(a[k], b[k]);
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = rare_int_binary(op == RB200_OP_POW ? RB200_OP_POWI : op, a[k], b[k]);
       break;
     case RB200_OP_GT:
     case RB200_OP_LT:
@@ -515,6 +516,113 @@ template <class S, int V, class C> __device__ __forceinline__ void exec_cvt_from
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// specialised handlers: operand kinds, compute class and opcode are template parameters; the host
+// assigns one to every instruction whose operands are the accumulator, a spill register, a scalar
+// or a staged (cp.async) view of the matching dtype (rb200_handlers.h).  For staged views the host
+// has already replaced the view index by the prefetch slot.
+template <class T, int SK, int V, class C> __device__ __forceinline__ void fetch_s(C& cx, int i, T (&out)[V]) {
+  if constexpr (SK == S_ACC) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = CT<T>::get(cx.acc[k]);
+  } else if constexpr (SK == S_REG) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = CT<T>::get(lds64(cx.reg_addr(i, k)));
+  } else if constexpr (SK == S_SCAL) {
+    const T s = CT<T>::get(cx.P.scalars[i]);
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = s;
+  } else if constexpr (SK == S_PFV) {  // staged view whose dtype is T's own storage type
+    const unsigned slot_s = cx.pf_s + (unsigned)(i * V * kThreads * 8);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      if constexpr (sizeof(T) == 8) out[k] = CT<T>::get(lds64(slot_s + (unsigned)((k * kThreads + cx.tid) * 8)));
+      else out[k] = CT<T>::get((u64)lds32(slot_s + (unsigned)((k * kThreads + cx.tid) * 4)));
+    }
+  } else {  // S_PFV32: staged float32 view read in float64
+    const unsigned slot_s = cx.pf_s + (unsigned)(i * V * kThreads * 8);
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = (T)__uint_as_float(lds32(slot_s + (unsigned)((k * kThreads + cx.tid) * 4)));
+  }
+}
+
+template <int OP, class T, int AK, int BK, int V, class C> __device__ __forceinline__ void h_bin(C& cx, const rb200_insn& I) {
+  T a[V], b[V], r[V];
+  fetch_s<T, AK, V>(cx, I.a_idx, a);
+  fetch_s<T, BK, V>(cx, I.b_idx, b);
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if constexpr (sizeof(T) == 8 && !std::is_integral<T>::value) {
+      r[k] = OP == RB200_OP_ADD ? __dadd_rn(a[k], b[k]) : OP == RB200_OP_SUB ? __dsub_rn(a[k], b[k]) : __dmul_rn(a[k], b[k]);
+    } else if constexpr (sizeof(T) == 4) {
+      r[k] = OP == RB200_OP_ADD ? __fadd_rn(a[k], b[k]) : OP == RB200_OP_SUB ? __fsub_rn(a[k], b[k]) : __fmul_rn(a[k], b[k]);
+    } else {
+      r[k] = OP == RB200_OP_ADD ? a[k] + b[k] : OP == RB200_OP_SUB ? a[k] - b[k] : a[k] * b[k];
+    }
+  }
+  cx.template finish<T>(I, r);
+}
+
+template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ void h_un(C& cx, const rb200_insn& I) {
+  T a[V], r[V];
+  fetch_s<T, AK, V>(cx, I.a_idx, a);
+  if constexpr (OP == RB200_OP_SIN || OP == RB200_OP_COS || OP == RB200_OP_SINCOS) {
+    if constexpr (!std::is_integral<T>::value) {
+      T sn[V], cs[V];
+      sincos_v<V>(a, sn, cs);
+      const bool want_cos = (OP == RB200_OP_COS) || (OP == RB200_OP_SINCOS && I.imm);
+#pragma unroll
+      for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
+      if constexpr (OP == RB200_OP_SINCOS) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) sts64(cx.reg_addr(I.st2, k), CT<T>::bits(want_cos ? sn[k] : cs[k]));
+      }
+    }
+    cx.template finish<T>(I, r);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if constexpr (OP == RB200_OP_MOV) r[k] = a[k];
+    else if constexpr (OP == RB200_OP_NEG) r[k] = -a[k];
+    else if constexpr (OP == RB200_OP_ABS) {
+      if constexpr (std::is_integral<T>::value) r[k] = a[k] < 0 ? -a[k] : a[k];
+      else r[k] = fabs(a[k]);
+    } else if constexpr (OP == RB200_OP_SQUARE || OP == RB200_OP_POWI) {  // POWI here: exponent 2 (host-checked)
+      if constexpr (std::is_integral<T>::value) r[k] = a[k] * a[k];
+      else if constexpr (sizeof(T) == 8) r[k] = __dmul_rn(a[k], a[k]);
+      else r[k] = __fmul_rn(a[k], a[k]);
+    } else if constexpr (OP == RB200_OP_SQRT) r[k] = sqrt(a[k]);
+    else if constexpr (OP == RB200_OP_SIN) r[k] = sin(a[k]);
+    else if constexpr (OP == RB200_OP_COS) r[k] = cos(a[k]);
+    else if constexpr (OP == RB200_OP_SINCOS) {
+      T sn, cs;
+      sincos(a[k], &sn, &cs);
+      r[k] = I.imm ? cs : sn;
+      sts64(cx.reg_addr(I.st2, k), CT<T>::bits(I.imm ? sn : cs));
+    }
+  }
+  cx.template finish<T>(I, r);
+}
+
+template <class T, int AK, int V, bool AX, class C>
+__device__ __forceinline__ void h_red(C& cx, const rb200_insn& I, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
+  T a[V];
+  fetch_s<T, AK, V>(cx, I.a_idx, a);
+  const int slot = I.b_idx;
+  const int rop = (int)I.imm;
+#pragma unroll
+  for (int s = 0; s < RB200_MAX_REDS; ++s)
+    if (s == slot) {
+#pragma unroll
+      for (int k = 0; k < V; ++k)
+        if ((cx.valid >> k) & 1u) {
+          u64& t = racc[s][AX ? k : 0];
+          t = CT<T>::bits(red_combine<T>(rop, CT<T>::get(t), a[k]));
+        }
+    }
+}
+
 // one interpreter pass over the op list for the thread's V elements.
 // racc: reduction accumulators (raw bits), [slot][0] (global mode, AX=false) or [slot][k] (axis mode)
 template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C& cx, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
@@ -523,6 +631,16 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
 #pragma unroll 1
   for (int pc = 0; pc < n; ++pc) {
     const rb200_insn I = P.insns[pc];
+#ifndef RB200_NO_FAST_HANDLERS
+    const int h = P.handler[pc];
+    if (h != H_GENERIC) {
+      switch (h) {
+#include "rb200_handlers.inc"
+        default: break;
+      }
+      continue;
+    }
+#endif
     if (I.op == RB200_OP_CVT) {
       switch (I.imm & 0xff) {
         case RB200_T_F64: exec_cvt_from<double, V>(cx, I); break;

@@ -230,7 +230,6 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     long long blocks = P.n_tiles;
     long long cap = (long long)sms * 4;
     if (blocks > cap) blocks = cap;
-    assign_handlers(P, op);
     e = launch_vm_axis_reduce(P, (unsigned)blocks, reg_bytes, stream);
     if (e != cudaSuccess) return fail_cuda("vm_axis_reduce_kernel launch", e);
     g_launches.fetch_add(1);

@@ -1,4 +1,6 @@
 // rb200_axis.cu — K6: axis reduction (column form).
+// generic decode path only (the specialised handlers with an N-d context blow up build time)
+#define RB200_NO_FAST_HANDLERS 1
 #include "rb200_interp.cuh"
 #include "rb200_launch.h"
 namespace rb200 {

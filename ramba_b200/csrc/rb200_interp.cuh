@@ -12,6 +12,52 @@
 
 namespace rb200 {
 
+// one op-list instruction unpacked from its 16 bytes (two 8-byte constant-bank loads; fields that a
+// path does not use cost nothing)
+struct UInsn {
+  unsigned op, ctype, a_kind, a_idx, b_kind, b_idx, c_kind, c_idx, st_reg, st_view, st2, mask_reg, imm;
+  __device__ __forceinline__ UInsn(const rb200_insn* p) {
+    const uint2 lo = *reinterpret_cast<const uint2*>(p);
+    const uint2 hi = *(reinterpret_cast<const uint2*>(p) + 1);
+    op = lo.x & 0xffu;
+    ctype = (lo.x >> 8) & 0xffu;
+    a_kind = (lo.x >> 16) & 0xffu;
+    a_idx = lo.x >> 24;
+    b_kind = lo.y & 0xffu;
+    b_idx = (lo.y >> 8) & 0xffu;
+    c_kind = (lo.y >> 16) & 0xffu;
+    c_idx = lo.y >> 24;
+    st_reg = hi.x & 0xffu;
+    st_view = (hi.x >> 8) & 0xffu;
+    st2 = (hi.x >> 16) & 0xffu;
+    mask_reg = hi.x >> 24;
+    imm = hi.y;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Out-of-line store of the thread's V results for 1-D ops (one copy per compute class instead of one
+// inlined copy per specialised handler: keeps the kernel small enough for the instruction cache and
+// for ptxas).  Everything travels in registers: values as raw bits, the element offset of element 0
+// and the per-k step.
+template <class R, int V>
+__device__ __noinline__ void store_line(char* base, int dtype, long long off0, long long step, unsigned mask, u64 b0, u64 b1, u64 b2, u64 b3) {
+  static_assert(V == 4, "store_line is written for V == 4");
+  long long off[V] = {off0, off0 + step, off0 + 2 * step, off0 + 3 * step};
+  R r[V] = {CT<R>::get(b0), CT<R>::get(b1), CT<R>::get(b2), CT<R>::get(b3)};
+  constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+  if (dtype == own) {
+    store_direct<R, R, V>(base, off, mask, r);
+  } else if (dtype == RB200_BOOL) {
+    long long b[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
+    store_view<long long, V>(base, RB200_U8, off, mask, b);
+  } else {
+    store_view<R, V>(base, dtype, off, mask, r);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-thread interpreter state.  ND = number of iteration dims this instantiation handles
 // (ND == 1: collapsed 1-D op, the hot path; element k of the thread is e0 + k*256).
@@ -106,7 +152,7 @@ template <int V, int ND> struct Ctx {
     }
   }
 
-  template <class R> __device__ __forceinline__ void finish(const rb200_insn& I, const R (&r)[V]) {
+  template <class R> __device__ __forceinline__ void finish(const UInsn& I, const R (&r)[V]) {
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = CT<R>::bits(r[k]);
     if (I.st_reg != RB200_NOSTORE) {
@@ -121,18 +167,23 @@ template <int V, int ND> struct Ctx {
         for (int k = 0; k < V; ++k)
           if (lds64(reg_addr(I.mask_reg, k)) == 0ull) m &= ~(1u << k);
       }
-      long long off[V];
-      offsets(vw, off);
-      constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
-      if (vw.dtype == own) {
-        store_direct<R, R, V>(vw.base, off, m, r);
-      } else if (vw.dtype == RB200_BOOL) {
-        long long b[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
-        store_view<long long, V>(vw.base, RB200_U8, off, m, b);
+      if constexpr (ND == 1 && V == 4) {
+        const long long st = vw.stride[0];
+        store_line<R, V>(vw.base, vw.dtype, e0 * st, st * kThreads, m, acc[0], acc[1], acc[2], acc[3]);
       } else {
-        store_view<R, V>(vw.base, vw.dtype, off, m, r);
+        long long off[V];
+        offsets(vw, off);
+        constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+        if (vw.dtype == own) {
+          store_direct<R, R, V>(vw.base, off, m, r);
+        } else if (vw.dtype == RB200_BOOL) {
+          long long b[V];
+#pragma unroll
+          for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
+          store_view<long long, V>(vw.base, RB200_U8, off, m, b);
+        } else {
+          store_view<R, V>(vw.base, vw.dtype, off, m, r);
+        }
       }
     }
   }
@@ -162,7 +213,7 @@ static __device__ __noinline__ long long rare_int_binary(int op, long long a, lo
 
 // ---------------------------------------------------------------------------------------------
 // floating-point instruction set (F = double | float)
-template <class F, int V, class C> __device__ __forceinline__ void exec_float(C& cx, const rb200_insn& I) {
+template <class F, int V, class C> __device__ __forceinline__ void exec_float(C& cx, const UInsn& I) {
   F a[V], b[V], r[V];
   long long p[V];
   const int op = I.op;
@@ -355,7 +406,7 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
 }
 
 // integer instruction set (all integer arithmetic is int64, like Numba's intp promotion)
-template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const rb200_insn& I) {
+template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const UInsn& I) {
   long long a[V], b[V], r[V];
   cx.template fetch<long long>(I.a_kind, I.a_idx, a);
   if (I.b_kind != RB200_K_NONE) cx.template fetch<long long>(I.b_kind, I.b_idx, b);
@@ -486,7 +537,7 @@ template <class T> __device__ __forceinline__ T through_storage(T x, int dt) {
   }
 }
 
-template <class S, int V, class C> __device__ __forceinline__ void exec_cvt_from(C& cx, const rb200_insn& I) {
+template <class S, int V, class C> __device__ __forceinline__ void exec_cvt_from(C& cx, const UInsn& I) {
   S a[V];
   cx.template fetch<S>(I.a_kind, I.a_idx, a);
   const int through = (int)(I.imm >> 8);
@@ -546,7 +597,7 @@ template <class T, int SK, int V, class C> __device__ __forceinline__ void fetch
   }
 }
 
-template <int OP, class T, int AK, int BK, int V, class C> __device__ __forceinline__ void h_bin(C& cx, const rb200_insn& I) {
+template <int OP, class T, int AK, int BK, int V, class C> __device__ __forceinline__ void h_bin(C& cx, const UInsn& I) {
   T a[V], b[V], r[V];
   fetch_s<T, AK, V>(cx, I.a_idx, a);
   fetch_s<T, BK, V>(cx, I.b_idx, b);
@@ -563,7 +614,7 @@ template <int OP, class T, int AK, int BK, int V, class C> __device__ __forceinl
   cx.template finish<T>(I, r);
 }
 
-template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ void h_un(C& cx, const rb200_insn& I) {
+template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ void h_un(C& cx, const UInsn& I) {
   T a[V], r[V];
   fetch_s<T, AK, V>(cx, I.a_idx, a);
   if constexpr (OP == RB200_OP_SIN || OP == RB200_OP_COS || OP == RB200_OP_SINCOS) {
@@ -606,7 +657,7 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
 }
 
 template <class T, int AK, int V, bool AX, class C>
-__device__ __forceinline__ void h_red(C& cx, const rb200_insn& I, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
+__device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
   T a[V];
   fetch_s<T, AK, V>(cx, I.a_idx, a);
   const int slot = I.b_idx;
@@ -630,7 +681,7 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
   const int n = P.n_insns;
 #pragma unroll 1
   for (int pc = 0; pc < n; ++pc) {
-    const rb200_insn I = P.insns[pc];
+    const UInsn I(&P.insns[pc]);
 #ifndef RB200_NO_FAST_HANDLERS
     const int h = P.handler[pc];
     if (h != H_GENERIC) {

@@ -139,8 +139,9 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   if (sms <= 0) return fail("no usable CUDA device (libramba_b200 has no CPU path)");
   cudaStream_t stream = (cudaStream_t)stream_v;
 
-  constexpr int V = kV;
-  constexpr long long TILE = (long long)kThreads * V;
+  // the 1-D kernel owns 8 elements per thread, the N-d and axis kernels 4
+  const int V = (op->ndim == 1 && op->n_axis_red_dims == 0) ? kV1 : kV;
+  const long long TILE = (long long)kThreads * V;
   KParams P;
   memset(&P, 0, sizeof(P));
   P.ndim = op->ndim;
@@ -245,7 +246,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     for (int i = 0; i < op->n_views && P.n_pf < kMaxPf; ++i) {
       const int dt = op->views[i].dtype;
       const bool wide_ok = (dt == RB200_F64 || dt == RB200_F32 || dt == RB200_I64 || dt == RB200_I32);
-      if (view_read[i] && !view_masked[i] && wide_ok && reg_bytes + (size_t)(P.n_pf + 1) * 2 * V * kThreads * 8 <= 96 * 1024) {
+      if (view_read[i] && !view_masked[i] && wide_ok && reg_bytes + (size_t)(P.n_pf + 1) * 2 * V * kThreads * 8 <= 108 * 1024) {
         P.views[i].pf_slot = P.n_pf;
         P.pf_view[P.n_pf] = i;
         P.n_pf++;
@@ -277,7 +278,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   }
   // persistent-style grid: SM count x resident CTAs per SM (smem / register limited), capped by
   // the number of tiles; every CTA walks tiles b, b+grid, ...
-  int per_sm = (op->ndim == 1) ? 3 : 2;
+  int per_sm = 2;
   if (smem > 0) {
     int by_smem = (int)((220 * 1024) / (smem + 1024));
     if (by_smem < 1) by_smem = 1;

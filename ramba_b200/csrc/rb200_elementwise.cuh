@@ -8,7 +8,7 @@ namespace rb200 {
 
 // Persistent-style grid (a multiple of the SM count): CTA b walks tiles b, b+grid, ...
 // Shared memory layout (dynamic): [prefetch: 2 stages * n_pf * V*256*8 B][register file: n_regs*V*256*8 B]
-template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1) ? 3 : 2) vm_elementwise_kernel(const __grid_constant__ KParams P) {
+template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elementwise_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) u64 mbar_store[2];
   constexpr int TILE = kThreads * V;

@@ -40,9 +40,9 @@ struct UInsn {
 // inlined copy per specialised handler: keeps the kernel small enough for the instruction cache and
 // for ptxas).  Everything travels in registers: values as raw bits, the element offset of element 0
 // and the per-k step.
-template <class R, int V>
+template <class R>
 __device__ __noinline__ void store_line(char* base, int dtype, long long off0, long long step, unsigned mask, u64 b0, u64 b1, u64 b2, u64 b3) {
-  static_assert(V == 4, "store_line is written for V == 4");
+  constexpr int V = 4;  // four elements per call; wider tiles call it once per group of four
   long long off[V] = {off0, off0 + step, off0 + 2 * step, off0 + 3 * step};
   R r[V] = {CT<R>::get(b0), CT<R>::get(b1), CT<R>::get(b2), CT<R>::get(b3)};
   constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
@@ -167,9 +167,15 @@ template <int V, int ND> struct Ctx {
         for (int k = 0; k < V; ++k)
           if (lds64(reg_addr(I.mask_reg, k)) == 0ull) m &= ~(1u << k);
       }
-      if constexpr (ND == 1 && V == 4) {
+      if constexpr (ND == 1 && V % 4 == 0) {
         const long long st = vw.stride[0];
-        store_line<R, V>(vw.base, vw.dtype, e0 * st, st * kThreads, m, acc[0], acc[1], acc[2], acc[3]);
+        const long long step = st * kThreads;
+        char* const base = vw.base;
+        const int dt = vw.dtype;
+#pragma unroll
+        for (int g = 0; g < V / 4; ++g)
+          store_line<R>(base, dt, (e0 + (long long)g * 4 * kThreads) * st, step, (m >> (4 * g)) & 0xfu, acc[4 * g], acc[4 * g + 1],
+                        acc[4 * g + 2], acc[4 * g + 3]);
       } else {
         long long off[V];
         offsets(vw, off);
@@ -685,10 +691,7 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
 #ifndef RB200_NO_FAST_HANDLERS
     const int h = P.handler[pc];
     if (h != H_GENERIC) {
-      switch (h) {
 #include "rb200_handlers.inc"
-        default: break;
-      }
       continue;
     }
 #endif

@@ -2,7 +2,8 @@
 #include "rb200_vm.cuh"
 
 namespace rb200 {
-constexpr int kV = 4;  // elements per thread per tile
+constexpr int kV = 4;   // elements per thread per tile (N-d and axis kernels)
+constexpr int kV1 = 8;  // elements per thread per tile of the 1-D kernel (halves the per-instruction decode cost)
 // launchers (one translation unit per kernel instantiation so that they compile in parallel)
 cudaError_t launch_vm_elementwise_nd1(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_vm_elementwise_nd2(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);

@@ -15,25 +15,51 @@ namespace rb200 {
 // one op-list instruction unpacked from its 16 bytes (two 8-byte constant-bank loads; fields that a
 // path does not use cost nothing)
 struct UInsn {
-  unsigned op, ctype, a_kind, a_idx, b_kind, b_idx, c_kind, c_idx, st_reg, st_view, st2, mask_reg, imm;
+  uint2 lo, hi;
   __device__ __forceinline__ UInsn(const rb200_insn* p) {
-    const uint2 lo = *reinterpret_cast<const uint2*>(p);
-    const uint2 hi = *(reinterpret_cast<const uint2*>(p) + 1);
-    op = lo.x & 0xffu;
-    ctype = (lo.x >> 8) & 0xffu;
-    a_kind = (lo.x >> 16) & 0xffu;
-    a_idx = lo.x >> 24;
-    b_kind = lo.y & 0xffu;
-    b_idx = (lo.y >> 8) & 0xffu;
-    c_kind = (lo.y >> 16) & 0xffu;
-    c_idx = lo.y >> 24;
-    st_reg = hi.x & 0xffu;
-    st_view = (hi.x >> 8) & 0xffu;
-    st2 = (hi.x >> 16) & 0xffu;
-    mask_reg = hi.x >> 24;
-    imm = hi.y;
+    lo = *reinterpret_cast<const uint2*>(p);
+    hi = *(reinterpret_cast<const uint2*>(p) + 1);
   }
+  __device__ __forceinline__ unsigned op() const { return lo.x & 0xffu; }
+  __device__ __forceinline__ unsigned ctype() const { return (lo.x >> 8) & 0xffu; }
+  __device__ __forceinline__ unsigned a_kind() const { return (lo.x >> 16) & 0xffu; }
+  __device__ __forceinline__ unsigned a_idx() const { return lo.x >> 24; }
+  __device__ __forceinline__ unsigned b_kind() const { return lo.y & 0xffu; }
+  __device__ __forceinline__ unsigned b_idx() const { return (lo.y >> 8) & 0xffu; }
+  __device__ __forceinline__ unsigned c_kind() const { return (lo.y >> 16) & 0xffu; }
+  __device__ __forceinline__ unsigned c_idx() const { return lo.y >> 24; }
+  __device__ __forceinline__ unsigned st_reg() const { return hi.x & 0xffu; }
+  __device__ __forceinline__ unsigned st_view() const { return (hi.x >> 8) & 0xffu; }
+  __device__ __forceinline__ unsigned st2() const { return (hi.x >> 16) & 0xffu; }
+  __device__ __forceinline__ unsigned mask_reg() const { return hi.x >> 24; }
+  __device__ __forceinline__ unsigned imm() const { return hi.y; }
 };
+
+// compile-time unrolled loops over k with the shared-memory offset as an immediate
+template <class T, int V, int K = 0> __device__ __forceinline__ void lds_vec64(unsigned base, T (&out)[V]) {
+  if constexpr (K < V) {
+    out[K] = CT<T>::get(lds64o<K * kThreads * 8>(base));
+    lds_vec64<T, V, K + 1>(base, out);
+  }
+}
+template <class T, int V, int K = 0> __device__ __forceinline__ void lds_vec32(unsigned base, T (&out)[V]) {  // float / int32 staged views
+  if constexpr (K < V) {
+    out[K] = CT<T>::get((u64)lds32o<K * kThreads * 4>(base));
+    lds_vec32<T, V, K + 1>(base, out);
+  }
+}
+template <int V, int K = 0> __device__ __forceinline__ void lds_vec32_as_f64(unsigned base, double (&out)[V]) {
+  if constexpr (K < V) {
+    out[K] = (double)__uint_as_float(lds32o<K * kThreads * 4>(base));
+    lds_vec32_as_f64<V, K + 1>(base, out);
+  }
+}
+template <int V, int K = 0> __device__ __forceinline__ void sts_vec64(unsigned base, const u64 (&v)[V]) {
+  if constexpr (K < V) {
+    sts64o<K * kThreads * 8>(base, v[K]);
+    sts_vec64<V, K + 1>(base, v);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Out-of-line store of the thread's V results for 1-D ops (one copy per compute class instead of one
@@ -96,6 +122,7 @@ template <int V, int ND> struct Ctx {
   }
 
   __device__ __forceinline__ unsigned reg_addr(int r, int k) const { return regfile_s + (unsigned)((r * V + k) * kThreads * 8); }
+  __device__ __forceinline__ unsigned reg_base(int r) const { return regfile_s + (unsigned)(r * V * kThreads * 8); }
 
   template <class T> __device__ __forceinline__ void fetch(int kind, int i, T (&out)[V]) {
     switch (kind) {
@@ -155,23 +182,29 @@ template <int V, int ND> struct Ctx {
   template <class R> __device__ __forceinline__ void finish(const UInsn& I, const R (&r)[V]) {
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = CT<R>::bits(r[k]);
-    if (I.st_reg != RB200_NOSTORE) {
-#pragma unroll
-      for (int k = 0; k < V; ++k) sts64(reg_addr(I.st_reg, k), acc[k]);
-    }
-    if (I.st_view != RB200_NOSTORE) {
-      const KView& vw = P.views[I.st_view];
+    if (I.st_reg() != RB200_NOSTORE) sts_vec64<V>(reg_base(I.st_reg()), acc);
+    if (I.st_view() != RB200_NOSTORE) {
+      const KView& vw = P.views[I.st_view()];
       unsigned m = valid;
-      if (I.mask_reg != RB200_NOSTORE) {
+      if (I.mask_reg() != RB200_NOSTORE) {
 #pragma unroll
         for (int k = 0; k < V; ++k)
-          if (lds64(reg_addr(I.mask_reg, k)) == 0ull) m &= ~(1u << k);
+          if (lds64(reg_addr(I.mask_reg(), k)) == 0ull) m &= ~(1u << k);
       }
       if constexpr (ND == 1 && V % 4 == 0) {
         const long long st = vw.stride[0];
         const long long step = st * kThreads;
         char* const base = vw.base;
         const int dt = vw.dtype;
+        constexpr int own1 = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+        if (dt == own1 && st == 1 && m == ((1u << V) - 1u)) {
+          // full tile of a contiguous view in the result's own dtype: V coalesced stores at
+          // immediate offsets from one address
+          R* p = reinterpret_cast<R*>(base) + e0;
+#pragma unroll
+          for (int k = 0; k < V; ++k) stg<R>(p + k * kThreads, r[k]);
+          return;
+        }
 #pragma unroll
         for (int g = 0; g < V / 4; ++g)
           store_line<R>(base, dt, (e0 + (long long)g * 4 * kThreads) * st, step, (m >> (4 * g)) & 0xfu, acc[4 * g], acc[4 * g + 1],
@@ -222,9 +255,9 @@ static __device__ __noinline__ long long rare_int_binary(int op, long long a, lo
 template <class F, int V, class C> __device__ __forceinline__ void exec_float(C& cx, const UInsn& I) {
   F a[V], b[V], r[V];
   long long p[V];
-  const int op = I.op;
-  cx.template fetch<F>(I.a_kind, I.a_idx, a);
-  if (I.b_kind != RB200_K_NONE && op != RB200_OP_POWI) cx.template fetch<F>(I.b_kind, I.b_idx, b);
+  const int op = I.op();
+  cx.template fetch<F>(I.a_kind(), I.a_idx(), a);
+  if (I.b_kind() != RB200_K_NONE && op != RB200_OP_POWI) cx.template fetch<F>(I.b_kind(), I.b_idx(), b);
   switch (op) {
     // ---- binary arithmetic.  __d*/__f*_rn: no FMA contraction across op-list instructions, every
     // op rounds once like the reference's separate scalar statements
@@ -279,7 +312,7 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
       return;
     case RB200_OP_POWI: {
       long long e[V];
-      cx.template fetch<long long>(I.b_kind, I.b_idx, e);
+      cx.template fetch<long long>(I.b_kind(), I.b_idx(), e);
       bool sq = true;
 #pragma unroll
       for (int k = 0; k < V; ++k) sq = sq && (e[k] == 2);
@@ -374,12 +407,12 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
     case RB200_OP_SINCOS: {
       F sn[V], cs[V];
       sincos_v<V>(a, sn, cs);
-      const bool want_cos = (op == RB200_OP_COS) || (op == RB200_OP_SINCOS && I.imm);  // imm 1: accumulator half is cos
+      const bool want_cos = (op == RB200_OP_COS) || (op == RB200_OP_SINCOS && I.imm());  // imm 1: accumulator half is cos
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
       if (op == RB200_OP_SINCOS) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) sts64(cx.reg_addr(I.st2, k), CT<F>::bits(want_cos ? sn[k] : cs[k]));
+        for (int k = 0; k < V; ++k) sts64(cx.reg_addr(I.st2(), k), CT<F>::bits(want_cos ? sn[k] : cs[k]));
       }
       cx.template finish<F>(I, r);
       return;
@@ -400,7 +433,7 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
       return;
     case RB200_OP_WHERE: {
       F c[V];
-      cx.template fetch<F>(I.c_kind, I.c_idx, c);
+      cx.template fetch<F>(I.c_kind(), I.c_idx(), c);
       // condition arrives in `a`, already converted to the compute class (non-zero = true)
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = (a[k] != F(0)) ? b[k] : c[k];
@@ -414,9 +447,9 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
 // integer instruction set (all integer arithmetic is int64, like Numba's intp promotion)
 template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const UInsn& I) {
   long long a[V], b[V], r[V];
-  cx.template fetch<long long>(I.a_kind, I.a_idx, a);
-  if (I.b_kind != RB200_K_NONE) cx.template fetch<long long>(I.b_kind, I.b_idx, b);
-  const int op = I.op;
+  cx.template fetch<long long>(I.a_kind(), I.a_idx(), a);
+  if (I.b_kind() != RB200_K_NONE) cx.template fetch<long long>(I.b_kind(), I.b_idx(), b);
+  const int op = I.op();
   switch (op) {
     case RB200_OP_MOV:
 #pragma unroll
@@ -498,7 +531,7 @@ template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const 
       break;
     case RB200_OP_INVERT:
 #pragma unroll
-      for (int k = 0; k < V; ++k) r[k] = (I.imm == 1) ? (a[k] == 0 ? 1 : 0) : ~a[k];  // imm 1: bool operand
+      for (int k = 0; k < V; ++k) r[k] = (I.imm() == 1) ? (a[k] == 0 ? 1 : 0) : ~a[k];  // imm 1: bool operand
       break;
     case RB200_OP_LNOT:
 #pragma unroll
@@ -517,7 +550,7 @@ template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const 
       break;
     case RB200_OP_WHERE: {
       long long c[V];
-      cx.template fetch<long long>(I.c_kind, I.c_idx, c);
+      cx.template fetch<long long>(I.c_kind(), I.c_idx(), c);
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = (a[k] != 0) ? b[k] : c[k];
     } break;
@@ -545,13 +578,13 @@ template <class T> __device__ __forceinline__ T through_storage(T x, int dt) {
 
 template <class S, int V, class C> __device__ __forceinline__ void exec_cvt_from(C& cx, const UInsn& I) {
   S a[V];
-  cx.template fetch<S>(I.a_kind, I.a_idx, a);
-  const int through = (int)(I.imm >> 8);
+  cx.template fetch<S>(I.a_kind(), I.a_idx(), a);
+  const int through = (int)(I.imm() >> 8);
   if (through != 0) {
 #pragma unroll
     for (int k = 0; k < V; ++k) a[k] = through_storage<S>(a[k], through - 1);
   }
-  switch (I.ctype) {
+  switch (I.ctype()) {
     case RB200_T_F64: {
       double r[V];
 #pragma unroll
@@ -583,30 +616,25 @@ template <class T, int SK, int V, class C> __device__ __forceinline__ void fetch
 #pragma unroll
     for (int k = 0; k < V; ++k) out[k] = CT<T>::get(cx.acc[k]);
   } else if constexpr (SK == S_REG) {
-#pragma unroll
-    for (int k = 0; k < V; ++k) out[k] = CT<T>::get(lds64(cx.reg_addr(i, k)));
+    lds_vec64<T, V>(cx.reg_base(i), out);
   } else if constexpr (SK == S_SCAL) {
     const T s = CT<T>::get(cx.P.scalars[i]);
 #pragma unroll
     for (int k = 0; k < V; ++k) out[k] = s;
   } else if constexpr (SK == S_PFV) {  // staged view whose dtype is T's own storage type
     const unsigned slot_s = cx.pf_s + (unsigned)(i * V * kThreads * 8);
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      if constexpr (sizeof(T) == 8) out[k] = CT<T>::get(lds64(slot_s + (unsigned)((k * kThreads + cx.tid) * 8)));
-      else out[k] = CT<T>::get((u64)lds32(slot_s + (unsigned)((k * kThreads + cx.tid) * 4)));
-    }
+    if constexpr (sizeof(T) == 8) lds_vec64<T, V>(slot_s + cx.tid * 8u, out);
+    else lds_vec32<T, V>(slot_s + cx.tid * 4u, out);
   } else {  // S_PFV32: staged float32 view read in float64
     const unsigned slot_s = cx.pf_s + (unsigned)(i * V * kThreads * 8);
-#pragma unroll
-    for (int k = 0; k < V; ++k) out[k] = (T)__uint_as_float(lds32(slot_s + (unsigned)((k * kThreads + cx.tid) * 4)));
+    if constexpr (std::is_same<T, double>::value) lds_vec32_as_f64<V>(slot_s + cx.tid * 4u, out);
   }
 }
 
 template <int OP, class T, int AK, int BK, int V, class C> __device__ __forceinline__ void h_bin(C& cx, const UInsn& I) {
   T a[V], b[V], r[V];
-  fetch_s<T, AK, V>(cx, I.a_idx, a);
-  fetch_s<T, BK, V>(cx, I.b_idx, b);
+  fetch_s<T, AK, V>(cx, I.a_idx(), a);
+  fetch_s<T, BK, V>(cx, I.b_idx(), b);
 #pragma unroll
   for (int k = 0; k < V; ++k) {
     if constexpr (sizeof(T) == 8 && !std::is_integral<T>::value) {
@@ -622,17 +650,19 @@ template <int OP, class T, int AK, int BK, int V, class C> __device__ __forceinl
 
 template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ void h_un(C& cx, const UInsn& I) {
   T a[V], r[V];
-  fetch_s<T, AK, V>(cx, I.a_idx, a);
+  fetch_s<T, AK, V>(cx, I.a_idx(), a);
   if constexpr (OP == RB200_OP_SIN || OP == RB200_OP_COS || OP == RB200_OP_SINCOS) {
     if constexpr (!std::is_integral<T>::value) {
       T sn[V], cs[V];
       sincos_v<V>(a, sn, cs);
-      const bool want_cos = (OP == RB200_OP_COS) || (OP == RB200_OP_SINCOS && I.imm);
+      const bool want_cos = (OP == RB200_OP_COS) || (OP == RB200_OP_SINCOS && I.imm());
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
       if constexpr (OP == RB200_OP_SINCOS) {
+        u64 park[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) sts64(cx.reg_addr(I.st2, k), CT<T>::bits(want_cos ? sn[k] : cs[k]));
+        for (int k = 0; k < V; ++k) park[k] = CT<T>::bits(want_cos ? sn[k] : cs[k]);
+        sts_vec64<V>(cx.reg_base(I.st2()), park);
       }
     }
     cx.template finish<T>(I, r);
@@ -655,8 +685,8 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
     else if constexpr (OP == RB200_OP_SINCOS) {
       T sn, cs;
       sincos(a[k], &sn, &cs);
-      r[k] = I.imm ? cs : sn;
-      sts64(cx.reg_addr(I.st2, k), CT<T>::bits(I.imm ? sn : cs));
+      r[k] = I.imm() ? cs : sn;
+      sts64(cx.reg_addr(I.st2(), k), CT<T>::bits(I.imm() ? sn : cs));
     }
   }
   cx.template finish<T>(I, r);
@@ -665,9 +695,9 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
 template <class T, int AK, int V, bool AX, class C>
 __device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
   T a[V];
-  fetch_s<T, AK, V>(cx, I.a_idx, a);
-  const int slot = I.b_idx;
-  const int rop = (int)I.imm;
+  fetch_s<T, AK, V>(cx, I.a_idx(), a);
+  const int slot = I.b_idx();
+  const int rop = (int)I.imm();
 #pragma unroll
   for (int s = 0; s < RB200_MAX_REDS; ++s)
     if (s == slot) {
@@ -695,20 +725,20 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
       continue;
     }
 #endif
-    if (I.op == RB200_OP_CVT) {
-      switch (I.imm & 0xff) {
+    if (I.op() == RB200_OP_CVT) {
+      switch (I.imm() & 0xff) {
         case RB200_T_F64: exec_cvt_from<double, V>(cx, I); break;
         case RB200_T_F32: exec_cvt_from<float, V>(cx, I); break;
         default: exec_cvt_from<long long, V>(cx, I);
       }
       continue;
     }
-    if (I.op == RB200_OP_RED) {
-      const int slot = I.b_idx;
-      const int rop = (int)I.imm;
-      if (I.ctype == RB200_T_F64) {
+    if (I.op() == RB200_OP_RED) {
+      const int slot = I.b_idx();
+      const int rop = (int)I.imm();
+      if (I.ctype() == RB200_T_F64) {
         double a[V];
-        cx.template fetch<double>(I.a_kind, I.a_idx, a);
+        cx.template fetch<double>(I.a_kind(), I.a_idx(), a);
 #pragma unroll
         for (int s = 0; s < RB200_MAX_REDS; ++s)
           if (s == slot) {
@@ -721,7 +751,7 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
           }
       } else {
         long long a[V];
-        cx.template fetch<long long>(I.a_kind, I.a_idx, a);
+        cx.template fetch<long long>(I.a_kind(), I.a_idx(), a);
 #pragma unroll
         for (int s = 0; s < RB200_MAX_REDS; ++s)
           if (s == slot) {
@@ -735,7 +765,7 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
       }
       continue;
     }
-    switch (I.ctype) {
+    switch (I.ctype()) {
       case RB200_T_F64: exec_float<double, V>(cx, I); break;
       case RB200_T_F32: exec_float<float, V>(cx, I); break;
       default: exec_int<V>(cx, I);

@@ -85,6 +85,20 @@ __device__ __forceinline__ u64 lds64(unsigned addr) {
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return v;
 }
+// immediate-offset forms: one address register serves all V accesses of an operand
+template <int OFF> __device__ __forceinline__ u64 lds64o(unsigned addr) {
+  u64 v;
+  asm volatile("ld.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF> __device__ __forceinline__ unsigned lds32o(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF> __device__ __forceinline__ void sts64o(unsigned addr, u64 v) {
+  asm volatile("st.shared.u64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "l"(v) : "memory");
+}
 __device__ __forceinline__ void sts64(unsigned addr, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 
 __device__ __forceinline__ unsigned lds32(unsigned addr) {
@@ -280,10 +294,11 @@ template <int V> __device__ __forceinline__ void sincos_v(const double (&x)[V], 
     pc = fma(z, pc, C2);
     pc = fma(z, pc, C1);
     const double cy = fma(z, fma(z, pc, -0.5), 1.0);
-    double sn = (q & 1) ? cy : sy;
-    double cs = (q & 1) ? sy : cy;
-    s[k] = (q & 2) ? -sn : sn;
-    c[k] = ((q + 1) & 2) ? -cs : cs;
+    const double sn = (q & 1) ? cy : sy;
+    const double cs = (q & 1) ? sy : cy;
+    // sign flips: XOR the sign bit (bit 31 of the high word) with quadrant bit 1
+    s[k] = __hiloint2double(__double2hiint(sn) ^ ((q & 2) << 30), __double2loint(sn));
+    c[k] = __hiloint2double(__double2hiint(cs) ^ (((q + 1) & 2) << 30), __double2loint(cs));
   }
 }
 template <int V> __device__ __forceinline__ void sincos_v(const float (&x)[V], float (&s)[V], float (&c)[V]) {

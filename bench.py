@@ -235,10 +235,6 @@ def run_ours(args):
         hD = torch.empty(n_per_gpu, dtype=torch.float64, pin_memory=True)
         hA.copy_(torch.arange(n_per_gpu, dtype=torch.float64) * 0.001)
         hA_np, hD_np = hA.numpy(), hD.numpy()
-        if W > 1:
-            # every rank uploads / downloads its own block through the same public calls
-            pass
-
         def e2e_step():
             Ah = rb.fromarray(hA_np) if W == 1 else rb.fromarray_local(hA_np, N)
             Bh = rb.sin(Ah)

@@ -278,7 +278,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   }
   // persistent-style grid: SM count x resident CTAs per SM (smem / register limited), capped by
   // the number of tiles; every CTA walks tiles b, b+grid, ...
-  int per_sm = 2;
+  int per_sm = (V == 4 && op->ndim == 1) ? 3 : 2;
   if (smem > 0) {
     int by_smem = (int)((220 * 1024) / (smem + 1024));
     if (by_smem < 1) by_smem = 1;

@@ -1381,6 +1381,41 @@ def fromarray(x, local_border=0, dtype=None, **kwargs):
     return new
 
 
+def fromarray_local(block, shape, dtype=None, **kwargs):
+    """SPMD extension (no reference counterpart): every rank supplies ITS OWN block of a global
+    array of shape `shape` (block shape = this rank's division under the default distribution).
+    Used when the global array never exists on one host (bench.py's multi-GPU e2e leg)."""
+    import torch
+
+    block = np.asarray(block)
+    if dtype is None:
+        dtype = block.dtype
+    new = ndarray(shapeToInt(shape), dtype=dtype, flex_dist=False, **kwargs)
+    deferred_op.do_ops()
+    w = common.worker_num
+    sv = new.distribution[w]
+    sh = RT.create_array(new.gid, _local_shape(new.bdarray.distribution, w), new.dtype)
+    if not shardview.is_empty(sv):
+        if tuple(block.shape) != tuple(int(x) for x in sv.size):
+            raise ValueError("fromarray_local: block shape %s != this rank's division %s" % (block.shape, tuple(int(x) for x in sv.size)))
+        blk = block if block.dtype == new.dtype else block.astype(new.dtype)
+        if not blk.flags.c_contiguous:
+            blk = np.ascontiguousarray(blk)
+        if new.dtype == np.bool_:
+            blk = blk.astype(np.uint8)
+        t = torch.from_numpy(blk.reshape(-1))
+        sh.buf[: t.numel()].copy_(t, non_blocking=True)
+    new.bdarray.remote_constructed = True
+    new.bdarray.flex_dist = False
+    return new
+
+
+def local_block_to_host(nd, out=None):
+    """SPMD extension: this rank's block of `nd` as a host array (no gather)."""
+    deferred_op.do_ops()
+    return _part_to_host(nd, common.worker_num, out=out)
+
+
 def array(x, dtype=None, copy=True, **kwargs):
     if isinstance(x, ndarray):
         return x.copy() if copy else x

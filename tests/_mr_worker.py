@@ -9,9 +9,11 @@ sys.path.insert(0, HERE)
 
 import numpy as onp  # noqa: E402
 
-import _oracle_backend  # noqa: E402
+MODE = sys.argv[2] if len(sys.argv) > 2 else "oracle"
+if MODE == "oracle":
+    import _oracle_backend  # noqa: E402
 
-_oracle_backend.install()
+    _oracle_backend.install()
 
 import _programs  # noqa: E402
 import ramba_b200 as rb  # noqa: E402
@@ -33,6 +35,10 @@ def main():
             ok = g.shape == e.shape and (onp.allclose(g, e, rtol=1e-13, atol=1e-15) if e.dtype.kind == "f" else onp.array_equal(g, e))
             if not ok:
                 failures.append("%s[%d]" % (prog.__name__, i))
+    if MODE == "cuda":
+        from ramba_b200 import _cabi
+
+        assert not RT.test_mode and _cabi.launch_count() > 0, "the CUDA library did not run"
     print("RANK %d/%d launches=%d bytes_sent=%d failures=%s" % (common.worker_num, common.num_workers, RT.launches, RT.bytes_sent, failures))
     sys.stdout.flush()
     import torch.distributed as dist

@@ -1,0 +1,48 @@
+"""-m gpu, needs >= 2 GPUs: the N>1 path on real devices — one process per GPU, NCCL for the pieces
+that cross GPUs (halo planes, broadcast operands, reduction partials), CUDA kernels for the op lists.
+Every program must reproduce NumPy like in the single-GPU parity tests."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_programs_multigpu(world):
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ)
+        env.update({"RANK": str(r), "WORLD_SIZE": str(world), "LOCAL_RANK": str(r), "MASTER_ADDR": "127.0.0.1",
+                    "MASTER_PORT": str(port)})
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_mr_worker.py"), "all", "cuda"], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append((p.returncode, o))
+    for rc, o in outs:
+        assert rc == 0, o[-3000:]
+    assert any("bytes_sent=0" not in o for _, o in outs)

@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -225,7 +225,7 @@ def run_ours(args):
     k_ms = sum(kern_ms) / max(1, len(kern_ms))
     achieved = n_per_gpu * BYTES_PER_ELEM / (k_ms * 1e-3) / 1e9 if kern_ms else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "kernel": "vm_elementwise_kernel<4>", "kernel_ms": k_ms, "launches_timed": len(kern_ms),
+                "traffic": None, "kernel": "vm_elementwise_kernel<8,1>", "kernel_ms": k_ms, "launches_timed": len(kern_ms),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n_per_gpu * BYTES_PER_ELEM}
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----------------
@@ -275,7 +275,7 @@ def run_ours(args):
             "metric": "fused-elementwise GB/s (fp64 sin/cos/mul/add chain)", "value": value, "unit": "GB/s",
             "n_gpus": W, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "1e9-element fp64 arange/sin/cos/mul/add fused chain on 1 B200 (BASELINE configs[1]); timed loop of sample/test-ramba.py",
+            "config": {"workload": "1e9-element fp64 arange/sin/cos/mul/add fused chain per B200 (BASELINE configs[1]) x %d GPU(s); timed loop of sample/test-ramba.py" % W,
                        "elements_per_gpu": n_per_gpu, "global_elements": N, "bytes_per_element": BYTES_PER_ELEM,
                        "l2": "inputs (8 GB/GPU) >> 126 MB L2, no flush needed", "parallelism": "block partition, %d rank(s), no collective" % W},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -61,7 +61,7 @@ def main():
         for b in range(4):
             cnt[(a + b) % 4] += ci[a] * cj[b]
     expect = float(sum(cnt[v] * (2 * v + 1) for v in range(4)))
-    out["config3"] = {"shape": [n, n], "seconds": dt, "GBps_algorithmic_4B": n * n * 4 / dt / 1e9, "exact": s == onp.float32(expect), "value": s}
+    out["config3"] = {"shape": [n, n], "seconds": dt, "GBps_algorithmic_4B": n * n * 4 / dt / 1e9, "exact": bool(s == float(onp.float32(expect))), "value": float(s), "expected": expect}
 
     # ---- config 5: (2^20, 4096) fp32 broadcast-add + axis-0 sum
     r, c = int((1 << 20) * args.scale), 4096

@@ -131,7 +131,8 @@ enum rb200_op {
                            (imm >> 8) != 0 first wrap/round through storage dtype
                            ((imm >> 8) - 1), i.e. the value a store + reload yields */
   RB200_OP_SINCOS = 49, /* acc = sin(a), regs[st2] = cos(a) (imm 1: swapped); one range
-                           reduction for both                                        */
+                           reduction for both.  If c_kind == RB200_K_VIEW the parked
+                           half is also stored to views[c_idx]                       */
   RB200_OP_RED = 50,    /* red[b_idx] = red[b_idx] (+,*,min,max by imm) a          */
   RB200_OP_CBRT = 51,
   RB200_NUM_OPS = 52

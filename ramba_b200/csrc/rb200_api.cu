@@ -105,7 +105,7 @@ static void assign_handlers(KParams& P, const rb200_fused_op* op) {
     } else if (I.op == RB200_OP_POWI) {
       // only x ** 2 with a scalar exponent (Numba int_power gives exactly x*x)
       if (I.b_kind == RB200_K_SCAL && (long long)op->scalars[I.b_idx] == 2) h = handler_un(I.op, I.ctype, ak);
-    } else if (I.c_kind == RB200_K_NONE && I.b_kind == RB200_K_NONE) {
+    } else if ((I.c_kind == RB200_K_NONE || I.op == RB200_OP_SINCOS) && I.b_kind == RB200_K_NONE) {
       h = handler_un(I.op, I.ctype, ak);
     }
     if (h != H_GENERIC) {
@@ -167,7 +167,11 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     const uint8_t kinds[3] = {I.a_kind, I.b_kind, I.c_kind};
     const uint8_t idxs[3] = {I.a_idx, I.b_idx, I.c_idx};
     for (int q = 0; q < 3; ++q) {
-      if (I.op == RB200_OP_RED && q == 1) continue;  // b_idx is the slot
+      if (I.op == RB200_OP_RED && q == 1) continue;     // b_idx is the slot
+      if (I.op == RB200_OP_SINCOS && q == 2) {          // c names the view the parked half is stored to
+        if (kinds[q] == RB200_K_VIEW && idxs[q] >= op->n_views) return fail("view index out of range");
+        continue;
+      }
       switch (kinds[q]) {
         case RB200_K_NONE:
         case RB200_K_ACC: break;

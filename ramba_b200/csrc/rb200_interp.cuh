@@ -179,51 +179,56 @@ template <int V, int ND> struct Ctx {
     }
   }
 
+  // store V results (already in registers as r[] and as raw bits in bits[]) into views[view]
+  template <class R> __device__ __forceinline__ void store_out(int view, const R (&r)[V], const u64 (&bits)[V], unsigned m) {
+    const KView& vw = P.views[view];
+    if constexpr (ND == 1 && V % 4 == 0) {
+      const long long st = vw.stride[0];
+      const long long step = st * kThreads;
+      char* const base = vw.base;
+      const int dt = vw.dtype;
+      constexpr int own1 = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+      if (dt == own1 && st == 1 && m == ((1u << V) - 1u)) {
+        // full tile of a contiguous view in the result's own dtype: V coalesced stores at
+        // immediate offsets from one address
+        R* p = reinterpret_cast<R*>(base) + e0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) stg<R>(p + k * kThreads, r[k]);
+        return;
+      }
+#pragma unroll
+      for (int g = 0; g < V / 4; ++g)
+        store_line<R>(base, dt, (e0 + (long long)g * 4 * kThreads) * st, step, (m >> (4 * g)) & 0xfu, bits[4 * g], bits[4 * g + 1],
+                      bits[4 * g + 2], bits[4 * g + 3]);
+    } else {
+      long long off[V];
+      offsets(vw, off);
+      constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+      if (vw.dtype == own) {
+        store_direct<R, R, V>(vw.base, off, m, r);
+      } else if (vw.dtype == RB200_BOOL) {
+        long long b[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
+        store_view<long long, V>(vw.base, RB200_U8, off, m, b);
+      } else {
+        store_view<R, V>(vw.base, vw.dtype, off, m, r);
+      }
+    }
+  }
+
   template <class R> __device__ __forceinline__ void finish(const UInsn& I, const R (&r)[V]) {
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = CT<R>::bits(r[k]);
     if (I.st_reg() != RB200_NOSTORE) sts_vec64<V>(reg_base(I.st_reg()), acc);
     if (I.st_view() != RB200_NOSTORE) {
-      const KView& vw = P.views[I.st_view()];
       unsigned m = valid;
       if (I.mask_reg() != RB200_NOSTORE) {
 #pragma unroll
         for (int k = 0; k < V; ++k)
           if (lds64(reg_addr(I.mask_reg(), k)) == 0ull) m &= ~(1u << k);
       }
-      if constexpr (ND == 1 && V % 4 == 0) {
-        const long long st = vw.stride[0];
-        const long long step = st * kThreads;
-        char* const base = vw.base;
-        const int dt = vw.dtype;
-        constexpr int own1 = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
-        if (dt == own1 && st == 1 && m == ((1u << V) - 1u)) {
-          // full tile of a contiguous view in the result's own dtype: V coalesced stores at
-          // immediate offsets from one address
-          R* p = reinterpret_cast<R*>(base) + e0;
-#pragma unroll
-          for (int k = 0; k < V; ++k) stg<R>(p + k * kThreads, r[k]);
-          return;
-        }
-#pragma unroll
-        for (int g = 0; g < V / 4; ++g)
-          store_line<R>(base, dt, (e0 + (long long)g * 4 * kThreads) * st, step, (m >> (4 * g)) & 0xfu, acc[4 * g], acc[4 * g + 1],
-                        acc[4 * g + 2], acc[4 * g + 3]);
-      } else {
-        long long off[V];
-        offsets(vw, off);
-        constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
-        if (vw.dtype == own) {
-          store_direct<R, R, V>(vw.base, off, m, r);
-        } else if (vw.dtype == RB200_BOOL) {
-          long long b[V];
-#pragma unroll
-          for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
-          store_view<long long, V>(vw.base, RB200_U8, off, m, b);
-        } else {
-          store_view<R, V>(vw.base, vw.dtype, off, m, r);
-        }
-      }
+      store_out<R>(I.st_view(), r, acc, m);
     }
   }
 };
@@ -411,8 +416,15 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
       if (op == RB200_OP_SINCOS) {
+        u64 park[V];
+        F parkv[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) sts64(cx.reg_addr(I.st2(), k), CT<F>::bits(want_cos ? sn[k] : cs[k]));
+        for (int k = 0; k < V; ++k) {
+          parkv[k] = want_cos ? sn[k] : cs[k];
+          park[k] = CT<F>::bits(parkv[k]);
+        }
+        sts_vec64<V>(cx.reg_base(I.st2()), park);
+        if (I.c_kind() == RB200_K_VIEW) cx.template store_out<F>(I.c_idx(), parkv, park, cx.valid);
       }
       cx.template finish<F>(I, r);
       return;
@@ -659,10 +671,16 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
       if constexpr (OP == RB200_OP_SINCOS) {
+        // the parked half goes to a spill register and, if c names a view, straight to that view
         u64 park[V];
+        T parkv[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) park[k] = CT<T>::bits(want_cos ? sn[k] : cs[k]);
+        for (int k = 0; k < V; ++k) {
+          parkv[k] = want_cos ? sn[k] : cs[k];
+          park[k] = CT<T>::bits(parkv[k]);
+        }
         sts_vec64<V>(cx.reg_base(I.st2()), park);
+        if (I.c_kind() == RB200_K_VIEW) cx.template store_out<T>(I.c_idx(), parkv, park, cx.valid);
       }
     }
     cx.template finish<T>(I, r);

@@ -111,7 +111,7 @@ class TV:
 
 class Node:
     __slots__ = ("op", "ctype", "rcls", "is_bool", "args", "imm", "store", "mask", "red_slot", "pseudo", "pos",
-                 "uses", "mask_use", "reg", "cos_node")
+                 "uses", "mask_use", "reg", "cos_node", "store2")
 
     def __init__(self, op, ctype, rcls, is_bool, args, imm=0):
         self.op = op
@@ -129,6 +129,7 @@ class Node:
         self.mask_use = False
         self.reg = None
         self.cos_node = None
+        self.store2 = None  # SINCOS: view the parked half is stored to
 
 
 _FLOAT_UNARY = {"sqrt", "sin", "cos", "tan", "sinh", "cosh", "tanh", "asin", "acos", "atan", "exp", "log", "cbrt"}
@@ -424,9 +425,21 @@ class Lowering:
             f.cos_node = p
             self.nodes.insert(self.nodes.index(f) + 1, p)
             i += 1
-            # the second node becomes a read-back of the parked half
+            # the second node becomes a read-back of the parked half ...
             n.op = "mov"
             n.args = [TV(f.rcls, False, "node", p)]
+            # ... unless all it does is store the value in its own dtype: then SINCOS stores the parked
+            # half itself and every later use reads the parked register directly
+            own = {T_F64: cabi.F64, T_F32: cabi.F32}[f.rcls]
+            if n.mask is None and not n.mask_use and (n.store is None or self.view_dtypes[n.store] == own):
+                f.store2 = n.store
+                n.store = None
+                for m in self.nodes:
+                    for a in m.args:
+                        if a.kind == "node" and a.ref is n:
+                            a.ref = p
+                    if m.mask is n:
+                        m.mask = p
 
     # ---- emission
     def finish(self):
@@ -446,8 +459,10 @@ class Lowering:
                 mark(n.mask)
 
         for n in nodes:
-            if n.store is not None or n.red_slot is not None:
+            if n.store is not None or n.red_slot is not None or n.store2 is not None:
                 mark(n)
+                if n.store2 is not None and n.cos_node is not None:
+                    mark(n.cos_node)
         nodes = [n for n in nodes if id(n) in live]
         # a SINCOS whose parked half died is a plain sin / cos again
         for n in nodes:
@@ -528,6 +543,10 @@ class Lowering:
                 fields[names[i] + "_idx"] = idx
             if n.op == "red":
                 fields["b_idx"] = n.red_slot
+            if n.op == "sincos" and n.store2 is not None:
+                fields["c_kind"] = K_VIEW
+                fields["c_idx"] = n.store2
+                prog.view_written[n.store2] = True
             if n.mask is not None:
                 if n.mask.reg is None:
                     raise ProgramError("internal: mask not in a register")

@@ -224,8 +224,15 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     k_ms = sum(kern_ms) / max(1, len(kern_ms))
     achieved = n_per_gpu * BYTES_PER_ELEM / (k_ms * 1e-3) / 1e9 if kern_ms else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if int(tj.get("elements_per_launch", 0)) == n_per_gpu:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None, "kernel": "vm_elementwise_kernel<8,1>", "kernel_ms": k_ms, "launches_timed": len(kern_ms),
+                "traffic": traffic, "kernel": "vm_elementwise_kernel<8,1>", "kernel_ms": k_ms, "launches_timed": len(kern_ms),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": n_per_gpu * BYTES_PER_ELEM}
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----------------

@@ -84,7 +84,7 @@ class bdarray:
                 distribution = shardview.default_distribution(shape, **kwargs)
             else:
                 # a new array: same boxes, fresh buffer coordinates
-                distribution = [shardview.clean_range(s) for s in distribution]
+                distribution = shardview.clean_dist(distribution)
             bd = cls(shape, distribution, gid, pad, flexible_dist, dtype)
         bd.nrefs += 1
         return bd

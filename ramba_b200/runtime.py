@@ -230,20 +230,29 @@ class Runtime:
             fop.views[v].dtype = bv[2]
             fop.views[v].flags = 1 if program.view_written.get(v) else 0
         fop.n_scalars = len(program.scalars)
-        for i, bits in enumerate(program.scalars):
-            fop.scalars[i] = bits
         fop.n_insns = len(program.insns)
-        for i, f in enumerate(program.insns):
-            ins = fop.insns[i]
-            for k_, v_ in f.items():
-                setattr(ins, k_, v_)
-            for nm in ("a", "b", "c"):
-                if getattr(ins, nm + "_kind") == cabi.K_IOTA:
-                    od = getattr(ins, nm + "_idx")
-                    if od not in iota_remap:
-                        # extent-1 dim was dropped: its index is the constant global_start
-                        raise cabi.CabiError("internal: iota over a collapsed dim")
-                    setattr(ins, nm + "_idx", iota_remap[od])
+        # op list and scalar table are packed once per program and copied in one go
+        packed = program.__dict__.get("_packed")
+        if packed is None:
+            import struct
+
+            ib = b"".join(struct.pack("<12BI", f["op"], f["ctype"], f["a_kind"], f["a_idx"], f["b_kind"], f["b_idx"], f["c_kind"],
+                                      f["c_idx"], f["st_reg"], f["st_view"], f["st2"], f["mask_reg"], f["imm"]) for f in program.insns)
+            sb = struct.pack("<%dQ" % len(program.scalars), *program.scalars) if program.scalars else b""
+            packed = program.__dict__["_packed"] = (ib, sb)
+        if packed[0]:
+            ctypes.memmove(ctypes.addressof(fop.insns), packed[0], len(packed[0]))
+        if packed[1]:
+            ctypes.memmove(ctypes.addressof(fop.scalars), packed[1], len(packed[1]))
+        if iota_dims:
+            for i, f in enumerate(program.insns):
+                ins = fop.insns[i]
+                for nm in ("a", "b", "c"):
+                    if f[nm + "_kind"] == cabi.K_IOTA:
+                        od = f[nm + "_idx"]
+                        if od not in iota_remap:
+                            raise cabi.CabiError("internal: iota over a collapsed dim")
+                        setattr(ins, nm + "_idx", iota_remap[od])
         fop.n_regs = program.n_regs
         fop.n_reds = len(program.reds)
         fop.n_axis_red_dims = sum(1 for m in merged if m[4])

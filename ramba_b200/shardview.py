@@ -24,7 +24,7 @@ I64 = np.int64
 
 
 class ShardView:
-    __slots__ = ("size", "start", "axis_map", "steps", "base_offset")
+    __slots__ = ("size", "start", "axis_map", "steps", "base_offset", "_k")
 
     def __init__(self, size, start=None, base_offset=None, axis_map=None, steps=None):
         size = np.asarray(size, dtype=I64)
@@ -35,6 +35,14 @@ class ShardView:
         self.axis_map = np.arange(k, dtype=I64) if axis_map is None else np.asarray(axis_map, dtype=I64).copy()
         self.steps = np.ones(k, dtype=I64) if steps is None else np.asarray(steps, dtype=I64).copy()
         self.base_offset = np.zeros(k, dtype=I64) if base_offset is None else np.asarray(base_offset, dtype=I64).copy()
+        self._k = None
+
+    def key(self):
+        """Hashable identity (box, addressing); cached — shardviews are not mutated once in use."""
+        if self._k is None:
+            self._k = (tuple(self.size.tolist()), tuple(self.start.tolist()), tuple(self.axis_map.tolist()),
+                       tuple(self.steps.tolist()), tuple(self.base_offset.tolist()))
+        return self._k
 
     def copy(self):
         return ShardView(self.size, self.start, self.base_offset, self.axis_map, self.steps)
@@ -95,19 +103,18 @@ def len_base_offset(sv):
 
 # ---- predicates
 def is_eq(a, b):
-    return (np.array_equal(a.size, b.size) and np.array_equal(a.start, b.start)
-            and np.array_equal(a.base_offset, b.base_offset) and np.array_equal(a.axis_map, b.axis_map)
-            and np.array_equal(a.steps, b.steps))
+    return a is b or a.key() == b.key()
 
 
 def is_empty(sv):
-    return bool((sv.size == 0).any())
+    return 0 in sv.key()[0]
 
 
 def is_compat(a, b):
     """Same box (size and start) — the operand is aligned with the iteration range
     (ramba/shardview_array.py:183-186)."""
-    return np.array_equal(a.size, b.size) and np.array_equal(a.start, b.start)
+    ka, kb = a.key(), b.key()
+    return ka[0] == kb[0] and ka[1] == kb[1]
 
 
 def overlaps(a, b):
@@ -124,8 +131,23 @@ def has_index(sv, index):
     return bool(np.all((sv.start <= index) & (index < _stop(sv))))
 
 
+_IDENT = {}
+
+
+def _is_clean(sv):
+    k = sv.key()
+    n = len(k[0])
+    ident = _IDENT.get(n)
+    if ident is None:
+        ident = _IDENT[n] = (tuple(range(n)), (1,) * n, (0,) * n)
+    return k[2] == ident[0] and k[3] == ident[1] and k[4] == ident[2]
+
+
 def clean_range(sv):
-    """Just the box: drop offset, axis map and steps (ramba/shardview_array.py:207-208)."""
+    """Just the box: drop offset, axis map and steps (ramba/shardview_array.py:207-208).
+    An already clean shardview is returned as is (shardviews are immutable once in use)."""
+    if _is_clean(sv):
+        return sv
     return ShardView(sv.size, sv.start)
 
 
@@ -287,7 +309,7 @@ def compatible_distributions(d1, d2):
 
 
 def dist_is_eq(d1, d2):
-    return len(d1) == len(d2) and all(is_eq(a, b) for a, b in zip(d1, d2))
+    return d1 is d2 or (len(d1) == len(d2) and all(is_eq(a, b) for a, b in zip(d1, d2)))
 
 
 def dist_has_neg_step(dist):
@@ -326,11 +348,24 @@ def distribution_to_divisions(dist):
     return out
 
 
+_dist_cache = {}
+
+
 def default_distribution(size, dims_do_not_distribute=(), dist_dims=None, num_workers=None):
     """Block distribution of an array of shape `size` over all workers
-    (ramba/shardview_array.py:908-935)."""
+    (ramba/shardview_array.py:908-935; cached like dist_cache there)."""
     W = common.num_workers if num_workers is None else num_workers
     size = tuple(int(s) for s in size)
+    ck = (size, tuple(dims_do_not_distribute or ()), tuple(dist_dims) if isinstance(dist_dims, (list, tuple)) else dist_dims, W)
+    hit = _dist_cache.get(ck)
+    if hit is not None:
+        return list(hit)
+    out = _default_distribution(size, dims_do_not_distribute, dist_dims, W)
+    _dist_cache[ck] = tuple(out)
+    return out
+
+
+def _default_distribution(size, dims_do_not_distribute, dist_dims, W):
     k = len(size)
     if isinstance(dist_dims, int):
         dist_dims = [dist_dims]
@@ -385,8 +420,8 @@ def reduce_axes(size, dist, axes):
     (ramba/shardview_array.py:1046-1066): the partial array keeps ONE element per division along
     every reduced axis (shape rsz, distribution rdist); bdist views it back at the source's shape
     with the reduced axes broadcast."""
-    rdist = clean_dist(dist)
-    bdist = clean_dist(dist)
+    rdist = [ShardView(s.size, s.start) for s in dist]  # fresh objects: they are edited below
+    bdist = [ShardView(s.size, s.start) for s in dist]
     rsz = list(size)
     for j in axes:
         divs = sorted(set(int(dist[i].start[j]) for i in range(len(dist)) if not is_empty(dist[i])))
@@ -399,6 +434,10 @@ def reduce_axes(size, dist, axes):
         for i in range(len(bdist)):
             bdist[i].axis_map[j] = -1
         rsz[j] = len(divs)
+    for sv in rdist + bdist:
+        sv._k = None
+        if (sv.size == 0).any():
+            sv.size[:] = 0
     return tuple(rsz), rdist, bdist
 
 

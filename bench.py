@@ -43,7 +43,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, index):
         self.index = index
@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "10"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -61,7 +61,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region (the sampler itself is started earlier: nvidia-smi needs ~100 ms
+        to produce its first line)."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -71,8 +76,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t1 = time.time()
+        t0 = getattr(self, "t0", 0.0)
+        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.05]
+        if len(inside) < 2:  # region shorter than the sampling period: take the samples around it
+            inside = [ln for (ts, ln) in self.lines if t0 - 0.3 <= ts <= t1 + 0.3]
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -105,8 +115,10 @@ def cpu_chain_baseline(n, iters, warm=1):
     from oracle import chain  # bench.py's cpu_baseline / reference legs may execute the oracle
 
     n = int(n)
-    A = np.arange(n, dtype=np.float64) * 0.001
+    # first touch in parallel (same static schedule as the timed loop): pages land next to their threads
+    A = np.empty(n, dtype=np.float64)
     B = np.empty_like(A); C = np.empty_like(A); D = np.empty_like(A)
+    chain.chain_f64(A, B, C, D, global_start=0, make_A=True)
     for _ in range(warm):
         chain.chain_f64(A, B, C, D)
     best = []
@@ -127,8 +139,9 @@ def run_reference(args):
 
     from oracle import chain
 
-    A = np.arange(n, dtype=np.float64) * 0.001
+    A = np.empty(n, dtype=np.float64)
     B = np.empty_like(A); C = np.empty_like(A); D = np.empty_like(A)
+    chain.chain_f64(A, B, C, D, global_start=0, make_A=True)  # parallel first touch
     for _ in range(max(1, args.warmup)):
         chain.chain_f64(A, B, C, D)
     t0 = time.perf_counter()
@@ -186,12 +199,13 @@ def run_ours(args):
         rb.sync()
         return B, C, D
 
+    sampler = ClockSampler(common.local_rank)
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         out = step()
     del out
-    sampler = ClockSampler(common.local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     _cabi.reset_launch_count()
     RT.profile_events = []
     e0 = torch.cuda.Event(enable_timing=True)

@@ -1,0 +1,280 @@
+"""API-level parity in the style of the reference's own suite
+(ramba/tests/test_distributed_array.py: `run_both(func)` runs the same function under ramba and
+NumPy and compares, exact by default, :240-259).  Every case runs twice here: on the oracle executor
+(CPU, always) and through the CUDA library (-m gpu).  Array sizes straddle distribute_min_size = 100
+like the reference's (:… 100, 120, 200)."""
+import numpy as onp
+import pytest
+
+CASES = []
+
+
+def case(f):
+    CASES.append(f)
+    return f
+
+
+def _h(x):
+    if hasattr(x, "asarray"):
+        return x.asarray()
+    return onp.asarray(x)
+
+
+# ---- creation / fillers (TestBasic)
+@case
+def arange_plain(np):
+    return [_h(np.arange(120)), _h(np.arange(5, 125)), _h(np.arange(3, 300, 7))]
+
+
+@case
+def fills(np):
+    return [_h(np.zeros(150)), _h(np.ones((20, 10))), _h(np.full((7, 30), 2.5)), _h(np.zeros(130, dtype=onp.int32)),
+            _h(np.ones(50)), _h(np.full((3,), 7))]
+
+
+@case
+def linspace_like(np):
+    return [_h(np.arange(101) * (5.0 / 100) + 1.0)]
+
+
+@case
+def fromfunction_2d(np):
+    return [_h(np.fromfunction(lambda i, j: i * 10 + j, (40, 30))), _h(np.fromfunction(lambda i, j: (i + j) % 3, (12, 11), dtype=onp.int64))]
+
+
+@case
+def eye_like(np):
+    return [_h(np.fromfunction(lambda i, j: i == j, (30, 30)).astype(onp.float64))]
+
+
+# ---- arithmetic over {array, scalar} x operand order (TestOps)
+@case
+def ops_array_array(np):
+    a = np.arange(200) * 1.0
+    b = np.arange(200) * 2.0 + 1.0
+    return [_h(a + b), _h(a - b), _h(a * b), _h(a // b), _h(b % (a + 1.0))]
+
+
+@case
+def ops_array_scalar(np):
+    a = np.arange(120) * 1.0
+    return [_h(a + 7), _h(7 + a), _h(a - 7), _h(7 - a), _h(a * 7), _h(7 * a), _h(a // 7), _h(a % 7), _h(a * 13.0), _h(13.0 * a),
+            _h(a * onp.float64(1.5)), _h(a + onp.int64(3))]
+
+
+@case
+def ops_small_nondistributed(np):
+    a = np.arange(50) * 1.0  # < 100 elements: lives on worker 0 only
+    b = np.arange(50) + 10
+    return [_h(a + b), _h(a * 2), _h(b - a), onp.asarray((a + b).sum())]
+
+
+@case
+def ops_int(np):
+    a = np.arange(300)
+    return [_h(a + a), _h(a * 3 - 1), _h(a // 4), _h(a % 4), _h(-a), _h(a ** 2), _h(a & 5), _h(a | 8), _h(a ^ 3), _h(a << 2), _h(a >> 1)]
+
+
+@case
+def ops_inplace(np):
+    a = np.ones(150)
+    a += 4
+    a *= 3.0
+    a -= 1
+    b = np.arange(150)
+    b += 2
+    b *= b
+    return [_h(a), _h(b)]
+
+
+@case
+def ops_mixed_dtypes(np):
+    f32 = (np.arange(128) % 16).astype(onp.float32)
+    i64 = np.arange(128)
+    return [_h(f32 + f32), _h(f32 * 2), _h(f32 * 2.5), _h(f32 + i64), _h(i64 * 1.5), _h((f32 * f32).astype(onp.float64)), _h(i64.astype(onp.int32) + 1)]
+
+
+@case
+def unary_math(np):
+    a = np.arange(200) * 0.01 + 0.5
+    return [_h(np.sqrt(a)), _h(np.exp(a)), _h(np.log(a)), _h(np.tanh(a)), _h(np.arctan(a)), _h(np.square(a)), _h(abs(a - 1.2)), _h(-a)]
+
+
+@case
+def predicates(np):
+    a = np.arange(100) * 1.0 - 50.0
+    return [_h(a > 0), _h(a <= -10), _h(a == 0), _h(a != 3), _h(np.logical_and(a > -5, a < 5)), _h(np.logical_not(a > 0)),
+            _h(np.isnan(a)), _h(np.isfinite(a))]
+
+
+# ---- where / clip / minimum / maximum
+@case
+def where_clip(np):
+    a = np.arange(160) * 1.0
+    b = 160.0 - a
+    return [_h(np.where(a > b, a, b)), _h(np.where(a > 80, a, 0.0)), _h(a.clip(10.0, 100.0)), _h(np.minimum(a, b)), _h(np.maximum(a, 30.0))]
+
+
+# ---- views: slices, steps, negative steps, setitem (TestBasic test_slice*, test_setitem)
+@case
+def slices_1d(np):
+    a = np.arange(200)
+    return [_h(a[10:50]), _h(a[:-20]), _h(a[::2]), _h(a[5::3]), _h(a[::-1]), _h(a[150:20:-3]), _h(a[-30:]), _h(a[10:50][5:20]), _h(a[::2][::3])]
+
+
+@case
+def slices_2d(np):
+    a = np.fromfunction(lambda i, j: i * 100 + j, (30, 40))
+    return [_h(a[2:10, 5:15]), _h(a[:, 3]), _h(a[7]), _h(a[::2, ::3]), _h(a[::-1, :]), _h(a[1:-1, 1:-1] + a[:-2, 1:-1])]
+
+
+@case
+def setitem_slices(np):
+    a = np.zeros(200)
+    a[10:20] = 5.0
+    a[::50] = 1.0
+    b = np.arange(200) * 1.0
+    a[100:150] = b[0:50]
+    c = np.zeros((20, 30))
+    c[2:5, :] = 3.0
+    c[:, 4] = 7.0
+    c[10:, 10:] = c[:10, :20] + 1.0
+    return [_h(a), _h(c)]
+
+
+@case
+def view_aliasing(np):
+    # writes through a view are visible through the base and other views (views never copy)
+    a = np.arange(150) * 1.0
+    v = a[50:100]
+    v += 1000.0
+    w = a[::2]
+    return [_h(a), _h(v), _h(w)]
+
+
+@case
+def shifted_update_hazard(np):
+    # read-after-write through shifted views must not fuse wrongly (tests/…:23-45 of the reference)
+    a = np.arange(120) * 1.0
+    a[1:] = a[:-1] + a[1:]
+    b = np.arange(120) * 1.0
+    b[:-1] = b[1:] * 2.0
+    return [_h(a), _h(b)]
+
+
+# ---- broadcast (TestBroadcast)
+@case
+def broadcast_ops(np):
+    m = np.fromfunction(lambda i, j: i + j, (20, 30))
+    v = np.arange(30) * 1.0
+    c = np.arange(20) * 1.0
+    return [_h(m + v), _h(m * v), _h(v + m), _h(m - 3.0 * v), _h((m.T + c).T)]
+
+
+# ---- reductions (TestReduction)
+@case
+def reductions_full(np):
+    a = np.fromfunction(lambda i, j: (i * 7 + j) % 5, (40, 25))
+    i = np.arange(300)
+    return [onp.asarray(a.sum()), onp.asarray(i.sum()), onp.asarray((i % 7).prod() == 0), onp.asarray(a.min()), onp.asarray(a.max()),
+            onp.asarray((a > 10).any()), onp.asarray((a >= 0).all()), onp.asarray(a.mean())]
+
+
+@case
+def reductions_axis(np):
+    a = np.fromfunction(lambda i, j, k: (i + 2 * j + 3 * k) % 11, (10, 12, 14))
+    return [_h(a.sum(axis=0)), _h(a.sum(axis=1)), _h(a.sum(axis=2)), _h(a.sum(axis=(0, 2))), _h(a.max(axis=1)), _h(a.min(axis=0))]
+
+
+@case
+def reductions_of_views(np):
+    a = np.fromfunction(lambda i, j: i * 3 + j, (30, 20))
+    return [onp.asarray(a.T.sum()), _h(a.T.sum(axis=0)), _h(a[5:25, 2:18].sum(axis=1)), onp.asarray(a[::2, ::-1].sum())]
+
+
+@case
+def reduction_fusion_equalities(np):
+    # sum(axis=0).sum() == sum(axis=1).sum() == sum() on exactly representable data (TestStencil::test_reduction_fusion)
+    a = np.fromfunction(lambda i, j: (i + j) % 9, (50, 60))
+    s0 = a.sum(axis=0).sum()
+    s1 = a.sum(axis=1).sum()
+    s = a.sum()
+    return [onp.asarray(s0), onp.asarray(s1), onp.asarray(s), onp.asarray(float(s0) == float(s) == float(s1))]
+
+
+# ---- stencils through slice views (TestStencil)
+@case
+def stencil_weighted_2d(np):
+    a = np.fromfunction(lambda i, j: (i * 5 + j * 3) % 32, (40, 50))
+    b = np.zeros((40, 50))
+    b[1:-1, 1:-1] = 0.25 * (a[:-2, 1:-1] + a[2:, 1:-1] + a[1:-1, :-2] + a[1:-1, 2:]) - a[1:-1, 1:-1]
+    return [_h(b), onp.asarray(b.sum())]
+
+
+@case
+def stencil_3d_laplacian(np):
+    u = np.fromfunction(lambda i, j, k: (i + 2 * j + 3 * k) % 64, (16, 18, 20), dtype=onp.float32)
+    v = np.zeros((16, 18, 20), dtype=onp.float32)
+    v[1:-1, 1:-1, 1:-1] = (u[:-2, 1:-1, 1:-1] + u[2:, 1:-1, 1:-1] + u[1:-1, :-2, 1:-1] + u[1:-1, 2:, 1:-1]
+                           + u[1:-1, 1:-1, :-2] + u[1:-1, 1:-1, 2:] - 6.0 * u[1:-1, 1:-1, 1:-1])
+    return [_h(v)]
+
+
+# ---- apps (TestApps): pi integration, manual matmul via broadcast + axis sum
+@case
+def pi_integration(np):
+    n = 100000
+    x = (np.arange(n) + 0.5) * (1.0 / n)
+    return [onp.asarray(int((4.0 / (1.0 + x * x)).sum() * (1.0 / n) * 1e8))]
+
+
+@case
+def manual_matmul(np):
+    a = np.fromfunction(lambda i, j: (i + j) % 4, (12, 15))
+    b = np.fromfunction(lambda i, j: (i * 2 + j) % 3, (15, 10))
+    # c[i, k] = sum_j a[i, j] * b[j, k] through broadcast + transposes + axis sum
+    prods = [_h((a * b.T[k]).sum(axis=1)) for k in range(3)]
+    return prods
+
+
+# ---- masks (test_masked*)
+@case
+def masked_assign(np):
+    a = np.arange(150) * 1.0
+    a[a > 100.0] = -1.0
+    b = np.arange(150) * 1.0
+    m = b % 2 == 0
+    b[m] += 1000.0
+    return [_h(a), _h(b)]
+
+
+def _compare(got, exp, name):
+    assert len(got) == len(exp), name
+    for i, (g, e) in enumerate(zip(got, exp)):
+        g, e = onp.asarray(g), onp.asarray(e)
+        assert g.shape == e.shape, "%s[%d]: shape %s vs %s" % (name, i, g.shape, e.shape)
+        if e.dtype.kind == "f":
+            assert g.dtype.kind == "f"
+            assert onp.allclose(g, e, rtol=1e-13 if e.dtype == onp.float64 else 1e-6, atol=1e-15), "%s[%d]" % (name, i)
+        else:
+            assert onp.array_equal(g, e), "%s[%d]: %r vs %r" % (name, i, g.reshape(-1)[:8], e.reshape(-1)[:8])
+
+
+@pytest.mark.parametrize("f", CASES, ids=lambda f: f.__name__)
+def test_run_both_oracle(oracle_engine, f):
+    import ramba_b200 as rb
+
+    _compare(f(rb), f(onp), f.__name__)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("f", CASES, ids=lambda f: f.__name__)
+def test_run_both_cuda(gpu_engine, f):
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    got = f(rb)
+    assert not RT.test_mode and _cabi.launch_count() > before
+    _compare(got, f(onp), f.__name__)

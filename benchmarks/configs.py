@@ -22,17 +22,28 @@ from ramba_b200 import common  # noqa: E402
 from ramba_b200.runtime import RT  # noqa: E402
 
 
-def timed(fn, iters=5, warm=2):
+KERNEL_MS = {}
+
+
+def timed(fn, iters=5, warm=2, name=None):
+    """(wall seconds per iteration incl. Python, result); also records the summed CUDA-event time of
+    the library's launches per iteration in KERNEL_MS[name]."""
     for _ in range(warm):
         r = fn()
     np.sync()
     torch.cuda.synchronize()
+    RT.profile_events = []
     t0 = time.perf_counter()
     for _ in range(iters):
         r = fn()
     np.sync()
     torch.cuda.synchronize()
-    return (time.perf_counter() - t0) / iters, r
+    dt = (time.perf_counter() - t0) / iters
+    ev = RT.profile_events
+    RT.profile_events = None
+    if name is not None:
+        KERNEL_MS[name] = {"kernel_ms_per_iter": sum(a.elapsed_time(b) for (a, b, _) in ev) / iters, "launches_per_iter": len(ev) / iters}
+    return dt, r
 
 
 def main():
@@ -49,7 +60,7 @@ def main():
     n = int(32768 * args.scale)
     X = np.fromfunction(lambda i, j: (i * 131 + j * 31) % 4, (n, n), dtype=onp.float32)
     np.sync()
-    dt, s = timed(lambda: float((X * 2.0 + 1.0).sum(asarray=True).asarray()[0]))
+    dt, s = timed(lambda: float((X * 2.0 + 1.0).sum(asarray=True).asarray()[0]), name="config3")
     # closed form: sum over i,j of 2*((131 i + 31 j) mod 4) + 1 — computed exactly with integers on the host for a stripe
     ii = onp.arange(n, dtype=onp.int64)
     cnt = onp.zeros(4, dtype=onp.int64)
@@ -68,7 +79,7 @@ def main():
     M = np.fromfunction(lambda i, j: (i + 3 * j) % 8, (r, c), dtype=onp.float32)
     v = (np.arange(c) % 8).astype(onp.float32)
     np.sync()
-    dt, res = timed(lambda: (M + v).sum(axis=0), iters=3, warm=1)
+    dt, res = timed(lambda: (M + v).sum(axis=0), iters=3, warm=1, name="config5")
     got = res.asarray()
     j = onp.arange(c, dtype=onp.int64)
     # column sum of (i + 3j) % 8 over i in [0, r): r/8 full cycles (r is a multiple of 8) -> 28 * r/8, plus v
@@ -89,7 +100,7 @@ def main():
                                + U[1:-1, 1:-1, :-2] + U[1:-1, 1:-1, 2:] - 6.0 * U[1:-1, 1:-1, 1:-1])
         return None
 
-    dt, _ = timed(lap, iters=3, warm=1)
+    dt, _ = timed(lap, iters=3, warm=1, name="config4")
     # check a sub-block against NumPy
     sub = V[1:9, 1:9, 1:m - 1].asarray()
     i, jj, k = onp.meshgrid(onp.arange(0, 10), onp.arange(0, 10), onp.arange(m), indexing="ij")
@@ -98,6 +109,8 @@ def main():
            - 6.0 * u[1:-1, 1:-1, 1:-1]).astype(onp.float32)
     out["config4"] = {"shape": [m, m, m], "seconds": dt, "GBps_algorithmic_8B": (m - 2) ** 3 * 8 / dt / 1e9,
                       "exact": bool(onp.array_equal(sub, ref)), "bytes_sent_per_rank": RT.bytes_sent}
+    for k_, v_ in KERNEL_MS.items():
+        out[k_].update(v_)
     if rank == 0:
         print(json.dumps(out))
     if W > 1:

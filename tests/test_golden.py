@@ -56,3 +56,17 @@ def test_c_oracle_chain_matches_reference(golden_programs):
     A2 = onp.empty_like(A)
     chain.chain_f64(A2, B, C, D, global_start=0, make_A=True)
     assert onp.array_equal(A2, A), "arange * 0.001 must be bit-identical to the reference"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", [p for p in _programs.ALL if p.__name__ not in _programs.NOT_IN_REFERENCE], ids=lambda p: p.__name__)
+def test_cuda_matches_reference(gpu_engine, golden_programs, prog):
+    """The CUDA path directly against the outputs of the real reference (Numba CPU path)."""
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+
+    z, status = golden_programs
+    before = _cabi.launch_count()
+    got = prog(rb)
+    assert _cabi.launch_count() > before
+    compare_to_golden(prog.__name__, got, z, transcendental_tol=(prog.__name__ == "chain"))

@@ -1,5 +1,6 @@
 // rb200_api.cu — the C-ABI declared in include/ramba_b200.h (host side) and small helper kernels.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
@@ -9,6 +10,10 @@
 #include "rb200_handlers.h"
 
 namespace rb200 {
+__global__ void fill_u64_kernel(u64* p, long long n, u64 bits) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = bits;
+}
+
 // stage 2 helper: out[j] = reduce_k part[k*stride_k + j]
 template <class T> __global__ void reduce_partials_kernel(T* out, const T* part, long long n, long long k, long long stride_k, int op) {
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
@@ -89,6 +94,17 @@ static int static_kind(const KParams& P, int kind, int* idx, int ctype) {
     }
     default: return -1;
   }
+}
+
+static unsigned long long host_red_identity_bits(int op, int ctype) {
+  if (ctype == RB200_T_F64) {
+    double d = (op == RB200_RED_ADD) ? 0.0 : (op == RB200_RED_MUL) ? 1.0 : (op == RB200_RED_MIN) ? INFINITY : -INFINITY;
+    unsigned long long b;
+    memcpy(&b, &d, 8);
+    return b;
+  }
+  long long i = (op == RB200_RED_ADD) ? 0ll : (op == RB200_RED_MUL) ? 1ll : (op == RB200_RED_MIN) ? 0x7fffffffffffffffll : (long long)0x8000000000000000ull;
+  return (unsigned long long)i;
 }
 
 static void assign_handlers(KParams& P, const rb200_fused_op* op) {
@@ -231,6 +247,78 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     for (int s = 0; s < op->n_reds; ++s) {
       P.reds[s].op = op->reds[s].op;
       P.reds[s].ctype = op->reds[s].ctype;
+    }
+    // ---- axis-as-1-D fast path: [R reduced rows][C kept elements], every view contiguous over the box
+    // or broadcast over the rows, C a multiple of the 1-D tile, one reduction slot, no index operands:
+    // run the staged 1-D kernel with V column accumulators per thread (rb200_elementwise_ax1d.cu)
+    {
+      const long long TILE1 = (long long)kThreads * kV1;
+      bool ok = (op->ndim == 2 && nred == 1 && op->n_reds == 1 && kept % TILE1 == 0 && kept / TILE1 <= (long long)sms * 2 && red_len >= 2);
+      for (int i = 0; i < op->n_insns && ok; ++i) {
+        const rb200_insn& I = op->insns[i];
+        if (I.a_kind == RB200_K_IOTA || I.b_kind == RB200_K_IOTA || I.c_kind == RB200_K_IOTA) ok = false;
+        if (I.st_view != RB200_NOSTORE) ok = false;  // stage 1 of an axis reduction only reads
+      }
+      for (int i = 0; i < op->n_views && ok; ++i) {
+        const rb200_view& v = op->views[i];
+        if (!view_read[i]) continue;
+        if (v.stride[1] != 1 || !(v.stride[0] == kept || v.stride[0] == 0)) ok = false;
+      }
+      if (ok) {
+        KParams Q = P;
+        const int V1 = kV1;
+        Q.ndim = 1;
+        Q.total = red_len * kept;
+        Q.n_tiles = Q.total / TILE1;
+        Q.shape[0] = Q.total;
+        Q.gstart[0] = 0;
+        Q.wide = 1;
+        const int n_chunks = (int)(kept / TILE1);
+        long long cap1 = (long long)sms * 2;
+        int n_split_eff = (int)(cap1 / n_chunks);
+        if (n_split_eff > n_split) n_split_eff = n_split;
+        if ((long long)n_split_eff > red_len) n_split_eff = (int)red_len;
+        if (n_split_eff < 1) n_split_eff = 1;
+        Q.n_split_chunks = n_chunks;
+        Q.n_split = n_split_eff;
+        Q.red_len = kept;  // in this mode: elements per row (partials are [split][kept])
+        Q.n_pf = 0;
+        size_t pf_bytes1 = 0;
+        for (int i = 0; i < op->n_views; ++i) {
+          KView& k = Q.views[i];
+          const rb200_view& v = op->views[i];
+          k.stride[0] = 1;
+          k.pf_slot = -1;
+          if (!view_read[i]) continue;
+          const int dt = v.dtype;
+          const bool wide_ok = (dt == RB200_F64 || dt == RB200_F32 || dt == RB200_I64 || dt == RB200_I32);
+          if (v.stride[0] == 0) {
+            k.pf_slot = -2;  // periodic: broadcast over the rows
+          } else if (wide_ok && Q.n_pf < kMaxPf && reg_bytes + (size_t)(Q.n_pf + 1) * 2 * V1 * kThreads * 8 <= 108 * 1024) {
+            k.pf_slot = Q.n_pf;
+            Q.pf_view[Q.n_pf] = i;
+            Q.n_pf++;
+          }
+        }
+        pf_bytes1 = (size_t)Q.n_pf * 2 * V1 * kThreads * 8;
+        Q.bulk = Q.n_pf > 0 ? 1 : 0;
+        for (int j = 0; j < Q.n_pf; ++j)
+          if ((((uintptr_t)op->views[Q.pf_view[j]].base) & 15u) != 0) Q.bulk = 0;
+        const size_t reg_bytes1 = (size_t)op->n_regs * V1 * kThreads * 8;
+        assign_handlers(Q, op);
+        e = launch_vm_elementwise_ax1d(Q, (unsigned)(n_split_eff * n_chunks), reg_bytes1 + pf_bytes1, stream);
+        if (e != cudaSuccess) return fail_cuda("vm_elementwise_kernel (axis-as-1-D) launch", e);
+        g_launches.fetch_add(1);
+        if (n_split_eff < n_split) {
+          const long long n_fill = (long long)(n_split - n_split_eff) * kept;
+          fill_u64_kernel<<<(unsigned)((n_fill + 255) / 256 > 1184 ? 1184 : (n_fill + 255) / 256), 256, 0, stream>>>(
+              (u64*)op->red_scratch + (long long)n_split_eff * kept, n_fill, host_red_identity_bits(op->reds[0].op, op->reds[0].ctype));
+          e = cudaGetLastError();
+          if (e != cudaSuccess) return fail_cuda("fill_u64_kernel launch", e);
+          g_launches.fetch_add(1);
+        }
+        return 0;
+      }
     }
     long long blocks = P.n_tiles;
     long long cap = (long long)sms * 4;

@@ -68,7 +68,7 @@ template <int V> __global__ void __launch_bounds__(kThreads, 2) vm_axis_reduce_k
           for (int k = 0; k < V; ++k) cx.idx[k][d] = v;
         }
       }
-      run_program<V, true>(cx, racc);
+      run_program<V, true, RB200_MAX_REDS>(cx, racc);
     }
     for (int s = 0; s < P.n_reds; ++s) {
 #pragma unroll

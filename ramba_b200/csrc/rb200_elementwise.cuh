@@ -8,7 +8,13 @@ namespace rb200 {
 
 // Persistent-style grid (a multiple of the SM count): CTA b walks tiles b, b+grid, ...
 // Shared memory layout (dynamic): [prefetch: 2 stages * n_pf * V*256*8 B][register file: n_regs*V*256*8 B]
-template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elementwise_kernel(const __grid_constant__ KParams P) {
+// AX1D: axis reduction run as a 1-D op (ND == 1 only).  The box is [reduced rows][C kept elements] with
+// C a multiple of the tile and the grid a multiple of C/TILE, so a CTA always lands on the same column
+// chunk: every thread keeps V column accumulators in registers across all its rows, views that are
+// broadcast over the rows are "periodic" (pf_slot == -2), and the per-CTA accumulators are written as
+// partials[(split)*C + column] with split = blockIdx / (C/TILE).
+template <int V, int ND, bool AX1D = false>
+__global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elementwise_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) u64 mbar_store[2];
   constexpr int TILE = kThreads * V;
@@ -33,9 +39,14 @@ template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1 &&
     __syncthreads();
   }
 
-  u64 racc[RB200_MAX_REDS][1];
+  constexpr int NS = AX1D ? 1 : RB200_MAX_REDS;
+  u64 racc[NS][AX1D ? V : 1];
 #pragma unroll
-  for (int s = 0; s < RB200_MAX_REDS; ++s) racc[s][0] = red_identity_bits(s < P.n_reds ? P.reds[s].op : 0, s < P.n_reds ? P.reds[s].ctype : 0);
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < (AX1D ? V : 1); ++k) racc[s][k] = red_identity_bits(s < P.n_reds ? P.reds[s].op : 0, s < P.n_reds ? P.reds[s].ctype : 0);
+  if constexpr (AX1D) cx.pe0 = (long long)(blockIdx.x % (unsigned)P.n_split_chunks) * TILE + threadIdx.x;
+  else cx.pe0 = 0;
 
   // --- staging of the read-only inputs of tile t into stage `st` (ND == 1 only) --------------
   // full tiles of contiguous, 16-byte aligned views: ONE bulk async copy per view by one thread
@@ -136,10 +147,18 @@ template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1 &&
       }
     }
     cx.valid = valid;
-    run_program<V, false>(cx, racc);
+    run_program<V, AX1D, NS>(cx, racc);
   }
   if (n_pf > 0 && !bulk) cp_async_wait<0>();
 
+  if constexpr (AX1D) {
+    // per-CTA column accumulators -> partials[split][column]
+    const long long split = blockIdx.x / (unsigned)P.n_split_chunks;
+    const long long col0 = cx.pe0;
+#pragma unroll
+    for (int k = 0; k < V; ++k) P.red_partials[split * P.red_len + col0 + (long long)k * kThreads] = racc[0][k];
+    return;
+  }
   // ---- global reductions: thread -> warp shuffle -> block -> per-block partial -> last block
   if (P.n_reds > 0) {
     __shared__ u64 wpart[RB200_MAX_REDS][kThreads / 32];
@@ -149,7 +168,7 @@ template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1 &&
       const int op = P.reds[s].op, ct = P.reds[s].ctype;
       u64 v = racc[0][0];
 #pragma unroll
-      for (int q = 0; q < RB200_MAX_REDS; ++q)
+      for (int q = 0; q < NS; ++q)
         if (q == s) v = racc[q][0];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, ct, v, __shfl_down_sync(0xffffffffu, v, o));
@@ -208,12 +227,12 @@ template <int V, int ND> __global__ void __launch_bounds__(kThreads, (ND == 1 &&
   }
 }
 
-template <int V, int ND> cudaError_t launch_vm_elementwise_nd(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
+template <int V, int ND, bool AX1D = false> cudaError_t launch_vm_elementwise_nd(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
   if (smem + 2048 > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(vm_elementwise_kernel<V, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(vm_elementwise_kernel<V, ND, AX1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  vm_elementwise_kernel<V, ND><<<blocks, kThreads, smem, stream>>>(P);
+  vm_elementwise_kernel<V, ND, AX1D><<<blocks, kThreads, smem, stream>>>(P);
   return cudaGetLastError();
 }
 

@@ -93,6 +93,7 @@ template <int V, int ND> struct Ctx {
   unsigned pf_s;         // shared-window byte address of the current prefetch stage (element e of slot j at pf_s + j*V*2048 + e*itemsize)
   unsigned tid;
   long long e0;          // ND == 1: index of element 0 of this thread in the tile
+  long long pe0;         // ND == 1, axis-as-1-D mode: e0 modulo the period of "periodic" (row-broadcast) views
   long long idx[V][ND];  // ND  > 1: N-d index of every element
   unsigned valid;        // bit k: element k exists
   u64 acc[V];
@@ -104,7 +105,7 @@ template <int V, int ND> struct Ctx {
     if constexpr (ND == 1) {
       const long long s = vw.stride[0];
       const long long step = s * kThreads;  // uniform
-      long long o = e0 * s;
+      long long o = (vw.pf_slot == -2 ? pe0 : e0) * s;  // pf_slot -2: periodic view (broadcast over the reduced rows)
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         off[k] = o;
@@ -710,14 +711,14 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
   cx.template finish<T>(I, r);
 }
 
-template <class T, int AK, int V, bool AX, class C>
-__device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
+template <class T, int AK, int V, bool AX, int NS, class C>
+__device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[NS][AX ? V : 1]) {
   T a[V];
   fetch_s<T, AK, V>(cx, I.a_idx(), a);
   const int slot = I.b_idx();
   const int rop = (int)I.imm();
 #pragma unroll
-  for (int s = 0; s < RB200_MAX_REDS; ++s)
+  for (int s = 0; s < NS; ++s)
     if (s == slot) {
 #pragma unroll
       for (int k = 0; k < V; ++k)
@@ -730,7 +731,9 @@ __device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[RB200_M
 
 // one interpreter pass over the op list for the thread's V elements.
 // racc: reduction accumulators (raw bits), [slot][0] (global mode, AX=false) or [slot][k] (axis mode)
-template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C& cx, u64 (&racc)[RB200_MAX_REDS][AX ? V : 1]) {
+// NS = number of reduction slots carried (RB200_MAX_REDS, or 1 when V accumulators per slot must stay
+// in registers)
+template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_program(C& cx, u64 (&racc)[NS][AX ? V : 1]) {
   const KParams& P = cx.P;
   const int n = P.n_insns;
 #pragma unroll 1
@@ -758,7 +761,7 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
         double a[V];
         cx.template fetch<double>(I.a_kind(), I.a_idx(), a);
 #pragma unroll
-        for (int s = 0; s < RB200_MAX_REDS; ++s)
+        for (int s = 0; s < NS; ++s)
           if (s == slot) {
 #pragma unroll
             for (int k = 0; k < V; ++k)
@@ -771,7 +774,7 @@ template <int V, bool AX, class C> __device__ __forceinline__ void run_program(C
         long long a[V];
         cx.template fetch<long long>(I.a_kind(), I.a_idx(), a);
 #pragma unroll
-        for (int s = 0; s < RB200_MAX_REDS; ++s)
+        for (int s = 0; s < NS; ++s)
           if (s == slot) {
 #pragma unroll
             for (int k = 0; k < V; ++k)

@@ -9,5 +9,6 @@ cudaError_t launch_vm_elementwise_nd1(const KParams& P, unsigned blocks, size_t 
 cudaError_t launch_vm_elementwise_nd2(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_vm_elementwise_nd3(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_vm_elementwise_nd5(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
+cudaError_t launch_vm_elementwise_ax1d(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_vm_axis_reduce(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 }  // namespace rb200

@@ -29,7 +29,7 @@ struct KView {
   char* base;
   long long stride[kMaxD];  // elements
   int dtype;
-  int pf_slot;  // >= 0: staged by cp.async into prefetch slot pf_slot; -1: read directly
+  int pf_slot;  // >= 0: staged into prefetch slot pf_slot; -1: read directly; -2: read directly, periodic (axis-as-1-D)
 };
 
 struct KRed {
@@ -53,6 +53,8 @@ struct KParams {
   long long red_split;
   int n_split;
   int red_ndim;
+  int n_split_chunks;  // axis-as-1-D mode: column chunks (C / tile) = CTAs per split
+  int pad1;
   KView views[RB200_MAX_VIEWS];
   u64 scalars[RB200_MAX_SCALARS];
   rb200_insn insns[RB200_MAX_INSNS];

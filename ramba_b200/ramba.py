@@ -1455,10 +1455,39 @@ def create_array(shape, filler, local_border=0, dtype=None, distribution=None, n
         return new
     if filler is None:
         return new  # allocation is lazy; nothing to run (empty)
-    deferred_op.add_op([new, filler], new)
     if no_defer:
-        deferred_op.do_ops()
+        # out-of-band creation: allocate and fill now WITHOUT flushing the pending fused op, so that
+        # the producers of a reduction stay fused with it (ramba/ramba.py:5918, 8603-8627)
+        _fill_now(new, filler)
+        return new
+    deferred_op.add_op([new, filler], new)
     return new
+
+
+_fill_programs = {}
+
+
+def _fill_now(nd, value):
+    """Fill this worker's block of a brand-new array with a scalar, immediately."""
+    w = common.worker_num
+    bd = nd.bdarray
+    sv = bd.distribution[w]
+    sh = RT.create_array(nd.gid, _local_shape(bd.distribution, w), bd.dtype)
+    bd.remote_constructed = True
+    bd.flex_dist = False
+    if shardview.is_empty(sv):
+        return
+    code = rb_dtype(nd.dtype)
+    if isinstance(value, np.generic):
+        value = value.item()
+    key = (code, type(value), value)
+    prog = _fill_programs.get(key)
+    if prog is None:
+        lw = Lowering([code])
+        lw.store(0, lw.scalar(value))
+        prog = _fill_programs[key] = lw.finish()
+    n = int(np.prod(sh.shape)) if sh.shape else 1
+    RT.launch(prog, [n], [0], [(sh.buf.data_ptr(), [1], code)])
 
 
 def init_array(shape, filler, local_border=0, dtype=None, distribution=None, **kwargs):

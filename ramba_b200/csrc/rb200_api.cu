@@ -300,11 +300,16 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
             Q.n_pf++;
           }
         }
-        pf_bytes1 = (size_t)Q.n_pf * 2 * V1 * kThreads * 8;
+        const size_t reg_bytes1 = (size_t)op->n_regs * V1 * kThreads * 8;
         Q.bulk = Q.n_pf > 0 ? 1 : 0;
         for (int j = 0; j < Q.n_pf; ++j)
           if ((((uintptr_t)op->views[Q.pf_view[j]].base) & 15u) != 0) Q.bulk = 0;
-        const size_t reg_bytes1 = (size_t)op->n_regs * V1 * kThreads * 8;
+        Q.n_stages = 2;
+        if (Q.bulk) {
+          const int want = op->n_insns <= 4 ? 4 : (op->n_insns <= 8 ? 3 : 2);
+          while (Q.n_stages < want && reg_bytes1 + (size_t)Q.n_pf * (Q.n_stages + 1) * V1 * kThreads * 8 <= 108 * 1024) Q.n_stages++;
+        }
+        pf_bytes1 = (size_t)Q.n_pf * Q.n_stages * V1 * kThreads * 8;
         assign_handlers(Q, op);
         e = launch_vm_elementwise_ax1d(Q, (unsigned)(n_split_eff * n_chunks), reg_bytes1 + pf_bytes1, stream);
         if (e != cudaSuccess) return fail_cuda("vm_elementwise_kernel (axis-as-1-D) launch", e);
@@ -344,12 +349,23 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
         P.n_pf++;
       }
     }
-    pf_bytes = (size_t)P.n_pf * 2 * V * kThreads * 8;
+    // ring depth: light programs finish a tile faster than HBM + copy-engine latency, so they get
+    // a deeper ring (prefetch distance n_stages-1 tiles) as far as shared memory allows
+    P.n_stages = 2;
+    if (P.n_pf > 0) {
+      const int want = op->n_insns <= 4 ? 4 : (op->n_insns <= 8 ? 3 : 2);
+      while (P.n_stages < want && reg_bytes + (size_t)P.n_pf * (P.n_stages + 1) * V * kThreads * 8 <= 108 * 1024) P.n_stages++;
+    }
+    pf_bytes = (size_t)P.n_pf * P.n_stages * V * kThreads * 8;
     // whole-tile bulk copies need contiguous, 16-byte aligned sources
     P.bulk = P.n_pf > 0 ? 1 : 0;
     for (int j = 0; j < P.n_pf; ++j) {
       const rb200_view& v = op->views[P.pf_view[j]];
       if (v.stride[0] != 1 || (((uintptr_t)v.base) & 15u) != 0) P.bulk = 0;
+    }
+    if (!P.bulk && P.n_pf > 0) {
+      P.n_stages = 2;
+      pf_bytes = (size_t)P.n_pf * 2 * V * kThreads * 8;
     }
   }
   const size_t smem = reg_bytes + pf_bytes;

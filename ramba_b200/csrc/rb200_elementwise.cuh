@@ -16,24 +16,24 @@ namespace rb200 {
 template <int V, int ND, bool AX1D = false>
 __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elementwise_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) u64 mbar_store[2];
+  __shared__ __align__(8) u64 mbar_store[4];
   constexpr int TILE = kThreads * V;
   constexpr unsigned SLOT = (unsigned)(TILE * 8);  // bytes reserved per staged view per stage
   Ctx<V, ND> cx(P);
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
   cx.tid = threadIdx.x;
   const int n_pf = (ND == 1) ? P.n_pf : 0;
-  // layout: [prefetch stage 0][prefetch stage 1][register file]  (stages first: 128-byte aligned)
+  // layout: [prefetch stages 0..S-1][register file]  (stages first: 128-byte aligned)
   const unsigned pf_base = smem_s;
   const unsigned pf_stage_bytes = (unsigned)n_pf * SLOT;
-  cx.regfile_s = smem_s + 2u * pf_stage_bytes + threadIdx.x * 8u;
+  const bool bulk = (ND == 1) && n_pf > 0 && P.bulk;
+  const unsigned S = bulk ? (unsigned)P.n_stages : 2u;  // ring depth: prefetch distance S-1 tiles
+  cx.regfile_s = smem_s + (n_pf > 0 ? S : 0u) * pf_stage_bytes + threadIdx.x * 8u;
   cx.pf_s = pf_base;
   const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&mbar_store[0]);
-  const bool bulk = (ND == 1) && n_pf > 0 && P.bulk;
   if (bulk) {
     if (threadIdx.x == 0) {
-      mbar_init(mbar0, 1);
-      mbar_init(mbar0 + 8u, 1);
+      for (unsigned s = 0; s < S; ++s) mbar_init(mbar0 + s * 8u, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -91,10 +91,15 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
   auto tile_is_bulk = [&](long long t) { return bulk && (t + 1) * TILE <= P.total; };
 
   long long tile = blockIdx.x;
-  unsigned stage = 0, phase0 = 0, phase1 = 0;
+  unsigned stage = 0, phases = 0;  // bit s of `phases`: parity the next wait on stage s expects
   if (n_pf > 0 && tile < P.n_tiles) {
     if (bulk) {
-      if (tile_is_bulk(tile) && threadIdx.x == 0) issue_bulk(tile, 0);
+      // prologue: tiles 0 .. S-2 of this CTA into stages 0 .. S-2
+      if (threadIdx.x == 0) {
+        long long t = tile;
+        for (unsigned s = 0; s + 1 < S && t < P.n_tiles; ++s, t += gridDim.x)
+          if (tile_is_bulk(t)) issue_bulk(t, s);
+      }
     } else {
       issue_ldgsts(tile, 0);
       cp_async_commit();
@@ -103,15 +108,15 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
 #pragma unroll 1
   for (; tile < P.n_tiles; tile += gridDim.x) {
     if (n_pf > 0) {
-      const long long nxt = tile + gridDim.x;
       if (bulk) {
-        // everybody is done reading the other stage (previous iteration) before it is refilled
+        // everybody is done reading the stage used by the previous iteration before it is refilled
         __syncthreads();
-        if (nxt < P.n_tiles && tile_is_bulk(nxt) && threadIdx.x == 0) issue_bulk(nxt, stage ^ 1u);
+        const long long ahead = tile + (long long)(S - 1) * gridDim.x;
+        const unsigned refill = (stage + S - 1u) % S;
+        if (ahead < P.n_tiles && tile_is_bulk(ahead) && threadIdx.x == 0) issue_bulk(ahead, refill);
         if (tile_is_bulk(tile)) {
-          mbar_wait(mbar0 + stage * 8u, stage ? phase1 : phase0);
-          if (stage) phase1 ^= 1u;
-          else phase0 ^= 1u;
+          mbar_wait(mbar0 + stage * 8u, (phases >> stage) & 1u);
+          phases ^= (1u << stage);
         } else {  // the ragged last tile
           issue_ldgsts(tile, stage);
           cp_async_commit();
@@ -119,12 +124,13 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
         }
       } else {
         // per-thread pipeline (each thread re-reads only what it copied itself: no barrier)
+        const long long nxt = tile + gridDim.x;
         if (nxt < P.n_tiles) issue_ldgsts(nxt, stage ^ 1u);
         cp_async_commit();
         cp_async_wait<1>();
       }
       cx.pf_s = pf_base + stage * pf_stage_bytes;
-      stage ^= 1u;
+      stage = (stage + 1u == S) ? 0u : stage + 1u;
     }
     const long long e0 = tile * TILE + threadIdx.x;
     unsigned valid = 0;

@@ -54,7 +54,7 @@ struct KParams {
   int n_split;
   int red_ndim;
   int n_split_chunks;  // axis-as-1-D mode: column chunks (C / tile) = CTAs per split
-  int pad1;
+  int n_stages;        // depth of the staging ring (2..4)
   KView views[RB200_MAX_VIEWS];
   u64 scalars[RB200_MAX_SCALARS];
   rb200_insn insns[RB200_MAX_INSNS];

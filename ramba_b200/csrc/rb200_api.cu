@@ -306,7 +306,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
           if ((((uintptr_t)op->views[Q.pf_view[j]].base) & 15u) != 0) Q.bulk = 0;
         Q.n_stages = 2;
         if (Q.bulk) {
-          const int want = op->n_insns <= 4 ? 4 : (op->n_insns <= 8 ? 3 : 2);
+          const int want = 2;  // deeper rings measured slower (config 2: -7 %, config 3: no gain); kept configurable
           while (Q.n_stages < want && reg_bytes1 + (size_t)Q.n_pf * (Q.n_stages + 1) * V1 * kThreads * 8 <= 108 * 1024) Q.n_stages++;
         }
         pf_bytes1 = (size_t)Q.n_pf * Q.n_stages * V1 * kThreads * 8;
@@ -353,7 +353,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     // a deeper ring (prefetch distance n_stages-1 tiles) as far as shared memory allows
     P.n_stages = 2;
     if (P.n_pf > 0) {
-      const int want = op->n_insns <= 4 ? 4 : (op->n_insns <= 8 ? 3 : 2);
+      const int want = 2;  // deeper rings measured slower (config 2: -7 %, config 3: no gain); kept configurable
       while (P.n_stages < want && reg_bytes + (size_t)P.n_pf * (P.n_stages + 1) * V * kThreads * 8 <= 108 * 1024) P.n_stages++;
     }
     pf_bytes = (size_t)P.n_pf * P.n_stages * V * kThreads * 8;

@@ -112,12 +112,15 @@ static void assign_handlers(KParams& P, const rb200_fused_op* op) {
     rb200_insn I = P.insns[i];
     int h = H_GENERIC;
     int ai = I.a_idx, bi = I.b_idx;
-    const int ak = static_kind(P, I.a_kind, &ai, I.ctype);
+    // CVT fetches its operand in the SOURCE class (imm & 0xff)
+    const int ak = static_kind(P, I.a_kind, &ai, I.op == RB200_OP_CVT ? (int)(I.imm & 0xff) : (int)I.ctype);
     if (I.op == RB200_OP_ADD || I.op == RB200_OP_SUB || I.op == RB200_OP_MUL) {
       const int bk = static_kind(P, I.b_kind, &bi, I.ctype);
       h = handler_bin(I.op, I.ctype, ak, bk);
     } else if (I.op == RB200_OP_RED) {
       h = handler_red(I.ctype, ak);
+    } else if (I.op == RB200_OP_CVT) {
+      if ((I.imm >> 8) == 0) h = handler_cvt((int)(I.imm & 0xff), I.ctype, ak);
     } else if (I.op == RB200_OP_POWI) {
       // only x ** 2 with a scalar exponent (Numba int_power gives exactly x*x)
       if (I.b_kind == RB200_K_SCAL && (long long)op->scalars[I.b_idx] == 2) h = handler_un(I.op, I.ctype, ak);
@@ -300,7 +303,35 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
             Q.n_pf++;
           }
         }
-        const size_t reg_bytes1 = (size_t)op->n_regs * V1 * kThreads * 8;
+        // hoist periodic views into extra spill registers when every use agrees on the compute class
+        for (int i = 0; i < op->n_views && Q.n_hoist < kMaxPf; ++i) {
+          if (Q.views[i].pf_slot != -2 || Q.n_regs >= RB200_MAX_REGS) continue;
+          int cls = -1;
+          bool same = true;
+          for (int q = 0; q < Q.n_insns; ++q) {
+            const rb200_insn& I = Q.insns[q];
+            const int use_cls = (I.op == RB200_OP_CVT) ? (int)(I.imm & 0xff) : (int)I.ctype;
+            const bool uses = (I.a_kind == RB200_K_VIEW && I.a_idx == i) || (I.b_kind == RB200_K_VIEW && I.b_idx == i && I.op != RB200_OP_RED) ||
+                              (I.c_kind == RB200_K_VIEW && I.c_idx == i && I.op != RB200_OP_SINCOS);
+            if (!uses) continue;
+            if (I.op == RB200_OP_POWI && I.b_kind == RB200_K_VIEW && I.b_idx == i) same = false;  // integer exponent operand
+            if (cls < 0) cls = use_cls;
+            else if (cls != use_cls) same = false;
+          }
+          if (cls < 0 || !same) continue;
+          const int r = Q.n_regs++;
+          Q.hoist_view[Q.n_hoist] = i;
+          Q.hoist_reg[Q.n_hoist] = r;
+          Q.hoist_cls[Q.n_hoist] = cls;
+          Q.n_hoist++;
+          for (int q = 0; q < Q.n_insns; ++q) {
+            rb200_insn& I = Q.insns[q];
+            if (I.a_kind == RB200_K_VIEW && I.a_idx == i) { I.a_kind = RB200_K_REG; I.a_idx = (uint8_t)r; }
+            if (I.b_kind == RB200_K_VIEW && I.b_idx == i && I.op != RB200_OP_RED) { I.b_kind = RB200_K_REG; I.b_idx = (uint8_t)r; }
+            if (I.c_kind == RB200_K_VIEW && I.c_idx == i && I.op != RB200_OP_SINCOS) { I.c_kind = RB200_K_REG; I.c_idx = (uint8_t)r; }
+          }
+        }
+        const size_t reg_bytes1 = (size_t)Q.n_regs * V1 * kThreads * 8;
         Q.bulk = Q.n_pf > 0 ? 1 : 0;
         for (int j = 0; j < Q.n_pf; ++j)
           if ((((uintptr_t)op->views[Q.pf_view[j]].base) & 15u) != 0) Q.bulk = 0;
@@ -310,6 +341,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
           while (Q.n_stages < want && reg_bytes1 + (size_t)Q.n_pf * (Q.n_stages + 1) * V1 * kThreads * 8 <= 108 * 1024) Q.n_stages++;
         }
         pf_bytes1 = (size_t)Q.n_pf * Q.n_stages * V1 * kThreads * 8;
+        if (reg_bytes1 + pf_bytes1 > 200 * 1024) goto general_axis;  // does not fit: use the general kernel
         assign_handlers(Q, op);
         e = launch_vm_elementwise_ax1d(Q, (unsigned)(n_split_eff * n_chunks), reg_bytes1 + pf_bytes1, stream);
         if (e != cudaSuccess) return fail_cuda("vm_elementwise_kernel (axis-as-1-D) launch", e);
@@ -325,6 +357,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
         return 0;
       }
     }
+  general_axis:
     long long blocks = P.n_tiles;
     long long cap = (long long)sms * 4;
     if (blocks > cap) blocks = cap;

@@ -45,8 +45,38 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
   for (int s = 0; s < NS; ++s)
 #pragma unroll
     for (int k = 0; k < (AX1D ? V : 1); ++k) racc[s][k] = red_identity_bits(s < P.n_reds ? P.reds[s].op : 0, s < P.n_reds ? P.reds[s].ctype : 0);
-  if constexpr (AX1D) cx.pe0 = (long long)(blockIdx.x % (unsigned)P.n_split_chunks) * TILE + threadIdx.x;
-  else cx.pe0 = 0;
+  if constexpr (AX1D) {
+    cx.pe0 = (long long)(blockIdx.x % (unsigned)P.n_split_chunks) * TILE + threadIdx.x;
+    cx.e0 = cx.pe0;
+    cx.valid = (1u << V) - 1u;
+    // hoist the row-broadcast operands: this CTA always works on the same column chunk
+#pragma unroll 1
+    for (int h = 0; h < P.n_hoist; ++h) {
+      const KView& vw = P.views[P.hoist_view[h]];
+      long long off[V];
+      cx.offsets(vw, off);
+      u64 bits[V];
+      if (P.hoist_cls[h] == RB200_T_F64) {
+        double t[V];
+        load_view<double, V>(vw.base, vw.dtype, off, cx.valid, t);
+#pragma unroll
+        for (int k = 0; k < V; ++k) bits[k] = CT<double>::bits(t[k]);
+      } else if (P.hoist_cls[h] == RB200_T_F32) {
+        float t[V];
+        load_view<float, V>(vw.base, vw.dtype, off, cx.valid, t);
+#pragma unroll
+        for (int k = 0; k < V; ++k) bits[k] = CT<float>::bits(t[k]);
+      } else {
+        long long t[V];
+        load_view<long long, V>(vw.base, vw.dtype, off, cx.valid, t);
+#pragma unroll
+        for (int k = 0; k < V; ++k) bits[k] = CT<long long>::bits(t[k]);
+      }
+      sts_vec64<V>(cx.reg_base(P.hoist_reg[h]), bits);
+    }
+  } else {
+    cx.pe0 = 0;
+  }
 
   // --- staging of the read-only inputs of tile t into stage `st` (ND == 1 only) --------------
   // full tiles of contiguous, 16-byte aligned views: ONE bulk async copy per view by one thread

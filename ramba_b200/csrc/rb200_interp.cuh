@@ -711,6 +711,15 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
   cx.template finish<T>(I, r);
 }
 
+template <class TS, class TD, int AK, int V, class C> __device__ __forceinline__ void h_cvt(C& cx, const UInsn& I) {
+  TS a[V];
+  TD r[V];
+  fetch_s<TS, AK, V>(cx, I.a_idx(), a);
+#pragma unroll
+  for (int k = 0; k < V; ++k) r[k] = (TD)a[k];
+  cx.template finish<TD>(I, r);
+}
+
 template <class T, int AK, int V, bool AX, int NS, class C>
 __device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[NS][AX ? V : 1]) {
   T a[V];

@@ -55,6 +55,10 @@ struct KParams {
   int red_ndim;
   int n_split_chunks;  // axis-as-1-D mode: column chunks (C / tile) = CTAs per split
   int n_stages;        // depth of the staging ring (2..4)
+  // axis-as-1-D mode: row-broadcast ("periodic") views are loop invariant for a CTA — they are loaded
+  // once into spill registers before the row loop
+  int n_hoist, pad2;
+  int hoist_view[kMaxPf], hoist_reg[kMaxPf], hoist_cls[kMaxPf];
   KView views[RB200_MAX_VIEWS];
   u64 scalars[RB200_MAX_SCALARS];
   rb200_insn insns[RB200_MAX_INSNS];

@@ -726,16 +726,34 @@ __device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[NS][AX 
   fetch_s<T, AK, V>(cx, I.a_idx(), a);
   const int slot = I.b_idx();
   const int rop = (int)I.imm();
-#pragma unroll
-  for (int s = 0; s < NS; ++s)
-    if (s == slot) {
+  if constexpr (!AX) {
+    // fold the thread's V elements first (tree, no per-element branches), then one update of the
+    // accumulator; elements past the end of the box are replaced by the identity
+    const T ident = CT<T>::get(red_identity_bits(rop, std::is_integral<T>::value ? RB200_T_I64 : RB200_T_F64));
+    if (cx.valid != ((1u << V) - 1u)) {
 #pragma unroll
       for (int k = 0; k < V; ++k)
-        if ((cx.valid >> k) & 1u) {
-          u64& t = racc[s][AX ? k : 0];
-          t = CT<T>::bits(red_combine<T>(rop, CT<T>::get(t), a[k]));
-        }
+        if (!((cx.valid >> k) & 1u)) a[k] = ident;
     }
+#pragma unroll
+    for (int w = V / 2; w >= 1; w >>= 1)
+#pragma unroll
+      for (int k = 0; k < w; ++k) a[k] = red_combine<T>(rop, a[k], a[k + w]);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (s == slot) racc[s][0] = CT<T>::bits(red_combine<T>(rop, CT<T>::get(racc[s][0]), a[0]));
+  } else {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (s == slot) {
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if ((cx.valid >> k) & 1u) {
+            u64& t = racc[s][k];
+            t = CT<T>::bits(red_combine<T>(rop, CT<T>::get(t), a[k]));
+          }
+      }
+  }
 }
 
 // one interpreter pass over the op list for the thread's V elements.

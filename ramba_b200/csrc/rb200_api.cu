@@ -73,15 +73,20 @@ constexpr int kRedScratchPartials = 4096;  // max grid size of a launch with glo
 
 // static operand kind of an op-list operand for the specialised handlers (-1: needs the generic path);
 // staged views are addressed by their prefetch slot (*idx is rewritten)
-static int static_kind(const KParams& P, int kind, int* idx, int ctype) {
+static int static_kind(const KParams& P, int set, int kind, int* idx, int ctype) {
   switch (kind) {
     case RB200_K_ACC: return S_ACC;
     case RB200_K_REG: return S_REG;
     case RB200_K_SCAL: return S_SCAL;
     case RB200_K_VIEW: {
       const KView& v = P.views[*idx];
-      if (v.pf_slot < 0) return -1;
       const int own = ctype == RB200_T_F64 ? RB200_F64 : ctype == RB200_T_F32 ? RB200_F32 : RB200_I64;
+      if (set == 2) {  // N-d kernels: direct views
+        if (v.dtype == own) return S_VIEW;
+        if (ctype == RB200_T_F64 && v.dtype == RB200_F32) return S_VIEW32;
+        return -1;
+      }
+      if (v.pf_slot < 0) return -1;
       if (v.dtype == own) {
         *idx = v.pf_slot;
         return S_PFV;
@@ -107,25 +112,25 @@ static unsigned long long host_red_identity_bits(int op, int ctype) {
   return (unsigned long long)i;
 }
 
-static void assign_handlers(KParams& P, const rb200_fused_op* op) {
+static void assign_handlers(KParams& P, const rb200_fused_op* op, int set) {
   for (int i = 0; i < P.n_insns; ++i) {
     rb200_insn I = P.insns[i];
     int h = H_GENERIC;
     int ai = I.a_idx, bi = I.b_idx;
     // CVT fetches its operand in the SOURCE class (imm & 0xff)
-    const int ak = static_kind(P, I.a_kind, &ai, I.op == RB200_OP_CVT ? (int)(I.imm & 0xff) : (int)I.ctype);
+    const int ak = static_kind(P, set, I.a_kind, &ai, I.op == RB200_OP_CVT ? (int)(I.imm & 0xff) : (int)I.ctype);
     if (I.op == RB200_OP_ADD || I.op == RB200_OP_SUB || I.op == RB200_OP_MUL) {
-      const int bk = static_kind(P, I.b_kind, &bi, I.ctype);
-      h = handler_bin(I.op, I.ctype, ak, bk);
+      const int bk = static_kind(P, set, I.b_kind, &bi, I.ctype);
+      h = handler_bin(set, I.op, I.ctype, ak, bk);
     } else if (I.op == RB200_OP_RED) {
-      h = handler_red(I.ctype, ak);
+      h = handler_red(set, I.ctype, ak);
     } else if (I.op == RB200_OP_CVT) {
-      if ((I.imm >> 8) == 0) h = handler_cvt((int)(I.imm & 0xff), I.ctype, ak);
+      if ((I.imm >> 8) == 0) h = handler_cvt(set, (int)(I.imm & 0xff), I.ctype, ak);
     } else if (I.op == RB200_OP_POWI) {
       // only x ** 2 with a scalar exponent (Numba int_power gives exactly x*x)
-      if (I.b_kind == RB200_K_SCAL && (long long)op->scalars[I.b_idx] == 2) h = handler_un(I.op, I.ctype, ak);
+      if (I.b_kind == RB200_K_SCAL && (long long)op->scalars[I.b_idx] == 2) h = handler_un(set, I.op, I.ctype, ak);
     } else if ((I.c_kind == RB200_K_NONE || I.op == RB200_OP_SINCOS) && I.b_kind == RB200_K_NONE) {
-      h = handler_un(I.op, I.ctype, ak);
+      h = handler_un(set, I.op, I.ctype, ak);
     }
     if (h != H_GENERIC) {
       I.a_idx = (uint8_t)ai;
@@ -342,7 +347,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
         }
         pf_bytes1 = (size_t)Q.n_pf * Q.n_stages * V1 * kThreads * 8;
         if (reg_bytes1 + pf_bytes1 > 200 * 1024) goto general_axis;  // does not fit: use the general kernel
-        assign_handlers(Q, op);
+        assign_handlers(Q, op, 1);
         e = launch_vm_elementwise_ax1d(Q, (unsigned)(n_split_eff * n_chunks), reg_bytes1 + pf_bytes1, stream);
         if (e != cudaSuccess) return fail_cuda("vm_elementwise_kernel (axis-as-1-D) launch", e);
         g_launches.fetch_add(1);
@@ -402,7 +407,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     }
   }
   const size_t smem = reg_bytes + pf_bytes;
-  if (op->ndim == 1) assign_handlers(P, op);  // N-d instantiations are generic-only
+  assign_handlers(P, op, op->ndim == 1 ? 1 : 2);
   if (op->n_reds > 0) {
     if (!op->red_scratch) return fail("global reduction needs red_scratch");
     P.red_counter = (unsigned int*)op->red_scratch;

@@ -1,8 +1,7 @@
 // rb200_elementwise_nd3.cu — instantiation of the fused elementwise kernel for iteration rank 3
 // (one translation unit per rank so that they compile in parallel).
-// N-d ops take the generic decode path only (keeps build time down; the 1-D and axis kernels carry
-// the specialised handlers)
-#define RB200_NO_FAST_HANDLERS 1
+// N-d ops use handler set 2 (direct views instead of staged ones)
+#define RB200_HANDLER_SET 2
 #include "rb200_elementwise.cuh"
 namespace rb200 {
 cudaError_t launch_vm_elementwise_nd3(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {

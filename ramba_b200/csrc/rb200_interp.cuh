@@ -638,9 +638,19 @@ template <class T, int SK, int V, class C> __device__ __forceinline__ void fetch
     const unsigned slot_s = cx.pf_s + (unsigned)(i * V * kThreads * 8);
     if constexpr (sizeof(T) == 8) lds_vec64<T, V>(slot_s + cx.tid * 8u, out);
     else lds_vec32<T, V>(slot_s + cx.tid * 4u, out);
-  } else {  // S_PFV32: staged float32 view read in float64
+  } else if constexpr (SK == S_PFV32) {  // staged float32 view read in float64
     const unsigned slot_s = cx.pf_s + (unsigned)(i * V * kThreads * 8);
     if constexpr (std::is_same<T, double>::value) lds_vec32_as_f64<V>(slot_s + cx.tid * 4u, out);
+  } else if constexpr (SK == S_VIEW) {  // direct view in T's own storage type
+    const KView& vw = cx.P.views[i];
+    long long off[V];
+    cx.offsets(vw, off);
+    load_direct<T, T, V>(vw.base, off, cx.valid, out);
+  } else {  // S_VIEW32: direct float32 view read in float64
+    const KView& vw = cx.P.views[i];
+    long long off[V];
+    cx.offsets(vw, off);
+    if constexpr (std::is_same<T, double>::value) load_direct<double, float, V>(vw.base, off, cx.valid, out);
   }
 }
 
@@ -769,7 +779,11 @@ template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_p
 #ifndef RB200_NO_FAST_HANDLERS
     const int h = P.handler[pc];
     if (h != H_GENERIC) {
-#include "rb200_handlers.inc"
+#if RB200_HANDLER_SET == 2
+#include "rb200_handlers_set2.inc"
+#else
+#include "rb200_handlers_set1.inc"
+#endif
       continue;
     }
 #endif

@@ -406,7 +406,27 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
       pf_bytes = (size_t)P.n_pf * 2 * V * kThreads * 8;
     }
   }
-  const size_t smem = reg_bytes + pf_bytes;
+  size_t ocls_bytes = 0;
+  if (op->ndim > 1) {
+    // offset classes: views with identical stride vectors (the shifted views of a stencil, operands
+    // of the same shape) share their per-tile element offsets
+    for (int i = 0; i < op->n_views; ++i) {
+      int c = -1;
+      for (int q = 0; q < P.n_ocls && c < 0; ++q) {
+        bool same = true;
+        for (int d = 0; d < op->ndim; ++d)
+          if (op->views[P.ocls_view[q]].stride[d] != op->views[i].stride[d]) same = false;
+        if (same) c = q;
+      }
+      if (c < 0 && P.n_ocls < kMaxOcls) {
+        c = P.n_ocls;
+        P.ocls_view[P.n_ocls++] = i;
+      }
+      P.views[i].pf_slot = c;
+    }
+    ocls_bytes = (size_t)P.n_ocls * V * kThreads * 8;
+  }
+  const size_t smem = reg_bytes + pf_bytes + ocls_bytes;
   assign_handlers(P, op, op->ndim == 1 ? 1 : 2);
   if (op->n_reds > 0) {
     if (!op->red_scratch) return fail("global reduction needs red_scratch");

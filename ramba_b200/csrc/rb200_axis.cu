@@ -20,6 +20,7 @@ template <int V> __global__ void __launch_bounds__(kThreads, 2) vm_axis_reduce_k
   cx.regfile_s = smem_s + threadIdx.x * 8u;
   cx.pf_s = 0;
   cx.tid = threadIdx.x;
+  cx.ocls_s = 0;
   const int nk0 = P.red_ndim;       // first kept dim
   const long long kept = P.total;   // kept elements
   const long long tiles_per_split = (kept + TILE - 1) / TILE;

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
   const bool bulk = (ND == 1) && n_pf > 0 && P.bulk;
   const unsigned S = bulk ? (unsigned)P.n_stages : 2u;  // ring depth: prefetch distance S-1 tiles
   cx.regfile_s = smem_s + (n_pf > 0 ? S : 0u) * pf_stage_bytes + threadIdx.x * 8u;
+  cx.ocls_s = cx.regfile_s + (unsigned)(P.n_regs * V * kThreads * 8);  // offset-class table follows the register file
   cx.pf_s = pf_base;
   const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&mbar_store[0]);
   if (bulk) {
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
       }
     }
     cx.valid = valid;
+    cx.fill_offset_classes();
     run_program<V, AX1D, NS>(cx, racc);
   }
   if (n_pf > 0 && !bulk) cp_async_wait<0>();

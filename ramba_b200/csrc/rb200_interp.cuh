@@ -91,6 +91,7 @@ template <int V, int ND> struct Ctx {
   const KParams& P;      // the __grid_constant__ kernel parameter: constant-bank (LDC) accesses
   unsigned regfile_s;    // shared-window byte address of this thread's column of the register file
   unsigned pf_s;         // shared-window byte address of the current prefetch stage (element e of slot j at pf_s + j*V*2048 + e*itemsize)
+  unsigned ocls_s;       // ND > 1: shared-window byte address of this thread's column of the offset-class table
   unsigned tid;
   long long e0;          // ND == 1: index of element 0 of this thread in the tile
   long long pe0;         // ND == 1, axis-as-1-D mode: e0 modulo the period of "periodic" (row-broadcast) views
@@ -112,12 +113,36 @@ template <int V, int ND> struct Ctx {
         o += step;
       }
     } else {
+      const int c = vw.pf_slot;  // offset class: offsets were computed once for this tile
+      if (c >= 0) {
+        lds_vec64<long long, V>(ocls_s + (unsigned)(c * V * kThreads * 8), off);
+        return;
+      }
+      compute_offsets(vw, off);
+    }
+  }
+  __device__ __forceinline__ void compute_offsets(const KView& vw, long long (&off)[V]) const {
+    if constexpr (ND > 1) {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         long long o = 0;
 #pragma unroll
         for (int d = 0; d < ND; ++d) o += idx[k][d] * vw.stride[d];
         off[k] = o;
+      }
+    }
+  }
+  // ND > 1: after the tile's indices are decoded, compute the element offsets of every offset class
+  __device__ __forceinline__ void fill_offset_classes() {
+    if constexpr (ND > 1) {
+#pragma unroll 1
+      for (int c = 0; c < P.n_ocls; ++c) {
+        long long off[V];
+        compute_offsets(P.views[P.ocls_view[c]], off);
+        u64 b[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) b[k] = (u64)off[k];
+        sts_vec64<V>(ocls_s + (unsigned)(c * V * kThreads * 8), b);
       }
     }
   }
@@ -139,7 +164,7 @@ template <int V, int ND> struct Ctx {
         const KView& vw = P.views[i];
         const int slot = vw.pf_slot;
         const int dt = vw.dtype;
-        if (slot >= 0) {
+        if (ND == 1 && slot >= 0) {  // (N-d kernels reuse pf_slot as the offset class)
           const unsigned slot_s = pf_s + (unsigned)(slot * V * kThreads * 8);
 #pragma unroll
           for (int k = 0; k < V; ++k) out[k] = staged_load<T>(slot_s, k * kThreads + (int)tid, dt);

@@ -23,13 +23,15 @@ typedef unsigned long long u64;
 
 constexpr int kThreads = 256;
 constexpr int kMaxD = RB200_MAX_DIMS;
-constexpr int kMaxPf = 4;  // input views staged through shared memory
+constexpr int kMaxPf = 4;    // input views staged through shared memory
+constexpr int kMaxOcls = 6;  // N-d kernels: distinct stride signatures whose element offsets are cached per tile
 
 struct KView {
   char* base;
   long long stride[kMaxD];  // elements
   int dtype;
-  int pf_slot;  // >= 0: staged into prefetch slot pf_slot; -1: read directly; -2: read directly, periodic (axis-as-1-D)
+  int pf_slot;  // 1-D: >= 0: staged into prefetch slot pf_slot; -1: read directly; -2: read directly, periodic (axis-as-1-D)
+                // N-d: >= 0: offset class (views with identical strides share per-tile element offsets); -1: none
 };
 
 struct KRed {
@@ -57,7 +59,9 @@ struct KParams {
   int n_stages;        // depth of the staging ring (2..4)
   // axis-as-1-D mode: row-broadcast ("periodic") views are loop invariant for a CTA — they are loaded
   // once into spill registers before the row loop
-  int n_hoist, pad2;
+  int n_hoist;
+  int n_ocls;  // N-d kernels: number of offset classes; ocls_view[c] = a view carrying class c's strides
+  int ocls_view[kMaxOcls];
   int hoist_view[kMaxPf], hoist_reg[kMaxPf], hoist_cls[kMaxPf];
   KView views[RB200_MAX_VIEWS];
   u64 scalars[RB200_MAX_SCALARS];

@@ -255,6 +255,8 @@ class Lowering:
             if cls == T_I64:
                 cls = T_F64
             return self._node("pow", cls, cls, False, [self.coerce(x, cls), self.coerce(y, cls)])
+        if op in ("add", "mul") and x.kind == "scal" and y.kind != "scal":
+            x, y = y, x  # commutative: keep the scalar as the second operand (the specialised handlers expect it there)
         if op in _ARITH:
             cls = unify_cls(x.cls, y.cls, x.is_bool, y.is_bool)
             is_bool = False

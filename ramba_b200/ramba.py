@@ -822,13 +822,15 @@ class ndarray:
         return self
 
     # ---- host round trip (ramba/ramba.py:5735-5765)
-    def asarray(self, out=None):
-        """NumPy copy of the whole array on every rank.  `out` (optional, ramba_b200 extension):
-        a preallocated C-contiguous host array (e.g. a view of pinned memory) to fill."""
+    def asarray(self, out=None, non_blocking=False):
+        """NumPy copy of the whole array on every rank.  ramba_b200 extensions: `out`, a preallocated
+        C-contiguous host array (e.g. a view of pinned memory) to fill; `non_blocking=True` (single
+        rank, pinned `out`) only enqueues the device->host copy on the current CUDA stream — the
+        caller synchronises before reading `out` (lets transfers of different streams overlap)."""
         if self.shape == ():
             return self.distribution
         deferred_op.do_ops()
-        return gather_to_host(self, out=out)
+        return gather_to_host(self, out=out, non_blocking=non_blocking)
 
     def __array__(self, dtype=None, copy=None):
         a = self.asarray()
@@ -1272,7 +1274,7 @@ def _is_whole_shard(sv, sh):
                                                 and int(sv.size[d]) == sh.shape[d] for d in range(k)))
 
 
-def _part_to_host(nd, w, out=None):
+def _part_to_host(nd, w, out=None, non_blocking=False):
     """This worker's part of view `nd` as a contiguous host array (get_view, ramba/ramba.py:2160-2176)."""
     import torch
 
@@ -1287,7 +1289,8 @@ def _part_to_host(nd, w, out=None):
     if _is_whole_shard(sv, sh) and nd.dtype != np.bool_:
         n = int(np.prod(shape))
         if out is not None and out.flags.c_contiguous and out.dtype == nd.dtype and out.size == n:
-            torch.from_numpy(out.reshape(-1)).copy_(sh.buf[:n])  # straight DMA (pinned `out`: full PCIe rate)
+            # straight DMA (pinned `out`: full PCIe rate)
+            torch.from_numpy(out.reshape(-1)).copy_(sh.buf[:n], non_blocking=non_blocking)
             return out.reshape(shape)
         return sh.buf[:n].cpu().numpy().reshape(shape)
     bc = [int(a) < 0 for a in sv.axis_map]
@@ -1304,7 +1307,7 @@ def _part_to_host(nd, w, out=None):
     return host
 
 
-def gather_to_host(nd, out=None):
+def gather_to_host(nd, out=None, non_blocking=False):
     """Full NumPy copy of a distributed view on every rank (asarray, ramba/ramba.py:5735-5765)."""
     import torch
 
@@ -1313,7 +1316,7 @@ def gather_to_host(nd, out=None):
         sv = nd.distribution[0]
         if shardview.is_empty(sv):
             return np.empty(nd.shape, dtype=nd.dtype) if out is None else out
-        mine = _part_to_host(nd, w, out=out)
+        mine = _part_to_host(nd, w, out=out, non_blocking=non_blocking)
         if tuple(mine.shape) == tuple(nd.shape):
             return mine
         ret = np.empty(nd.shape, dtype=nd.dtype) if out is None else out
@@ -1410,10 +1413,10 @@ def fromarray_local(block, shape, dtype=None, **kwargs):
     return new
 
 
-def local_block_to_host(nd, out=None):
+def local_block_to_host(nd, out=None, non_blocking=False):
     """SPMD extension: this rank's block of `nd` as a host array (no gather)."""
     deferred_op.do_ops()
-    return _part_to_host(nd, common.worker_num, out=out)
+    return _part_to_host(nd, common.worker_num, out=out, non_blocking=non_blocking)
 
 
 def array(x, dtype=None, copy=True, **kwargs):

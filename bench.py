@@ -11,6 +11,7 @@ Weak scaling: every GPU owns `--n` (default 1e9) elements of one global array.
 Inputs (8 GB per GPU) are far larger than the 126 MB L2, so no explicit L2 flush is needed.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -211,6 +212,7 @@ def run_ours(args):
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    gc.disable()  # like timeit: no collector pauses inside the timed region
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
@@ -218,6 +220,7 @@ def run_ours(args):
     e1.record()
     barrier()
     wall = time.perf_counter() - t0
+    gc.enable()
     launches = _cabi.launch_count()
     clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)

@@ -167,9 +167,13 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
     unsigned valid = 0;
     if constexpr (ND == 1) {
       cx.e0 = e0;
+      if ((tile + 1) * TILE <= P.total) {  // full tile (uniform): no per-element bounds checks
+        valid = (1u << V) - 1u;
+      } else {
 #pragma unroll
-      for (int k = 0; k < V; ++k)
-        if (e0 + (long long)k * kThreads < P.total) valid |= (1u << k);
+        for (int k = 0; k < V; ++k)
+          if (e0 + (long long)k * kThreads < P.total) valid |= (1u << k);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < V; ++k) {

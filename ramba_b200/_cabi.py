@@ -102,7 +102,8 @@ _LIB = None
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libramba_b200.so")
+    # RAMBA_B200_LIB: A/B-test another build of the same ABI (development aid)
+    return os.environ.get("RAMBA_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libramba_b200.so")
 
 
 class CabiError(RuntimeError):

@@ -11,7 +11,7 @@ from numpy import (bool_, dtype, e, float32, float64, inf, int8, int16, int32, i
 from . import common  # noqa: F401
 from .ramba import *  # noqa: F401,F403
 from .ramba import (ndarray, bdarray, deferred_op, sync, arange, empty, zeros, ones, full, fromarray, fromfunction,  # noqa: F401
-                    asarray, array, where, HANDLED_FUNCTIONS, fromarray_local, local_block_to_host)
+                    asarray, array, where, HANDLED_FUNCTIONS, fromarray_local, local_block_to_host, stencil, sstencil)
 from . import ramba as _ramba
 
 globals().update(_ramba.api)  # abs/min/max/sum/all/any shadow the builtins like in the reference

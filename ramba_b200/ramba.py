@@ -1744,6 +1744,82 @@ for _n in ("where", "clip", "transpose", "swapaxes", "moveaxis", "broadcast_to",
     HANDLED_FUNCTIONS[_n] = globals()[_n]
 
 
+# ---- stencil skeleton (ramba/ramba.py:441-541, 9987-10054) ---------------------------------------
+class StencilMetadata:
+    """`@stencil` function with relative indexing (`a[-1, 0] + a[1, 0]`).  The reference compiles it
+    with numba.stencil; here it is evaluated symbolically: every relative access becomes a shifted
+    slice view of the interior, so the whole stencil is one fused op on the N-d kernel."""
+
+    def __init__(self, func):
+        self.func = func
+        self.neighborhood = None
+
+    def __call__(self, *args, **kwargs):
+        return sstencil(self, *args, **kwargs)
+
+
+def stencil(*args, **kwargs):
+    if len(args) == 1 and callable(args[0]) and not kwargs:
+        return StencilMetadata(args[0])
+
+    def rdec(func):
+        return StencilMetadata(func)
+
+    return rdec
+
+
+class _RelRecorder:
+    """First pass: records the relative offsets a stencil function touches."""
+
+    def __init__(self, ndim, offsets):
+        self.ndim, self.offsets = ndim, offsets
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        if len(idx) != self.ndim or not builtins.all(isinstance(i, numbers.Integral) for i in idx):
+            raise IndexError("stencil functions index their array arguments with one constant relative offset per dimension")
+        self.offsets.append(tuple(int(i) for i in idx))
+        return 1.0
+
+
+class _RelView:
+    """Second pass: a relative access is the interior box shifted by the offset."""
+
+    def __init__(self, arr, lo, hi):
+        self.arr, self.lo, self.hi = arr, lo, hi
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        sl = tuple(slice(-self.lo[d] + idx[d], self.arr.shape[d] - self.hi[d] + idx[d]) for d in range(len(idx)))
+        return self.arr[sl]
+
+
+def sstencil(func, *args, out=None, **kwargs):
+    """Apply a `@stencil` function to distributed arrays: interior = stencil expression, border = 0
+    (numba.stencil's cval) or left untouched when `out` is given."""
+    if not isinstance(func, StencilMetadata):
+        func = StencilMetadata(func)
+    arrays = [a for a in args if isinstance(a, ndarray)]
+    assert len(arrays) > 0, "sstencil needs at least one distributed array argument"
+    shape = arrays[0].shape
+    for a in arrays:
+        assert a.shape == shape, "sstencil: array arguments must have the same shape"
+    k = len(shape)
+    if func.neighborhood is None:
+        offs = []
+        func.func(*[_RelRecorder(k, offs) if isinstance(a, ndarray) else a for a in args])
+        lo = tuple(builtins.min([0] + [o[d] for o in offs]) for d in range(k))
+        hi = tuple(builtins.max([0] + [o[d] for o in offs]) for d in range(k))
+        func.neighborhood = tuple((lo[d], hi[d]) for d in range(k))
+    lo = tuple(n[0] for n in func.neighborhood)
+    hi = tuple(n[1] for n in func.neighborhood)
+    res = func.func(*[_RelView(a, lo, hi) if isinstance(a, ndarray) else a for a in args])
+    new = out if out is not None else zeros(shape, dtype=res.dtype if isinstance(res, ndarray) else np.float64)
+    interior = tuple(slice(-lo[d], shape[d] - hi[d]) for d in range(k))
+    new[interior] = res
+    return new
+
+
 def sync():
     """Flush pending fused ops and wait for this rank's GPU (ramba/ramba.py:9843-9849)."""
     t0 = timer()

@@ -220,6 +220,27 @@ def stencil_3d_laplacian(np):
     return [_h(v)]
 
 
+@case
+def sstencil_skeleton(np):
+    # TestStencil::test1-style: a relative-index stencil function applied to a distributed array
+    def star(a):
+        return 0.25 * (a[-1, 0] + a[1, 0] + a[0, -1] + a[0, 1]) + a[0, 0]
+
+    def wide(a, b):
+        return a[0, -2] + a[0, 2] - 2.0 * b[0, 0]
+
+    n, m = 30, 40
+    x = np.fromfunction(lambda i, j: (i * 7 + j * 3) % 16, (n, m))
+    y = np.fromfunction(lambda i, j: (i + j) % 5, (n, m))
+    if np is onp:
+        r1 = onp.zeros((n, m))
+        r1[1:-1, 1:-1] = 0.25 * (x[:-2, 1:-1] + x[2:, 1:-1] + x[1:-1, :-2] + x[1:-1, 2:]) + x[1:-1, 1:-1]
+        r2 = onp.zeros((n, m))
+        r2[:, 2:-2] = x[:, :-4] + x[:, 4:] - 2.0 * y[:, 2:-2]
+        return [r1, r2]
+    return [_h(np.sstencil(np.stencil(star), x)), _h(np.stencil(wide)(x, y))]
+
+
 # ---- apps (TestApps): pi integration, manual matmul via broadcast + axis sum
 @case
 def pi_integration(np):

@@ -1828,6 +1828,23 @@ def sync():
     add_time("sync", timer() - t0)
 
 
+def timing_summary():
+    """Per-phase wall-clock totals (RAMBA_TIMING, ramba/ramba.py:954-997, 7620-7627)."""
+    txt = common.get_timing_str(details=True)
+    if txt:
+        print("ramba_b200 timing (rank %d):\n%s\nlaunches: %d, bytes sent to peers: %d" % (common.worker_num, txt, RT.launches, RT.bytes_sent))
+
+
+def print_comm_stats():
+    print("ramba_b200 rank %d: %d bytes sent to peers, %d kernel launches" % (common.worker_num, RT.bytes_sent, RT.launches))
+
+
+if common.ntiming > 0:
+    import atexit
+
+    atexit.register(timing_summary)
+
+
 def get_timing(details=False):
     return common.get_timing(details)
 

@@ -120,6 +120,7 @@ def cpu_chain_baseline(n, iters, warm=1):
     A = np.empty(n, dtype=np.float64)
     B = np.empty_like(A); C = np.empty_like(A); D = np.empty_like(A)
     chain.chain_f64(A, B, C, D, global_start=0, make_A=True)
+    chain.calibrate_threads(A, B, C, D)  # all logical CPUs vs one thread per physical core: keep the faster
     for _ in range(warm):
         chain.chain_f64(A, B, C, D)
     best = []
@@ -143,6 +144,7 @@ def run_reference(args):
     A = np.empty(n, dtype=np.float64)
     B = np.empty_like(A); C = np.empty_like(A); D = np.empty_like(A)
     chain.chain_f64(A, B, C, D, global_start=0, make_A=True)  # parallel first touch
+    chain.calibrate_threads(A, B, C, D)  # all logical CPUs vs one thread per physical core: keep the faster
     for _ in range(max(1, args.warmup)):
         chain.chain_f64(A, B, C, D)
     t0 = time.perf_counter()

@@ -19,6 +19,8 @@ def lib():
         L.sum_affine_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double]
         L.sum_affine_f32.restype = ctypes.c_double
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+        L.oracle_set_num_threads.restype = None
         _LIB = L
     return _LIB
 
@@ -36,3 +38,27 @@ def sum_affine_f32(X, mul, add):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+def calibrate_threads(A, B, C, D):
+    """Pick the faster of {all logical CPUs, half of them (one per physical core with SMT)} for the
+    chain loop — the CPU baseline should be the reference path at its best on this host."""
+    import os
+    import time
+
+    cands = sorted({os.cpu_count() or 1, max(1, (os.cpu_count() or 2) // 2)}, reverse=True)
+    best = None
+    for t in cands:
+        set_num_threads(t)
+        chain_f64(A, B, C, D)
+        t0 = time.perf_counter()
+        chain_f64(A, B, C, D)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, t)
+    set_num_threads(best[1])
+    return best[1]

@@ -51,3 +51,4 @@ double sum_affine_f32(const float* X, int64_t n, double mul, double add) {
 }
 
 int oracle_num_threads(void) { return omp_get_max_threads(); }
+void oracle_set_num_threads(int n) { omp_set_num_threads(n); }

@@ -527,7 +527,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                         RT.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
                                   [(src_ptr, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
                                    (buf.data_ptr(), cst, vcode[i])])
-                        ops.append(dist.P2POp(dist.isend, buf, peer))
+                        ops.append(dist.P2POp(dist.isend, buf.view(torch.uint8), peer))
                         sends_keep.append(buf)
                         RT.bytes_sent += buf.numel() * buf.element_size()
                 # what I need from `peer`
@@ -537,7 +537,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                         shp = [1 if bc[d] else int(part.size[d]) for d in range(len(bc))]
                         cst, n = _contig_strides(shp, bc)
                         buf = torch.empty(max(n, 1), dtype=torch_dtype(views[i][1].dtype), device=RT.device)
-                        ops.append(dist.P2POp(dist.irecv, buf, peer))
+                        ops.append(dist.P2POp(dist.irecv, buf.view(torch.uint8), peer))
                         recv_bufs.append(buf)
                         parts[i].append((shardview.clean_range(part), buf.data_ptr(), cst, None))
         if ops:
@@ -1327,19 +1327,23 @@ def gather_to_host(nd, out=None, non_blocking=False):
     RT.ensure_process_group()
     import torch.distributed as dist
 
+    store_dt = np.dtype(np.uint8) if nd.dtype == np.bool_ else nd.dtype
     for i in range(W):
         sv = nd.distribution[i]
         if shardview.is_empty(sv):
             continue
         shape = [int(x) for x in sv.size]
+        nbytes = int(np.prod(shape)) * store_dt.itemsize
+        # collectives move raw bytes: not every backend knows uint16/uint32
         if i == w:
-            t = torch.from_numpy(np.ascontiguousarray(mine.astype(np.uint8) if nd.dtype == np.bool_ else mine))
+            host = np.ascontiguousarray(mine.astype(np.uint8) if nd.dtype == np.bool_ else mine)
+            t = torch.from_numpy(host.view(np.uint8).reshape(-1))
         else:
-            t = torch.empty(shape, dtype=torch_dtype(nd.dtype))
+            t = torch.empty(nbytes, dtype=torch.uint8)
         if not RT.test_mode:
             t = t.to(RT.device)
         dist.broadcast(t, src=i)
-        part = t.cpu().numpy()
+        part = t.cpu().numpy().view(store_dt).reshape(shape)
         if nd.dtype == np.bool_:
             part = part.astype(np.bool_)
         ret[shardview.to_slice(sv)] = part

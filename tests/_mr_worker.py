@@ -25,7 +25,11 @@ def main():
     names = sys.argv[1].split(",")
     RT.ensure_process_group()
     failures = []
-    for prog in _programs.ALL:
+    import test_api_parity
+    import test_edges
+
+    progs = list(_programs.ALL) + list(test_api_parity.CASES) + [test_edges._ragged, test_edges._empty, test_edges._dtypes]
+    for prog in progs:
         if prog.__name__ not in names and names != ["all"]:
             continue
         got = prog(rb)

@@ -43,7 +43,7 @@ def _run(world, names):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_programs_multirank(world):
     outs = _run(world, "all")
     # the stencil / broadcast / axis-sum programs must really have crossed ranks

@@ -84,6 +84,41 @@ __device__ __noinline__ void store_line(char* base, int dtype, long long off0, l
   }
 }
 
+// Everything about a 1-D store that is not "full tile, contiguous, own dtype": write masks, ragged
+// tiles, strided or converting views.  Out of line so that the specialised handlers stay small (the
+// hot loop's instruction footprint is what the kernel is sensitive to).
+template <class R, int V>
+__device__ __noinline__ void store_slow_1d(char* base, int dtype, long long stride, long long e0, unsigned valid, unsigned mask_addr,
+                                           u64 b0, u64 b1, u64 b2, u64 b3, u64 b4, u64 b5, u64 b6, u64 b7) {
+  static_assert(V == 4 || V == 8, "store_slow_1d handles 4 or 8 elements per thread");
+  unsigned m = valid;
+  if (mask_addr != 0xffffffffu) {
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      if (lds64(mask_addr + (unsigned)(k * kThreads * 8)) == 0ull) m &= ~(1u << k);
+  }
+  const long long step = stride * kThreads;
+  store_line<R>(base, dtype, e0 * stride, step, m & 0xfu, b0, b1, b2, b3);
+  if constexpr (V == 8) store_line<R>(base, dtype, (e0 + 4ll * kThreads) * stride, step, (m >> 4) & 0xfu, b4, b5, b6, b7);
+}
+
+// N-d counterpart (V == 4): explicit element offsets
+template <class R>
+__device__ __noinline__ void store_slow_nd(char* base, int dtype, unsigned mask, long long o0, long long o1, long long o2, long long o3, u64 b0,
+                                           u64 b1, u64 b2, u64 b3) {
+  constexpr int V = 4;
+  long long off[V] = {o0, o1, o2, o3};
+  R r[V] = {CT<R>::get(b0), CT<R>::get(b1), CT<R>::get(b2), CT<R>::get(b3)};
+  if (dtype == RB200_BOOL) {
+    long long b[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
+    store_view<long long, V>(base, RB200_U8, off, mask, b);
+  } else {
+    store_view<R, V>(base, dtype, off, mask, r);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-thread interpreter state.  ND = number of iteration dims this instantiation handles
 // (ND == 1: collapsed 1-D op, the hot path; element k of the thread is e0 + k*256).
@@ -248,13 +283,46 @@ template <int V, int ND> struct Ctx {
     for (int k = 0; k < V; ++k) acc[k] = CT<R>::bits(r[k]);
     if (I.st_reg() != RB200_NOSTORE) sts_vec64<V>(reg_base(I.st_reg()), acc);
     if (I.st_view() != RB200_NOSTORE) {
-      unsigned m = valid;
-      if (I.mask_reg() != RB200_NOSTORE) {
+      if constexpr (ND == 1 && (V == 4 || V == 8)) {
+        const KView& vw = P.views[I.st_view()];
+        constexpr int own1 = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+        const long long st = vw.stride[0];
+        if (vw.dtype == own1 && st == 1 && valid == ((1u << V) - 1u) && I.mask_reg() == RB200_NOSTORE) {
+          R* p = reinterpret_cast<R*>(vw.base) + e0;
 #pragma unroll
-        for (int k = 0; k < V; ++k)
-          if (lds64(reg_addr(I.mask_reg(), k)) == 0ull) m &= ~(1u << k);
+          for (int k = 0; k < V; ++k) stg<R>(p + k * kThreads, r[k]);
+        } else {
+          const unsigned maddr = I.mask_reg() == RB200_NOSTORE ? 0xffffffffu : reg_base(I.mask_reg());
+          store_slow_1d<R, V>(vw.base, vw.dtype, st, e0, valid, maddr, acc[0], acc[1], acc[2], acc[3], V == 8 ? acc[4 % V] : 0ull,
+                              V == 8 ? acc[5 % V] : 0ull, V == 8 ? acc[6 % V] : 0ull, V == 8 ? acc[7 % V] : 0ull);
+        }
+      } else if constexpr (ND > 1 && V == 4) {
+        const KView& vw = P.views[I.st_view()];
+        constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+        long long off[V];
+        offsets(vw, off);
+        if (vw.dtype == own && valid == 0xfu && I.mask_reg() == RB200_NOSTORE) {
+          R* p = reinterpret_cast<R*>(vw.base);
+#pragma unroll
+          for (int k = 0; k < V; ++k) stg<R>(p + off[k], r[k]);
+        } else {
+          unsigned m = valid;
+          if (I.mask_reg() != RB200_NOSTORE) {
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+              if (lds64(reg_addr(I.mask_reg(), k)) == 0ull) m &= ~(1u << k);
+          }
+          store_slow_nd<R>(vw.base, vw.dtype, m, off[0], off[1], off[2], off[3], acc[0], acc[1], acc[2], acc[3]);
+        }
+      } else {
+        unsigned m = valid;
+        if (I.mask_reg() != RB200_NOSTORE) {
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            if (lds64(reg_addr(I.mask_reg(), k)) == 0ull) m &= ~(1u << k);
+        }
+        store_out<R>(I.st_view(), r, acc, m);
       }
-      store_out<R>(I.st_view(), r, acc, m);
     }
   }
 };

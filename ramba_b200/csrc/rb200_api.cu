@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <string>
@@ -150,6 +151,8 @@ void rb200_reset_launch_count(void) { g_launches.store(0); }
 int rb200_device_sm_count(void) { return sm_count(); }
 int64_t rb200_red_scratch_bytes(void) { return (int64_t)(256 + 8 * RB200_MAX_REDS * kRedScratchPartials); }
 
+
+
 int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   if (!op) return fail("null fused op");
   if (op->abi_version != RB200_ABI_VERSION) return fail("ABI version mismatch between caller and libramba_b200");
@@ -231,7 +234,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     for (int d = 0; d < op->ndim; ++d) k.stride[d] = v.stride[d];
   }
   cudaError_t e;
-  const size_t reg_bytes = (size_t)op->n_regs * V * kThreads * 8;
+  const size_t reg_bytes = (size_t)(op->n_regs + 1) * V * kThreads * 8;  // + the scratch column of the out-of-line stores
 
   if (op->n_axis_red_dims != 0) {
     // axis mode: the first n_axis_red_dims dims are the reduced ones (host permutes)
@@ -336,15 +339,11 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
             if (I.c_kind == RB200_K_VIEW && I.c_idx == i && I.op != RB200_OP_SINCOS) { I.c_kind = RB200_K_REG; I.c_idx = (uint8_t)r; }
           }
         }
-        const size_t reg_bytes1 = (size_t)Q.n_regs * V1 * kThreads * 8;
+        const size_t reg_bytes1 = (size_t)(Q.n_regs + 1) * V1 * kThreads * 8;
         Q.bulk = Q.n_pf > 0 ? 1 : 0;
         for (int j = 0; j < Q.n_pf; ++j)
           if ((((uintptr_t)op->views[Q.pf_view[j]].base) & 15u) != 0) Q.bulk = 0;
         Q.n_stages = 2;
-        if (Q.bulk) {
-          const int want = 2;  // deeper rings measured slower (config 2: -7 %, config 3: no gain); kept configurable
-          while (Q.n_stages < want && reg_bytes1 + (size_t)Q.n_pf * (Q.n_stages + 1) * V1 * kThreads * 8 <= 108 * 1024) Q.n_stages++;
-        }
         pf_bytes1 = (size_t)Q.n_pf * Q.n_stages * V1 * kThreads * 8;
         if (reg_bytes1 + pf_bytes1 > 200 * 1024) goto general_axis;  // does not fit: use the general kernel
         assign_handlers(Q, op, 1);
@@ -374,6 +373,18 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
 
   P.total = total;
   P.n_tiles = (total + TILE - 1) / TILE;
+  P.row_chunks = 0;
+  if (op->ndim > 1) {
+    // row mode: tiles are cut along the innermost dim only, so the outer indices are decoded once per
+    // tile instead of once per element (no per-element divisions); used when rows fill their tiles well
+    const long long inner = op->itershape[op->ndim - 1];
+    const long long chunks = (inner + TILE - 1) / TILE;
+    static const bool row_mode_off = getenv("RB200_NO_ROW_MODE") != nullptr;  // debugging aid: always take the flat mode
+    if (!row_mode_off && inner * 5 >= chunks * TILE * 4 && chunks < (1ll << 30)) {
+      P.row_chunks = (int)chunks;
+      P.n_tiles = (total / inner) * chunks;
+    }
+  }
   P.wide = (total >= (1ll << 31)) ? 1 : 0;
   // stage read-only 4/8-byte input views of 1-D ops one tile ahead through shared memory
   size_t pf_bytes = 0;
@@ -387,23 +398,13 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
         P.n_pf++;
       }
     }
-    // ring depth: light programs finish a tile faster than HBM + copy-engine latency, so they get
-    // a deeper ring (prefetch distance n_stages-1 tiles) as far as shared memory allows
-    P.n_stages = 2;
-    if (P.n_pf > 0) {
-      const int want = 2;  // deeper rings measured slower (config 2: -7 %, config 3: no gain); kept configurable
-      while (P.n_stages < want && reg_bytes + (size_t)P.n_pf * (P.n_stages + 1) * V * kThreads * 8 <= 108 * 1024) P.n_stages++;
-    }
+    P.n_stages = 2;  // two-stage ring: the next tile is in flight while the current one is interpreted
     pf_bytes = (size_t)P.n_pf * P.n_stages * V * kThreads * 8;
     // whole-tile bulk copies need contiguous, 16-byte aligned sources
     P.bulk = P.n_pf > 0 ? 1 : 0;
     for (int j = 0; j < P.n_pf; ++j) {
       const rb200_view& v = op->views[P.pf_view[j]];
       if (v.stride[0] != 1 || (((uintptr_t)v.base) & 15u) != 0) P.bulk = 0;
-    }
-    if (!P.bulk && P.n_pf > 0) {
-      P.n_stages = 2;
-      pf_bytes = (size_t)P.n_pf * 2 * V * kThreads * 8;
     }
   }
   size_t ocls_bytes = 0;

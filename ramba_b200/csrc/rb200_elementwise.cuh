@@ -14,7 +14,10 @@ namespace rb200 {
 // broadcast over the rows are "periodic" (pf_slot == -2), and the per-CTA accumulators are written as
 // partials[(split)*C + column] with split = blockIdx / (C/TILE).
 template <int V, int ND, bool AX1D = false>
-__global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elementwise_kernel(const __grid_constant__ KParams P) {
+#ifndef RB200_MIN_BLOCKS
+#define RB200_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : RB200_MIN_BLOCKS) vm_elementwise_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) u64 mbar_store[4];
   constexpr int TILE = kThreads * V;
@@ -27,9 +30,9 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
   const unsigned pf_base = smem_s;
   const unsigned pf_stage_bytes = (unsigned)n_pf * SLOT;
   const bool bulk = (ND == 1) && n_pf > 0 && P.bulk;
-  const unsigned S = bulk ? (unsigned)P.n_stages : 2u;  // ring depth: prefetch distance S-1 tiles
+  constexpr unsigned S = 2u;  // ring depth (deeper rings measured no faster, see profiles/r01_optimisation_log.md)
   cx.regfile_s = smem_s + (n_pf > 0 ? S : 0u) * pf_stage_bytes + threadIdx.x * 8u;
-  cx.ocls_s = cx.regfile_s + (unsigned)(P.n_regs * V * kThreads * 8);  // offset-class table follows the register file
+  cx.ocls_s = cx.regfile_s + (unsigned)((P.n_regs + 1) * V * kThreads * 8);  // behind the register file and its scratch column  // offset-class table follows the register file
   cx.pf_s = pf_base;
   const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(&mbar_store[0]);
   if (bulk) {
@@ -40,12 +43,14 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
     __syncthreads();
   }
 
-  constexpr int NS = AX1D ? 1 : RB200_MAX_REDS;
+  // reduction accumulators: slot 0 in registers; slots 1.. (multi-reduction ops) in shared memory
+  constexpr int NS = 1;
+  __shared__ u64 racc_extra[RB200_MAX_REDS - 1][kThreads];
   u64 racc[NS][AX1D ? V : 1];
 #pragma unroll
-  for (int s = 0; s < NS; ++s)
-#pragma unroll
-    for (int k = 0; k < (AX1D ? V : 1); ++k) racc[s][k] = red_identity_bits(s < P.n_reds ? P.reds[s].op : 0, s < P.n_reds ? P.reds[s].ctype : 0);
+  for (int k = 0; k < (AX1D ? V : 1); ++k) racc[0][k] = red_identity_bits(0 < P.n_reds ? P.reds[0].op : 0, 0 < P.n_reds ? P.reds[0].ctype : 0);
+  cx.racc_s = (unsigned)__cvta_generic_to_shared(&racc_extra[0][threadIdx.x]);
+  for (int s = 1; s < P.n_reds; ++s) racc_extra[s - 1][threadIdx.x] = red_identity_bits(P.reds[s].op, P.reds[s].ctype);
   if constexpr (AX1D) {
     cx.pe0 = (long long)(blockIdx.x % (unsigned)P.n_split_chunks) * TILE + threadIdx.x;
     cx.e0 = cx.pe0;
@@ -121,47 +126,56 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
   };
   auto tile_is_bulk = [&](long long t) { return bulk && (t + 1) * TILE <= P.total; };
 
-  long long tile = blockIdx.x;
-  unsigned stage = 0, phases = 0;  // bit s of `phases`: parity the next wait on stage s expects
-  if (n_pf > 0 && tile < P.n_tiles) {
+  // Ring protocol (bulk mode).  Stage s = it mod S holds the CTA's it-th tile (S a power of two); its
+  // "full" mbarrier completes once per refill, so the it-th tile waits for parity (it / S) & 1.  One
+  // CTA-wide barrier per tile guards the refill of the stage the previous tile used.  (A barrier-free
+  // variant -- warps count themselves out of a stage, the last one out refills it -- measured 8 % slower
+  // on config 2: the barrier keeps the eight warps in step, which the instruction cache likes.)
+  constexpr unsigned lgS = 1u;
+  if (n_pf > 0 && (long long)blockIdx.x < P.n_tiles) {
     if (bulk) {
-      // prologue: tiles 0 .. S-2 of this CTA into stages 0 .. S-2
       if (threadIdx.x == 0) {
-        long long t = tile;
-        for (unsigned s = 0; s + 1 < S && t < P.n_tiles; ++s, t += gridDim.x)
+        long long t = blockIdx.x;
+        for (unsigned s = 0; s < S && t < P.n_tiles; ++s, t += gridDim.x)
           if (tile_is_bulk(t)) issue_bulk(t, s);
       }
     } else {
-      issue_ldgsts(tile, 0);
+      issue_ldgsts(blockIdx.x, 0);
       cp_async_commit();
     }
   }
 #pragma unroll 1
-  for (; tile < P.n_tiles; tile += gridDim.x) {
+  for (unsigned it = 0;; ++it) {
+    // per-tile quantities are re-derived from the tile counter and constant-bank values (kept opaque so
+    // that they are not hoisted into registers that stay live across the whole interpreter)
+    unsigned grid = gridDim.x;
+    asm volatile("" : "+r"(grid));
+    const long long tile = (long long)blockIdx.x + (long long)it * grid;
+    if (tile >= P.n_tiles) break;
+    const unsigned stage = bulk ? (it & (S - 1u)) : (it & 1u);
     if (n_pf > 0) {
       if (bulk) {
         // everybody is done reading the stage used by the previous iteration before it is refilled
         __syncthreads();
-        const long long ahead = tile + (long long)(S - 1) * gridDim.x;
-        const unsigned refill = (stage + S - 1u) % S;
-        if (ahead < P.n_tiles && tile_is_bulk(ahead) && threadIdx.x == 0) issue_bulk(ahead, refill);
+        if (it > 0 && threadIdx.x == 0) {
+          const long long nxt = tile + (long long)(S - 1u) * grid;
+          if (nxt < P.n_tiles && tile_is_bulk(nxt)) issue_bulk(nxt, (it - 1u) & (S - 1u));
+        }
         if (tile_is_bulk(tile)) {
-          mbar_wait(mbar0 + stage * 8u, (phases >> stage) & 1u);
-          phases ^= (1u << stage);
-        } else {  // the ragged last tile
+          mbar_wait(mbar0 + stage * 8u, (it >> lgS) & 1u);
+        } else {  // the ragged last tile: every thread copies (and later reads) only its own column
           issue_ldgsts(tile, stage);
           cp_async_commit();
           cp_async_wait<0>();
         }
       } else {
         // per-thread pipeline (each thread re-reads only what it copied itself: no barrier)
-        const long long nxt = tile + gridDim.x;
+        const long long nxt = tile + grid;
         if (nxt < P.n_tiles) issue_ldgsts(nxt, stage ^ 1u);
         cp_async_commit();
         cp_async_wait<1>();
       }
       cx.pf_s = pf_base + stage * pf_stage_bytes;
-      stage = (stage + 1u == S) ? 0u : stage + 1u;
     }
     const long long e0 = tile * TILE + threadIdx.x;
     unsigned valid = 0;
@@ -173,6 +187,38 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
 #pragma unroll
         for (int k = 0; k < V; ++k)
           if (e0 + (long long)k * kThreads < P.total) valid |= (1u << k);
+      }
+    } else if (P.row_chunks > 0) {
+      // row mode: this tile is chunk `ch` of row `row` of the innermost dim; outer indices are per tile
+      long long row, ch;
+      if (((tile | (long long)P.row_chunks) >> 31) == 0) row = (long long)((unsigned)tile / (unsigned)P.row_chunks);
+      else row = tile / P.row_chunks;
+      ch = tile - row * P.row_chunks;
+      long long oidx[ND];
+#pragma unroll
+      for (int d = ND - 1; d >= 0; --d) {
+        if (d >= P.ndim - 1) {
+          oidx[d] = 0;
+        } else if (d == 0) {
+          oidx[d] = row;
+        } else {
+          const long long sd = P.shape[d];
+          long long q;
+          if (((row | sd) >> 31) == 0) q = (long long)((unsigned)row / (unsigned)sd);
+          else q = row / sd;
+          oidx[d] = row - q * sd;
+          row = q;
+        }
+      }
+      const long long inner = P.shape[P.ndim - 1];
+      const long long j0 = ch * TILE + threadIdx.x;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const long long j = j0 + (long long)k * kThreads;
+        const bool ok = j < inner;
+        if (ok) valid |= (1u << k);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) cx.idx[k][d] = (d == P.ndim - 1) ? (ok ? j : 0) : (ok ? oidx[d] : 0);
       }
     } else {
 #pragma unroll
@@ -208,10 +254,7 @@ __global__ void __launch_bounds__(kThreads, (ND == 1 && V <= 4) ? 3 : 2) vm_elem
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int s = 0; s < P.n_reds; ++s) {
       const int op = P.reds[s].op, ct = P.reds[s].ctype;
-      u64 v = racc[0][0];
-#pragma unroll
-      for (int q = 0; q < NS; ++q)
-        if (q == s) v = racc[q][0];
+      u64 v = (s == 0) ? racc[0][0] : racc_extra[s > 0 ? s - 1 : 0][threadIdx.x];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, ct, v, __shfl_down_sync(0xffffffffu, v, o));
       if (lane == 0) wpart[s][warp] = v;

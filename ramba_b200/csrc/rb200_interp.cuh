@@ -84,39 +84,42 @@ __device__ __noinline__ void store_line(char* base, int dtype, long long off0, l
   }
 }
 
+// One converted store (any view dtype) of a value of compute class R
+template <class R> __device__ __forceinline__ void store_one(char* base, int dtype, long long off, R x) {
+  switch (dtype) {
+    case RB200_F64: reinterpret_cast<double*>(base)[off] = (double)x; break;
+    case RB200_F32: reinterpret_cast<float*>(base)[off] = (float)x; break;
+    case RB200_I64: reinterpret_cast<long long*>(base)[off] = (long long)x; break;
+    case RB200_I32: reinterpret_cast<int*>(base)[off] = (int)x; break;
+    default: store_narrow_one<R>(base, dtype, off, x);
+  }
+}
+
 // Everything about a 1-D store that is not "full tile, contiguous, own dtype": write masks, ragged
-// tiles, strided or converting views.  Out of line so that the specialised handlers stay small (the
-// hot loop's instruction footprint is what the kernel is sensitive to).
+// tiles, strided or converting views.  Out of line, one element at a time, the values handed over
+// through the thread's scratch column in shared memory: the call sites in the specialised handlers
+// stay small and need no extra registers (the hot loop is sensitive to both).
 template <class R, int V>
 __device__ __noinline__ void store_slow_1d(char* base, int dtype, long long stride, long long e0, unsigned valid, unsigned mask_addr,
-                                           u64 b0, u64 b1, u64 b2, u64 b3, u64 b4, u64 b5, u64 b6, u64 b7) {
-  static_assert(V == 4 || V == 8, "store_slow_1d handles 4 or 8 elements per thread");
-  unsigned m = valid;
-  if (mask_addr != 0xffffffffu) {
-#pragma unroll
-    for (int k = 0; k < V; ++k)
-      if (lds64(mask_addr + (unsigned)(k * kThreads * 8)) == 0ull) m &= ~(1u << k);
-  }
+                                           unsigned vals_addr) {
   const long long step = stride * kThreads;
-  store_line<R>(base, dtype, e0 * stride, step, m & 0xfu, b0, b1, b2, b3);
-  if constexpr (V == 8) store_line<R>(base, dtype, (e0 + 4ll * kThreads) * stride, step, (m >> 4) & 0xfu, b4, b5, b6, b7);
+  long long off = e0 * stride;
+#pragma unroll 1
+  for (int k = 0; k < V; ++k, off += step) {
+    if (!((valid >> k) & 1u)) continue;
+    if (mask_addr != 0xffffffffu && lds64(mask_addr + (unsigned)(k * kThreads * 8)) == 0ull) continue;
+    store_one<R>(base, dtype, off, CT<R>::get(lds64(vals_addr + (unsigned)(k * kThreads * 8))));
+  }
 }
 
 // N-d counterpart (V == 4): explicit element offsets
 template <class R>
-__device__ __noinline__ void store_slow_nd(char* base, int dtype, unsigned mask, long long o0, long long o1, long long o2, long long o3, u64 b0,
-                                           u64 b1, u64 b2, u64 b3) {
-  constexpr int V = 4;
-  long long off[V] = {o0, o1, o2, o3};
-  R r[V] = {CT<R>::get(b0), CT<R>::get(b1), CT<R>::get(b2), CT<R>::get(b3)};
-  if (dtype == RB200_BOOL) {
-    long long b[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) b[k] = (r[k] != R(0)) ? 1 : 0;
-    store_view<long long, V>(base, RB200_U8, off, mask, b);
-  } else {
-    store_view<R, V>(base, dtype, off, mask, r);
-  }
+__device__ __noinline__ void store_slow_nd(char* base, int dtype, unsigned mask, long long o0, long long o1, long long o2, long long o3,
+                                           unsigned vals_addr) {
+  if (mask & 1u) store_one<R>(base, dtype, o0, CT<R>::get(lds64(vals_addr)));
+  if (mask & 2u) store_one<R>(base, dtype, o1, CT<R>::get(lds64(vals_addr + (unsigned)(kThreads * 8))));
+  if (mask & 4u) store_one<R>(base, dtype, o2, CT<R>::get(lds64(vals_addr + (unsigned)(2 * kThreads * 8))));
+  if (mask & 8u) store_one<R>(base, dtype, o3, CT<R>::get(lds64(vals_addr + (unsigned)(3 * kThreads * 8))));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -125,6 +128,7 @@ __device__ __noinline__ void store_slow_nd(char* base, int dtype, unsigned mask,
 template <int V, int ND> struct Ctx {
   const KParams& P;      // the __grid_constant__ kernel parameter: constant-bank (LDC) accesses
   unsigned regfile_s;    // shared-window byte address of this thread's column of the register file
+  unsigned racc_s;       // this thread's accumulator of reduction slot 1 (slots 2.. follow at kThreads*8); global mode only
   unsigned pf_s;         // shared-window byte address of the current prefetch stage (element e of slot j at pf_s + j*V*2048 + e*itemsize)
   unsigned ocls_s;       // ND > 1: shared-window byte address of this thread's column of the offset-class table
   unsigned tid;
@@ -278,52 +282,68 @@ template <int V, int ND> struct Ctx {
     }
   }
 
+  // store V results (values r, raw bits b) to view `vi`, optionally masked by register `mreg`:
+  // full contiguous tiles of the view's own dtype inline, everything else out of line
+  template <class R> __device__ __forceinline__ void store_res(int vi, int mreg, const R (&r)[V], const u64 (&b)[V]) {
+    if constexpr (ND == 1 && (V == 4 || V == 8)) {
+      const KView& vw = P.views[vi];
+      constexpr int own1 = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+      const long long st = vw.stride[0];
+      const bool plain = st == 1 && valid == ((1u << V) - 1u) && mreg == RB200_NOSTORE;
+      if (plain && vw.dtype == own1) {
+        R* p = reinterpret_cast<R*>(vw.base) + e0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) stg<R>(p + k * kThreads, r[k]);
+      } else if (std::is_same<R, double>::value && plain && vw.dtype == RB200_F32) {
+        // float32 arrays computed in float64 (a Python float in the expression): the common converting store
+        float* p = reinterpret_cast<float*>(vw.base) + e0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) stg<float>(p + k * kThreads, (float)r[k]);
+      } else {
+        const unsigned maddr = mreg == RB200_NOSTORE ? 0xffffffffu : reg_base(mreg);
+        sts_vec64<V>(reg_base(P.n_regs), b);  // scratch column behind the register file
+        store_slow_1d<R, V>(vw.base, vw.dtype, st, e0, valid, maddr, reg_base(P.n_regs));
+      }
+    } else if constexpr (ND > 1 && V == 4) {
+      const KView& vw = P.views[vi];
+      constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
+      long long off[V];
+      offsets(vw, off);
+      const bool plain = valid == 0xfu && mreg == RB200_NOSTORE;
+      if (plain && vw.dtype == own) {
+        R* p = reinterpret_cast<R*>(vw.base);
+#pragma unroll
+        for (int k = 0; k < V; ++k) stg<R>(p + off[k], r[k]);
+      } else if (std::is_same<R, double>::value && plain && vw.dtype == RB200_F32) {
+        float* p = reinterpret_cast<float*>(vw.base);
+#pragma unroll
+        for (int k = 0; k < V; ++k) stg<float>(p + off[k], (float)r[k]);
+      } else {
+        unsigned m = valid;
+        if (mreg != RB200_NOSTORE) {
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            if (lds64(reg_addr(mreg, k)) == 0ull) m &= ~(1u << k);
+        }
+        sts_vec64<V>(reg_base(P.n_regs), b);  // scratch column behind the register file
+        store_slow_nd<R>(vw.base, vw.dtype, m, off[0], off[1], off[2], off[3], reg_base(P.n_regs));
+      }
+    } else {
+      unsigned m = valid;
+      if (mreg != RB200_NOSTORE) {
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if (lds64(reg_addr(mreg, k)) == 0ull) m &= ~(1u << k);
+      }
+      store_out<R>(vi, r, b, m);
+    }
+  }
+
   template <class R> __device__ __forceinline__ void finish(const UInsn& I, const R (&r)[V]) {
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = CT<R>::bits(r[k]);
     if (I.st_reg() != RB200_NOSTORE) sts_vec64<V>(reg_base(I.st_reg()), acc);
-    if (I.st_view() != RB200_NOSTORE) {
-      if constexpr (ND == 1 && (V == 4 || V == 8)) {
-        const KView& vw = P.views[I.st_view()];
-        constexpr int own1 = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
-        const long long st = vw.stride[0];
-        if (vw.dtype == own1 && st == 1 && valid == ((1u << V) - 1u) && I.mask_reg() == RB200_NOSTORE) {
-          R* p = reinterpret_cast<R*>(vw.base) + e0;
-#pragma unroll
-          for (int k = 0; k < V; ++k) stg<R>(p + k * kThreads, r[k]);
-        } else {
-          const unsigned maddr = I.mask_reg() == RB200_NOSTORE ? 0xffffffffu : reg_base(I.mask_reg());
-          store_slow_1d<R, V>(vw.base, vw.dtype, st, e0, valid, maddr, acc[0], acc[1], acc[2], acc[3], V == 8 ? acc[4 % V] : 0ull,
-                              V == 8 ? acc[5 % V] : 0ull, V == 8 ? acc[6 % V] : 0ull, V == 8 ? acc[7 % V] : 0ull);
-        }
-      } else if constexpr (ND > 1 && V == 4) {
-        const KView& vw = P.views[I.st_view()];
-        constexpr int own = std::is_same<R, double>::value ? RB200_F64 : std::is_same<R, float>::value ? RB200_F32 : RB200_I64;
-        long long off[V];
-        offsets(vw, off);
-        if (vw.dtype == own && valid == 0xfu && I.mask_reg() == RB200_NOSTORE) {
-          R* p = reinterpret_cast<R*>(vw.base);
-#pragma unroll
-          for (int k = 0; k < V; ++k) stg<R>(p + off[k], r[k]);
-        } else {
-          unsigned m = valid;
-          if (I.mask_reg() != RB200_NOSTORE) {
-#pragma unroll
-            for (int k = 0; k < V; ++k)
-              if (lds64(reg_addr(I.mask_reg(), k)) == 0ull) m &= ~(1u << k);
-          }
-          store_slow_nd<R>(vw.base, vw.dtype, m, off[0], off[1], off[2], off[3], acc[0], acc[1], acc[2], acc[3]);
-        }
-      } else {
-        unsigned m = valid;
-        if (I.mask_reg() != RB200_NOSTORE) {
-#pragma unroll
-          for (int k = 0; k < V; ++k)
-            if (lds64(reg_addr(I.mask_reg(), k)) == 0ull) m &= ~(1u << k);
-        }
-        store_out<R>(I.st_view(), r, acc, m);
-      }
-    }
+    if (I.st_view() != RB200_NOSTORE) store_res<R>(I.st_view(), I.mask_reg(), r, acc);
   }
 };
 
@@ -770,7 +790,11 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
   if constexpr (OP == RB200_OP_SIN || OP == RB200_OP_COS || OP == RB200_OP_SINCOS) {
     if constexpr (!std::is_integral<T>::value) {
       T sn[V], cs[V];
+#ifdef RB200_EXP_NOTRIG
+      for (int k = 0; k < V; ++k) { sn[k] = a[k]; cs[k] = -a[k]; }
+#else
       sincos_v<V>(a, sn, cs);
+#endif
       const bool want_cos = (OP == RB200_OP_COS) || (OP == RB200_OP_SINCOS && I.imm());
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
@@ -784,7 +808,7 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
           park[k] = CT<T>::bits(parkv[k]);
         }
         sts_vec64<V>(cx.reg_base(I.st2()), park);
-        if (I.c_kind() == RB200_K_VIEW) cx.template store_out<T>(I.c_idx(), parkv, park, cx.valid);
+        if (I.c_kind() == RB200_K_VIEW) cx.template store_res<T>(I.c_idx(), RB200_NOSTORE, parkv, park);
       }
     }
     cx.template finish<T>(I, r);
@@ -838,13 +862,24 @@ __device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[NS][AX 
       for (int k = 0; k < V; ++k)
         if (!((cx.valid >> k) & 1u)) a[k] = ident;
     }
+    // slot 0 lives in registers, the (rare) further slots of a multi-reduction op in shared memory
+    if (rop == RB200_RED_ADD) {  // the common reduction: no per-combine operator test
 #pragma unroll
-    for (int w = V / 2; w >= 1; w >>= 1)
+      for (int w = V / 2; w >= 1; w >>= 1)
 #pragma unroll
-      for (int k = 0; k < w; ++k) a[k] = red_combine<T>(rop, a[k], a[k + w]);
+        for (int k = 0; k < w; ++k) a[k] = a[k] + a[k + w];
+    } else {
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
-      if (s == slot) racc[s][0] = CT<T>::bits(red_combine<T>(rop, CT<T>::get(racc[s][0]), a[0]));
+      for (int w = V / 2; w >= 1; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) a[k] = red_combine<T>(rop, a[k], a[k + w]);
+    }
+    if (slot == 0) {
+      racc[0][0] = CT<T>::bits(red_combine<T>(rop, CT<T>::get(racc[0][0]), a[0]));
+    } else {
+      const unsigned addr = cx.racc_s + (unsigned)(slot - 1) * (unsigned)(kThreads * 8);
+      sts64(addr, CT<T>::bits(red_combine<T>(rop, CT<T>::get(lds64(addr)), a[0])));
+    }
   } else {
 #pragma unroll
     for (int s = 0; s < NS; ++s)
@@ -859,41 +894,23 @@ __device__ __forceinline__ void h_red(C& cx, const UInsn& I, u64 (&racc)[NS][AX 
   }
 }
 
-// one interpreter pass over the op list for the thread's V elements.
-// racc: reduction accumulators (raw bits), [slot][0] (global mode, AX=false) or [slot][k] (axis mode)
-// NS = number of reduction slots carried (RB200_MAX_REDS, or 1 when V accumulators per slot must stay
-// in registers)
-template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_program(C& cx, u64 (&racc)[NS][AX ? V : 1]) {
-  const KParams& P = cx.P;
-  const int n = P.n_insns;
-#pragma unroll 1
-  for (int pc = 0; pc < n; ++pc) {
-    const UInsn I(&P.insns[pc]);
-#ifndef RB200_NO_FAST_HANDLERS
-    const int h = P.handler[pc];
-    if (h != H_GENERIC) {
-#if RB200_HANDLER_SET == 2
-#include "rb200_handlers_set2.inc"
-#else
-#include "rb200_handlers_set1.inc"
-#endif
-      continue;
+// the generic path of one instruction (any opcode, class and operand kinds)
+template <int V, bool AX, int NS, class C> __device__ __forceinline__ void generic_body(C& cx, const UInsn& I, u64 (&racc)[NS][AX ? V : 1]) {
+  if (I.op() == RB200_OP_CVT) {
+    switch (I.imm() & 0xff) {
+      case RB200_T_F64: exec_cvt_from<double, V>(cx, I); break;
+      case RB200_T_F32: exec_cvt_from<float, V>(cx, I); break;
+      default: exec_cvt_from<long long, V>(cx, I);
     }
-#endif
-    if (I.op() == RB200_OP_CVT) {
-      switch (I.imm() & 0xff) {
-        case RB200_T_F64: exec_cvt_from<double, V>(cx, I); break;
-        case RB200_T_F32: exec_cvt_from<float, V>(cx, I); break;
-        default: exec_cvt_from<long long, V>(cx, I);
-      }
-      continue;
-    }
-    if (I.op() == RB200_OP_RED) {
-      const int slot = I.b_idx();
-      const int rop = (int)I.imm();
-      if (I.ctype() == RB200_T_F64) {
-        double a[V];
-        cx.template fetch<double>(I.a_kind(), I.a_idx(), a);
+    return;
+  }
+  if (I.op() == RB200_OP_RED) {
+    const int slot = I.b_idx();
+    const int rop = (int)I.imm();
+    if (I.ctype() == RB200_T_F64) {
+      double a[V];
+      cx.template fetch<double>(I.a_kind(), I.a_idx(), a);
+      if constexpr (AX) {
 #pragma unroll
         for (int s = 0; s < NS; ++s)
           if (s == slot) {
@@ -905,8 +922,18 @@ template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_p
               }
           }
       } else {
-        long long a[V];
-        cx.template fetch<long long>(I.a_kind(), I.a_idx(), a);
+        const unsigned addr = cx.racc_s + (unsigned)(slot - 1) * (unsigned)(kThreads * 8);
+        u64 t = slot == 0 ? racc[0][0] : lds64(addr);
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if ((cx.valid >> k) & 1u) t = CT<double>::bits(red_combine<double>(rop, CT<double>::get(t), a[k]));
+        if (slot == 0) racc[0][0] = t;
+        else sts64(addr, t);
+      }
+    } else {
+      long long a[V];
+      cx.template fetch<long long>(I.a_kind(), I.a_idx(), a);
+      if constexpr (AX) {
 #pragma unroll
         for (int s = 0; s < NS; ++s)
           if (s == slot) {
@@ -917,14 +944,102 @@ template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_p
                 t = (u64)red_combine<long long>(rop, (long long)t, a[k]);
               }
           }
+      } else {
+        const unsigned addr = cx.racc_s + (unsigned)(slot - 1) * (unsigned)(kThreads * 8);
+        u64 t = slot == 0 ? racc[0][0] : lds64(addr);
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if ((cx.valid >> k) & 1u) t = (u64)red_combine<long long>(rop, (long long)t, a[k]);
+        if (slot == 0) racc[0][0] = t;
+        else sts64(addr, t);
       }
+    }
+    return;
+  }
+  switch (I.ctype()) {
+    case RB200_T_F64: exec_float<double, V>(cx, I); break;
+    case RB200_T_F32: exec_float<float, V>(cx, I); break;
+    default: exec_int<V>(cx, I);
+  }
+}
+
+#ifndef RB200_NO_FAST_HANDLERS
+// Out of line in the kernels that have specialised handlers: the generic path needs several operand
+// arrays at once, and inlined it would set the register allocation of the whole dispatch loop.  The
+// interpreter state travels by value, the results come back through two small local arrays.
+template <int V, bool AX, int NS, class C> __device__ __noinline__ void generic_step(C cx, int pc, u64* acc_out, u64* racc_io) {
+  u64 racc[NS][AX ? V : 1];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < (AX ? V : 1); ++k) racc[s][k] = racc_io[s * (AX ? V : 1) + k];
+  const UInsn I(&cx.P.insns[pc]);
+  generic_body<V, AX, NS>(cx, I, racc);
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc_out[k] = cx.acc[k];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < (AX ? V : 1); ++k) racc_io[s * (AX ? V : 1) + k] = racc[s][k];
+}
+#endif
+
+// one interpreter pass over the op list for the thread's V elements.
+// racc: reduction accumulators (raw bits), [slot][0] (global mode, AX=false) or [slot][k] (axis mode)
+// NS = number of reduction slots carried in registers
+template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_program(C& cx, u64 (&racc)[NS][AX ? V : 1]) {
+  const KParams& P = cx.P;
+  const int n = P.n_insns;
+  const unsigned valid_tile = cx.valid;
+#pragma unroll 1
+  for (int pc = 0; pc < n; ++pc) {
+#ifdef RB200_PC_VEC
+    const int pcv = pc | (int)((unsigned long long)cx.e0 >> 62);  // always pc, but per-thread as far as ptxas can tell
+    const UInsn I(&P.insns[pcv]);
+#else
+    const int pcv = pc;
+    const UInsn I(&P.insns[pc]);
+#endif
+    {
+      // opaque per-instruction copy of the tile's element mask: keeps the compiler from hoisting the
+      // per-bit tests of the rare paths out of this loop into eight more live registers
+      unsigned v = valid_tile;
+#ifndef RB200_NO_OPAQUE_VALID
+      asm volatile("" : "+r"(v));
+#endif
+      cx.valid = v;
+    }
+#ifndef RB200_NO_FAST_HANDLERS
+    const int h = P.handler[pcv];
+    if (h != H_GENERIC) {
+#if RB200_HANDLER_SET == 2
+#include "rb200_handlers_set2.inc"
+#else
+#include "rb200_handlers_set1.inc"
+#endif
       continue;
     }
-    switch (I.ctype()) {
-      case RB200_T_F64: exec_float<double, V>(cx, I); break;
-      case RB200_T_F32: exec_float<float, V>(cx, I); break;
-      default: exec_int<V>(cx, I);
+#ifdef RB200_GENERIC_INLINE
+    generic_body<V, AX, NS>(cx, I, racc);
+    continue;
+#endif
+    {
+      u64 acc_tmp[V], racc_tmp[NS * (AX ? V : 1)];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int k = 0; k < (AX ? V : 1); ++k) racc_tmp[s * (AX ? V : 1) + k] = racc[s][k];
+      generic_step<V, AX, NS, C>(cx, pc, acc_tmp, racc_tmp);
+#pragma unroll
+      for (int k = 0; k < V; ++k) cx.acc[k] = acc_tmp[k];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int k = 0; k < (AX ? V : 1); ++k) racc[s][k] = racc_tmp[s * (AX ? V : 1) + k];
     }
+#else
+    generic_body<V, AX, NS>(cx, I, racc);
+#endif
   }
 }
 

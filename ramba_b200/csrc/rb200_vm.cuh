@@ -49,14 +49,15 @@ struct KParams {
   long long shape[kMaxD];
   long long gstart[kMaxD];
   long long total;    // elements of the (kept) iteration space
-  long long n_tiles;  // ceil(total / (kThreads*V))
+  long long n_tiles;  // ceil(total / (kThreads*V)); row mode: rows * row_chunks
+  int row_chunks;     // N-d row mode (> 0): tiles per row of the innermost dim; a tile never crosses a row, the outer indices are per-tile
   // axis reduction (column form): leading red_ndim dims are walked sequentially
   long long red_len;
   long long red_split;
   int n_split;
   int red_ndim;
   int n_split_chunks;  // axis-as-1-D mode: column chunks (C / tile) = CTAs per split
-  int n_stages;        // depth of the staging ring (2..4)
+  int n_stages;        // depth of the staging ring (2)
   // axis-as-1-D mode: row-broadcast ("periodic") views are loop invariant for a CTA — they are loaded
   // once into spill registers before the row loop
   int n_hoist;
@@ -268,13 +269,33 @@ __device__ __forceinline__ void store_view(char* base, int dtype, const long lon
 // for |x| < 2^31*pi/2), fdlibm kernel polynomials on [-pi/4, pi/4], quadrant select.  Measured
 // against 200-bit references: <= 1.31 ulp on [0, 1e6] and +-1e9.  Anything larger (or NaN/Inf) takes
 // the CUDA library routine.
+// library routines out of line: their large-argument paths keep a table in local memory and would
+// otherwise be inlined once per element into every trigonometric handler
+static __device__ __noinline__ double2 sincos_lib(double x) {
+  double2 r;
+  sincos(x, &r.x, &r.y);
+  return r;
+}
+static __device__ __noinline__ float2 sincosf_lib(float x) {
+  float2 r;
+  sincosf(x, &r.x, &r.y);
+  return r;
+}
 template <int V> __device__ __forceinline__ void sincos_v(const double (&x)[V], double (&s)[V], double (&c)[V]) {
   bool big = false;
 #pragma unroll
   for (int k = 0; k < V; ++k) big = big || !(fabs(x[k]) < 1.0e9);
   if (big) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) sincos(x[k], &s[k], &c[k]);
+    for (int k = 0; k < V; ++k) {
+#ifdef RB200_SINCOS_INLINE
+      sincos(x[k], &s[k], &c[k]);
+#else
+      const double2 r = sincos_lib(x[k]);
+      s[k] = r.x;
+      c[k] = r.y;
+#endif
+    }
     return;
   }
   const double TWO_OVER_PI = 0.6366197723675814, MAGIC = 6755399441055744.0;
@@ -313,7 +334,15 @@ template <int V> __device__ __forceinline__ void sincos_v(const double (&x)[V], 
 }
 template <int V> __device__ __forceinline__ void sincos_v(const float (&x)[V], float (&s)[V], float (&c)[V]) {
 #pragma unroll
-  for (int k = 0; k < V; ++k) sincosf(x[k], &s[k], &c[k]);
+  for (int k = 0; k < V; ++k) {
+#ifdef RB200_SINCOS_INLINE
+    sincosf(x[k], &s[k], &c[k]);
+#else
+    const float2 r = sincosf_lib(x[k]);
+    s[k] = r.x;
+    c[k] = r.y;
+#endif
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

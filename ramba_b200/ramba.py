@@ -1824,6 +1824,145 @@ def sstencil(func, *args, out=None, **kwargs):
     return new
 
 
+# =============================================================================================
+# skeletons over user functions: smap / smap_index / sreduce / sreduce_index / cumsum
+# (ramba/ramba.py:9863-9984, 9675-9679, 10057-10116).  The reference pickles the function to its workers and
+# lets Numba compile it per element; here the function is evaluated ONCE on lazy arrays and lands in the same
+# fused op list as every other expression, so it has to be built from array operators and ramba functions
+# (no data-dependent Python control flow; `where` is the select).
+# =============================================================================================
+def _user_function(func):
+    """A callable, or a string holding a lambda (the reference's string form, ramba/ramba.py:9877-9891)."""
+    if isinstance(func, str):
+        import sys
+
+        mod = sys.modules[__name__.rsplit(".", 1)[0]]  # the package: numpy-like namespace for the lambda's globals
+        return eval(func, {"numpy": mod, "np": mod, "ramba": mod, "math": mod})
+    if not callable(func):
+        raise TypeError("expected a function or a string holding a lambda")
+    return func
+
+
+def _first_array(args, what):
+    arrays = [a for a in args if isinstance(a, ndarray)]
+    assert len(arrays) > 0, what + " needs at least one distributed array argument"
+    for a in arrays:
+        assert a.shape == arrays[0].shape, what + ": array arguments must have the same shape"
+    return arrays[0]
+
+
+def _index_arrays(shape):
+    idx = []
+    for d in range(len(shape)):
+        a = empty(shape, dtype=np.int64)
+        deferred_op.add_op([a, Iota(d)], a)
+        idx.append(a)
+    return idx
+
+
+_KEEP_DTYPE = object()  # sreduce: keep the mapped values in the function's own result dtype
+
+
+def _smap(what, func, args, dtype, axis, with_index):
+    if axis is not None:
+        raise NotImplementedError(what + "(axis=...) (slice-wise functions) is not supported by the op-list backend")
+    f = _user_function(func)
+    first = _first_array(args, what)
+    if with_index:
+        idx = _index_arrays(first.shape)
+        # 1-D: the index is a scalar, N-d: a tuple (ramba/ramba.py:9881-9885)
+        res = f(idx[0] if first.ndim == 1 else tuple(idx), *args)
+    else:
+        res = f(*args)
+    if not isinstance(res, ndarray):
+        res = full(first.shape, res)
+    # the output has the dtype of the first array argument unless told otherwise (ramba/ramba.py:9872-9873, 9913-9914)
+    if res.shape != first.shape:
+        res = broadcast_to(res, first.shape) + zeros(first.shape, dtype=res.dtype)
+    if dtype is _KEEP_DTYPE:
+        return res
+    out_dtype = np.dtype(first.dtype if dtype is None else dtype)
+    return res if res.dtype == out_dtype else res.astype(out_dtype)
+
+
+def smap(func, *args, dtype=None, parallel=True, axis=None, imports=[]):
+    """Elementwise map of `func` over the array arguments (scalars pass through)."""
+    return _smap("smap", func, args, dtype, axis, False)
+
+
+def smap_index(func, *args, dtype=None, parallel=True, imports=[]):
+    """Like smap; `func` receives the global index first (a scalar for 1-D arrays, a tuple otherwise)."""
+    return _smap("smap_index", func, args, dtype, None, True)
+
+
+class SreduceReducer:
+    """(worker function, driver function) pair of the reference's sreduce (ramba/ramba.py:9934-9939)."""
+
+    __slots__ = ("worker_func", "driver_func")
+
+    def __init__(self, worker_func, driver_func):
+        self.worker_func = worker_func
+        self.driver_func = driver_func
+
+
+def _classify_reducer(reducer):
+    """The op-list backend reduces with +, *, min or max: recognise which one `reducer` is by probing it."""
+    probes = [(3, 5), (-2, 7), (4, 4), (0.5, -8.0)]
+    table = {"sum": lambda a, b: a + b, "prod": lambda a, b: a * b, "min": builtins.min, "max": builtins.max}
+    for name, ref in table.items():
+        try:
+            if builtins.all(reducer(a, b) == ref(a, b) for a, b in probes):
+                return name
+        except Exception:
+            pass
+    raise NotImplementedError("sreduce: the reducer must be +, *, min or max (element-by-element Python reducers cannot run on the GPU)")
+
+
+def _sreduce(what, func, reducer, identity, args, with_index):
+    if isinstance(reducer, SreduceReducer):
+        reducer = reducer.worker_func
+    red = _user_function(reducer)
+    kind = _classify_reducer(red)
+    mapped = _smap(what, func, args, _KEEP_DTYPE, None, with_index)
+    total = getattr(mapped, kind)()
+    if isinstance(total, ndarray):
+        total = total.asarray().reshape(-1)[0]
+    return red(identity, total)
+
+
+def sreduce(func, reducer, identity, *args, parallel=True):
+    """reduce(reducer, map(func, elements), identity) (ramba/ramba.py:9942-9980)."""
+    return _sreduce("sreduce", func, reducer, identity, args, False)
+
+
+def sreduce_index(func, reducer, identity, *args, parallel=True):
+    return _sreduce("sreduce_index", func, reducer, identity, args, True)
+
+
+def cumsum(a, axis=None, dtype=None, out=None):
+    """Cumulative sum along `axis` (ramba/ramba.py:9675-9679).  The reference scans each worker's part and
+    then adds the boundary values worker by worker; here it is log2(n) fused shifted-slice additions
+    (Hillis-Steele), which run on the elementwise kernels and cross shards through the ordinary halo
+    exchange.  Integer and exactly representable data agree with NumPy bit for bit; floating-point sums are
+    associated differently (as they are in the reference)."""
+    a = _as_nd(a)
+    if a.ndim == 1 and axis is None:
+        axis = 0
+    assert isinstance(axis, numbers.Number) and 0 <= axis < a.ndim, "cumsum needs an axis for N-d arrays"
+    assert out is None, "cumsum(out=...) is not supported (nor by the reference, ramba/ramba.py:10071-10075)"
+    cur = a.astype(dtype) if dtype is not None and np.dtype(dtype) != a.dtype else a + 0
+    n = a.shape[axis]
+    d = 1
+    while d < n:
+        nxt = cur + 0  # fresh array: a step reads the previous one at two offsets, it cannot run in place
+        hi = tuple(slice(d, None) if k == axis else slice(None) for k in range(a.ndim))
+        lo = tuple(slice(0, n - d) if k == axis else slice(None) for k in range(a.ndim))
+        nxt[hi] = cur[hi] + cur[lo]
+        cur = nxt
+        d *= 2
+    return cur
+
+
 def sync():
     """Flush pending fused ops and wait for this rank's GPU (ramba/ramba.py:9843-9849)."""
     t0 = timer()

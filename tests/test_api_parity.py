@@ -269,6 +269,59 @@ def masked_assign(np):
     return [_h(a), _h(b)]
 
 
+# ---- skeletons over user functions (test_smap1-3, test_smap_index1-3, :919-972) and cumsum (:1368-1386)
+@case
+def smap_family(np):
+    a = np.arange(100)
+    a2 = a * a
+    g = np.fromfunction(lambda i, j: i + j, (100, 100))
+    if np is onp:
+        return [3 * a - 7, 3 * a - 7, 3 * g - 7, 3 * a2 - 7 * a, 3 * a2 - 7 * a, (a * 0.5).astype(onp.int64), a * 0.5,
+                (onp.sin(a * 0.25) * 10).astype(onp.int64)]
+    return [_h(np.smap("lambda x: 3*x-7", a)), _h(np.smap(lambda x: 3 * x - 7, a)), _h(np.smap("lambda x: 3*x-7", g)),
+            _h(np.smap("lambda x,y: 3*x-7*y", a2, a)), _h(np.smap(lambda x, y: 3 * x - 7 * y, a2, a)),
+            _h(np.smap(lambda x: x * 0.5, a)),  # result takes the dtype of the first array
+            _h(np.smap(lambda x: x * 0.5, a, dtype=onp.float64)),
+            _h(np.smap("lambda x: numpy.sin(x*0.25)*10", a))]  # string lambdas see the package as `numpy`
+
+
+@case
+def smap_index_family(np):
+    a = np.arange(100) - 25
+    a2 = np.arange(100) * a
+    o = np.ones((100, 100))
+    if np is onp:
+        i = onp.arange(100)
+        return [7 * i + a, 7 * i + a, onp.fromfunction(lambda i, j: 7 * i - j + 1, (100, 100)), 7 * i + a - 4 * a2]
+    return [_h(np.smap_index("lambda i,x: 7*i+x", a)), _h(np.smap_index(lambda i, x: 7 * i + x, a)),
+            _h(np.smap_index("lambda i,x: 7*i[0]-i[1]+x", o)), _h(np.smap_index(lambda i, x, y: 7 * i + x - 4 * y, a, a2))]
+
+
+@case
+def sreduce_family(np):
+    a = np.arange(300) - 100
+    if np is onp:
+        return [onp.asarray((a * a).sum()), onp.asarray(onp.max(2 * a + 1)), onp.asarray(5 + (a * onp.arange(300)).sum()),
+                onp.asarray(onp.min(a * 0.5))]
+    return [onp.asarray(np.sreduce(lambda x: x * x, lambda p, q: p + q, 0, a)),
+            onp.asarray(np.sreduce("lambda x: 2*x+1", lambda p, q: max(p, q), -10**9, a)),
+            onp.asarray(np.sreduce_index(lambda i, x: i * x, "lambda p,q: p+q", 5, a)),
+            onp.asarray(np.sreduce(lambda x: x * 0.5, np.SreduceReducer(min, min), 1e300, a))]
+
+
+@case
+def cumsum_family(np):
+    out = [_h(np.cumsum(np.arange(200))), _h(np.cumsum(np.arange(150) * 0.5)), _h(np.cumsum(np.arange(7)))]
+    for shp in [(4, 50), (20, 20), (50, 4)]:
+        a = np.arange(shp[0] * shp[1]) if np is onp else None
+        for axis in range(2):
+            if np is onp:
+                out.append(onp.cumsum(a.reshape(shp), axis=axis))
+            else:
+                out.append(_h(np.cumsum(np.fromfunction(lambda i, j: i * shp[1] + j, shp, dtype=onp.int64), axis=axis)))
+    return out
+
+
 def _compare(got, exp, name):
     assert len(got) == len(exp), name
     for i, (g, e) in enumerate(zip(got, exp)):

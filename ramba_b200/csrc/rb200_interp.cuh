@@ -126,6 +126,7 @@ __device__ __noinline__ void store_slow_nd(char* base, int dtype, unsigned mask,
 // per-thread interpreter state.  ND = number of iteration dims this instantiation handles
 // (ND == 1: collapsed 1-D op, the hot path; element k of the thread is e0 + k*256).
 template <int V, int ND> struct Ctx {
+  static constexpr int kND = ND;
   const KParams& P;      // the __grid_constant__ kernel parameter: constant-bank (LDC) accesses
   unsigned regfile_s;    // shared-window byte address of this thread's column of the register file
   unsigned racc_s;       // this thread's accumulator of reduction slot 1 (slots 2.. follow at kThreads*8); global mode only
@@ -1004,9 +1005,9 @@ template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_p
       // opaque per-instruction copy of the tile's element mask: keeps the compiler from hoisting the
       // per-bit tests of the rare paths out of this loop into eight more live registers
       unsigned v = valid_tile;
-#ifndef RB200_NO_OPAQUE_VALID
-      asm volatile("" : "+r"(v));
-#endif
+      // (1-D kernels only: the N-d kernels predicate every direct view load with these bits and are better off
+      // with the hoisted tests)
+      if constexpr (C::kND == 1) asm volatile("" : "+r"(v));
       cx.valid = v;
     }
 #ifndef RB200_NO_FAST_HANDLERS

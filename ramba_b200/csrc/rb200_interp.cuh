@@ -791,11 +791,7 @@ template <int OP, class T, int AK, int V, class C> __device__ __forceinline__ vo
   if constexpr (OP == RB200_OP_SIN || OP == RB200_OP_COS || OP == RB200_OP_SINCOS) {
     if constexpr (!std::is_integral<T>::value) {
       T sn[V], cs[V];
-#ifdef RB200_EXP_NOTRIG
-      for (int k = 0; k < V; ++k) { sn[k] = a[k]; cs[k] = -a[k]; }
-#else
       sincos_v<V>(a, sn, cs);
-#endif
       const bool want_cos = (OP == RB200_OP_COS) || (OP == RB200_OP_SINCOS && I.imm());
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = want_cos ? cs[k] : sn[k];
@@ -994,13 +990,7 @@ template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_p
   const unsigned valid_tile = cx.valid;
 #pragma unroll 1
   for (int pc = 0; pc < n; ++pc) {
-#ifdef RB200_PC_VEC
-    const int pcv = pc | (int)((unsigned long long)cx.e0 >> 62);  // always pc, but per-thread as far as ptxas can tell
-    const UInsn I(&P.insns[pcv]);
-#else
-    const int pcv = pc;
     const UInsn I(&P.insns[pc]);
-#endif
     {
       // opaque per-instruction copy of the tile's element mask: keeps the compiler from hoisting the
       // per-bit tests of the rare paths out of this loop into eight more live registers
@@ -1011,7 +1001,7 @@ template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_p
       cx.valid = v;
     }
 #ifndef RB200_NO_FAST_HANDLERS
-    const int h = P.handler[pcv];
+    const int h = P.handler[pc];
     if (h != H_GENERIC) {
 #if RB200_HANDLER_SET == 2
 #include "rb200_handlers_set2.inc"
@@ -1020,10 +1010,6 @@ template <int V, bool AX, int NS, class C> __device__ __forceinline__ void run_p
 #endif
       continue;
     }
-#ifdef RB200_GENERIC_INLINE
-    generic_body<V, AX, NS>(cx, I, racc);
-    continue;
-#endif
     {
       u64 acc_tmp[V], racc_tmp[NS * (AX ? V : 1)];
 #pragma unroll

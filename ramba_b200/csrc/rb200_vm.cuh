@@ -288,13 +288,9 @@ template <int V> __device__ __forceinline__ void sincos_v(const double (&x)[V], 
   if (big) {
 #pragma unroll
     for (int k = 0; k < V; ++k) {
-#ifdef RB200_SINCOS_INLINE
-      sincos(x[k], &s[k], &c[k]);
-#else
       const double2 r = sincos_lib(x[k]);
       s[k] = r.x;
       c[k] = r.y;
-#endif
     }
     return;
   }
@@ -335,13 +331,9 @@ template <int V> __device__ __forceinline__ void sincos_v(const double (&x)[V], 
 template <int V> __device__ __forceinline__ void sincos_v(const float (&x)[V], float (&s)[V], float (&c)[V]) {
 #pragma unroll
   for (int k = 0; k < V; ++k) {
-#ifdef RB200_SINCOS_INLINE
-    sincosf(x[k], &s[k], &c[k]);
-#else
     const float2 r = sincosf_lib(x[k]);
     s[k] = r.x;
     c[k] = r.y;
-#endif
   }
 }
 

@@ -1825,6 +1825,101 @@ def sstencil(func, *args, out=None, **kwargs):
 
 
 # =============================================================================================
+# index-driven builders: triu / tril / select / mgrid / meshgrid.  The reference runs a per-worker NumPy
+# routine for each (ramba/ramba.py:2091-2111 triu, 8993-9050 mgrid/meshgrid, 9079-9092 select); here they are
+# ordinary fused elementwise ops over iota operands.
+# =============================================================================================
+def triu(m, k=0):
+    """Upper triangle of a 2-D array: elements below the k-th diagonal zeroed (ramba/ramba.py:9053-9076)."""
+    m = _as_nd(m)
+    assert m.ndim == 2, "triu needs a 2-D array"
+    i, j = _index_arrays(m.shape)
+    return where(j - i >= k, m, zeros(m.shape, dtype=m.dtype))
+
+
+def tril(m, k=0):
+    """Lower triangle of a 2-D array (NumPy's tril; the reference has only triu)."""
+    m = _as_nd(m)
+    assert m.ndim == 2, "tril needs a 2-D array"
+    i, j = _index_arrays(m.shape)
+    return where(j - i <= k, m, zeros(m.shape, dtype=m.dtype))
+
+
+def select(condlist, choicelist, default=0):
+    """NumPy's select over same-shape arrays: the first true condition picks the choice."""
+    assert len(condlist) == len(choicelist) and len(condlist) > 0
+    shape = condlist[0].shape
+    for c in list(condlist) + [x for x in choicelist if isinstance(x, ndarray)]:
+        assert c.shape == shape
+    out = full(shape, default)
+    for cond, choice in zip(reversed(list(condlist)), reversed(list(choicelist))):
+        out = where(cond, choice, out)
+    return out
+
+
+def _stack_by_first_index(parts, shape, dtype):
+    """Array of shape (len(parts),) + shape whose slab d is parts[d](index arrays of the trailing dims)."""
+    idx = _index_arrays((len(parts),) + tuple(shape))
+    out = parts[-1](idx[1:])
+    if not isinstance(out, ndarray):
+        out = full((len(parts),) + tuple(shape), out, dtype=dtype)
+    for d in range(len(parts) - 2, -1, -1):
+        out = where(idx[0] == d, parts[d](idx[1:]), out)
+    return out if out.dtype == np.dtype(dtype) else out.astype(dtype)
+
+
+class MgridGen:
+    """`mgrid[a0:b0, a1:b1, ...]` -> int64 array of shape (k, b0-a0, b1-a1, ...) (ramba/ramba.py:9001-9018:
+    unit steps only)."""
+
+    def __getitem__(self, index):
+        index = index if isinstance(index, tuple) else (index,)
+        starts, sizes = [], []
+        for ix in index:
+            if isinstance(ix, numbers.Integral):
+                starts.append(0)
+                sizes.append(int(ix))
+            else:
+                assert isinstance(ix, slice) and ix.step is None, "mgrid supports unit-step slices"
+                starts.append(0 if ix.start is None else int(ix.start))
+                sizes.append(int(ix.stop) - starts[-1])
+        parts = [(lambda tail, d=d: tail[d] + starts[d]) for d in range(len(index))]
+        return _stack_by_first_index(parts, sizes, np.int64)
+
+
+mgrid = MgridGen()
+
+
+def meshgrid(*xi, copy=True, sparse=False, indexing="xy"):
+    """`meshgrid(x0, x1, ..., indexing='ij')` of equal-dtype 1-D arrays as ONE array of shape (k, n0, n1, ...)
+    (the reference's restrictions, ramba/ramba.py:9028-9050)."""
+    if indexing != "ij":
+        raise ValueError("Unsupported meshgrid indexing option %s" % (indexing,))
+    if sparse is not False:
+        raise ValueError("Unsupported meshgrid sparse option %s" % (sparse,))
+    if copy is not True:
+        raise ValueError("Unsupported meshgrid copy option %s" % (copy,))
+    xs = [_as_nd(x) if isinstance(x, (ndarray, np.ndarray)) else x for x in xi]
+    if builtins.any(not (isinstance(x, ndarray) and x.ndim == 1) for x in xs):
+        raise ValueError("Unsupported argument to meshgrid")
+    if not builtins.all(x.dtype == xs[0].dtype for x in xs):
+        raise ValueError("Mis-matching dtypes to meshgrid")
+    k = len(xs)
+    sizes = [x.shape[0] for x in xs]
+    full_shape = (k,) + tuple(sizes)
+
+    def part(d):
+        # x_d varies along axis d+1 of the result and is broadcast along the others
+        def f(tail):
+            others = [sizes[e] for e in range(k) if e != d]
+            b = broadcast_to(xs[d], (k,) + tuple(others) + (sizes[d],))  # x_d along the last axis ...
+            return moveaxis(b, -1, d + 1)  # ... moved to its own axis
+        return f
+
+    return _stack_by_first_index([part(d) for d in range(k)], sizes, xs[0].dtype)
+
+
+# =============================================================================================
 # skeletons over user functions: smap / smap_index / sreduce / sreduce_index / cumsum
 # (ramba/ramba.py:9863-9984, 9675-9679, 10057-10116).  The reference pickles the function to its workers and
 # lets Numba compile it per element; here the function is evaluated ONCE on lazy arrays and lands in the same

@@ -269,6 +269,35 @@ def masked_assign(np):
     return [_h(a), _h(b)]
 
 
+# ---- index-driven builders (test_triu1-3 :1023-1045, test_mgrid_1-4 :1135-1163, meshgrid, select)
+@case
+def triu_tril(np):
+    a = np.fromfunction(lambda i, j: i + j, (50, 50), dtype=int)
+    r = np.fromfunction(lambda i, j: i * 100 + j, (30, 120), dtype=onp.float64)
+    return [_h(np.triu(a)), _h(np.triu(a, k=-2)), _h(np.triu(a, k=2)), _h(np.triu(r, k=5)), _h(np.tril(a)), _h(np.tril(r, k=-3))]
+
+
+@case
+def mgrid_meshgrid(np):
+    out = [_h(np.mgrid[0:20, 0:20]), _h(np.mgrid[0:5, 0:5]), _h(np.mgrid[2:9, 0:30, 1:4])]
+    m, n = np.mgrid[0:20, 0:20]
+    out += [_h(m), _h(n)]
+    x, y = np.arange(30) * 0.5, np.arange(12) * 2.0
+    if np is onp:
+        out.append(onp.stack(onp.meshgrid(x, y, indexing="ij")))
+    else:
+        out.append(_h(np.meshgrid(x, y, indexing="ij")))
+    return out
+
+
+@case
+def select_family(np):
+    a = np.arange(200) - 50
+    conds = [a < 0, a < 50, a < 100]
+    choices = [a * 0, a * 2, a * 3]
+    return [_h(np.select(conds, choices, default=-7))]
+
+
 # ---- skeletons over user functions (test_smap1-3, test_smap_index1-3, :919-972) and cumsum (:1368-1386)
 @case
 def smap_family(np):

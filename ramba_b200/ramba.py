@@ -1034,6 +1034,40 @@ class ndarray:
         newshape, newdist = shardview.remap_axis(self.shape, self.distribution, newmap)
         return ndarray(newshape, base=self, distribution=newdist, local_border=0, readonly=self.readonly)
 
+    def expand_dims(self, axis):
+        axes = (axis,) if isinstance(axis, numbers.Integral) else tuple(axis)
+        k = self.ndim + len(axes)
+        axes = sorted(a % k for a in axes)
+        if len(set(axes)) != len(axes):
+            raise ValueError("repeated axis")
+        if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
+            deferred_op.do_ops()
+        newshape, newdist = shardview.expand_unit_dims(self.shape, self.distribution, axes)
+        return ndarray(newshape, base=self, distribution=newdist, local_border=0, readonly=True)
+
+    def squeeze(self, axis=None):
+        if axis is None:
+            axes = tuple(i for i in range(self.ndim) if self.shape[i] == 1)
+        else:
+            axes = tuple(a % self.ndim for a in ((axis,) if isinstance(axis, numbers.Integral) else tuple(axis)))
+        if not builtins.all(self.shape[a] == 1 for a in axes):
+            raise ValueError("cannot select an axis to squeeze out which has size not equal to one")
+        return self.remapped_axis([i for i in range(self.ndim) if i not in axes])
+
+    def reshape(self, *shape):
+        """Only reshapes that insert or remove unit dims are views here; anything else is a redistribution
+        (the reference's reshape_copy, ramba/ramba.py:9241-9277) and outside this path."""
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        shape = shapeToInt(shape)
+        if shape == self.shape:
+            return self
+        if [s for s in shape if s != 1] != [s for s in self.shape if s != 1]:
+            raise NotImplementedError("reshape %s -> %s moves data between shards (reshape_copy): not on this path" % (self.shape, shape))
+        flat = self.squeeze() if builtins.any(s == 1 for s in self.shape) else self
+        axes = [i for i, s in enumerate(shape) if s == 1]
+        return flat.expand_dims(axes) if axes else flat
+
     def transpose(self, *args):
         nd = self.ndim
         if len(args) == 0 or (len(args) == 1 and args[0] is None):
@@ -1731,6 +1765,18 @@ def broadcast_to(a, shape):
     return a.broadcast_to(shape)
 
 
+def expand_dims(a, axis):
+    return _as_nd(a).expand_dims(axis)
+
+
+def squeeze(a, axis=None):
+    return _as_nd(a).squeeze(axis)
+
+
+def reshape(a, *shape):
+    return _as_nd(a).reshape(*shape)
+
+
 def ndim(a):
     return a.ndim if hasattr(a, "ndim") else np.ndim(a)
 
@@ -1743,7 +1789,7 @@ def isscalar(x):
     return np.isscalar(x)
 
 
-for _n in ("where", "clip", "transpose", "swapaxes", "moveaxis", "broadcast_to", "ndim", "result_type", "allclose",
+for _n in ("where", "clip", "transpose", "swapaxes", "moveaxis", "broadcast_to", "expand_dims", "squeeze", "reshape", "ndim", "result_type", "allclose",
            "isclose", "empty_like", "zeros_like", "ones_like", "full_like", "copy", "array"):
     HANDLED_FUNCTIONS[_n] = globals()[_n]
 

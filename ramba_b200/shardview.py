@@ -403,6 +403,30 @@ def broadcast(distribution, broadcasted_dims, size):
     return out
 
 
+def expand_unit_dims(size, distribution, axes):
+    """Distribution of the same array viewed with unit dims inserted at positions `axes` of the NEW shape
+    (no storage behind them: axis_map -1, like a broadcast dim of extent 1).  The reference gets there through
+    reshape (ramba/ramba.py:9438-9453, 9125-9238)."""
+    k = len(size) + len(axes)
+    old_pos = [j for j in range(k) if j not in axes]
+    d0 = distribution[0]
+    amap = np.full(k, -1, dtype=I64)
+    amap[old_pos] = d0.axis_map
+    new_size = [1] * k
+    for j, o in zip(old_pos, range(len(size))):
+        new_size[j] = size[o]
+    out = []
+    for sv in distribution:
+        nsz = np.ones(k, dtype=I64)
+        nst = np.zeros(k, dtype=I64)
+        nstep = np.ones(k, dtype=I64)
+        nsz[old_pos], nst[old_pos], nstep[old_pos] = sv.size, sv.start, sv.steps
+        if is_empty(sv):
+            nsz = np.zeros(k, dtype=I64)
+        out.append(ShardView(nsz, nst, sv.base_offset, amap, nstep))
+    return tuple(new_size), out
+
+
 def remap_axis(size, distribution, newmap):
     """Re-order / drop axes (transpose family, ramba/shardview_array.py:1024-1042)."""
     old = distribution[0].axis_map

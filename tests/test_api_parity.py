@@ -269,6 +269,19 @@ def masked_assign(np):
     return [_h(a), _h(b)]
 
 
+# ---- unit-dim views (expand_dims / squeeze, ramba/ramba.py:9438-9476)
+@case
+def unit_dim_views(np):
+    a = np.fromfunction(lambda i, j: i * 10 + j, (30, 8))
+    v = np.arange(120) * 1.0
+    e0, e1, e2 = np.expand_dims(a, 0), np.expand_dims(a, 1), np.expand_dims(a, (0, 3))
+    col = np.expand_dims(v, 1)          # (120, 1)
+    row = np.expand_dims(v[:8], 0)      # (1, 8)
+    out = [_h(e0), _h(e1), _h(e2), _h(e1 * 2.0 + 1.0), _h(np.squeeze(e2)), _h(np.squeeze(e1, axis=1) - a),
+           _h(col[:30] + row), _h((e0 + 1.0).sum(axis=0)), _h(np.reshape(v, (120, 1, 1))), _h(np.reshape(e2, (30, 8)))]
+    return out
+
+
 # ---- index-driven builders (test_triu1-3 :1023-1045, test_mgrid_1-4 :1135-1163, meshgrid, select)
 @case
 def triu_tril(np):

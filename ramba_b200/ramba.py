@@ -977,6 +977,15 @@ class ndarray:
         return np.dtype(dtype).type(s / n)
 
     # ---- views
+    @staticmethod
+    def _plain_index(index):
+        """Index as a tuple; 0-d arrays of an integer dtype index like the integer they hold
+        (ramba/tests/test_distributed_array.py:712-752)."""
+        if not isinstance(index, tuple):
+            index = (index,)
+        return tuple(int(i.distribution.item()) if isinstance(i, ndarray) and i.shape == () and i.dtype.kind in "iu" else i
+                     for i in index)
+
     def __getitem__(self, index):
         if isinstance(index, ndarray) and index.dtype == np.bool_:
             if not index.broadcastable_to(self.shape):
@@ -984,12 +993,35 @@ class ndarray:
             m = index if index.shape == self.shape else index.broadcast_to(self.shape)
             return ndarray(self.shape, base=self, distribution=self.distribution, local_border=0,
                            readonly=self.readonly, maskarray=m)
-        if not isinstance(index, tuple):
-            index = (index,)
+        index = self._plain_index(index)
+        if builtins.any(i is None for i in index):
+            # newaxis: slice without the None terms, then insert unit dims where they stood
+            n_spec = builtins.sum(1 for i in index if i is not None and i is not Ellipsis)
+            terms = []
+            for i in index:
+                if i is Ellipsis:
+                    terms.extend([slice(None)] * (self.ndim - n_spec))
+                else:
+                    terms.append(i)
+            sub = self[tuple(t for t in terms if t is not None)]
+            if not isinstance(sub, ndarray):
+                raise NotImplementedError("newaxis on a single element")
+            axes, out_pos = [], 0
+            for t in terms:
+                if t is None:
+                    axes.append(out_pos)
+                    out_pos += 1
+                elif isinstance(t, slice):
+                    out_pos += 1
+            return sub.expand_dims(tuple(axes))
         if builtins.any(i is Ellipsis for i in index):
             pos = [j for j, i in enumerate(index) if i is Ellipsis][0]
             fill = self.ndim - (len(index) - 1)
             index = index[:pos] + (slice(None),) * fill + index[pos + 1:]
+        if self.shape == ():
+            if len(index) != 0:
+                raise IndexError("too many indices for array: array is 0-dimensional, but %d were indexed" % len(index))
+            return self.distribution[()]
         if builtins.all(isinstance(i, numbers.Integral) for i in index) and len(index) == self.ndim:
             cindex = canonical_index(index, self.shape)
             deferred_op.do_ops()
@@ -1009,6 +1041,13 @@ class ndarray:
             raise ValueError("assignment destination is read-only")
         if isinstance(value, (list, tuple)):
             value = np.array(value)
+        if self.shape == ():  # 0-d arrays keep their value on the host (like the reference)
+            if self._plain_index(index) not in ((), (Ellipsis,)):
+                raise IndexError("too many indices for array: array is 0-dimensional")
+            self.distribution[()] = value.distribution.item() if isinstance(value, ndarray) else value
+            return
+        if not (isinstance(index, ndarray) and index.dtype == np.bool_):
+            index = self._plain_index(index)
         view = self[index]
         if not isinstance(view, ndarray):  # single element
             cindex = canonical_index(index, self.shape)

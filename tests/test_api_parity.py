@@ -269,6 +269,22 @@ def masked_assign(np):
     return [_h(a), _h(b)]
 
 
+# ---- 0-d arrays and index terms (test_0d_* :705-759), newaxis
+@case
+def zero_d_and_newaxis(np):
+    a0 = np.array(7)
+    a0[()] = 3
+    a = np.arange(200)
+    b = np.array(7, dtype=int)
+    a[b] = 0
+    o = np.ones((20, 20))
+    o[:, b] = 0
+    c = np.ones((6, 7, 8)) * 3
+    return [onp.asarray(np.array(7)[()]), onp.asarray(a0[()]), onp.asarray(a[b]), _h(a), _h(o[:, b]), _h(o), onp.asarray(float(np.array(7))),
+            _h(np.arange(120)[:, None] * 1.0), _h(np.arange(120)[None, :] + np.arange(30)[:, None]), _h(c[2, None, ..., None, 1:5]),
+            _h(c[None].sum(axis=0))]
+
+
 # ---- unit-dim views (expand_dims / squeeze, ramba/ramba.py:9438-9476)
 @case
 def unit_dim_views(np):

@@ -443,9 +443,33 @@ class Lowering:
                     if m.mask is n:
                         m.mask = p
 
+    def _drop_dead_stores(self):
+        """A store is dead when a later unmasked store of the same fused op overwrites the same view and no
+        read in between can observe it (`a += 1` ten times in one flush writes `a` once; the reference's
+        fused loop also stores every time, but its stores hit the cache line it just wrote).
+        view_gids (set by the fuser) tells which views alias the same array; without it any view read is
+        assumed to observe every pending store."""
+        gids = getattr(self, "view_gids", None)
+        pending = {}  # view idx -> node whose store is not yet known to be observed
+        for n in self.nodes:
+            for a in n.args:
+                if a.kind == "view":
+                    for v in list(pending):
+                        if gids is None or v == a.ref or gids[v] == gids[a.ref]:
+                            pending.pop(v)
+            if n.store2 is not None:
+                pending.pop(n.store2, None)
+            if n.store is not None:
+                prev = pending.get(n.store)
+                if prev is not None and n.mask is None:
+                    prev.store = None
+                    prev.mask = None
+                pending[n.store] = n
+
     # ---- emission
     def finish(self):
         self._fuse_sincos()
+        self._drop_dead_stores()
         nodes = self.nodes
         # dead code elimination (values nobody uses and that have no side effect)
         live = set()

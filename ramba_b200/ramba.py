@@ -335,6 +335,7 @@ class deferred_op:
             return
 
         lw = Lowering([rb_dtype(det.dtype) for (_, det) in views])
+        lw.view_gids = [g for (g, _) in views]
         lw.note_view_reads(reads)
         temps = {}
         dead_values = {}

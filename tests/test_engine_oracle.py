@@ -25,3 +25,85 @@ def test_program_matches_numpy(oracle_engine, prog):
     got = prog(rb)
     exp = prog(onp)
     _check(got, exp, prog.__name__)
+
+
+def _captured_programs(monkeypatch):
+    """Record the op list of every flush (the lowered Program objects)."""
+    from ramba_b200 import ramba
+
+    progs = []
+    orig = ramba.run_deferred_ops
+
+    def spy(uuid, views, prog, *args, **kwargs):
+        progs.append(prog)
+        return orig(uuid, views, prog, *args, **kwargs)
+
+    monkeypatch.setattr(ramba, "run_deferred_ops", spy)
+    return progs
+
+
+def test_fusion_like_the_reference(oracle_engine, monkeypatch):
+    """TestFusion (ramba/tests/test_distributed_array.py:112-198): ten `a += 1` between two syncs are ONE
+    fused op that reads and writes `a` once; ten `a[i:] += 1` cannot fuse (ten flushes); an expression with
+    several temporaries materialises none of them."""
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+
+    progs = _captured_programs(monkeypatch)
+    a = rb.zeros(1000, dtype=float)
+    rb.sync()
+    del progs[:]
+    for _ in range(10):
+        a += 1
+    rb.sync()
+    assert len(progs) == 1
+    stores = [i for i in progs[0].insns if i["st_view"] != _cabi.NOSTORE]
+    loads = [i for i in progs[0].insns for k in ("a", "b", "c") if i[k + "_kind"] == _cabi.K_VIEW]
+    assert len(stores) == 1 and len(loads) == 1, "dead stores / repeated loads were not removed"
+    assert onp.array_equal(a.asarray(), onp.full(1000, 10.0))
+
+    del progs[:]
+    for i in range(10):
+        a[i:] += 1
+    rb.sync()
+    assert len(progs) == 10
+    exp = onp.full(1000, 10.0)
+    for i in range(10):
+        exp[i:] += 1
+    assert onp.array_equal(a.asarray(), exp)
+
+    b = rb.ones(1000, dtype=float)
+    rb.sync()
+    del progs[:]
+    b += (7 * b - 3) + (4 * b + 5 * b)
+    assert b[0] == 14
+    assert len(progs) == 1 and len({i["st_view"] for i in progs[0].insns if i["st_view"] != _cabi.NOSTORE}) == 1
+
+
+def test_dead_store_elimination_respects_masks_and_aliases(oracle_engine, monkeypatch):
+    import ramba_b200 as rb
+
+    b = rb.arange(200) * 1.0
+    rb.sync()
+    b[b > 100.0] = -1.0   # masked store: the elements it leaves alone must survive
+    b += 1
+    c = b[:-1] + 0        # reads b through another view
+    b += 1
+    rb.sync()
+    e = onp.arange(200) * 1.0
+    e[e > 100.0] = -1.0
+    e += 1
+    ce = e[:-1] + 0
+    e += 1
+    assert onp.array_equal(b.asarray(), e) and onp.array_equal(c.asarray(), ce)
+    # unmasked store first, masked one after it: both must reach memory
+    d = rb.zeros(150)
+    rb.sync()
+    d += 5
+    d[d > 1.0] = 2.0
+    d[rb.arange(150) % 2 == 0] = 7.0
+    de = onp.zeros(150)
+    de += 5
+    de[de > 1.0] = 2.0
+    de[onp.arange(150) % 2 == 0] = 7.0
+    assert onp.array_equal(d.asarray(), de)

@@ -269,6 +269,56 @@ def masked_assign(np):
     return [_h(a), _h(b)]
 
 
+# ---- deletion while ops are pending (TestDel :1398-1432)
+@case
+def delete_pending(np):
+    a = np.ones(100)
+    b = a + 3
+    del a
+    s = 0
+    c = np.ones(100)
+    d = c * 3
+    del c
+    for i in range(20):
+        a = np.ones(200)
+        v = a[37:137]
+        c = v * 3
+        s += c[42]
+    d += s
+    return [_h(b), _h(d)]
+
+
+# ---- randomised elementwise / transpose / slice mixes (the commented-out TestGeneric :1435-1560, seeded)
+@case
+def random_generic(np):
+    rng = onp.random.RandomState(20260922)
+    fa = (lambda x: x) if np is onp else np.fromarray
+    out = []
+    for _ in range(6):
+        x, y = int(rng.randint(1, 60)), int(rng.randint(1, 60))
+        al, bl = rng.randint(200, size=(x, y)) * 0.5, rng.randint(200, size=(x, y)) * 0.5
+        dl = rng.randint(200, size=(y, x)) * 0.5
+        a, b, d = fa(al), fa(bl), fa(dl)
+        out += [_h(2 * (a + b)), _h(d.T * b - a), _h((d.T + b).sum(axis=0)), onp.asarray((a * b).sum())]
+
+    def rand_slices(k):
+        lo = int(rng.randint(0, k - 1))
+        hi = int(rng.randint(lo, k))
+        n = hi - lo
+        c = int(rng.randint(0, k - n + 1))
+        return slice(lo, hi), slice(c, c + n)
+
+    Al, Bl = rng.randint(20, size=(120, 90)), rng.randint(20, size=(150, 130))
+    A, B = fa(Al), fa(Bl)
+    for _ in range(6):
+        s1, s2 = rand_slices(120)
+        t1, t2 = rand_slices(90)
+        out += [_h(A[s1, t1] * 3 + B[s2, t2]), _h(A[s1, t1] - A[s2, t2])]
+        A[s1, t1] = B[s2, t2] + 1
+    out.append(_h(A))
+    return out
+
+
 # ---- 0-d arrays and index terms (test_0d_* :705-759), newaxis
 @case
 def zero_d_and_newaxis(np):

@@ -162,8 +162,6 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   if (op->n_insns < 0 || op->n_insns > RB200_MAX_INSNS) return fail("too many instructions");
   if (op->n_regs < 0 || op->n_regs > RB200_MAX_REGS) return fail("too many spill registers");
   if (op->n_reds < 0 || op->n_reds > RB200_MAX_REDS) return fail("too many reductions");
-  const int sms = sm_count();
-  if (sms <= 0) return fail("no usable CUDA device (libramba_b200 has no CPU path)");
   cudaStream_t stream = (cudaStream_t)stream_v;
 
   // the 1-D kernel owns 8 elements per thread, the N-d and axis kernels 4
@@ -233,6 +231,9 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     k.pf_slot = -1;
     for (int d = 0; d < op->ndim; ++d) k.stride[d] = v.stride[d];
   }
+  // the op list is valid; from here on a device is needed (there is no CPU path)
+  const int sms = sm_count();
+  if (sms <= 0) return fail("no usable CUDA device (libramba_b200 has no CPU path)");
   cudaError_t e;
   const size_t reg_bytes = (size_t)(op->n_regs + 1) * V * kThreads * 8;  // + the scratch column of the out-of-line stores
 

@@ -1602,9 +1602,14 @@ def ones_like(other, dtype=None, shape=None, **kwargs):
 
 
 def full(shape, v, dtype=None, local_border=0, **kwargs):
-    if dtype is None:
-        dtype = np.asarray(v).dtype
-    return create_array(shape, v, local_border=local_border, dtype=dtype, **kwargs)
+    """Constant fill.  Like every creation routine of the reference the dtype defaults to float64 whatever the
+    fill value is (ramba/ramba.py:8753-8754 -> init_array -> bdarray default, 1125-1126)."""
+    return create_array(shape, v, local_border=local_border, dtype=np.float64 if dtype is None else dtype, **kwargs)
+
+
+def _full_of(shape, v):
+    """Constant array in the value's own dtype (internal: scalar results of traced user functions)."""
+    return create_array(shape, v, dtype=np.asarray(v).dtype)
 
 
 def full_like(other, v, dtype=None, **kwargs):
@@ -1660,7 +1665,7 @@ def fromfunction(function, shape, dtype=None, **kwargs):
         idx.append(a)
     out = function(*idx)
     if not isinstance(out, ndarray):
-        out = full(shape, out)
+        out = _full_of(shape, out)
     if np.dtype(dtype) != out.dtype:
         out = out.astype(dtype)
     return out
@@ -1932,15 +1937,18 @@ def tril(m, k=0):
 
 
 def select(condlist, choicelist, default=0):
-    """NumPy's select over same-shape arrays: the first true condition picks the choice."""
+    """The reference's select (ramba/ramba.py:9079-9092), reproduced as written: a float64 array filled with
+    `default`, then masked assignments in the order condlist[0], condlist[-1], condlist[-2], ... (its loop
+    indexes with -i), so where several conditions hold the one applied LAST wins - not NumPy's first-match
+    rule."""
     assert len(condlist) == len(choicelist) and len(condlist) > 0
     shape = condlist[0].shape
     for c in list(condlist) + [x for x in choicelist if isinstance(x, ndarray)]:
         assert c.shape == shape
-    out = full(shape, default)
-    for cond, choice in zip(reversed(list(condlist)), reversed(list(choicelist))):
-        out = where(cond, choice, out)
-    return out
+    temp = full(shape, default)
+    for i in range(len(choicelist)):
+        temp[condlist[-i]] = choicelist[-i]
+    return temp
 
 
 def _stack_by_first_index(parts, shape, dtype):
@@ -1959,6 +1967,9 @@ class MgridGen:
     unit steps only)."""
 
     def __getitem__(self, index):
+        if isinstance(index, slice):  # NumPy: a bare slice gives the 1-D grid itself
+            assert index.step is None, "mgrid supports unit-step slices"
+            return arange(0 if index.start is None else int(index.start), int(index.stop))
         index = index if isinstance(index, tuple) else (index,)
         starts, sizes = [], []
         for ix in index:
@@ -2056,7 +2067,7 @@ def _smap(what, func, args, dtype, axis, with_index):
     else:
         res = f(*args)
     if not isinstance(res, ndarray):
-        res = full(first.shape, res)
+        res = _full_of(first.shape, res)
     # the output has the dtype of the first array argument unless told otherwise (ramba/ramba.py:9872-9873, 9913-9914)
     if res.shape != first.shape:
         res = broadcast_to(res, first.shape) + zeros(first.shape, dtype=res.dtype)

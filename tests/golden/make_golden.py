@@ -8,6 +8,9 @@ are committed next to this script:
                             intersections, range splits) for several worker counts
     programs_golden.npz     outputs of tests/_programs.py run under `import ramba`
                             (RAMBA_NON_DIST=1, Numba CPU path) — pins the oracle and the CUDA path
+    api_golden.npz          outputs of the API-level cases of tests/test_api_parity.py run under `import ramba`;
+                            cases the reference cannot run here (functions it does not have, its NumPy-2
+                            incompatibilities) are recorded with the reason in __status__
 
 Usage (from the repo root; needs /root/reference, numba; Ray is replaced by a 10-line stub because
 NON_DIST mode never calls it — SURVEY.md Appendix C):
@@ -125,6 +128,28 @@ if mode == "partition":
             G["splits"].append({"W": W, "shape": list(shape), "splits": sorted([svl(x)[:2] for x in sp])})
     with open(out_path, "w") as f:
         json.dump(G, f)
+elif mode == "api":
+    import test_api_parity
+    res = {}
+    status = {}
+    only = [n for n in os.environ.get("RB_GOLDEN_CASES", "").split(",") if n]
+    for f in test_api_parity.CASES:
+        if only and f.__name__ not in only:
+            continue
+        try:
+            outs = f(ramba)
+            ramba.sync()
+            outs = [onp.asarray(o) for o in outs]
+            for i, o in enumerate(outs):
+                res["%s__%d" % (f.__name__, i)] = o
+            status[f.__name__] = "ok"
+        except BaseException as ex:  # the reference lacks the function, or trips over NumPy 2 (SURVEY §8c)
+            status[f.__name__] = "reference failed: %s: %s" % (type(ex).__name__, str(ex)[:200])
+            for k in [k for k in res if k.startswith(f.__name__ + "__")]:
+                del res[k]
+    res["__status__"] = onp.array(json.dumps(status))
+    onp.savez_compressed(out_path, **res)
+    print(json.dumps(status, indent=1))
 else:
     res = {}
     status = {}
@@ -156,9 +181,33 @@ def main():
         env = dict(os.environ)
         env.update({"RAMBA_NON_DIST": "1", "RAMBA_NUM_THREADS": "2", "RAMBA_BIG_DATA": "1",
                     "PYTHONPATH": tmp + ":" + REF, "NUMBA_CACHE_DIR": os.path.join(tmp, "nbcache")})
-        for mode, name in (("partition", "partition_golden.json"), ("programs", "programs_golden.npz")):
+        only = sys.argv[1:]
+        for mode, name in (("partition", "partition_golden.json"), ("programs", "programs_golden.npz"), ("api", "api_golden.npz")):
+            if only and mode not in only:
+                continue
             out = os.path.join(HERE, name)
             subprocess.check_call([sys.executable, child, mode, out], env=env, cwd=tmp)
+            if mode == "api":
+                # a case that fails inside the reference can leave its pending-op state broken for the cases
+                # after it: give every failed case a second run alone in a fresh process
+                import numpy as onp
+
+                z = dict(onp.load(out))
+                status = json.loads(str(z["__status__"]))
+                for name in [n for n, st in status.items() if st != "ok"]:
+                    alone = os.path.join(tmp, "alone.npz")
+                    env2 = dict(env)
+                    env2["RB_GOLDEN_CASES"] = name
+                    subprocess.check_call([sys.executable, child, mode, alone], env=env2, cwd=tmp)
+                    z2 = dict(onp.load(alone))
+                    st2 = json.loads(str(z2["__status__"]))
+                    status[name] = st2[name]
+                    for k, v in z2.items():
+                        if k != "__status__":
+                            z[k] = v
+                z["__status__"] = onp.array(json.dumps(status))
+                onp.savez_compressed(out, **z)
+                print(json.dumps(status, indent=1))
             print("wrote", out, os.path.getsize(out), "bytes")
 
 

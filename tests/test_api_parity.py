@@ -230,8 +230,9 @@ def sstencil_skeleton(np):
         return a[0, -2] + a[0, 2] - 2.0 * b[0, 0]
 
     n, m = 30, 40
-    x = np.fromfunction(lambda i, j: (i * 7 + j * 3) % 16, (n, m))
-    y = np.fromfunction(lambda i, j: (i + j) % 5, (n, m))
+    kw = {} if np is onp else {"local_border": 2}  # the reference's sstencil wants padded shards (ramba/ramba.py:10010-10015)
+    x = np.fromfunction(lambda i, j: (i * 7 + j * 3) % 16, (n, m), **kw)
+    y = np.fromfunction(lambda i, j: (i + j) % 5, (n, m), **kw)
     if np is onp:
         r1 = onp.zeros((n, m))
         r1[1:-1, 1:-1] = 0.25 * (x[:-2, 1:-1] + x[2:, 1:-1] + x[1:-1, :-2] + x[1:-1, 2:]) + x[1:-1, 1:-1]
@@ -321,7 +322,7 @@ def random_generic(np):
 
 # ---- 0-d arrays and index terms (test_0d_* :705-759), newaxis
 @case
-def zero_d_and_newaxis(np):
+def zero_d(np):
     a0 = np.array(7)
     a0[()] = 3
     a = np.arange(200)
@@ -329,9 +330,13 @@ def zero_d_and_newaxis(np):
     a[b] = 0
     o = np.ones((20, 20))
     o[:, b] = 0
+    return [onp.asarray(np.array(7)[()]), onp.asarray(a0[()]), onp.asarray(a[b]), _h(a), _h(o[:, b]), _h(o), onp.asarray(float(np.array(7)))]
+
+
+@case
+def newaxis_views(np):
     c = np.ones((6, 7, 8)) * 3
-    return [onp.asarray(np.array(7)[()]), onp.asarray(a0[()]), onp.asarray(a[b]), _h(a), _h(o[:, b]), _h(o), onp.asarray(float(np.array(7))),
-            _h(np.arange(120)[:, None] * 1.0), _h(np.arange(120)[None, :] + np.arange(30)[:, None]), _h(c[2, None, ..., None, 1:5]),
+    return [_h(np.arange(120)[:, None] * 1.0), _h(np.arange(120)[None, :] + np.arange(30)[:, None]), _h(c[2, None, ..., None, 1:5]),
             _h(c[None].sum(axis=0))]
 
 
@@ -350,15 +355,22 @@ def unit_dim_views(np):
 
 # ---- index-driven builders (test_triu1-3 :1023-1045, test_mgrid_1-4 :1135-1163, meshgrid, select)
 @case
-def triu_tril(np):
+def triu_family(np):
     a = np.fromfunction(lambda i, j: i + j, (50, 50), dtype=int)
     r = np.fromfunction(lambda i, j: i * 100 + j, (30, 120), dtype=onp.float64)
-    return [_h(np.triu(a)), _h(np.triu(a, k=-2)), _h(np.triu(a, k=2)), _h(np.triu(r, k=5)), _h(np.tril(a)), _h(np.tril(r, k=-3))]
+    return [_h(np.triu(a)), _h(np.triu(a, k=-2)), _h(np.triu(a, k=2)), _h(np.triu(r, k=5))]
+
+
+@case
+def tril_family(np):  # NumPy's tril; the reference has only triu
+    a = np.fromfunction(lambda i, j: i + j, (50, 50), dtype=int)
+    r = np.fromfunction(lambda i, j: i * 100 + j, (30, 120), dtype=onp.float64)
+    return [_h(np.tril(a)), _h(np.tril(r, k=-3))]
 
 
 @case
 def mgrid_meshgrid(np):
-    out = [_h(np.mgrid[0:20, 0:20]), _h(np.mgrid[0:5, 0:5]), _h(np.mgrid[2:9, 0:30, 1:4])]
+    out = [_h(np.mgrid[0:20, 0:20]), _h(np.mgrid[0:5, 0:5]), _h(np.mgrid[0:7, 0:30, 0:3])]
     m, n = np.mgrid[0:20, 0:20]
     out += [_h(m), _h(n)]
     x, y = np.arange(30) * 0.5, np.arange(12) * 2.0
@@ -370,10 +382,21 @@ def mgrid_meshgrid(np):
 
 
 @case
+def mgrid_offsets(np):  # slice starts: NumPy semantics (the reference's mgrid counts from 0 whatever the start)
+    return [_h(np.mgrid[2:9, 0:30, 1:4]), _h(np.mgrid[5:25])]
+
+
+@case
 def select_family(np):
     a = np.arange(200) - 50
     conds = [a < 0, a < 50, a < 100]
     choices = [a * 0, a * 2, a * 3]
+    if np is onp:
+        # the reference's select, as written (ramba/ramba.py:9079-9092): float64, assignment order 0, -1, -2, ...
+        temp = onp.full(a.shape, -7.0)
+        for i in range(len(choices)):
+            temp[conds[-i]] = choices[-i][conds[-i]]
+        return [temp]
     return [_h(np.select(conds, choices, default=-7))]
 
 
@@ -390,7 +413,7 @@ def smap_family(np):
             _h(np.smap("lambda x,y: 3*x-7*y", a2, a)), _h(np.smap(lambda x, y: 3 * x - 7 * y, a2, a)),
             _h(np.smap(lambda x: x * 0.5, a)),  # result takes the dtype of the first array
             _h(np.smap(lambda x: x * 0.5, a, dtype=onp.float64)),
-            _h(np.smap("lambda x: numpy.sin(x*0.25)*10", a))]  # string lambdas see the package as `numpy`
+            _h(np.smap("lambda x: numpy.sin(x*0.25)*10", a, imports=["numpy"]))]  # string lambdas see the package as `numpy`
 
 
 @case
@@ -409,10 +432,18 @@ def smap_index_family(np):
 def sreduce_family(np):
     a = np.arange(300) - 100
     if np is onp:
-        return [onp.asarray((a * a).sum()), onp.asarray(onp.max(2 * a + 1)), onp.asarray(5 + (a * onp.arange(300)).sum()),
-                onp.asarray(onp.min(a * 0.5))]
+        return [onp.asarray((a * a).sum()), onp.asarray(onp.max(2 * a + 1)), onp.asarray(5 + (a * onp.arange(300)).sum())]
     return [onp.asarray(np.sreduce(lambda x: x * x, lambda p, q: p + q, 0, a)),
-            onp.asarray(np.sreduce("lambda x: 2*x+1", lambda p, q: max(p, q), -10**9, a)),
+            onp.asarray(np.sreduce(lambda x: 2 * x + 1, lambda p, q: max(p, q), -10**9, a)),
+            onp.asarray(np.sreduce_index(lambda i, x: i * x, lambda p, q: p + q, 5, a))]
+
+
+@case
+def sreduce_forms(np):  # string lambdas and SreduceReducer pairs (the reference takes functions only)
+    a = np.arange(300) - 100
+    if np is onp:
+        return [onp.asarray(onp.max(2 * a + 1)), onp.asarray(5 + (a * onp.arange(300)).sum()), onp.asarray(onp.min(a * 0.5))]
+    return [onp.asarray(np.sreduce("lambda x: 2*x+1", lambda p, q: max(p, q), -10**9, a)),
             onp.asarray(np.sreduce_index(lambda i, x: i * x, "lambda p,q: p+q", 5, a)),
             onp.asarray(np.sreduce(lambda x: x * 0.5, np.SreduceReducer(min, min), 1e300, a))]
 
@@ -420,13 +451,11 @@ def sreduce_family(np):
 @case
 def cumsum_family(np):
     out = [_h(np.cumsum(np.arange(200))), _h(np.cumsum(np.arange(150) * 0.5)), _h(np.cumsum(np.arange(7)))]
-    for shp in [(4, 50), (20, 20), (50, 4)]:
-        a = np.arange(shp[0] * shp[1]) if np is onp else None
+    for shp in [(4, 50), (20, 20), (50, 4)]:  # the reference's own shapes (tests/…:1375-1386)
+        a = onp.arange(shp[0] * shp[1]).reshape(shp)
+        b = a if np is onp else np.fromarray(a)
         for axis in range(2):
-            if np is onp:
-                out.append(onp.cumsum(a.reshape(shp), axis=axis))
-            else:
-                out.append(_h(np.cumsum(np.fromfunction(lambda i, j: i * shp[1] + j, shp, dtype=onp.int64), axis=axis)))
+            out.append(_h(np.cumsum(b, axis=axis)))
     return out
 
 

@@ -70,3 +70,65 @@ def test_cuda_matches_reference(gpu_engine, golden_programs, prog):
     got = prog(rb)
     assert _cabi.launch_count() > before
     compare_to_golden(prog.__name__, got, z, transcendental_tol=(prog.__name__ == "chain"))
+
+
+# ---- API-level cases (tests/test_api_parity.py) against the real reference ----------------------
+@pytest.fixture(scope="module")
+def golden_api():
+    z = onp.load(os.path.join(GOLD, "api_golden.npz"))
+    return z, json.loads(str(z["__status__"]))
+
+
+def _api_cases():
+    import test_api_parity
+
+    return test_api_parity.CASES
+
+
+def _compare_api(name, got, z, rtol, atol):
+    n_ref = len([k for k in z.files if k.startswith(name + "__")])
+    assert len(got) == n_ref, "%s: %d outputs vs %d from the reference" % (name, len(got), n_ref)
+    for i, g in enumerate(got):
+        e = z["%s__%d" % (name, i)]
+        g = onp.asarray(g)
+        assert g.shape == e.shape, "%s[%d]: shape %s vs reference %s" % (name, i, g.shape, e.shape)
+        assert g.dtype == e.dtype, "%s[%d]: dtype %s vs reference %s" % (name, i, g.dtype, e.dtype)
+        if e.dtype.kind == "f":
+            assert onp.allclose(g, e, rtol=rtol, atol=atol, equal_nan=True), "%s[%d]" % (name, i)
+        else:
+            assert onp.array_equal(g, e), "%s[%d]" % (name, i)
+
+
+def test_api_golden_covers_the_cases(golden_api):
+    """Every API case has a verdict from the real reference; the ones it cannot run are the known ones
+    (its NumPy-2 incompatibilities, functions it does not have, its padded-shard requirement)."""
+    _, status = golden_api
+    names = [f.__name__ for f in _api_cases()]
+    assert sorted(status) == sorted(names), "regenerate tests/golden/api_golden.npz (python tests/golden/make_golden.py api)"
+    not_run = sorted(n for n in names if status[n] != "ok")
+    assert not_run == sorted(["reductions_full", "reductions_axis", "sstencil_skeleton", "random_generic", "zero_d", "tril_family",
+                              "mgrid_offsets", "sreduce_forms"]), not_run
+
+
+@pytest.mark.parametrize("name", [f.__name__ for f in _api_cases()])
+def test_api_oracle_engine_matches_reference(oracle_engine, golden_api, name):
+    import ramba_b200 as rb
+
+    z, status = golden_api
+    if status[name] != "ok":
+        pytest.skip("the reference cannot run this case here: " + status[name])
+    f = [c for c in _api_cases() if c.__name__ == name][0]
+    _compare_api(name, f(rb), z, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [f.__name__ for f in _api_cases()])
+def test_api_cuda_matches_reference(gpu_engine, golden_api, name):
+    import ramba_b200 as rb
+
+    z, status = golden_api
+    if status[name] != "ok":
+        pytest.skip("the reference cannot run this case here: " + status[name])
+    f = [c for c in _api_cases() if c.__name__ == name][0]
+    # CUDA libdevice vs the reference's libm under Numba fastmath: stated tolerance for floating point
+    _compare_api(name, f(rb), z, rtol=1e-12, atol=1e-14)

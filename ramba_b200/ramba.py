@@ -1671,12 +1671,14 @@ def fromfunction(function, shape, dtype=None, **kwargs):
     return out
 
 
-def eye(N, M=None, k=0, dtype=float64, **kwargs):
+def eye(N, M=None, k=0, dtype=float32, **kwargs):
+    """Ones on the k-th diagonal.  The default dtype is float32 as in the reference (ramba/ramba.py:8765-8779),
+    not NumPy's float64."""
     M = N if M is None else M
     return fromfunction(lambda i, j: (i + k) == j, (N, M)).astype(dtype)
 
 
-def identity(n, dtype=float64):
+def identity(n, dtype=float32):
     return eye(n, dtype=dtype)
 
 

@@ -270,6 +270,53 @@ def masked_assign(np):
     return [_h(a), _h(b)]
 
 
+# ---- the reference's TestBasic cases, as written there (masks :975-990, where :992-1021, linspace :1093-1133,
+# identity/eye :773-792, transposes :1047-1073, transposed reductions :1332-1366)
+@case
+def ref_masked(np):
+    a = np.arange(200)
+    a[a % 5 == 1] -= 50
+    g = np.fromfunction(lambda i, j: i + j, (50, 50), dtype=int)
+    return [_h(a), onp.asarray(g[g < 20].sum())]
+
+
+@case
+def ref_where(np):
+    a = np.arange(200)
+    b = np.ones(200)
+    g = np.fromfunction(lambda i, j: i + j, (50, 50), dtype=int)
+    col = np.ones((50, 1))
+    e = np.fromfunction(lambda i, j: 500 + i + j, (50, 50), dtype=int)
+    bc = np.fromfunction(lambda i, j: i + 200, (50, 1), dtype=int)
+    out = [np.where(a > 133, a, b), np.where(g > 33, g, col), np.where(bc > 233, g, e)]
+    if np is onp:
+        # the reference materialises `where` in the dtype of its first value operand (where_executor,
+        # ramba/ramba.py:9785: empty(..., dtype=a.dtype)) even though it announces result_type(a, b)
+        out = [o.astype(onp.int64) for o in out]
+    return [_h(o) for o in out]
+
+
+@case
+def ref_linspace(np):
+    l3 = np.linspace(1, 5, num=10, endpoint=False, retstep=True)
+    l4 = np.linspace(1, 5, num=200, endpoint=False, retstep=True)
+    return [_h(np.linspace(1, 5, num=10)), _h(np.linspace(1, 5, num=200)), _h(l3[0]), _h(l4[0]), onp.asarray(l3[1]), onp.asarray(l4[1]),
+            _h(np.linspace(10, 30, dtype=int))]
+
+
+@case
+def ref_identity_eye(np):
+    return [_h(np.identity(100)), _h(np.eye(100, 50)), _h(np.eye(50, 100, k=3))]
+
+
+@case
+def ref_transposes(np):
+    a = np.fromfunction(lambda i, j: i * 100 + j, (30, 40))
+    b = np.fromfunction(lambda i, j, k: i * 10000 + j * 100 + k, (12, 15, 10))
+    return [_h(np.transpose(a)), _h(np.transpose(b)), _h(np.transpose(b, (1, 0, 2))), _h(b.transpose(2, 0, 1)),
+            _h(a.T.sum(axis=0)), _h(a.T[5:30, 3:20].sum(axis=1)), onp.asarray(b.transpose(1, 2, 0)[2:9, :, 3:].sum())]
+
+
 # ---- deletion while ops are pending (TestDel :1398-1432)
 @case
 def delete_pending(np):

@@ -914,10 +914,10 @@ class ndarray:
         new_dtype = unify_args(self.dtype, rhs, dtype)
         if op == "__truediv__":
             # division becomes multiplication by the reciprocal (ramba/ramba.py:6121-6126)
-            optext = "mul"
+            op, optext = "__mul__", "mul"
             rhs = 1.0 / rhs
         elif op == "__itruediv__":
-            optext = "mul"
+            op, optext = "__imul__", "mul"
             rhs = 1.0 / rhs
         new_shape, selfview, rhsview = ndarray.broadcast(self, rhs)
         if new_shape is None:  # 0-d with scalar: compute on the host
@@ -1502,6 +1502,8 @@ def array(x, dtype=None, copy=True, **kwargs):
         return x.copy() if copy else x
     a = np.array(x, dtype=dtype)
     if a.shape == ():
+        if dtype is None:
+            a = a.astype(np.float64)  # 0-d arrays default to float64 like every array of the reference (ramba/ramba.py:8831-8837)
         nd = ndarray((), dtype=a.dtype)
         nd.distribution = a
         nd.bdarray.distribution = a
@@ -1571,9 +1573,13 @@ def _fill_now(nd, value):
     RT.launch(prog, [n], [0], [(sh.buf.data_ptr(), [1], code)])
 
 
-def init_array(shape, filler, local_border=0, dtype=None, distribution=None, **kwargs):
+def init_array(shape, filler, local_border=0, dtype=None, distribution=None, tuple_arg=True, **kwargs):
+    """Array filled by `filler`: a constant, or a function of the global index - which it receives as ONE tuple
+    unless tuple_arg is False (ramba/ramba.py:8658-8676; fromfunction is the tuple_arg=False form, 8904-8905)."""
     if callable(filler):
-        return fromfunction(filler, shape, dtype=dtype)
+        if isinstance(shape, numbers.Integral):
+            shape = (shape,)
+        return fromfunction((lambda *idx: filler(idx)) if tuple_arg else filler, shape, dtype=dtype)
     return create_array(shape, filler, local_border=local_border, dtype=dtype, distribution=distribution, **kwargs)
 
 

@@ -270,6 +270,45 @@ def masked_assign(np):
     return [_h(a), _h(b)]
 
 
+# ---- TestOps (:262-432): the five arithmetic operators over every pairing of distributed / small / 0-d ramba
+# arrays, NumPy arrays and Python / NumPy scalars, in both operand orders; TestBroadcast (:202-237)
+@case
+def ref_ops_matrix(np):
+    out = []
+    pairs = [
+        lambda: (np.ones((100, 100)), np.ones((100, 100))), lambda: (np.ones((5, 5)), np.ones((5, 5))), lambda: (np.ones(()), np.ones(())),
+        lambda: (np.ones((100, 100)), onp.ones((100, 100))), lambda: (onp.ones((100, 100)), np.ones((100, 100))),
+        lambda: (np.ones((5, 5)), onp.ones((5, 5))), lambda: (onp.ones((5, 5)), np.ones((5, 5))),
+        lambda: (np.ones((100, 100)) * 3, 7.0), lambda: (7.0, np.ones((100, 100)) * 3), lambda: (np.ones((5, 5)) * 3, 7), lambda: (7, np.ones((5, 5)) * 3),
+        lambda: (np.array(13), 7), lambda: (7, np.array(13)), lambda: (np.array(13), 7.0), lambda: (7.0, np.array(13)),
+        lambda: (np.ones((100, 100)) * 3, onp.ones(1)[0] * 7), lambda: (onp.ones(1)[0] * 7, np.ones((100, 100)) * 3),
+        lambda: (np.array(13), onp.ones(1)[0]), lambda: (onp.ones(1)[0], np.array(13)),
+    ]
+    for mk in pairs:
+        for op in ("+", "-", "*", "/", "//"):
+            a, b = mk()
+            out.append(_h(eval("a" + op + "b")))
+    return out
+
+
+@case
+def ref_broadcast(np):
+    out = []
+    for N in (10, 100):
+        a = np.arange(N)
+        X = np.fromfunction(lambda x, y: x + y, (N, 1))
+        out += [_h(a), _h(X), _h(a + X)]
+    return out
+
+
+@case
+def ref_init_array(np):  # TestBasic::test7-12 (:646-694): fillers receive the global index as one tuple
+    if np is onp:
+        return [onp.arange(120) * 100.0, onp.fromfunction(lambda i, j: (i + j) * 5, (120, 100)), onp.fromfunction(lambda i, j: i * j + 7, (120, 100))]
+    return [_h(np.init_array(120, lambda index: index[0] * 100)), _h(np.init_array((120, 100), lambda index: (index[0] + index[1]) * 5)),
+            _h(np.init_array((120, 100), lambda x: (x[0] * x[1]) + 7))]
+
+
 # ---- the reference's TestBasic cases, as written there (masks :975-990, where :992-1021, linspace :1093-1133,
 # identity/eye :773-792, transposes :1047-1073, transposed reductions :1332-1366)
 @case

@@ -1049,10 +1049,18 @@ class ndarray:
             return
         if not (isinstance(index, ndarray) and index.dtype == np.bool_):
             index = self._plain_index(index)
+            if builtins.any(i is Ellipsis for i in index) and not builtins.any(i is None for i in index):
+                pos = [j for j, i in enumerate(index) if i is Ellipsis][0]
+                index = index[:pos] + (slice(None),) * (self.ndim - (len(index) - 1)) + index[pos + 1:]
         view = self[index]
         if not isinstance(view, ndarray):  # single element
             cindex = canonical_index(index, self.shape)
             view = self[tuple(slice(s.start, s.start + 1) for s in cindex)]
+        if isinstance(value, np.ndarray):
+            while value.ndim > view.ndim and value.shape[0] == 1:  # NumPy drops extra leading unit dims of the value
+                value = value[0]
+            if value.size == 1:
+                value = value.reshape(())
         if isinstance(value, (numbers.Number, np.generic)) or (isinstance(value, np.ndarray) and value.shape == ()):
             deferred_op.add_op([view, value if not isinstance(value, np.ndarray) else value.item()], view)
             return

@@ -309,6 +309,95 @@ def ref_init_array(np):  # TestBasic::test7-12 (:646-694): fillers receive the g
             _h(np.init_array((120, 100), lambda x: (x[0] * x[1]) + 7))]
 
 
+# ---- TestStencil / TestApps / view tests of the reference, as written there (:23-73, :761-872, :1277-1306)
+@case
+def ref_weighted_subarrays(np):
+    def weighted(update_all):
+        A = np.ones(100, dtype=float)
+        B = np.zeros(100, dtype=float)
+        for _ in range(10):
+            B[2:-2] += 0.2 * A[:-4] - 0.5 * A[1:-3] + 0.4 * A[2:-2] - 0.5 * A[3:-1] + 0.2 * A[4:]
+            if update_all:
+                A *= 1.1
+            else:
+                A[2:-2] *= 1.1   # same size as the stencil: needs read-after-write detection, no fusion
+        return onp.asarray(int(abs(B).sum() * 1e8))
+
+    return [weighted(True), weighted(False)]
+
+
+@case
+def ref_reduction_fusion(np):
+    A = np.ones((50, 5))
+    e = 0.2 * A[:-2] + 0.5 * A[1:-1] + 0.3 * A[2:]
+    v = (0.2 * A[:-2] + 0.5 * A[1:-1] + 0.3 * A[2:]).sum(axis=0).sum()
+    h = (0.2 * A[:-2] + 0.5 * A[1:-1] + 0.3 * A[2:]).sum(axis=1).sum()
+    z = (0.2 * A[:-2] + 0.5 * A[1:-1] + 0.3 * A[2:]).sum()
+    return [onp.asarray(v), onp.asarray(h), onp.asarray(z), onp.asarray(bool(v == h and h == z)), _h(e)]
+
+
+@case
+def ref_matmul(np):
+    A = np.fromfunction(lambda x, y: x + y, (20, 30))
+    B = np.fromfunction(lambda x, y: x + y, (30, 40))
+    return [_h((np.broadcast_to(A.T, (40, 30, 20)).T * np.broadcast_to(B, (20, 30, 40))).sum(axis=1)),
+            _h((np.expand_dims(A, 2) * B).sum(axis=1))]
+
+
+@case
+def ref_setitem(np):
+    a = np.ones((10, 20))
+    a[2:5] = 5
+    a[..., 8:12] += 12
+    a[4, 17] = -3
+    a[1, ..., 1] += 32
+    a[7, 3] = onp.zeros((1, 1, 1))
+    b = np.ones(120)
+    v = b[10:50]
+    b += 7
+    return [_h(a), _h(v)]
+
+
+@case
+def ref_slices(np):
+    a = np.arange(200)
+    a[20:120] += 50
+    b = a[40:140]
+    b -= 20
+    c = a[60:160] - 25
+    d = b + a[80:180]
+    r1 = b + c + d
+    a = np.arange(200)
+    a[20:120:3] += 50
+    b = a[40:108:2]
+    b -= 20
+    c = a[60:196:4] - 25
+    d = b + a[80:180:3]
+    return [_h(r1), _h(b + c + d)]
+
+
+@case
+def ref_skipslice2(np):
+    a = np.fromfunction(lambda i, j: i + j, (500, 50), dtype=int)
+    b = a[40:340:3, 20::2]
+    b[b > 50] -= 20
+    c = np.broadcast_to(b.T, (70, 15, 100))
+    d = c[15:25:2, 2:7, ::7] - c[20:30:2, 6:11, 1::7] + 4
+    e = np.sum(d)
+    return [_h(d + e)]
+
+
+@case
+def ref_negative_skipslice(np):
+    a = np.fromfunction(lambda i, j: i + j, (500, 50), dtype=int)
+    b = a[340:40:-3, :20:-2]
+    b[b > 50] -= 20
+    c = np.broadcast_to(b.T, (70, 15, 100))
+    d = c[15:25:2, 7:2:-1, ::-3] - c[30:20:-2, 6:11, -1::-3] + 4
+    e = np.sum(d)
+    return [_h(d + e)]
+
+
 # ---- the reference's TestBasic cases, as written there (masks :975-990, where :992-1021, linspace :1093-1133,
 # identity/eye :773-792, transposes :1047-1073, transposed reductions :1332-1366)
 @case

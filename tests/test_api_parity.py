@@ -398,6 +398,48 @@ def ref_negative_skipslice(np):
     return [_h(d + e)]
 
 
+# ---- test_clip1-4 (:1277-1306), TestReduction (:1308-1366)
+@case
+def ref_clip(np):
+    a = np.arange(200)
+    b = np.empty(200, dtype=int)
+    a.clip(30, 50, out=b)
+    c = np.arange(200)
+    c.clip(30, 50, out=c)
+    return [_h(a.clip(30, 50)), _h(np.clip(a, 30, 50)), _h(b), _h(c)]
+
+
+@case
+def ref_reduction_sum_prod(np):  # the sum / prod half of testFull, testAxis1, testAxis2 (min / max: see ref_reduction_min_max)
+    f = np.fromfunction(lambda i, j, k: 0.01 * i + 0.7 * j + 0.3 * k + 1, (8, 6, 4))
+    g = np.fromfunction(lambda i, j, k: 10 * i + 7 * j + k + 1, (8, 6, 4))
+    out = []
+    for op in ("sum", "prod"):
+        out += [onp.asarray(getattr(f, op)()), _h(getattr(g, op)(axis=1)), _h(getattr(g, op)(axis=(1, 0)))]
+    return out
+
+
+@case
+def ref_reduction_min_max(np):  # the reference cannot run these under NumPy 2 (np.NINF in getminmax)
+    f = np.fromfunction(lambda i, j, k: 0.01 * i + 0.7 * j + 0.3 * k + 1, (8, 6, 4))
+    g = np.fromfunction(lambda i, j, k: 10 * i + 7 * j + k + 1, (8, 6, 4))
+    out = []
+    for op in ("min", "max"):
+        out += [onp.asarray(getattr(f, op)()), _h(getattr(g, op)(axis=1)), _h(getattr(g, op)(axis=(1, 0)))]
+    return out
+
+
+@case
+def ref_transpose_reductions(np):
+    out = []
+    for sl in (slice(None), slice(50, 170), slice(150, 170)):
+        def mk():
+            return np.ones((200, 100), dtype=int)[sl]
+        out += [_h(np.sum(mk(), axis=0)), _h(np.sum(mk(), axis=1)), _h(np.sum(mk().T, axis=0)), _h(np.sum(mk().T, axis=1)),
+                onp.asarray(np.sum(mk())), onp.asarray(np.sum(mk().T))]
+    return out
+
+
 # ---- the reference's TestBasic cases, as written there (masks :975-990, where :992-1021, linspace :1093-1133,
 # identity/eye :773-792, transposes :1047-1073, transposed reductions :1332-1366)
 @case

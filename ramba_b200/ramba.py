@@ -1932,6 +1932,100 @@ def sstencil(func, *args, out=None, **kwargs):
 
 
 # =============================================================================================
+# joining and padding: concatenate / stack / pad.  The reference has dedicated redistribution executors
+# (ramba/ramba.py:9479-9590, 9280-9420); here the result is allocated with the default distribution and filled by
+# ordinary slice assignments, i.e. fused copy ops whose source pieces cross ranks through the generic piece
+# exchange of run_deferred_ops.
+# =============================================================================================
+def concatenate(arrayseq, axis=0, out=None, **kwargs):
+    assert out is None, "concatenate(out=...) is not supported"
+    arrays = [_as_nd(a) for a in arrayseq]
+    assert len(arrays) > 0 and builtins.any(isinstance(a, ndarray) for a in arrays)
+    first = arrays[0]
+    axis = axis % first.ndim
+    out_shape = list(first.shape)
+    for a in arrays[1:]:
+        assert a.ndim == first.ndim, "all the input arrays must have the same number of dimensions"
+        assert a.dtype == first.dtype, "concatenate: dtypes must match (ramba/ramba.py:9566)"
+        for i in range(first.ndim):
+            if i == axis:
+                out_shape[i] += a.shape[i]
+            else:
+                assert a.shape[i] == first.shape[i], "all the input array dimensions except for the concatenation axis must match"
+    res = empty(tuple(out_shape), dtype=first.dtype)
+    at = 0
+    for a in arrays:
+        sl = tuple(slice(at, at + a.shape[i]) if i == axis else slice(None) for i in range(first.ndim))
+        if a.shape[axis] > 0:
+            res[sl] = a
+        at += a.shape[axis]
+    return res
+
+
+def stack(arrays, axis=0, out=None):
+    assert out is None, "stack(out=...) is not supported"
+    arrays = [_as_nd(a) for a in arrays]
+    assert builtins.all(a.shape == arrays[0].shape for a in arrays), "all input arrays must have the same shape"
+    axis = axis % (arrays[0].ndim + 1)
+    return concatenate([a.expand_dims(axis) for a in arrays], axis=axis)
+
+
+def pad(arr, pad_width, mode="constant", **kwargs):
+    """NumPy's pad for the modes the reference has: constant (with constant_values), edge, wrap, empty
+    (ramba/ramba.py:9400-9420).  Axes are padded one after the other, like NumPy does, so corners come out right."""
+    arr = _as_nd(arr)
+    assert arr.ndim >= 1
+    assert mode in ("constant", "empty", "edge", "wrap")
+    if isinstance(pad_width, numbers.Integral):
+        pad_width = (pad_width, pad_width)
+    if not isinstance(pad_width[0], (tuple, list)):
+        pad_width = tuple(tuple(pad_width) if len(pad_width) == 2 else (pad_width[0], pad_width[0]) for _ in range(arr.ndim))
+    assert arr.ndim == len(pad_width)
+    cvals = kwargs.get("constant_values", 0)
+    if isinstance(cvals, numbers.Number):
+        cvals = ((cvals, cvals),) * arr.ndim
+    elif not isinstance(cvals[0], (tuple, list)):
+        cvals = (tuple(cvals),) * arr.ndim
+    elif len(cvals) == 1:
+        cvals = tuple(cvals) * arr.ndim
+    cur = arr
+    for ax in range(arr.ndim):
+        before, after = int(pad_width[ax][0]), int(pad_width[ax][1])
+        if before == 0 and after == 0:
+            continue
+        n = cur.shape[ax]
+        shape = tuple(cur.shape[i] + (before + after if i == ax else 0) for i in range(cur.ndim))
+
+        def region(lo, hi):
+            return tuple(slice(lo, hi) if i == ax else slice(None) for i in range(cur.ndim))
+
+        new = empty(shape, dtype=cur.dtype)
+        new[region(before, before + n)] = cur
+        if mode == "constant":
+            if before:
+                new[region(0, before)] = cvals[ax][0]
+            if after:
+                new[region(before + n, before + n + after)] = cvals[ax][1]
+        elif mode == "edge":
+            if before:
+                new[region(0, before)] = cur[region(0, 1)]
+            if after:
+                new[region(before + n, before + n + after)] = cur[region(n - 1, n)]
+        elif mode == "wrap":
+            assert before <= n and after <= n, "pad(mode='wrap') wider than the array is not supported"
+            if before:
+                new[region(0, before)] = cur[region(n - before, n)]
+            if after:
+                new[region(before + n, before + n + after)] = cur[region(0, after)]
+        cur = new
+    return cur if cur is not arr else copy(arr)
+
+
+for _n in ("concatenate", "stack", "pad"):
+    HANDLED_FUNCTIONS[_n] = globals()[_n]
+
+
+# =============================================================================================
 # index-driven builders: triu / tril / select / mgrid / meshgrid.  The reference runs a per-worker NumPy
 # routine for each (ramba/ramba.py:2091-2111 triu, 8993-9050 mgrid/meshgrid, 9079-9092 select); here they are
 # ordinary fused elementwise ops over iota operands.

@@ -440,6 +440,52 @@ def ref_transpose_reductions(np):
     return out
 
 
+# ---- joining and padding (test_concatenate_1-2 :1075-1091, test_pad1 / pad2 / pad1_slice :1189-1276)
+@case
+def ref_concatenate(np):
+    shape = (20, 4)
+    a = np.fromfunction(lambda i, j: i + j, shape, dtype=int)
+    b = np.fromfunction(lambda i, j: i + j, shape, dtype=int)
+    c = np.fromfunction(lambda i, j: i * 7 - j, (130, 4), dtype=int)
+    return [_h(np.concatenate([a, b], axis=0)), _h(np.concatenate([a, b], axis=1)), _h(np.concatenate([a, c, b], axis=0)), _h(np.concatenate([a, b]))]
+
+
+@case
+def stack_family(np):  # the reference declares stack but its executor is a stub (ramba/ramba.py:9576-9577)
+    a = np.fromfunction(lambda i, j: i + j, (20, 4), dtype=int)
+    b = np.fromfunction(lambda i, j: i * j, (20, 4), dtype=int)
+    return [_h(np.stack([a, b])), _h(np.stack([a, b, a], axis=2)), _h(np.stack([a, b], axis=-1))]
+
+
+@case
+def ref_pad_1d(np):
+    out = []
+    tests = [(2, {}), ((0, 1), {}), ((2, 0), {}), ((3, 4), {}), ((0, 3), {"constant_values": ((0, 7),)}), ((5, 0), {"constant_values": ((5, 0),)}),
+             ((1, 2), {"constant_values": ((3, 4),)})]
+    for mode in ("constant", "edge", "wrap"):
+        for width, kw in tests:
+            if kw and mode != "constant":
+                continue
+            out.append(_h(np.pad(np.arange(200), width, mode=mode, **kw)))
+            out.append(_h(np.pad(np.arange(300)[25:225], width, mode=mode, **kw)))
+    return out
+
+
+@case
+def ref_pad_2d(np):
+    out = []
+    tests = [2, (2, 3), ((0, 1), (0, 1)), ((2, 0), (3, 0)), ((2, 0), (0, 3)), ((0, 2), (3, 0)), ((2, 2), (0, 3)), ((0, 2), (3, 3)), ((4, 2), (3, 3))]
+    for shape in [(20, 30), (400, 1), (1, 300)]:
+        for mode in ("constant", "edge", "wrap"):
+            for width in tests:
+                if mode == "wrap" and 1 in shape and width in (2, (2, 3), ((2, 0), (3, 0)), ((2, 0), (0, 3)), ((0, 2), (3, 0)), ((2, 2), (0, 3)),
+                                                                ((0, 2), (3, 3)), ((4, 2), (3, 3))):
+                    continue  # wrapping wider than the axis
+                a = np.fromfunction(lambda i, j: i + j, shape, dtype=int)
+                out.append(_h(np.pad(a, width, mode=mode)))
+    return out
+
+
 # ---- the reference's TestBasic cases, as written there (masks :975-990, where :992-1021, linspace :1093-1133,
 # identity/eye :773-792, transposes :1047-1073, transposed reductions :1332-1366)
 @case

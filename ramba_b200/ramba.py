@@ -2021,7 +2021,23 @@ def pad(arr, pad_width, mode="constant", **kwargs):
     return cur if cur is not arr else copy(arr)
 
 
-for _n in ("concatenate", "stack", "pad"):
+def split(arr, indices_or_sections, axis=0):
+    """Equal sections (like the reference, ramba/ramba.py:9593-9611) or NumPy's list of split points, as views."""
+    arr = _as_nd(arr)
+    axis = axis % arr.ndim
+    n = arr.shape[axis]
+    if isinstance(indices_or_sections, numbers.Integral):
+        if n % indices_or_sections != 0:
+            raise ValueError(f"Cannot evenly divide array dimension of length {n} into {indices_or_sections} equal sections.")
+        step = n // indices_or_sections
+        bounds = [(k * step, (k + 1) * step) for k in range(indices_or_sections)]
+    else:
+        pts = [0] + [builtins.min(int(p), n) for p in indices_or_sections] + [n]
+        bounds = [(pts[k], builtins.max(pts[k], pts[k + 1])) for k in range(len(pts) - 1)]
+    return [arr[tuple(slice(lo, hi) if d == axis else slice(None) for d in range(arr.ndim))] for lo, hi in bounds]
+
+
+for _n in ("concatenate", "stack", "pad", "split"):
     HANDLED_FUNCTIONS[_n] = globals()[_n]
 
 

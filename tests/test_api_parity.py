@@ -451,6 +451,14 @@ def ref_concatenate(np):
 
 
 @case
+def split_family(np):
+    a = np.fromfunction(lambda i, j: i * 10 + j, (120, 6), dtype=int)
+    parts = np.split(a, 4)
+    cols = np.split(a, 3, axis=1)
+    return [_h(p) for p in parts] + [_h(c * 2) for c in cols] + [_h(parts[1] + parts[2])]
+
+
+@case
 def stack_family(np):  # the reference declares stack but its executor is a stub (ramba/ramba.py:9576-9577)
     a = np.fromfunction(lambda i, j: i + j, (20, 4), dtype=int)
     b = np.fromfunction(lambda i, j: i * j, (20, 4), dtype=int)

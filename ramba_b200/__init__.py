@@ -5,8 +5,8 @@ Mirrors ramba/__init__.py:13-19: re-exports the array API of `ramba_b200.ramba` 
 dtypes.  Execution goes through libramba_b200.so (hand-written sm_100a kernels) — there is no
 CPU path.
 """
-from numpy import (bool_, dtype, e, float32, float64, inf, int8, int16, int32, int64, nan, newaxis, pi, uint8,  # noqa: F401
-                   uint16, uint32)
+from numpy import (bool_, byte, double, dtype, e, float16, float32, float64, half, iinfo, finfo, inf, int8, int16, int32, int64, int_,  # noqa: F401
+                   intc, longlong, nan, newaxis, pi, short, single, ubyte, uint, uint8, uint16, uint32, uint64, uintc, ulonglong, ushort)
 
 from . import common  # noqa: F401
 from .ramba import *  # noqa: F401,F403

@@ -1156,6 +1156,36 @@ class ndarray:
     def allclose(self, other, rtol=1e-5, atol=1e-8, equal_nan=False):
         return bool(isclose(self, other, rtol=rtol, atol=atol, equal_nan=equal_nan).all())
 
+    def isclose(self, other, rtol=1e-5, atol=1e-8, equal_nan=False):
+        return isclose(self, other, rtol=rtol, atol=atol, equal_nan=equal_nan)
+
+    def nansum(self, asarray=False, **kwargs):
+        """Sum of the elements that are not NaN (ramba/ramba.py:6777-6781: a masked sum)."""
+        v = self[isnan(self).logical_not()].sum(asarray=True, **kwargs)  # noqa: F821
+        return v if asarray else v[0]
+
+    def nanmean(self, axis=None, dtype=None):
+        """Mean of the elements that are not NaN (whole array, like the reference: ramba/ramba.py:6766-6772)."""
+        assert axis is None, "nanmean over an axis is not implemented (nor by the reference, ramba/ramba.py:6760-6763)"
+        ok = isnan(self).logical_not()  # noqa: F821
+        return self[ok].sum() / ok.astype(np.int64).sum()  # (a bool sum stays bool, like in the reference)
+
+    def rollaxis(self, axis, start=0):
+        """NumPy's rollaxis (ramba/ramba.py:5643-5654)."""
+        nd = self.ndim
+        if not -nd <= axis < nd:
+            raise np.exceptions.AxisError(axis, nd)
+        axis %= nd
+        if not isinstance(start, numbers.Integral):
+            raise TypeError("integer argument expected")
+        if start < -nd or start > nd:
+            raise np.exceptions.AxisError("`start` arg requires %d <= start < %d but %d was passed in" % (-nd, nd + 1, start))
+        if start < 0:
+            start += nd
+        if start > axis:
+            start -= 1
+        return self.moveaxis(axis, start)
+
     # ---- NumPy protocol hooks (ramba/ramba.py:6825-6894)
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
         if method != "__call__" or kwargs.get("out") is not None:
@@ -2037,7 +2067,19 @@ def split(arr, indices_or_sections, axis=0):
     return [arr[tuple(slice(lo, hi) if d == axis else slice(None) for d in range(arr.ndim))] for lo, hi in bounds]
 
 
-for _n in ("concatenate", "stack", "pad", "split"):
+def rollaxis(a, axis, start=0):
+    return _as_nd(a).rollaxis(axis, start)
+
+
+def nansum(a, **kwargs):
+    return _as_nd(a).nansum(**kwargs)
+
+
+def nanmean(a, axis=None, dtype=None):
+    return _as_nd(a).nanmean(axis=axis, dtype=dtype)
+
+
+for _n in ("concatenate", "stack", "pad", "split", "rollaxis", "nansum", "nanmean"):
     HANDLED_FUNCTIONS[_n] = globals()[_n]
 
 
@@ -2255,6 +2297,29 @@ def sreduce(func, reducer, identity, *args, parallel=True):
 
 def sreduce_index(func, reducer, identity, *args, parallel=True):
     return _sreduce("sreduce_index", func, reducer, identity, args, True)
+
+
+def scumulative(local_func, final_func, array, axis=None, dtype=None, out=None):
+    """Inclusive scan with a user function (ramba/ramba.py:10057-10116): the reference scans every worker's part with
+    `local_func` and then folds the boundary values in with `final_func`; here `local_func(previous, current)` is
+    applied in log2(n) shifted-slice steps, so it has to be associative (and traceable, like smap functions)."""
+    array = _as_nd(array)
+    if array.ndim == 1 and axis is None:
+        axis = 0
+    assert isinstance(axis, numbers.Number) and 0 <= axis < array.ndim, "scumulative needs an axis for N-d arrays"
+    assert out is None, "scumulative(out=...) is not supported (nor by the reference, ramba/ramba.py:10071-10075)"
+    f = _user_function(local_func)
+    cur = array.astype(dtype) if dtype is not None and np.dtype(dtype) != array.dtype else array + 0
+    n = array.shape[axis]
+    d = 1
+    while d < n:
+        nxt = cur + 0
+        hi = tuple(slice(d, None) if k == axis else slice(None) for k in range(array.ndim))
+        lo = tuple(slice(0, n - d) if k == axis else slice(None) for k in range(array.ndim))
+        nxt[hi] = f(cur[lo], cur[hi])
+        cur = nxt
+        d *= 2
+    return cur
 
 
 def cumsum(a, axis=None, dtype=None, out=None):

@@ -451,6 +451,47 @@ def ref_concatenate(np):
 
 
 @case
+def nan_reductions(np):  # the reference's nansum / nanmean give NaN here (its masked sum does not keep the NaNs out)
+    v = onp.arange(240) * 0.5
+    v[::7] = onp.nan
+    a = v if np is onp else np.fromarray(v)
+    # (also isclose(equal_nan=True): the reference compiles its isclose with fastmath, which drops the isnan tests)
+    if np is onp:
+        return [onp.asarray(onp.nansum(a)), onp.asarray(onp.nanmean(a)), onp.isclose(a, a + 1e-9, equal_nan=True)]
+    return [onp.asarray(a.nansum()), onp.asarray(a.nanmean()), _h(a.isclose(a + 1e-9, equal_nan=True))]
+
+
+@case
+def isclose_and_rollaxis(np):
+    v = onp.arange(240) * 0.5
+    v[::7] = onp.nan
+    a = v if np is onp else np.fromarray(v)
+    b = np.fromfunction(lambda i, j, k: i * 100 + j * 10 + k, (6, 5, 4))
+    close = onp.isclose(a, a + 1e-9) if np is onp else a.isclose(a + 1e-9)
+    return [_h(close), _h(np.rollaxis(b, 2)), _h(np.rollaxis(b, 0, 3)), _h(np.rollaxis(b, 1, 0) * 2)]
+
+
+@case
+def scumulative_family(np):
+    a = np.fromfunction(lambda i: (i * 37) % 101, (300,), dtype=int)
+    g = np.fromfunction(lambda i, j: (i * 7 + j * 13) % 50, (40, 30), dtype=int)
+    if np is onp:
+        return [onp.cumsum(a), onp.cumsum(g, axis=0), onp.cumsum(g, axis=1)]
+    return [_h(np.scumulative(lambda x, y: x + y, lambda x, y: x + y, a, 0)), _h(np.scumulative(lambda x, y: x + y, lambda x, y: x + y, g, 0)),
+            _h(np.cumsum(g, axis=1))]
+
+
+@case
+def scumulative_forms(np):  # associative functions other than +, ramba functions inside, string lambdas
+    a = np.fromfunction(lambda i: (i * 37) % 101, (300,), dtype=int)
+    g = np.fromfunction(lambda i, j: (i * 7 + j * 13) % 50, (40, 30), dtype=int)
+    if np is onp:
+        return [onp.maximum.accumulate(a), onp.minimum.accumulate(g, axis=1)]
+    return [_h(np.scumulative(lambda x, y: np.maximum(x, y), lambda x, y: np.maximum(x, y), a)),
+            _h(np.scumulative("lambda x, y: numpy.minimum(x, y)", None, g, axis=1))]
+
+
+@case
 def split_family(np):
     a = np.fromfunction(lambda i, j: i * 10 + j, (120, 6), dtype=int)
     parts = np.split(a, 4)

@@ -582,6 +582,24 @@ def ref_transposes(np):
             _h(a.T.sum(axis=0)), _h(a.T[5:30, 3:20].sum(axis=1)), onp.asarray(b.transpose(1, 2, 0)[2:9, :, 3:].sum())]
 
 
+# ---- NumPy's own functions called on ramba arrays (__array_ufunc__ / __array_function__, ramba/ramba.py:6825-6894;
+# the mechanism tests/test_xarray.py:36-47 relies on)
+@case
+def numpy_protocol(np):
+    x = np.fromfunction(lambda i, j: i + j, (10, 20))
+    chain = onp.sin((x + 10.0) * 7.1).transpose().sum()
+    return [_h(onp.sin(x)), _h(onp.add(x, 10.0)), _h(onp.multiply(7.1, x)), onp.asarray(onp.sum(x)), _h(onp.sum(x, axis=0)),
+            _h(onp.where(x > 5, x, 0 * x)), _h(onp.clip(x, 3, 9)), _h(onp.sqrt(x)), _h(onp.maximum(x, 7.0)),
+            _h(onp.isnan(x)), _h(onp.square(x)), _h(onp.logical_and(x > 3, x < 9)), onp.asarray(chain)]
+
+
+@case
+def numpy_protocol_more(np):  # NumPy functions the reference does not register for its arrays
+    x = np.fromfunction(lambda i, j: i + j, (10, 20))
+    return [_h(onp.transpose(x)), _h(onp.concatenate([x, x])), _h(onp.expand_dims(x, 0)), onp.asarray(onp.mean(x)), onp.asarray(onp.min(x)),
+            _h(onp.moveaxis(x, 0, 1)), _h(onp.squeeze(onp.expand_dims(x, 1))), _h(onp.abs(x - 10)), _h(onp.power(x, 2))]
+
+
 # ---- deletion while ops are pending (TestDel :1398-1432)
 @case
 def delete_pending(np):

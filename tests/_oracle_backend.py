@@ -7,8 +7,38 @@ import sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 
+REJECTED = []  # (message, op list summary) of every op list the CUDA library's validation refused
+
+
+def _library_accepts(fop):
+    """Hand the op list to the real library's validation as well (CPU only: it validates the op list before it looks
+    for a device, and never touches the pointers).  Anything but 'no usable CUDA device' means the oracle executes
+    something the CUDA library would refuse."""
+    import ctypes as C
+
+    from ramba_b200 import _cabi
+
+    try:
+        lib = _cabi.load()
+    except _cabi.CabiError:
+        return  # library not built: test_cabi_exports complains about that
+    import torch
+
+    if torch.cuda.is_available():
+        return  # with a device present the call would launch on host pointers
+    rc = lib.rb200_run_deferred_ops(C.byref(fop), None)
+    msg = lib.rb200_last_error().decode() if rc != 0 else ""
+    if rc != 0 and "no usable CUDA device" not in msg:
+        REJECTED.append((msg, "ndim=%d n_views=%d n_insns=%d n_regs=%d" % (fop.ndim, fop.n_views, fop.n_insns, fop.n_regs)))
+        raise AssertionError("libramba_b200 would reject this op list: " + msg)
+
+
 def install():
     from oracle import vm
     from ramba_b200.runtime import RT
 
-    RT.set_test_executor(vm.run_deferred_ops, vm.reduce_partials, device="cpu")
+    def run(fop, stream=None):
+        _library_accepts(fop)
+        return vm.run_deferred_ops(fop, stream)
+
+    RT.set_test_executor(run, vm.reduce_partials, device="cpu")

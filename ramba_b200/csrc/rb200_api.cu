@@ -270,6 +270,7 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
         const rb200_insn& I = op->insns[i];
         if (I.a_kind == RB200_K_IOTA || I.b_kind == RB200_K_IOTA || I.c_kind == RB200_K_IOTA) ok = false;
         if (I.st_view != RB200_NOSTORE) ok = false;  // stage 1 of an axis reduction only reads
+        if (I.op == RB200_OP_SINCOS && I.c_kind == RB200_K_VIEW) ok = false;  // (the parked-half store is a write too)
       }
       for (int i = 0; i < op->n_views && ok; ++i) {
         const rb200_view& v = op->views[i];

@@ -157,6 +157,11 @@ class ProgramError(RuntimeError):
     pass
 
 
+class ProgramLimit(ProgramError):
+    """The op list would exceed a table size of the C-ABI (views, scalars, instructions, spill registers, reduction
+    slots): the fuser cuts the chain in two and retries (deferred_op._run_statements)."""
+
+
 class Program:
     """Lowered op list, independent of pointers and ranges."""
 
@@ -213,7 +218,7 @@ class Lowering:
         key = (cls, bits)
         if key not in self._scal_index:
             if len(self.scalars) >= cabi.MAX_SCALARS:
-                raise ProgramError("too many scalars in one fused op")
+                raise ProgramLimit("too many scalars in one fused op")
             self._scal_index[key] = len(self.scalars)
             self.scalars.append((cls, bits, value))
         return TV(cls, is_bool, "scal", self._scal_index[key])
@@ -309,6 +314,10 @@ class Lowering:
                 a = self.build(expr.args[1], resolve)
                 b = self.build(expr.args[2], resolve)
                 cls = unify_cls(a.cls, b.cls, a.is_bool, b.is_bool)
+                if not c.is_bool and c.cls != cls:
+                    # the condition is tested in ITS OWN class (`if c:` on a float 0.5 is true); only the resulting
+                    # 0/1 may be converted to the class of the branches
+                    c = self._node("ne", c.cls, T_I64, True, [c, self._intern(c.cls, 0, False)])
                 return self._node("where", cls, cls, a.is_bool and b.is_bool,
                                   [self.coerce(c, cls), self.coerce(a, cls), self.coerce(b, cls)])
             if op == "astype":
@@ -388,7 +397,7 @@ class Lowering:
         int and unifies to float64), integers and bools in int64."""
         cls = T_I64 if tv.cls == T_I64 else T_F64
         if len(self.reds) >= cabi.MAX_REDS:
-            raise ProgramError("too many reductions in one fused op")
+            raise ProgramLimit("too many reductions in one fused op")
         slot = len(self.reds)
         self.reds.append((redop, cls))
         x = self.coerce(tv, cls)
@@ -506,7 +515,7 @@ class Lowering:
                 n.pos = pos
                 pos += 1
         if pos > cabi.MAX_INSNS:
-            raise ProgramError("fused op too long (%d instructions)" % pos)
+            raise ProgramLimit("fused op too long (%d instructions)" % pos)
         # uses
         for n in nodes:
             n.uses = []
@@ -531,7 +540,7 @@ class Lowering:
         def alloc(last_use):
             nonlocal n_regs
             if not free:
-                raise ProgramError("fused op needs more than %d spill registers" % cabi.MAX_REGS)
+                raise ProgramLimit("fused op needs more than %d spill registers" % cabi.MAX_REGS)
             r = free.pop(0)
             n_regs = max(n_regs, r + 1)
             release.setdefault(last_use, []).append(r)

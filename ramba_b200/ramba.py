@@ -25,7 +25,7 @@ from . import _cabi as cabi
 from . import common
 from . import shardview
 from .common import dprint, timer, add_time
-from .program import E, Iota, Lowering, ProgramError, TempVar, dtype_class, rb_dtype
+from .program import E, Iota, Lowering, ProgramError, ProgramLimit, TempVar, dtype_class, rb_dtype
 from .runtime import RT, torch_dtype
 
 int64 = np.int64
@@ -290,10 +290,65 @@ class deferred_op:
             k: v for (k, v) in self.use_gids.items()
             if (bdarray.valid_gid(k) and k not in self.delete_gids) or k in self.preconstructed_gids
         }
-        # pin flexible distributions to the op's distribution (ramba/ramba.py:8130-8136)
-        for (_, (_, s, d, _, flex)) in live_gids.items():
+        self._pin(live_gids)
+        try:
+            self._run_statements(self.statements, live_gids)
+        finally:
+            self._finish(live_gids)
+        add_time("driver_deferred_op", timer() - t0)
+
+    def _pin(self, gids):
+        """Pin flexible distributions to the op's distribution (ramba/ramba.py:8130-8136)."""
+        for (_, (_, s, d, _, flex)) in gids.items():
             if flex and self.shape == s:
                 d[:] = shardview.clean_dist(self.distribution)
+
+    def _run_statements(self, statements, live_gids):
+        """Lower `statements` to one op list and launch it.  The reference never fails on the length of a fused chain
+        (Numba compiles whatever the fuser accumulated); a prebuilt library has table sizes (views, spill registers,
+        instructions, scalars, reduction slots), so a chain that exceeds one of them is cut in two at a statement
+        boundary and run as two launches: arrays that are written before the cut and read after it, and would
+        otherwise have stayed register temporaries, are materialised for the duration of the flush."""
+        try:
+            lowered = self._lower(statements, live_gids)
+        except ProgramLimit:
+            if len(statements) < 2:
+                raise
+            m = len(statements) // 2
+            first, second = statements[:m], statements[m:]
+            written = set()
+            for st in first:
+                if st[0] == "assign" and isinstance(st[1], ArrRef):
+                    written.add(st[1].gid)
+                elif st[0] == "assign" and isinstance(st[1], TempVar):
+                    raise
+            crossing = {}
+            for st in second:
+                for x in (st[2], st[3] if st[0] == "assign" else None):
+                    for o in _walk_operands(x, []):
+                        if isinstance(o, ArrRef) and o.shape != () and o.gid in written and o.gid not in live_gids:
+                            crossing[o.gid] = self.use_gids[o.gid]
+            self._pin(crossing)
+            both = dict(live_gids)
+            both.update(crossing)
+            try:
+                self._run_statements(first, both)
+                self._run_statements(second, both)
+            finally:
+                for g in crossing:
+                    RT.destroy_array(g)
+            return
+        if lowered is None:
+            return
+        views, prog, gred, ared = lowered
+        if common.debug_showcode and common.worker_num == 0:
+            print(format_program(prog, views, self.shape))
+        t1 = timer()
+        run_deferred_ops(self.uuid, views, prog, self.distribution, gred, ared,
+                         self.axis_reductions[0][0] if ared else None)
+        add_time("run_deferred_ops", timer() - t1)
+
+    def _lower(self, statements, live_gids):
         # view table
         views = []  # (gid, details)
         vindex = {}
@@ -318,7 +373,7 @@ class deferred_op:
                     i = view_of(o)
                     reads[i] = reads.get(i, 0) + 1
 
-        for st in self.statements:
+        for st in statements:
             if st[0] == "assign":
                 count_reads(st[2])
                 if st[3] is not None:
@@ -329,10 +384,9 @@ class deferred_op:
                 count_reads(st[2])
                 view_of(st[3])
         if len(views) > cabi.MAX_VIEWS:
-            raise ProgramError("fused op touches %d array views (max %d)" % (len(views), cabi.MAX_VIEWS))
-        if not views or not self.statements:
-            self._finish(live_gids)
-            return
+            raise ProgramLimit("fused op touches %d array views (max %d)" % (len(views), cabi.MAX_VIEWS))
+        if not views or not statements:
+            return None
 
         lw = Lowering([rb_dtype(det.dtype) for (_, det) in views])
         lw.view_gids = [g for (g, _) in views]
@@ -357,7 +411,7 @@ class deferred_op:
 
         gred = []  # (slot, red_view)
         ared = []
-        for st in self.statements:
+        for st in statements:
             if st[0] == "assign":
                 _, dst, expr, mask = st
                 tv = lw.build(expr, resolve)
@@ -377,14 +431,7 @@ class deferred_op:
                 slot = lw.reduce(redop, lw.build(expr, resolve))
                 ared.append((slot, red_view, redop))
         prog = lw.finish()
-        if common.debug_showcode and common.worker_num == 0:
-            print(format_program(prog, views, self.shape))
-        t1 = timer()
-        run_deferred_ops(self.uuid, views, prog, self.distribution, gred, ared,
-                         self.axis_reductions[0][0] if self.axis_reductions else None)
-        self._finish(live_gids)
-        add_time("driver_deferred_op", t1 - t0)
-        add_time("run_deferred_ops", timer() - t1)
+        return views, prog, gred, ared
 
     def _finish(self, live_gids):
         for g in self.delete_gids:
@@ -542,9 +589,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                         recv_bufs.append(buf)
                         parts[i].append((shardview.clean_range(part), buf.data_ptr(), cst, None))
         if ops:
-            if not RT.test_mode:
-                # the pack kernels run on the current stream; NCCL orders after them
-                pass
+            # (the pack kernels run on the current stream; NCCL orders after them)
             for r in dist.batch_isend_irecv(ops):
                 r.wait()
     if shardview.is_empty(subspace):
@@ -642,9 +687,9 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             RT.launch(_combine_program(vcode[i], acc_code, rop), kept_shape, gs_p[nred:],
                       [(rb[0], rb[1][nred:], rb[2]), (tot_ptr, cst, acc_code)])
         recv_bufs.append(partials)
-    if recv_bufs and not RT.test_mode:
-        # staging buffers must outlive the kernels that read them
-        torch.cuda.current_stream(RT.device).synchronize()
+    # staging buffers are torch allocations consumed on the launching stream: the caching allocator reuses them in
+    # stream order, so no host synchronisation is needed here (the references are kept until the next flush anyway)
+    RT.keepalive = recv_bufs
 
 
 def _remap_iota(prog, order):

@@ -73,6 +73,7 @@ class Runtime:
         self.test_mode = False
         self.launches = 0
         self.bytes_sent = 0
+        self.keepalive = None  # staging buffers of the last flush
         self.profile_events = None  # list -> (start, end, n_insns) CUDA events around every launch
 
     # ---- device / process group ---------------------------------------------------------

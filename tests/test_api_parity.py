@@ -789,6 +789,65 @@ def cumsum_family(np):
     return out
 
 
+# ---- chains longer than the op-list tables of the C-ABI: the fuser cuts them, it never raises (the reference compiles
+# whatever its fuser accumulated)
+@case
+def long_chain_many_arrays(np):  # 20 live arrays written by one flush (> 16 views)
+    xs = [np.arange(200) * float(i) for i in range(20)]
+    return [_h(x) for x in xs]
+
+
+@case
+def long_chain_many_operands(np):  # one expression over 21 arrays (> 16 views)
+    xs = [np.arange(150) * (i + 1) for i in range(21)]
+    if np is not onp:
+        np.sync()
+    t = xs[0]
+    for x in xs[1:]:
+        t = t + x
+    return [_h(t)]
+
+
+@case
+def long_chain_live_temporaries(np):  # 14 temporaries alive at once (> 12 spill registers)
+    a = np.arange(130) * 0.5
+    ts = [a * float(i + 2) for i in range(14)]
+    acc = ts[0]
+    for i in range(1, 14):
+        acc = acc * 0.5 + ts[i]
+    for i in range(14):
+        acc = acc - ts[i] * 0.25
+    del ts  # dead handles: the 14 values are register temporaries, all alive until the second loop used them
+    return [_h(acc)]
+
+
+@case
+def long_chain_many_instructions(np):  # > 96 instructions in one flush
+    a = np.arange(180) * 0.25
+    b = a
+    for i in range(70):
+        b = (b + float(i)) * 0.5 - a
+    return [_h(b), onp.asarray((b * 2.0).sum())]
+
+
+@case
+def long_chain_many_reductions(np):  # > 4 global reductions pending in one fused op
+    a = np.arange(210) * 0.5
+    if np is onp:
+        return [onp.asarray((a * float(i)).sum()) for i in range(7)]
+    parts = [(a * float(i)).sum(asarray=True) for i in range(7)]
+    return [onp.asarray(_h(p)[0]) for p in parts]
+
+
+@case
+def where_float_condition(np):  # the condition is tested in its own class before the branches' class applies
+    c = (np.arange(120) - 60) * 0.25
+    ia, ib = np.arange(120), np.arange(120) * -1
+    f32 = (np.arange(120) * 1.0).astype(onp.float32)
+    tiny = (np.arange(120) % 3) * 1e-300
+    return [_h(np.where(c, ia, ib)), _h(np.where(tiny, f32, f32 * onp.float32(2.0)))]
+
+
 def _compare(got, exp, name):
     assert len(got) == len(exp), name
     for i, (g, e) in enumerate(zip(got, exp)):

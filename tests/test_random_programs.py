@@ -27,7 +27,11 @@ def test_random_program_cuda(gpu_engine, f):
     from ramba_b200 import _cabi
     from ramba_b200.runtime import RT
 
-    before = _cabi.launch_count()
+    before, before_rt = _cabi.launch_count(), RT.launches
     got = f(rb)
-    assert not RT.test_mode and _cabi.launch_count() > before
+    assert not RT.test_mode
+    # a seed may draw only empty slices: then there is nothing to launch (RT.launches counts the op lists the
+    # engine handed to its executor); whenever the engine did launch, the CUDA library must have run them
+    if RT.launches > before_rt:
+        assert _cabi.launch_count() > before, "the CUDA library did not run"
     _check(got, f(onp), f.__name__)

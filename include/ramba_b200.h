@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RB200_ABI_VERSION 3
+#define RB200_ABI_VERSION 4
 
 #define RB200_MAX_DIMS 5     /* iteration dims after host-side collapsing            */
 #define RB200_MAX_VIEWS 16   /* distinct array views per fused op                    */
@@ -135,7 +135,13 @@ enum rb200_op {
                            half is also stored to views[c_idx]                       */
   RB200_OP_RED = 50,    /* red[b_idx] = red[b_idx] (+,*,min,max by imm) a          */
   RB200_OP_CBRT = 51,
-  RB200_NUM_OPS = 52
+  /* three-operand forms of `a (+/-) b*c`: the product and the sum are rounded SEPARATELY (no FMA), exactly like the
+     two statements of the reference's loop body they stand for; they exist so that a weighted term of a stencil
+     (`... - 6.0*U[...]`, ramba/ramba.py:8146-8188) does not need a spill register                                */
+  RB200_OP_MULADD = 52,  /* a + b*c                                                */
+  RB200_OP_MULSUB = 53,  /* a - b*c                                                */
+  RB200_OP_MULRSUB = 54, /* b*c - a                                                */
+  RB200_NUM_OPS = 55
 };
 
 enum rb200_redop { RB200_RED_ADD = 0, RB200_RED_MUL = 1, RB200_RED_MIN = 2, RB200_RED_MAX = 3 };
@@ -166,6 +172,11 @@ typedef struct rb200_view {
   int64_t stride[RB200_MAX_DIMS];
   int32_t dtype; /* rb200_dtype */
   int32_t flags; /* bit0: written by this op                                       */
+  /* [alloc_lo, alloc_hi): the device buffer `base` points into (the worker's shard, LocalNdarray.bcontainer,
+   * ramba/ramba.py:1208-1214).  Optional (both NULL = unknown).  The stencil kernel stages a tile plus its halo
+   * with whole-box TMA copies only when the box lies inside these bounds.                                       */
+  const void* alloc_lo;
+  const void* alloc_hi;
 } rb200_view;
 
 typedef struct rb200_red {

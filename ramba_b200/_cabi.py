@@ -10,7 +10,7 @@ raises.
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_DIMS = 5
 MAX_VIEWS = 16
 MAX_SCALARS = 32
@@ -31,7 +31,7 @@ OPS = [
     "GT", "LT", "GE", "LE", "EQ", "NE", "LAND", "LOR", "LXOR", "BAND", "BOR", "BXOR", "SHL", "SHR",
     "ABS", "SQUARE", "SQRT", "SIN", "COS", "TAN", "SINH", "COSH", "TANH", "ASIN", "ACOS", "ATAN",
     "NEG", "EXP", "LOG", "ISFINITE", "ISINF", "ISNAN", "ISNEGINF", "ISPOSINF", "LNOT", "INVERT",
-    "WHERE", "CVT", "SINCOS", "RED", "CBRT",
+    "WHERE", "CVT", "SINCOS", "RED", "CBRT", "MULADD", "MULSUB", "MULRSUB",
 ]
 OP = {name: i for i, name in enumerate(OPS)}
 RED_ADD, RED_MUL, RED_MIN, RED_MAX = range(4)
@@ -55,6 +55,8 @@ class View(C.Structure):
         ("stride", C.c_int64 * MAX_DIMS),
         ("dtype", C.c_int32),
         ("flags", C.c_int32),
+        ("alloc_lo", C.c_void_p),
+        ("alloc_hi", C.c_void_p),
     ]
 
 

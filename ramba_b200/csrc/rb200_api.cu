@@ -237,6 +237,18 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   cudaError_t e;
   const size_t reg_bytes = (size_t)(op->n_regs + 1) * V * kThreads * 8;  // + the scratch column of the out-of-line stores
 
+  // ---- specialised kernels first: float-arithmetic op lists over 2-D / 3-D boxes (shifted-view stencils with the
+  // halo tile staged in shared memory by TMA, and N-d elementwise maps) run on the lean machine of rb200_tile.cu
+  {
+    std::string terr;
+    const int r = launch_stencil_tile(op, sms, stream, &terr);
+    if (r == 0) {
+      g_launches.fetch_add(1);
+      return 0;
+    }
+    if (r == 2) return fail(terr);
+  }
+
   if (op->n_axis_red_dims != 0) {
     // axis mode: the first n_axis_red_dims dims are the reduced ones (host permutes)
     const int nred = op->n_axis_red_dims;

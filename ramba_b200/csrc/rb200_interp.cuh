@@ -567,6 +567,25 @@ template <class F, int V, class C> __device__ __forceinline__ void exec_float(C&
       cx.template finish<F>(I, r);
       return;
     }
+    case RB200_OP_MULADD:
+    case RB200_OP_MULSUB:
+    case RB200_OP_MULRSUB: {
+      F c[V];
+      cx.template fetch<F>(I.c_kind(), I.c_idx(), c);
+      // product and sum round separately (two statements of the reference's loop body)
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if constexpr (sizeof(F) == 8) {
+          const double p = __dmul_rn(b[k], c[k]);
+          r[k] = op == RB200_OP_MULADD ? __dadd_rn(a[k], p) : op == RB200_OP_MULSUB ? __dsub_rn(a[k], p) : __dsub_rn(p, a[k]);
+        } else {
+          const float p = __fmul_rn(b[k], c[k]);
+          r[k] = op == RB200_OP_MULADD ? __fadd_rn(a[k], p) : op == RB200_OP_MULSUB ? __fsub_rn(a[k], p) : __fsub_rn(p, a[k]);
+        }
+      }
+      cx.template finish<F>(I, r);
+      return;
+    }
     default: return;
   }
 }
@@ -680,6 +699,17 @@ template <int V, class C> __device__ __forceinline__ void exec_int(C& cx, const 
       cx.template fetch<long long>(I.c_kind(), I.c_idx(), c);
 #pragma unroll
       for (int k = 0; k < V; ++k) r[k] = (a[k] != 0) ? b[k] : c[k];
+    } break;
+    case RB200_OP_MULADD:
+    case RB200_OP_MULSUB:
+    case RB200_OP_MULRSUB: {
+      long long c[V];
+      cx.template fetch<long long>(I.c_kind(), I.c_idx(), c);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const long long p = b[k] * c[k];
+        r[k] = op == RB200_OP_MULADD ? a[k] + p : op == RB200_OP_MULSUB ? a[k] - p : p - a[k];
+      }
     } break;
     default: return;
   }

@@ -1,4 +1,6 @@
 #pragma once
+#include <string>
+
 #include "rb200_vm.cuh"
 
 namespace rb200 {
@@ -11,4 +13,7 @@ cudaError_t launch_vm_elementwise_nd3(const KParams& P, unsigned blocks, size_t 
 cudaError_t launch_vm_elementwise_nd5(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_vm_elementwise_ax1d(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
 cudaError_t launch_vm_axis_reduce(const KParams& P, unsigned blocks, size_t smem, cudaStream_t stream);
+// specialised kernels tried before the general interpreter.  Return 0: launched, 1: the op list is not of their form
+// (fall through), 2: error (*err set)
+int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, std::string* err);
 }  // namespace rb200

@@ -1,0 +1,512 @@
+// rb200_tile.cu — K2: the shifted-view stencil / N-d float arithmetic kernel (sm_100a).
+//
+// What it stands for in the reference: the "locally optimised" generated kernel for fused ops whose operands are
+// shifted slice views of one array - one base argument per array plus per-view offsets, body
+//   acc = U[o1_0+i0, o1_1+i1, o1_2+i2] + U[o2_0+i0, ...] + ... ; V[index] = acc - c*U[...]
+// (ramba/ramba.py:8146-8188, SURVEY §8a "textbook shifted-pointer stencil"), executed by RemoteState.run_deferred_ops
+// (ramba/ramba.py:3758-3780).
+//
+// Design (B200):
+//   * The iteration box (2-D or 3-D after host-side collapsing) is cut into tiles of TY x TX = 2048 outputs
+//     (256 threads x 8); a CTA takes a tile column and MARCHES along the outermost dim, ZC planes per work item.
+//   * The read-only views that are shifted copies of each other (same dtype, same strides, base offsets that decompose
+//     into small per-dim shifts) form the STAGED GROUP: for every plane the CTA needs, ONE box of
+//     (TY + halo_y) x (TX + halo_x) elements is copied global -> shared by the TMA engine
+//     (cp.async.bulk.tensor, SASS UTMALDG; completion on an mbarrier), into a ring of halo_z + 2 planes, one plane
+//     ahead of the computation.  Every element of the source array is read from HBM once per (tile column, plane);
+//     the 7 (or 5, 9, 13, 25...) neighbour reads of the op list become shared-memory loads at an offset known per
+//     instruction.  When the source does not meet the TMA rules (16-byte aligned strides) or the box could leave the
+//     shard buffer, the same box is filled by per-thread cp.async (LDGSTS) with bounds predicates.
+//   * Everything else the op list touches (other operands, the destination) is addressed directly in global memory,
+//     coalesced along x.
+//   * The op list itself runs on the lean machine (rb200_lean.cuh): same order, same classes, same roundings as the
+//     general interpreter.
+// Grid: persistent, 2 CTAs per SM.  Bound: HBM (read the source once + write the destination once).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "rb200_launch.h"
+#include "rb200_lean.cuh"
+#include "rb200_lean_plan.h"
+
+namespace rb200 {
+
+constexpr int kTileMaxStaged = RB200_MAX_VIEWS;
+constexpr int kTileMaxRing = 8;
+
+struct TileStagedOp {
+  int dzl;           // plane of the ring relative to the oldest needed plane (0 .. hz)
+  unsigned off;      // byte offset inside a plane: ((dy + hy_lo) * PX + dx + hx_lo) * elem
+};
+
+struct TileParams {
+  long long Z, Y, X;        // iteration extents (Z == 1 for 2-D ops)
+  int TX, logTX, RY, TY;    // tile: TX columns x TY rows = 2048 outputs; RY = 256 / TX rows per element step k
+  int nxt, nyt, nzc;        // tiles along x, y; chunks along z
+  long long ZC;             // planes per work item
+  long long n_items;
+  // staged group
+  int has_group, use_tma, elem;
+  int hz_lo, hz, hy_lo, hy, hx_lo, hx;  // halos: lo part and total (lo + hi)
+  int PX, PY, D;                         // plane box (elements) and ring depth
+  unsigned plane_bytes;
+  const char* gcorner;                   // address of group element (z = -hz_lo, y = -hy_lo, x = -hx_lo)
+  long long gs0, gs1;                    // group strides (elements) of z and y; x stride is 1
+  const char* safe_lo;                   // [safe_lo, safe_hi): bytes the cooperative loader may touch
+  const char* safe_hi;
+  int tma_shift;                         // elements the tensor-map base was moved down to reach 16-byte alignment
+  int n_staged;
+  TileStagedOp staged[kTileMaxStaged];
+  int n_direct;
+  LDirect direct[RB200_MAX_VIEWS];
+  int n_insns, n_regs;
+  LInsn insns[RB200_MAX_INSNS];
+  u64 scal[RB200_MAX_SCALARS];
+};
+
+__device__ __forceinline__ void tma_load_3d(unsigned sdst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned mbar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(sdst),
+      "l"(tmap), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned mbar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar) : "memory");
+}
+
+template <class TE> struct TileCtx {
+  const TileParams& P;
+  unsigned ring_s;  // shared-window address of the plane ring
+  unsigned reg_s;   // this thread's column of the spill-register file ([reg][k][thread], 8-byte slots)
+  unsigned tb0;     // byte offset of this thread's element k = 0 inside a plane (halo included)
+  unsigned kstep;   // byte step between elements k and k+1 inside a plane
+  int fb;           // ring slot holding plane (z - hz_lo)
+  long long z, gy0, gx;
+  unsigned valid;
+  unsigned alo[LV], ahi[LV];
+  __device__ __forceinline__ TileCtx(const TileParams& p) : P(p) {}
+
+  template <class F> __device__ __forceinline__ void fetch(int kind, int arg, F (&out)[LV]) {
+    switch (kind) {
+      case L_STAGED: {
+        const TileStagedOp t = P.staged[arg];
+        int slot = fb + t.dzl;
+        if (slot >= P.D) slot -= P.D;
+        unsigned addr = ring_s + (unsigned)slot * P.plane_bytes + t.off + tb0;
+#pragma unroll
+        for (int k = 0; k < LV; ++k, addr += kstep) out[k] = (F)lean_lds<TE>(addr);
+      } break;
+      case L_DIRECT: {
+        const LDirect& v = P.direct[arg];
+        const long long off = z * v.s0 + gy0 * v.s1 + gx * v.s2;
+        const long long step = (long long)P.RY * v.s1;
+        if (v.dtype == RB200_F32) {
+          const float* p = reinterpret_cast<const float*>(v.base) + off;
+#pragma unroll
+          for (int k = 0; k < LV; ++k, p += step) out[k] = ((valid >> k) & 1u) ? (F)ldg<float>(p) : F(0);
+        } else {
+          const double* p = reinterpret_cast<const double*>(v.base) + off;
+#pragma unroll
+          for (int k = 0; k < LV; ++k, p += step) out[k] = ((valid >> k) & 1u) ? (F)ldg<double>(p) : F(0);
+        }
+      } break;
+      case L_REG: {
+        const unsigned addr = reg_s + (unsigned)arg * (LV * kThreads * 8);
+#pragma unroll
+        for (int k = 0; k < LV; ++k) out[k] = lean_lds<F>(addr + k * kThreads * 8);
+      } break;
+      case L_SCAL: {
+        const u64 bits = P.scal[arg];
+        const F s = sizeof(F) == 8 ? (F)__longlong_as_double((long long)bits) : (F)__uint_as_float((unsigned)bits);
+#pragma unroll
+        for (int k = 0; k < LV; ++k) out[k] = s;
+      } break;
+      default:  // L_ACC
+#pragma unroll
+        for (int k = 0; k < LV; ++k) out[k] = LAcc<F>::get(alo[k], ahi[k]);
+    }
+  }
+  template <class F> __device__ __forceinline__ void store_reg(int reg, const F (&r)[LV]) {
+    const unsigned addr = reg_s + (unsigned)reg * (LV * kThreads * 8);
+#pragma unroll
+    for (int k = 0; k < LV; ++k) lean_sts<F>(addr + k * kThreads * 8, r[k]);
+  }
+  template <class F> __device__ __forceinline__ void store_view(int arg, const F (&r)[LV]) {
+    const LDirect& v = P.direct[arg];
+    const long long off = z * v.s0 + gy0 * v.s1 + gx * v.s2;
+    const long long step = (long long)P.RY * v.s1;
+    if (v.dtype == RB200_F32) {
+      float* p = reinterpret_cast<float*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step)
+        if ((valid >> k) & 1u) stg<float>(p, (float)r[k]);
+    } else {
+      double* p = reinterpret_cast<double*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step)
+        if ((valid >> k) & 1u) stg<double>(p, (double)r[k]);
+    }
+  }
+  template <class F> __device__ __forceinline__ void reduce(int, int, const F (&)[LV]) {}  // (no reductions in this kernel)
+};
+
+template <class TE>
+__global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_constant__ TileParams P, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const unsigned tid = threadIdx.x;
+  // layout: [ring: D planes][spill registers: n_regs * LV * 256 * 8][mbarriers: D * 8]
+  const unsigned ring_bytes = (unsigned)P.D * P.plane_bytes;
+  const unsigned regs_s = smem_s + ring_bytes;
+  const unsigned mbar_s = regs_s + (unsigned)P.n_regs * (LV * kThreads * 8);
+  if (P.has_group && tid == 0) {
+    for (int s = 0; s < P.D; ++s) mbar_init(mbar_s + 8u * s, P.use_tma ? 1u : (unsigned)kThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  TileCtx<TE> cx(P);
+  cx.ring_s = smem_s;
+  cx.reg_s = regs_s + tid * 8u;
+  const int x = (int)(tid & (unsigned)(P.TX - 1));
+  const int yrow = (int)(tid >> P.logTX);
+  cx.tb0 = (unsigned)(((yrow + P.hy_lo) * P.PX + x + P.hx_lo) * (int)sizeof(TE));
+  cx.kstep = (unsigned)(P.RY * P.PX * (int)sizeof(TE));
+  const int hz_hi = P.hz - P.hz_lo;
+  unsigned fills = 0;  // planes this CTA has requested so far (slot = fills % D, parity = (fills / D) & 1)
+
+  for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+    const int tx = (int)(item % P.nxt);
+    const long long r1 = item / P.nxt;
+    const int ty = (int)(r1 % P.nyt);
+    const long long zc = r1 / P.nyt;
+    const long long x0 = (long long)tx * P.TX, y0 = (long long)ty * P.TY;
+    const long long zb = zc * P.ZC;
+    long long ze = zb + P.ZC;
+    if (ze > P.Z) ze = P.Z;
+    cx.gx = x0 + x;
+    cx.gy0 = y0 + yrow;
+    unsigned valid = 0;
+    if (cx.gx < P.X) {
+#pragma unroll
+      for (int k = 0; k < LV; ++k)
+        if (cx.gy0 + (long long)k * P.RY < P.Y) valid |= 1u << k;
+    }
+    cx.valid = valid;
+
+    // request plane `pz` of the group (pz in halo coordinates: 0 = iteration z - hz_lo of z = 0)
+    auto request = [&](long long pz) {
+      const unsigned slot = fills % (unsigned)P.D;
+      const unsigned bar = mbar_s + 8u * slot;
+      const unsigned dst = smem_s + slot * P.plane_bytes;
+      if (P.use_tma) {
+        if (tid == 0) {
+          mbar_expect_tx(bar, (unsigned)(P.PX * P.PY * (int)sizeof(TE)));
+          tma_load_3d(dst, &tmap, (int)x0 + P.tma_shift, (int)y0, (int)pz, bar);
+        }
+      } else {
+        // rows of the box by warps, elements by lanes; out-of-range elements are zero-filled
+        const int lane = (int)(tid & 31u), warp = (int)(tid >> 5);
+        const long long Xh = P.X + P.hx, Yh = P.Y + P.hy, Zh = P.Z + P.hz;
+        for (int py = warp; py < P.PY; py += kThreads / 32) {
+          const long long gy = y0 + py;
+          const TE* row = reinterpret_cast<const TE*>(P.gcorner) + pz * P.gs0 + gy * P.gs1 + x0;
+          const unsigned drow = dst + (unsigned)(py * P.PX * (int)sizeof(TE));
+          const bool row_ok = gy < Yh && pz >= 0 && pz < Zh;
+          for (int px = lane; px < P.PX; px += 32) {
+            const TE* src = row + px;
+            const bool ok = row_ok && (x0 + px) < Xh && (const char*)src >= P.safe_lo && (const char*)(src + 1) <= P.safe_hi;
+            if constexpr (sizeof(TE) == 8) cp_async8(drow + px * 8u, ok ? (const void*)src : (const void*)P.safe_lo, ok);
+            else cp_async4(drow + px * 4u, ok ? (const void*)src : (const void*)P.safe_lo, ok);
+          }
+        }
+        cp_async_mbar_arrive(bar);
+      }
+      ++fills;
+    };
+
+    unsigned fill0 = fills;  // fill index of plane zb (halo coordinate zb)
+    if (P.has_group) {
+      __syncthreads();  // every thread is done with the planes of the previous item
+      for (int p = 0; p <= P.hz; ++p) request(zb + p);
+    }
+    for (long long z = zb; z < ze; ++z) {
+      if (P.has_group) {
+        const unsigned newest = fill0 + (unsigned)(z - zb) + (unsigned)P.hz;  // plane z + hz_hi
+        mbar_wait(mbar_s + 8u * (newest % (unsigned)P.D), (newest / (unsigned)P.D) & 1u);
+        __syncthreads();  // plane z - 1 - hz_lo is free now: its slot takes the plane after the newest
+        if (z + 1 < ze) request(z + 1 + P.hz);
+        cx.fb = (int)((fill0 + (unsigned)(z - zb)) % (unsigned)P.D);
+      }
+      cx.z = z;
+#pragma unroll 1
+      for (int pc = 0; pc < P.n_insns; ++pc) {
+        const LInsn I = P.insns[pc];
+        lean_dispatch(cx, I);
+      }
+    }
+  }
+  (void)hz_hi;
+}
+
+// =============================================================================================
+// host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static long long floor_div(long long a, long long b) {  // b > 0
+  long long q = a / b;
+  if ((a % b != 0) && (a < 0)) --q;
+  return q;
+}
+
+// 0: launched, 1: not eligible (caller falls back to the general interpreter), 2: error (*err set)
+int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, std::string* err) {
+  static const bool disabled = getenv("RB200_NO_TILE_KERNEL") != nullptr;  // debugging aid
+  if (disabled) return 1;
+  if (op->ndim != 2 && op->ndim != 3) return 1;
+  if (op->n_reds != 0 || op->n_axis_red_dims != 0) return 1;
+  if (!lean_eligible(op, false)) return 1;
+  const int nd = op->ndim;
+  TileParams P;
+  memset(&P, 0, sizeof(P));
+  P.Z = nd == 3 ? op->itershape[0] : 1;
+  P.Y = op->itershape[nd - 2];
+  P.X = op->itershape[nd - 1];
+  if (P.X >= (1ll << 31) || P.Y >= (1ll << 31) || P.Z >= (1ll << 31)) return 1;
+
+  // ---- which views are read / written
+  bool rd[RB200_MAX_VIEWS] = {false}, wr[RB200_MAX_VIEWS] = {false};
+  for (int i = 0; i < op->n_insns; ++i) {
+    const rb200_insn& I = op->insns[i];
+    const int lop = lean_opcode(op, I);
+    if (I.a_kind == RB200_K_VIEW) rd[I.a_idx] = true;
+    if (I.b_kind == RB200_K_VIEW && lop != LO_RED && lop != LO_SQUARE) rd[I.b_idx] = true;
+    if (I.c_kind == RB200_K_VIEW) rd[I.c_idx] = true;
+    if (I.st_view != RB200_NOSTORE) wr[I.st_view] = true;
+  }
+  auto S = [&](int v, int d) -> long long {  // stride of normalised dim d (0 = z, 1 = y, 2 = x)
+    if (nd == 3) return op->views[v].stride[d];
+    return d == 0 ? 0 : op->views[v].stride[d - 1];
+  };
+
+  // ---- staged group: the largest family of read-only views with equal dtype and strides (unit x stride) whose base
+  // offsets are small shifts of each other
+  int best_ref = -1, best_n = 0;
+  int member[RB200_MAX_VIEWS];
+  long long mdz[RB200_MAX_VIEWS], mdy[RB200_MAX_VIEWS], mdx[RB200_MAX_VIEWS];
+  for (int r = 0; r < op->n_views; ++r) {
+    if (!rd[r] || wr[r] || S(r, 2) != 1 || S(r, 1) < 64 || (nd == 3 && S(r, 0) < S(r, 1))) continue;
+    if (!op->views[r].alloc_lo || !op->views[r].alloc_hi) continue;
+    const int es = op->views[r].dtype == RB200_F64 ? 8 : 4;
+    int n = 0;
+    for (int v = 0; v < op->n_views; ++v) {
+      if (!rd[v] || wr[v] || op->views[v].dtype != op->views[r].dtype) continue;
+      if (S(v, 0) != S(r, 0) || S(v, 1) != S(r, 1) || S(v, 2) != 1) continue;
+      if (op->views[v].alloc_lo != op->views[r].alloc_lo) continue;
+      const long long db = (const char*)op->views[v].base - (const char*)op->views[r].base;
+      if (db % es != 0) continue;
+      long long delta = db / es, dz = 0;
+      if (nd == 3 && S(r, 0) > 0) {
+        dz = floor_div(delta + S(r, 0) / 2, S(r, 0));
+        delta -= dz * S(r, 0);
+      }
+      const long long dy = floor_div(delta + S(r, 1) / 2, S(r, 1));
+      const long long dx = delta - dy * S(r, 1);
+      if (dz < -3 || dz > 3 || dy < -8 || dy > 8 || dx < -16 || dx > 16) continue;
+      ++n;
+    }
+    if (n > best_n) {
+      best_n = n;
+      best_ref = r;
+    }
+  }
+  int view_kind[RB200_MAX_VIEWS], view_arg[RB200_MAX_VIEWS], store_arg[RB200_MAX_VIEWS];
+  for (int v = 0; v < op->n_views; ++v) {
+    view_kind[v] = L_DIRECT;
+    view_arg[v] = 0;
+    store_arg[v] = 0;
+  }
+  int es = 4;
+  if (best_n >= 2) {
+    const int r = best_ref;
+    es = op->views[r].dtype == RB200_F64 ? 8 : 4;
+    long long lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    int n = 0;
+    for (int v = 0; v < op->n_views; ++v) {
+      if (!rd[v] || wr[v] || op->views[v].dtype != op->views[r].dtype) continue;
+      if (S(v, 0) != S(r, 0) || S(v, 1) != S(r, 1) || S(v, 2) != 1) continue;
+      if (op->views[v].alloc_lo != op->views[r].alloc_lo) continue;
+      const long long db = (const char*)op->views[v].base - (const char*)op->views[r].base;
+      if (db % es != 0) continue;
+      long long delta = db / es, dz = 0;
+      if (nd == 3 && S(r, 0) > 0) {
+        dz = floor_div(delta + S(r, 0) / 2, S(r, 0));
+        delta -= dz * S(r, 0);
+      }
+      const long long dy = floor_div(delta + S(r, 1) / 2, S(r, 1));
+      const long long dx = delta - dy * S(r, 1);
+      if (dz < -3 || dz > 3 || dy < -8 || dy > 8 || dx < -16 || dx > 16) continue;
+      member[n] = v;
+      mdz[n] = dz; mdy[n] = dy; mdx[n] = dx;
+      if (dz < lo[0]) lo[0] = dz;
+      if (dz > hi[0]) hi[0] = dz;
+      if (dy < lo[1]) lo[1] = dy;
+      if (dy > hi[1]) hi[1] = dy;
+      if (dx < lo[2]) lo[2] = dx;
+      if (dx > hi[2]) hi[2] = dx;
+      ++n;
+    }
+    P.has_group = 1;
+    P.elem = es;
+    P.hz_lo = (int)-lo[0]; P.hz = (int)(hi[0] - lo[0]);
+    P.hy_lo = (int)-lo[1]; P.hy = (int)(hi[1] - lo[1]);
+    P.hx_lo = (int)-lo[2]; P.hx = (int)(hi[2] - lo[2]);
+    P.gs0 = S(r, 0);
+    P.gs1 = S(r, 1);
+    P.gcorner = (const char*)op->views[r].base - (P.hz_lo * P.gs0 + P.hy_lo * P.gs1 + P.hx_lo) * es;
+    P.n_staged = n;
+    // bytes any member may touch: from its first to its last element over the box
+    const char* slo = nullptr;
+    const char* shi = nullptr;
+    for (int j = 0; j < n; ++j) {
+      const char* b0 = (const char*)op->views[member[j]].base;
+      const char* b1 = b0 + ((P.Z - 1) * P.gs0 + (P.Y - 1) * P.gs1 + (P.X - 1) + 1) * es;
+      if (!slo || b0 < slo) slo = b0;
+      if (!shi || b1 > shi) shi = b1;
+    }
+    P.safe_lo = slo;
+    P.safe_hi = shi;
+  }
+
+  // ---- tile geometry
+  int TX = 128;
+  if (P.X <= 32) TX = 32;
+  else if (P.X <= 64) TX = 64;
+  P.TX = TX;
+  P.logTX = TX == 32 ? 5 : TX == 64 ? 6 : 7;
+  P.RY = kThreads / TX;
+  P.TY = LV * P.RY;
+  P.nxt = (int)((P.X + TX - 1) / TX);
+  P.nyt = (int)((P.Y + P.TY - 1) / P.TY);
+  if (P.has_group) {
+    const int per16 = 16 / es;
+    P.PX = ((TX + P.hx + per16 - 1) / per16) * per16;
+    P.PY = P.TY + P.hy;
+    P.D = P.hz + 2;
+    if (P.D > kTileMaxRing || P.PX > 256 || P.PY > 256) return 1;
+    P.plane_bytes = (unsigned)(((size_t)P.PX * P.PY * es + 127) / 128 * 128);
+    for (int j = 0; j < P.n_staged; ++j) {
+      P.staged[j].dzl = (int)(mdz[j] + P.hz_lo);
+      P.staged[j].off = (unsigned)(((mdy[j] + P.hy_lo) * P.PX + (mdx[j] + P.hx_lo)) * es);
+      view_kind[member[j]] = L_STAGED;
+      view_arg[member[j]] = j;
+    }
+  }
+  // direct views: every written view, every read view outside the group
+  for (int v = 0; v < op->n_views; ++v) {
+    if (view_kind[v] == L_STAGED) continue;
+    LDirect& d = P.direct[P.n_direct];
+    d.base = (char*)op->views[v].base;
+    d.s0 = S(v, 0); d.s1 = S(v, 1); d.s2 = S(v, 2);
+    d.dtype = op->views[v].dtype;
+    view_arg[v] = P.n_direct;
+    store_arg[v] = P.n_direct;
+    ++P.n_direct;
+  }
+  P.n_insns = op->n_insns;
+  P.n_regs = op->n_regs;
+  lean_translate(op, view_kind, view_arg, store_arg, P.insns);
+  for (int i = 0; i < op->n_scalars; ++i) P.scal[i] = op->scalars[i];
+
+  const size_t smem = (size_t)P.D * P.plane_bytes + (size_t)P.n_regs * LV * kThreads * 8 + (size_t)P.D * 8 + 16;
+  if (smem > 100 * 1024) return 1;  // (two CTAs per SM)
+
+  // ---- work items: z chunks so that every CTA of the persistent grid gets several
+  const long long grid_cap = (long long)sms * 2;
+  const long long xy = (long long)P.nxt * P.nyt;
+  long long want_chunks = (grid_cap * 6 + xy - 1) / xy;
+  if (want_chunks < 1) want_chunks = 1;
+  long long ZC = (P.Z + want_chunks - 1) / want_chunks;
+  const long long min_zc = P.has_group && P.hz > 0 ? 16 : 1;  // keep the re-read of halo planes small
+  if (ZC < min_zc) ZC = min_zc;
+  if (ZC > P.Z) ZC = P.Z;
+  P.ZC = ZC;
+  P.nzc = (int)((P.Z + ZC - 1) / ZC);
+  P.n_items = (long long)P.nzc * xy;
+  long long blocks = P.n_items < grid_cap ? P.n_items : grid_cap;
+
+  // ---- TMA descriptor over the halo'd source box
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (P.has_group) {
+    static const bool no_tma = getenv("RB200_NO_TMA") != nullptr;  // debugging aid: always the cooperative loader
+    EncodeTiledFn enc = encode_tiled_fn();
+    const uintptr_t corner = (uintptr_t)P.gcorner;
+    const int shift = (int)((corner & 15u) / (unsigned)es);
+    const char* tbase = P.gcorner - (size_t)shift * es;
+    const long long Xh = P.X + P.hx + shift, Yh = P.Y + P.hy, Zh = P.Z + P.hz;
+    const char* far_end = P.gcorner + ((Zh - 1) * P.gs0 + (Yh - 1) * P.gs1 + (P.X + P.hx)) * es;
+    const char* alo = (const char*)op->views[best_ref].alloc_lo;
+    const char* ahi = (const char*)op->views[best_ref].alloc_hi;
+    const bool aligned = (P.gs1 * es) % 16 == 0 && (nd == 2 || (P.gs0 * es) % 16 == 0) && (corner % (unsigned)es) == 0;
+    const bool inside = tbase >= alo && far_end <= ahi;
+    if (!no_tma && enc && aligned && inside && Xh < (1ll << 31)) {
+      cuuint64_t gdim[3] = {(cuuint64_t)Xh, (cuuint64_t)Yh, (cuuint64_t)Zh};
+      cuuint64_t gstr[2] = {(cuuint64_t)(P.gs1 * es), (cuuint64_t)((nd == 3 ? P.gs0 : P.gs1 * Yh) * es)};
+      cuuint32_t box[3] = {(cuuint32_t)P.PX, (cuuint32_t)P.PY, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult rc = enc(&tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)tbase, gdim, gstr, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc == CUDA_SUCCESS) {
+        P.use_tma = 1;
+        P.tma_shift = shift;
+      }
+    }
+  }
+
+  cudaError_t e;
+  if (es == 8) {
+    static bool attr8 = false;
+    if (!attr8) {
+      cudaFuncSetAttribute(stencil_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr8 = true;
+    }
+    stencil_tile_kernel<double><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+  } else {
+    static bool attr4 = false;
+    if (!attr4) {
+      cudaFuncSetAttribute(stencil_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      attr4 = true;
+    }
+    stencil_tile_kernel<float><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "stencil_tile_kernel launch (blocks=%lld smem=%zu group=%d tma=%d): %s", blocks, smem, P.has_group, P.use_tma,
+             cudaGetErrorString(e));
+    *err = buf;
+    return 2;
+  }
+  return 0;
+}
+
+}  // namespace rb200

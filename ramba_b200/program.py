@@ -475,6 +475,57 @@ class Lowering:
                     prev.mask = None
                 pending[n.store] = n
 
+    _LEAN_OPS = {"mov", "add", "sub", "mul", "div", "neg", "abs", "square", "min", "max", "cvt", "red"}
+
+    @staticmethod
+    def _fuse_muladd(nodes):
+        """`x + s*y`, `x - s*y`, `s*y - x`: when the product has no other use it is folded into the sum as a
+        three-operand instruction (MULADD / MULSUB / MULRSUB; product and sum still round separately), so that the
+        running sum stays in the accumulator instead of being parked in a spill register around the multiplication
+        - the shape of every weighted stencil term (ramba/ramba.py:8146-8188).  Applied only to op lists made of
+        plain float arithmetic (the ones the tile / stream kernels of the library take); anything with
+        transcendentals, integers, masks or index operands keeps the two-operand form its specialised handlers
+        expect."""
+        for n in nodes:
+            if n.pseudo or n.op not in Lowering._LEAN_OPS or n.ctype == T_I64 or n.mask is not None or n.mask_use:
+                return nodes
+            if n.op == "cvt" and ((n.imm >> 8) != 0 or (n.imm & 0xFF) == T_I64):
+                return nodes
+            if any(a.kind == "iota" for a in n.args):
+                return nodes
+        uses = {}
+        for n in nodes:
+            for a in n.args:
+                if a.kind == "node":
+                    uses[id(a.ref)] = uses.get(id(a.ref), 0) + 1
+
+        def product(tv, n):
+            if tv.kind != "node":
+                return None
+            m = tv.ref
+            if (m.op != "mul" or m.ctype != n.ctype or uses.get(id(m), 0) != 1 or m.store is not None
+                    or m.red_slot is not None or m.store2 is not None):
+                return None
+            return m
+
+        dropped = set()
+        for n in nodes:
+            if n.op not in ("add", "sub") or len(n.args) != 2:
+                continue
+            x, y = n.args
+            m = product(y, n)
+            if m is not None:
+                n.op = "muladd" if n.op == "add" else "mulsub"
+                n.args = [x, m.args[0], m.args[1]]
+                dropped.add(id(m))
+                continue
+            m = product(x, n)
+            if m is not None:
+                n.op = "muladd" if n.op == "add" else "mulrsub"
+                n.args = [y, m.args[0], m.args[1]]
+                dropped.add(id(m))
+        return [n for n in nodes if id(n) not in dropped]
+
     # ---- emission
     def finish(self):
         self._fuse_sincos()
@@ -506,6 +557,7 @@ class Lowering:
                 n.imm = 0
                 n.cos_node = None
 
+        nodes = self._fuse_muladd(nodes)
         # emission positions (pseudo nodes emit nothing)
         pos = 0
         for n in nodes:

@@ -638,7 +638,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             box, ptr, cst, sv = src
             if sv is not None:
                 off, st = RT.bind_view(sv, shards[i].strides, r)
-                bound.append((shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize, st, vcode[i]))
+                bound.append((shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize, st, vcode[i], shards[i].bounds))
             else:
                 off = 0
                 for d in range(k):
@@ -654,7 +654,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         # ---- axis reduction: stage 1 into per-split partials, then fold into the partial array
         shape_p = [shape_r[d] for d in order]
         gs_p = [gs[d] for d in order]
-        bound_p = [(b[0], [b[1][d] for d in order], b[2]) for b in bound]
+        bound_p = [(b[0], [b[1][d] for d in order], b[2]) + tuple(b[3:]) for b in bound]
         nred = len(red_axes)
         kept_elems = 1
         for d in range(nred, k):

@@ -48,7 +48,7 @@ class Shard:
     """This worker's block of one bdarray (LocalNdarray, ramba/ramba.py:1169-1357, without
     borders)."""
 
-    __slots__ = ("buf", "shape", "dtype", "strides")
+    __slots__ = ("buf", "shape", "dtype", "strides", "bounds")
 
     def __init__(self, buf, shape, dtype):
         self.buf = buf
@@ -60,6 +60,8 @@ class Shard:
             st.append(acc)
             acc *= max(1, s)
         self.strides = tuple(reversed(st))  # elements, C order
+        p = buf.data_ptr()
+        self.bounds = (p, p + buf.numel() * buf.element_size())  # [alloc_lo, alloc_hi) handed to the C-ABI
 
 
 class Runtime:
@@ -230,6 +232,8 @@ class Runtime:
                 fop.views[v].stride[i] = m[2][v]
             fop.views[v].dtype = bv[2]
             fop.views[v].flags = 1 if program.view_written.get(v) else 0
+            if len(bv) > 3 and bv[3] is not None:
+                fop.views[v].alloc_lo, fop.views[v].alloc_hi = bv[3]
         fop.n_scalars = len(program.scalars)
         fop.n_insns = len(program.insns)
         # op list and scalar table are packed once per program and copied in one go

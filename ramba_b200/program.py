@@ -302,6 +302,9 @@ class Lowering:
             return x
         if x.cls == cls and is_bool and x.is_bool:
             return x
+        if code in (cabi.F64, cabi.F32):
+            # a float storage dtype IS its compute class: the round trip is the plain class conversion
+            return self.coerce(x, cls)
         tv = self._node("cvt", cls, cls, is_bool, [x], imm=x.cls | ((code + 1) << 8))
         return tv
 

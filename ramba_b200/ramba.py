@@ -165,6 +165,7 @@ class deferred_op:
         self.statements = []
         self.axis_reductions = []
         self.keepalives = set()
+        self.elide_gids = set()  # arrays proven unobservable after the flush (dying temporaries of a reduction)
         self.uuid = "ramba_def_ops_%05d" % deferred_op.count
         deferred_op.count += 1
 
@@ -288,7 +289,7 @@ class deferred_op:
         t0 = timer()
         live_gids = {
             k: v for (k, v) in self.use_gids.items()
-            if (bdarray.valid_gid(k) and k not in self.delete_gids) or k in self.preconstructed_gids
+            if (bdarray.valid_gid(k) and k not in self.delete_gids and k not in self.elide_gids) or k in self.preconstructed_gids
         }
         self._pin(live_gids)
         try:
@@ -420,6 +421,10 @@ class deferred_op:
                 elif dst.gid in live_gids:
                     m = resolve(mask) if mask is not None else None
                     lw.store(view_of(dst), tv, m)
+                elif dst.gid in self.elide_gids:
+                    # an elided temporary keeps the value a store + reload would have given it (the reference
+                    # materialises it: ramba_b200 only skips the memory traffic, not the rounding)
+                    dead_values[dst.gid] = lw.astype(tv, rb_dtype(dst.dtype))
                 else:
                     dead_values[dst.gid] = tv
             elif st[0] == "gred":
@@ -1398,11 +1403,41 @@ for _n, (_t, _d) in array_unaryop_funcs.items():
 
 def _make_reduction(name, redop, init, dtype=None):
     def _method(self, axis=None, dtype=dtype, keepdims=False, asarray=False, **kwargs):
+        # `(X*2.0 + 1.0).sum()`: the operand is a temporary that nobody can observe once this call returns.  The global
+        # reduction flushes INSIDE the call, while the caller's expression still holds the temporary, so the reference
+        # materialises it (ramba/ramba.py:8123-8127 looks at handle liveness only); here a temporary whose only
+        # reference is the pending call is treated as already dead and never touches HBM.
+        if _sys_getrefcount(self) <= _TEMP_REFCOUNT and self.base is None and self.bdarray.nrefs == 1 \
+                and not self.bdarray.remote_constructed and deferred_op.ramba_deferred_ops is not None:
+            deferred_op.ramba_deferred_ops.elide_gids.add(self.gid)
         return self.array_unaryop(name, None, reduction=True, dtype=dtype, axis=axis, keepdims=keepdims, redop=redop,
                                   initval=init, asarray=asarray)
 
     _method.__name__ = name
     return _method
+
+
+from sys import getrefcount as _sys_getrefcount  # noqa: E402
+
+
+def _measure_temp_refcount():
+    """Reference count a method sees for `self` when it is called on a temporary (CPython: the frame's own
+    reference + getrefcount's argument).  Measured, not assumed: if the interpreter counts differently the
+    elision simply never triggers."""
+    class _Probe:
+        pass
+
+    def _method(self, axis=None, dtype=None, keepdims=False, asarray=False, **kwargs):
+        return _sys_getrefcount(self)
+
+    _Probe.m = _method
+    temp = _Probe().m()
+    named_obj = _Probe()
+    named = named_obj.m()
+    return temp if named > temp else -1
+
+
+_TEMP_REFCOUNT = _measure_temp_refcount()
 
 
 array_simple_reductions = {

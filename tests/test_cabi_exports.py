@@ -21,12 +21,36 @@ def test_library_exports_header_symbols():
     assert _cabi.load().rb200_abi_version() == _cabi.ABI_VERSION
 
 
-def test_struct_layout_matches_header():
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every struct as gcc sees include/ramba_b200.h == the ctypes mirror in _cabi.py."""
+    import subprocess
+
     from ramba_b200 import _cabi
 
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "ramba_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu\n", sizeof(rb200_insn), sizeof(rb200_view), sizeof(rb200_red), sizeof(rb200_fused_op));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(rb200_view, stride), offsetof(rb200_view, dtype), offsetof(rb200_view, alloc_lo),
+         offsetof(rb200_fused_op, views), offsetof(rb200_fused_op, insns));
+  printf("%zu %zu %zu %d %d\n", offsetof(rb200_fused_op, scalars), offsetof(rb200_fused_op, reds), offsetof(rb200_fused_op, red_scratch),
+         RB200_ABI_VERSION, RB200_NUM_OPS);
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    got = [int(x) for x in out]
+    F = _cabi.FusedOp
+    exp = [ctypes.sizeof(_cabi.Insn), ctypes.sizeof(_cabi.View), ctypes.sizeof(_cabi.Red), ctypes.sizeof(F),
+           _cabi.View.stride.offset, _cabi.View.dtype.offset, _cabi.View.alloc_lo.offset, F.views.offset, F.insns.offset,
+           F.scalars.offset, F.reds.offset, F.red_scratch.offset, _cabi.ABI_VERSION, len(_cabi.OPS)]
+    assert got == exp
     assert ctypes.sizeof(_cabi.Insn) == 16
-    assert ctypes.sizeof(_cabi.View) == 8 + 8 * _cabi.MAX_DIMS + 8
-    assert _cabi.FusedOp.views.offset % 8 == 0 and _cabi.FusedOp.insns.offset % 8 == 0
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -248,6 +248,16 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     }
     if (r == 2) return fail(terr);
   }
+  // float-arithmetic op lists over a contiguous 1-D space (incl. global reductions): the streaming kernel
+  if (op->ndim == 1 && op->n_axis_red_dims == 0) {
+    std::string terr;
+    const int r = launch_stream_1d(op, sms, kRedScratchPartials, stream, &terr);
+    if (r == 0) {
+      g_launches.fetch_add(1);
+      return 0;
+    }
+    if (r == 2) return fail(terr);
+  }
 
   if (op->n_axis_red_dims != 0) {
     // axis mode: the first n_axis_red_dims dims are the reduced ones (host permutes)
@@ -271,6 +281,25 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
     for (int s = 0; s < op->n_reds; ++s) {
       P.reds[s].op = op->reds[s].op;
       P.reds[s].ctype = op->reds[s].ctype;
+    }
+    // ---- column form on the streaming kernel of the lean machine (float arithmetic op lists)
+    {
+      std::string terr;
+      int eff = 0;
+      const int r = launch_stream_columns(op, sms, n_split, stream, &eff, &terr);
+      if (r == 2) return fail(terr);
+      if (r == 0) {
+        g_launches.fetch_add(1);
+        if (eff < n_split) {
+          const long long n_fill = (long long)(n_split - eff) * kept;
+          fill_u64_kernel<<<(unsigned)((n_fill + 255) / 256 > 1184 ? 1184 : (n_fill + 255) / 256), 256, 0, stream>>>(
+              (u64*)op->red_scratch + (long long)eff * kept, n_fill, host_red_identity_bits(op->reds[0].op, op->reds[0].ctype));
+          e = cudaGetLastError();
+          if (e != cudaSuccess) return fail_cuda("fill_u64_kernel launch", e);
+          g_launches.fetch_add(1);
+        }
+        return 0;
+      }
     }
     // ---- axis-as-1-D fast path: [R reduced rows][C kept elements], every view contiguous over the box
     // or broadcast over the rows, C a multiple of the 1-D tile, one reduction slot, no index operands:

@@ -16,4 +16,6 @@ cudaError_t launch_vm_axis_reduce(const KParams& P, unsigned blocks, size_t smem
 // specialised kernels tried before the general interpreter.  Return 0: launched, 1: the op list is not of their form
 // (fall through), 2: error (*err set)
 int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, std::string* err);
+int launch_stream_1d(const rb200_fused_op* op, int sms, int max_red_blocks, cudaStream_t stream, std::string* err);
+int launch_stream_columns(const rb200_fused_op* op, int sms, int n_split, cudaStream_t stream, int* n_split_eff_out, std::string* err);
 }  // namespace rb200

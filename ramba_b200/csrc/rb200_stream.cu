@@ -1,0 +1,553 @@
+// rb200_stream.cu — K1/K5/K6 for float-arithmetic op lists: the streaming kernel of the lean machine (sm_100a).
+//
+// What it stands for in the reference: the generated loop `for index in numba.pndindex(itershape): ...` over a
+// contiguous 1-D (collapsed) iteration space (ramba/ramba.py:8246-8255), with the pre/postcode of a global reduction
+// (`red[0] = red[0] + acc`, ramba/ramba.py:5798-5807), and the axis-reduction loop nest over a [rows][columns] box
+// (ramba/ramba.py:8231-8244) - for op lists made of plain float arithmetic (rb200_lean_plan.h).  Affine maps feeding
+// a sum (`(X*2.0 + 1.0).sum()`), broadcast-add + column sums (`(M + v).sum(axis=0)`), float32 streams in general:
+// at 4 bytes per element the general interpreter is bound by its own dispatch cost, this kernel by HBM.
+//
+//   * tile = 2048 consecutive elements (256 threads x 8, element k of thread t is k*256 + t: every access of a warp
+//     is 32 consecutive elements);
+//   * contiguous 16-byte aligned input views are STAGED: one elected thread issues one bulk async copy (TMA engine,
+//     SASS UBLKCP) per view and tile into a ring of up to 8 stages, completion on an mbarrier - the ring holds the
+//     bytes in flight that hide HBM latency, no registers are tied up by loads;
+//   * mode 0 (elementwise / global reductions): persistent CTAs walk tiles b, b+grid, ...; reduction slots are
+//     float64 accumulators in registers, folded warp -> CTA -> last CTA in a fixed order;
+//   * mode 1 (axis reduction in column form): a CTA owns a chunk of 2048 columns and a slice of the rows, walks the
+//     rows keeping 8 column accumulators per thread in registers, and writes partials[split][column]; operands that
+//     are broadcast over the rows are loaded once into the shared-memory register file.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "rb200_launch.h"
+#include "rb200_lean.cuh"
+#include "rb200_lean_plan.h"
+
+namespace rb200 {
+
+constexpr int kStreamMaxStaged = 4;
+constexpr int kStreamTile = LV * kThreads;  // 2048
+
+struct StreamStaged {
+  const char* base;
+  int es;        // element size (4 / 8)
+  int dview;     // the same view in the direct table (ragged last tile)
+  unsigned off;  // byte offset inside a stage
+  int pad;
+};
+
+struct StreamHoist {
+  int direct, reg, is_f32_class;
+};
+
+struct StreamParams {
+  int mode;
+  long long total, n_tiles;                  // mode 0
+  long long R, C, rows_per_split;            // mode 1: box [R][C]
+  int n_chunks, n_split;
+  int n_staged, depth;
+  unsigned stage_bytes;
+  StreamStaged staged[kStreamMaxStaged];
+  int n_direct;
+  LDirect direct[RB200_MAX_VIEWS];           // s1: row stride (mode 1), s2: element / column stride
+  int n_hoist;
+  StreamHoist hoist[kStreamMaxStaged];
+  int n_insns, n_regs;
+  LInsn insns[RB200_MAX_INSNS];
+  u64 scal[RB200_MAX_SCALARS];
+  int n_reds;
+  KRed reds[RB200_MAX_REDS];
+  u64* red_partials;
+  unsigned int* red_counter;
+};
+
+struct StreamCtx {
+  const StreamParams& P;
+  unsigned stage_s;  // shared-window address of the current stage
+  unsigned reg_s;    // this thread's column of the register file
+  unsigned tid;
+  bool staged_ok;    // the current tile was staged (false: ragged last tile, read directly)
+  long long row, e0; // row (mode 1, else 0); element / column of k = 0
+  unsigned valid;
+  unsigned alo[LV], ahi[LV];
+  double racc[RB200_MAX_REDS];  // mode 0: reduction slots
+  double cacc[LV];              // mode 1: column accumulators
+  __device__ __forceinline__ StreamCtx(const StreamParams& p) : P(p) {}
+
+  template <class F> __device__ __forceinline__ void fetch_direct(int arg, F (&out)[LV]) {
+    const LDirect& v = P.direct[arg];
+    const long long off = row * v.s1 + e0 * v.s2;
+    const long long step = (long long)kThreads * v.s2;
+    if (v.dtype == RB200_F32) {
+      const float* p = reinterpret_cast<const float*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step) out[k] = ((valid >> k) & 1u) ? (F)ldg<float>(p) : F(0);
+    } else {
+      const double* p = reinterpret_cast<const double*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step) out[k] = ((valid >> k) & 1u) ? (F)ldg<double>(p) : F(0);
+    }
+  }
+  template <class F> __device__ __forceinline__ void fetch(int kind, int arg, F (&out)[LV]) {
+    switch (kind) {
+      case L_STAGED: {
+        const StreamStaged& sv = P.staged[arg];
+        if (!staged_ok) {
+          fetch_direct<F>(sv.dview, out);
+          break;
+        }
+        if (sv.es == 4) {
+          const unsigned addr = stage_s + sv.off + tid * 4u;
+#pragma unroll
+          for (int k = 0; k < LV; ++k) out[k] = (F)lean_lds<float>(addr + k * kThreads * 4);
+        } else {
+          const unsigned addr = stage_s + sv.off + tid * 8u;
+#pragma unroll
+          for (int k = 0; k < LV; ++k) out[k] = (F)lean_lds<double>(addr + k * kThreads * 8);
+        }
+      } break;
+      case L_DIRECT: fetch_direct<F>(arg, out); break;
+      case L_REG: {
+        const unsigned addr = reg_s + (unsigned)arg * (LV * kThreads * 8);
+#pragma unroll
+        for (int k = 0; k < LV; ++k) out[k] = lean_lds<F>(addr + k * kThreads * 8);
+      } break;
+      case L_SCAL: {
+        const u64 bits = P.scal[arg];
+        const F s = sizeof(F) == 8 ? (F)__longlong_as_double((long long)bits) : (F)__uint_as_float((unsigned)bits);
+#pragma unroll
+        for (int k = 0; k < LV; ++k) out[k] = s;
+      } break;
+      default:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) out[k] = LAcc<F>::get(alo[k], ahi[k]);
+    }
+  }
+  template <class F> __device__ __forceinline__ void store_reg(int reg, const F (&r)[LV]) {
+    const unsigned addr = reg_s + (unsigned)reg * (LV * kThreads * 8);
+#pragma unroll
+    for (int k = 0; k < LV; ++k) lean_sts<F>(addr + k * kThreads * 8, r[k]);
+  }
+  template <class F> __device__ __forceinline__ void store_view(int arg, const F (&r)[LV]) {
+    const LDirect& v = P.direct[arg];
+    const long long off = row * v.s1 + e0 * v.s2;
+    const long long step = (long long)kThreads * v.s2;
+    if (v.dtype == RB200_F32) {
+      float* p = reinterpret_cast<float*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step)
+        if ((valid >> k) & 1u) stg<float>(p, (float)r[k]);
+    } else {
+      double* p = reinterpret_cast<double*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step)
+        if ((valid >> k) & 1u) stg<double>(p, (double)r[k]);
+    }
+  }
+  template <class F> __device__ __forceinline__ void reduce(int slot, int rop, const F (&a)[LV]) {
+    if constexpr (sizeof(F) == 8) {
+      if (P.mode == 1) {
+#pragma unroll
+        for (int k = 0; k < LV; ++k) cacc[k] = red_combine<double>(rop, cacc[k], a[k]);
+        return;
+      }
+      double x[LV];
+      const double ident = CT<double>::get(red_identity_bits(rop, RB200_T_F64));
+#pragma unroll
+      for (int k = 0; k < LV; ++k) x[k] = ((valid >> k) & 1u) ? (double)a[k] : ident;
+#pragma unroll
+      for (int w = LV / 2; w > 0; w >>= 1) {
+#pragma unroll
+        for (int k = 0; k < w; ++k) x[k] = red_combine<double>(rop, x[k], x[k + w]);
+      }
+#pragma unroll
+      for (int s = 0; s < RB200_MAX_REDS; ++s)
+        if (s == slot) racc[s] = red_combine<double>(rop, racc[s], x[0]);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(kThreads, 2) stream_kernel(const __grid_constant__ StreamParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const unsigned tid = threadIdx.x;
+  // layout: [ring: depth stages][register file: (n_regs + n_hoist) * 2048 * 8][mbarriers]
+  const unsigned ring_bytes = (unsigned)P.depth * P.stage_bytes;
+  const unsigned regs_s = smem_s + ring_bytes;
+  const unsigned mbar_s = regs_s + (unsigned)(P.n_regs + P.n_hoist) * (LV * kThreads * 8);
+  if (P.n_staged > 0 && tid == 0) {
+    for (int s = 0; s < P.depth; ++s) mbar_init(mbar_s + 8u * s, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  StreamCtx cx(P);
+  cx.tid = tid;
+  cx.reg_s = regs_s + tid * 8u;
+#pragma unroll
+  for (int s = 0; s < RB200_MAX_REDS; ++s) cx.racc[s] = 0.0;
+  for (int s = 0; s < P.n_reds; ++s) {
+    const double ident = CT<double>::get(red_identity_bits(P.reds[s].op, RB200_T_F64));
+#pragma unroll
+    for (int q = 0; q < RB200_MAX_REDS; ++q)
+      if (q == s) cx.racc[q] = ident;
+  }
+
+  // the CTA's sequence of tiles: it -> linear element offset of the tile inside the (contiguous) staged views
+  long long n_it, base0, step_it;  // element offset of tile `it` = base0 + it * step_it
+  long long split = 0, col0 = 0, r0 = 0;
+  if (P.mode == 0) {
+    n_it = (P.n_tiles - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+    base0 = (long long)blockIdx.x * kStreamTile;
+    step_it = (long long)gridDim.x * kStreamTile;
+    cx.row = 0;
+  } else {
+    split = blockIdx.x / (unsigned)P.n_chunks;
+    const long long chunk = blockIdx.x - split * P.n_chunks;
+    col0 = chunk * kStreamTile;
+    r0 = split * P.rows_per_split;
+    long long r1 = r0 + P.rows_per_split;
+    if (r1 > P.R) r1 = P.R;
+    n_it = r1 > r0 ? r1 - r0 : 0;
+    base0 = r0 * P.C + col0;
+    step_it = P.C;
+    const double ident = CT<double>::get(red_identity_bits(P.reds[0].op, RB200_T_F64));
+#pragma unroll
+    for (int k = 0; k < LV; ++k) cx.cacc[k] = ident;
+    cx.e0 = col0 + tid;
+    cx.valid = (1u << LV) - 1u;
+    cx.row = 0;
+    cx.staged_ok = false;
+    // operands broadcast over the rows: once into the register file
+    for (int h = 0; h < P.n_hoist; ++h) {
+      if (P.hoist[h].is_f32_class) {
+        float v[LV];
+        cx.fetch_direct<float>(P.hoist[h].direct, v);
+        cx.store_reg<float>(P.hoist[h].reg, v);
+      } else {
+        double v[LV];
+        cx.fetch_direct<double>(P.hoist[h].direct, v);
+        cx.store_reg<double>(P.hoist[h].reg, v);
+      }
+    }
+  }
+
+  auto tile_full = [&](long long it) -> bool { return P.mode == 1 || base0 + it * step_it + kStreamTile <= P.total; };
+  auto issue = [&](long long it) {
+    if (tid != 0) return;
+    const unsigned slot = (unsigned)(it % P.depth);
+    const unsigned bar = mbar_s + 8u * slot;
+    const unsigned dst = smem_s + slot * P.stage_bytes;
+    const long long eoff = base0 + it * step_it;
+    unsigned bytes = 0;
+    for (int j = 0; j < P.n_staged; ++j) bytes += (unsigned)(kStreamTile * P.staged[j].es);
+    mbar_expect_tx(bar, bytes);
+    for (int j = 0; j < P.n_staged; ++j)
+      bulk_g2s(dst + P.staged[j].off, P.staged[j].base + eoff * P.staged[j].es, (unsigned)(kStreamTile * P.staged[j].es), bar);
+  };
+
+  if (P.n_staged > 0) {
+    for (long long it = 0; it < P.depth - 1 && it < n_it; ++it)
+      if (tile_full(it)) issue(it);
+  }
+  for (long long it = 0; it < n_it; ++it) {
+    const bool full = tile_full(it);
+    if (P.n_staged > 0) {
+      __syncthreads();  // everyone is done with tile it-1: its stage takes tile it + depth - 1
+      const long long nx = it + P.depth - 1;
+      if (nx < n_it && tile_full(nx)) issue(nx);
+      if (full) mbar_wait(mbar_s + 8u * (unsigned)(it % P.depth), (unsigned)((it / P.depth) & 1));
+    }
+    cx.staged_ok = full && P.n_staged > 0;
+    cx.stage_s = smem_s + (unsigned)(it % (P.depth > 0 ? P.depth : 1)) * P.stage_bytes;
+    if (P.mode == 0) {
+      const long long e = base0 + it * step_it + tid;
+      cx.e0 = e;
+      unsigned valid = (1u << LV) - 1u;
+      if (!full) {
+        valid = 0;
+#pragma unroll
+        for (int k = 0; k < LV; ++k)
+          if (e + (long long)k * kThreads < P.total) valid |= 1u << k;
+      }
+      cx.valid = valid;
+    } else {
+      cx.row = r0 + it;
+    }
+#pragma unroll 1
+    for (int pc = 0; pc < P.n_insns; ++pc) {
+      const LInsn I = P.insns[pc];
+      lean_dispatch(cx, I);
+    }
+  }
+
+  if (P.mode == 1) {
+#pragma unroll
+    for (int k = 0; k < LV; ++k) P.red_partials[split * P.C + col0 + tid + (long long)k * kThreads] = CT<double>::bits(cx.cacc[k]);
+    return;
+  }
+  // ---- global reductions: thread -> warp -> CTA -> per-CTA partial -> last CTA (fixed order, deterministic per grid)
+  if (P.n_reds > 0) {
+    __shared__ u64 wpart[RB200_MAX_REDS][kThreads / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s = 0; s < P.n_reds; ++s) {
+      const int op = P.reds[s].op;
+      double mine = 0.0;
+#pragma unroll
+      for (int q = 0; q < RB200_MAX_REDS; ++q)
+        if (q == s) mine = cx.racc[q];
+      u64 v = CT<double>::bits(mine);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, RB200_T_F64, v, __shfl_down_sync(0xffffffffu, v, o));
+      if (lane == 0) wpart[s][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < P.n_reds; ++s) {
+        const int op = P.reds[s].op;
+        u64 v = wpart[s][0];
+        for (int q = 1; q < kThreads / 32; ++q) v = red_combine_bits(op, RB200_T_F64, v, wpart[s][q]);
+        P.red_partials[(long long)s * gridDim.x + blockIdx.x] = v;
+      }
+      __threadfence();
+      const unsigned prev = atomicAdd(P.red_counter, 1u);
+      is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      for (int s = 0; s < P.n_reds; ++s) {
+        const int op = P.reds[s].op;
+        u64 v = red_identity_bits(op, RB200_T_F64);
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads)
+          v = red_combine_bits(op, RB200_T_F64, v, __ldcg(&P.red_partials[(long long)s * gridDim.x + b]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, RB200_T_F64, v, __shfl_down_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if (lane == 0) wpart[s][warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          v = wpart[s][0];
+          for (int q = 1; q < kThreads / 32; ++q) v = red_combine_bits(op, RB200_T_F64, v, wpart[s][q]);
+          // red[0,..] = red[0,..] (op) acc  (ramba/ramba.py:5805-5806), rounded to the partial array's dtype on store
+          const double vd = CT<double>::get(v);
+          void* out = P.reds[s].out;
+          if (P.reds[s].out_dtype == RB200_F64) {
+            double* o = (double*)out;
+            *o = red_combine<double>(op, *o, vd);
+          } else {
+            float* o = (float*)out;
+            *o = (float)red_combine<double>(op, (double)*o, vd);
+          }
+        }
+      }
+      if (threadIdx.x == 0) *P.red_counter = 0u;
+    }
+  }
+}
+
+// =============================================================================================
+// host side
+
+static bool stream_translate(const rb200_fused_op* op, StreamParams& P, bool column_mode, long long row_len) {
+  // staged: read views that are contiguous along the iteration (and, in column mode, over the rows) with 16-byte
+  // aligned tiles; everything else direct
+  bool rd[RB200_MAX_VIEWS] = {false};
+  for (int i = 0; i < op->n_insns; ++i) {
+    const rb200_insn& I = op->insns[i];
+    const int lop = lean_opcode(op, I);
+    if (I.a_kind == RB200_K_VIEW) rd[I.a_idx] = true;
+    if (I.b_kind == RB200_K_VIEW && lop != LO_RED && lop != LO_SQUARE) rd[I.b_idx] = true;
+    if (I.c_kind == RB200_K_VIEW) rd[I.c_idx] = true;
+  }
+  int view_kind[RB200_MAX_VIEWS], view_arg[RB200_MAX_VIEWS], store_arg[RB200_MAX_VIEWS];
+  unsigned off = 0;
+  for (int v = 0; v < op->n_views; ++v) {
+    const rb200_view& vw = op->views[v];
+    const int es = vw.dtype == RB200_F64 ? 8 : 4;
+    LDirect& d = P.direct[P.n_direct];
+    d.base = (char*)vw.base;
+    d.s0 = 0;
+    d.s1 = column_mode ? vw.stride[0] : 0;
+    d.s2 = column_mode ? vw.stride[1] : vw.stride[0];
+    d.dtype = vw.dtype;
+    view_kind[v] = L_DIRECT;
+    view_arg[v] = store_arg[v] = P.n_direct;
+    const bool contiguous = d.s2 == 1 && (!column_mode || d.s1 == row_len);
+    const bool aligned = (((uintptr_t)vw.base) & 15u) == 0 && (!column_mode || (row_len * es) % 16 == 0);
+    if (rd[v] && contiguous && aligned && P.n_staged < kStreamMaxStaged) {
+      StreamStaged& s = P.staged[P.n_staged];
+      s.base = (const char*)vw.base;
+      s.es = es;
+      s.dview = P.n_direct;
+      s.off = off;
+      off += (unsigned)(kStreamTile * es);
+      view_kind[v] = L_STAGED;
+      view_arg[v] = P.n_staged;
+      ++P.n_staged;
+    }
+    ++P.n_direct;
+  }
+  P.stage_bytes = off;
+  P.n_insns = op->n_insns;
+  P.n_regs = op->n_regs;
+  lean_translate(op, view_kind, view_arg, store_arg, P.insns);
+  for (int i = 0; i < op->n_scalars; ++i) P.scal[i] = op->scalars[i];
+  if (column_mode) {
+    // row-broadcast operands fetched in ONE class move into the register file
+    for (int dv = 0; dv < P.n_direct && P.n_hoist < kStreamMaxStaged; ++dv) {
+      if (P.direct[dv].s1 != 0 || P.direct[dv].s2 != 1) continue;
+      int cls = -1;
+      bool same = true, used = false;
+      for (int i = 0; i < P.n_insns; ++i) {
+        const LInsn& L = P.insns[i];
+        const int lop = L.handler >> 2;
+        int fcls = (L.handler >> 1) & 1;  // 1: f32
+        if (lop == LO_CVT) fcls = 1 - fcls;  // CVT fetches its operand in the OTHER class
+        const bool uses = (L.a_kind == L_DIRECT && L.a_arg == dv) || (L.b_kind == L_DIRECT && L.b_arg == dv) || (L.c_kind == L_DIRECT && L.c_arg == dv);
+        if (!uses) continue;
+        used = true;
+        if (cls < 0) cls = fcls;
+        else if (cls != fcls) same = false;
+      }
+      if (!used || !same) continue;
+      const int reg = P.n_regs + P.n_hoist;
+      if (reg >= 255) break;
+      P.hoist[P.n_hoist].direct = dv;
+      P.hoist[P.n_hoist].reg = reg;
+      P.hoist[P.n_hoist].is_f32_class = cls;
+      ++P.n_hoist;
+      for (int i = 0; i < P.n_insns; ++i) {
+        LInsn& L = P.insns[i];
+        if (L.a_kind == L_DIRECT && L.a_arg == dv) { L.a_kind = L_REG; L.a_arg = (unsigned char)reg; }
+        if (L.b_kind == L_DIRECT && L.b_arg == dv) { L.b_kind = L_REG; L.b_arg = (unsigned char)reg; }
+        if (L.c_kind == L_DIRECT && L.c_arg == dv) { L.c_kind = L_REG; L.c_arg = (unsigned char)reg; }
+      }
+    }
+  }
+  return true;
+}
+
+static size_t stream_smem(StreamParams& P) {
+  const size_t regs = (size_t)(P.n_regs + P.n_hoist) * LV * kThreads * 8;
+  const size_t budget = 100 * 1024;
+  if (regs + 1024 > budget) return 0;
+  int depth = 0;
+  if (P.n_staged > 0) {
+    depth = (int)((budget - regs - 256) / P.stage_bytes);
+    if (depth > 8) depth = 8;
+    if (depth < 2) return 0;
+  }
+  P.depth = depth;
+  return (size_t)depth * P.stage_bytes + regs + (size_t)depth * 8 + 16;
+}
+
+static cudaError_t stream_launch(const StreamParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024);
+    attr = true;
+  }
+  stream_kernel<<<blocks, kThreads, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+// mode 0.  0: launched, 1: not of this form, 2: error
+int launch_stream_1d(const rb200_fused_op* op, int sms, int max_red_blocks, cudaStream_t stream, std::string* err) {
+  static const bool disabled = getenv("RB200_NO_STREAM_KERNEL") != nullptr;  // debugging aid
+  if (disabled) return 1;
+  if (op->ndim != 1 || op->n_axis_red_dims != 0) return 1;
+  if (!lean_eligible(op, true)) return 1;
+  for (int s = 0; s < op->n_reds; ++s) {
+    if (op->reds[s].ctype != RB200_T_F64) return 1;
+    if (op->reds[s].out_dtype != RB200_F64 && op->reds[s].out_dtype != RB200_F32) return 1;
+    if (!op->reds[s].out) return 1;
+  }
+  StreamParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = 0;
+  P.total = op->itershape[0];
+  P.n_tiles = (P.total + kStreamTile - 1) / kStreamTile;
+  stream_translate(op, P, false, 0);
+  const size_t smem = stream_smem(P);
+  if (smem == 0) return 1;
+  P.n_reds = op->n_reds;
+  if (op->n_reds > 0) {
+    if (!op->red_scratch) return 1;
+    P.red_counter = (unsigned int*)op->red_scratch;
+    P.red_partials = (u64*)((char*)op->red_scratch + 256);
+    for (int s = 0; s < op->n_reds; ++s) {
+      P.reds[s].op = op->reds[s].op;
+      P.reds[s].ctype = op->reds[s].ctype;
+      P.reds[s].out = op->reds[s].out;
+      P.reds[s].out_dtype = op->reds[s].out_dtype;
+    }
+  }
+  long long blocks = P.n_tiles;
+  long long cap = (long long)sms * 2;
+  if (op->n_reds > 0 && cap > max_red_blocks) cap = max_red_blocks;
+  if (blocks > cap) blocks = cap;
+  const cudaError_t e = stream_launch(P, (unsigned)blocks, smem, stream);
+  if (e != cudaSuccess) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "stream_kernel launch (blocks=%lld smem=%zu staged=%d depth=%d): %s", blocks, smem, P.n_staged, P.depth, cudaGetErrorString(e));
+    *err = buf;
+    return 2;
+  }
+  return 0;
+}
+
+// mode 1: axis reduction over the rows of a [R][C] box into partials[n_split_eff][C].  On success *n_split_eff_out is
+// the number of splits written (the caller fills the remaining ones with the identity).
+int launch_stream_columns(const rb200_fused_op* op, int sms, int n_split, cudaStream_t stream, int* n_split_eff_out, std::string* err) {
+  static const bool disabled = getenv("RB200_NO_STREAM_KERNEL") != nullptr;
+  if (disabled) return 1;
+  if (op->ndim != 2 || op->n_axis_red_dims != 1 || op->n_reds != 1) return 1;
+  if (!lean_eligible(op, true)) return 1;
+  if (op->reds[0].ctype != RB200_T_F64 || !op->red_scratch) return 1;
+  const long long R = op->itershape[0], C = op->itershape[1];
+  if (C % kStreamTile != 0 || C / kStreamTile > (long long)sms * 2 || R < 2) return 1;
+  for (int i = 0; i < op->n_insns; ++i)
+    if (op->insns[i].st_view != RB200_NOSTORE) return 1;
+  for (int v = 0; v < op->n_views; ++v) {
+    const rb200_view& vw = op->views[v];
+    if (vw.stride[1] != 1 || !(vw.stride[0] == C || vw.stride[0] == 0)) return 1;
+  }
+  StreamParams P;
+  memset(&P, 0, sizeof(P));
+  P.mode = 1;
+  P.R = R;
+  P.C = C;
+  P.total = R * C;
+  stream_translate(op, P, true, C);
+  const size_t smem = stream_smem(P);
+  if (smem == 0) return 1;
+  P.n_chunks = (int)(C / kStreamTile);
+  int eff = (int)(((long long)sms * 2) / P.n_chunks);
+  if (eff > n_split) eff = n_split;
+  if ((long long)eff > R) eff = (int)R;
+  if (eff < 1) eff = 1;
+  P.n_split = eff;
+  P.rows_per_split = (R + eff - 1) / eff;
+  P.n_reds = 1;
+  P.reds[0].op = op->reds[0].op;
+  P.reds[0].ctype = op->reds[0].ctype;
+  P.red_partials = (u64*)op->red_scratch;
+  const cudaError_t e = stream_launch(P, (unsigned)(eff * P.n_chunks), smem, stream);
+  if (e != cudaSuccess) {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "stream_kernel (columns) launch (blocks=%d smem=%zu staged=%d depth=%d): %s", eff * P.n_chunks, smem, P.n_staged, P.depth,
+             cudaGetErrorString(e));
+    *err = buf;
+    return 2;
+  }
+  *n_split_eff_out = eff;
+  return 0;
+}
+
+}  // namespace rb200

@@ -518,6 +518,48 @@ def _contig_strides(shape, bcast):
     return st, acc
 
 
+def _gatherable(vd, exec_dist, bc, vshape, W):
+    """Elements per rank if view distribution `vd` can be brought to every rank with one all-gather: every rank runs a
+    non-empty part of the iteration box, no rank holds what it needs, every rank needs every rank's WHOLE part, and the
+    parts are equal consecutive chunks along the outermost non-broadcast axis (so that rank order == C order).  All
+    ranks evaluate this on the same metadata, so they agree.  None otherwise."""
+    k = len(bc)
+    nb = [d for d in range(k) if not bc[d] and int(vshape[d]) > 1]
+    if not nb:
+        return None
+    a = nb[0]
+    m = None
+    for p in range(W):
+        part = vd[p]
+        ex = shardview.clean_range(exec_dist[p])
+        if shardview.is_empty(part) or shardview.is_empty(ex) or shardview.is_compat(ex, part):
+            return None
+        if builtins.any((int(part.axis_map[d]) < 0) != bc[d] for d in range(k)):
+            return None
+        for d in range(k):
+            if bc[d]:
+                continue
+            if d == a:
+                if m is None:
+                    m = int(part.size[d])
+                if int(part.size[d]) != m or int(part.start[d]) != p * m:
+                    return None
+            elif int(part.start[d]) != 0 or int(part.size[d]) != int(vshape[d]):
+                return None
+    # every rank's box must cover the whole operand along its non-broadcast axes
+    for j in range(W):
+        ex = shardview.clean_range(exec_dist[j])
+        for d in range(k):
+            if not bc[d] and (int(ex.start[d]) != 0 or int(ex.size[d]) != int(vshape[d])):
+                return None
+    n = m
+    for d in nb[1:]:
+        n *= int(vshape[d])
+    if m * W != int(vshape[a]) or n * W > (1 << 22):
+        return None
+    return n
+
+
 def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     """This worker's share of one flush (RemoteState.run_deferred_ops, ramba/ramba.py:3493-3819)."""
     import torch
@@ -552,18 +594,46 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     # parts[i] = list of (box, data_ptr, elem_strides or None(shard-addressed), sv)
     parts = [[] for _ in range(nviews)]
     recv_bufs = []
+    pending = []  # collectives / transfers in flight: waited for only before the first range that reads what they bring
     if W > 1 and not builtins.all(local_everywhere):
         RT.ensure_process_group()
         import torch.distributed as dist
 
         ops = []
-        sends_keep = []
         for i in range(nviews):
             if local_everywhere[i]:
                 continue
             if written[i]:
                 raise ProgramError("fused op writes a view that is not aligned with its iteration space")
             bc = [int(a) < 0 for a in vdist[i][0].axis_map]
+            itemsize = np.dtype(views[i][1].dtype).itemsize
+            g = _gatherable(vdist[i], exec_dist, bc, views[i][1].shape, W)
+            if g is not None:
+                # every rank needs every rank's part of this (small) operand and the parts are equal consecutive
+                # chunks: ONE all-gather into a buffer that then serves the whole iteration box as a single source
+                # (the reference ships W*(W-1) pickled pieces, ramba/ramba.py:3646-3693)
+                n = g
+                tdt = torch_dtype(views[i][1].dtype)
+                mine = torch.empty(n, dtype=tdt, device=RT.device)
+                part = shardview.clean_range(vdist[i][w])
+                shp = [1 if bc[d] else int(part.size[d]) for d in range(len(bc))]
+                cst, _ = _contig_strides(shp, bc)
+                off, st = RT.bind_view(vdist[i][w], shards[i].strides, part)
+                RT.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
+                          [(shards[i].buf.data_ptr() + off * itemsize, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
+                           (mine.data_ptr(), cst, vcode[i])])
+                full = torch.empty(W * n, dtype=tdt, device=RT.device)
+                pending.append(dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), async_op=True))
+                recv_bufs += [full, mine]
+                RT.bytes_sent += n * itemsize * (W - 1)
+                RT.collectives += 1
+                vshape = views[i][1].shape
+                fshape = [1 if bc[d] else int(vshape[d]) for d in range(len(bc))]
+                fst, _ = _contig_strides(fshape, bc)
+                box = shardview.ShardView(np.array([int(subspace.size[d]) if bc[d] else int(vshape[d]) for d in range(len(bc))], dtype=np.int64),
+                                          np.array([int(subspace.start[d]) if bc[d] else 0 for d in range(len(bc))], dtype=np.int64))
+                parts[i].append((box, full.data_ptr(), fst, None))
+                continue
             for peer in range(W):
                 if peer == w:
                     continue
@@ -581,7 +651,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                                   [(src_ptr, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
                                    (buf.data_ptr(), cst, vcode[i])])
                         ops.append(dist.P2POp(dist.isend, buf.view(torch.uint8), peer))
-                        sends_keep.append(buf)
+                        recv_bufs.append(buf)
                         RT.bytes_sent += buf.numel() * buf.element_size()
                 # what I need from `peer`
                 if not shardview.is_empty(subspace) and not shardview.is_compat(subspace, vdist[i][w]):
@@ -594,10 +664,14 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                         recv_bufs.append(buf)
                         parts[i].append((shardview.clean_range(part), buf.data_ptr(), cst, None))
         if ops:
-            # (the pack kernels run on the current stream; NCCL orders after them)
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()
+            # the pack kernels run on the current stream; NCCL orders its transfers after them.  The transfers are NOT
+            # waited for here: ranges whose operands are all local (the interior of a stencil) are launched first and
+            # overlap with them (the reference sends, then blocks in the receive loop, ramba/ramba.py:3646-3693)
+            pending += dist.batch_isend_irecv(ops)
     if shardview.is_empty(subspace):
+        for wk in pending:
+            wk.wait()
+        RT.keepalive = recv_bufs
         return
     # local parts
     for i in range(nviews):
@@ -625,7 +699,21 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             # this worker's element of the partial array: the first element of its (size-1) block
             off, _ = RT.bind_view(vdist[i][w], shards[i].strides, shardview.clean_range(vdist[i][w]))
             gred_out[slot] = (shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize, vcode[i])
+    def _needs_transfer(r):
+        for i in range(nviews):
+            for (box, ptr, cst, sv) in parts[i]:
+                if shardview.contains(box, r):
+                    if sv is None:
+                        return True
+                    break
+        return False
+
+    ranges = sorted(ranges, key=lambda r: 1 if (pending and _needs_transfer(r)) else 0)  # (stable: local ranges first)
     for r in ranges:
+        if pending and _needs_transfer(r):
+            for wk in pending:
+                wk.wait()  # the launching stream waits for the transfers; the host does not
+            pending = []
         bound = []
         ok = True
         for i in range(nviews):
@@ -692,6 +780,8 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             RT.launch(_combine_program(vcode[i], acc_code, rop), kept_shape, gs_p[nred:],
                       [(rb[0], rb[1][nred:], rb[2]), (tot_ptr, cst, acc_code)])
         recv_bufs.append(partials)
+    for wk in pending:  # (nothing needed them, e.g. an empty boundary)
+        wk.wait()
     # staging buffers are torch allocations consumed on the launching stream: the caching allocator reuses them in
     # stream order, so no host synchronisation is needed here (the references are kept until the next flush anyway)
     RT.keepalive = recv_bufs
@@ -1297,22 +1387,77 @@ def _np_reduce(op):
     return {"sum": np.sum, "prod": np.prod, "min": np.min, "max": np.max, "all": np.all, "any": np.any}[op]
 
 
+_ALLREDUCE_OP = {"sum": "SUM", "prod": "PRODUCT", "min": "MIN", "max": "MAX", "all": "MIN", "any": "MAX"}
+
+
+def _host_identity(op, dtype):
+    dtype = np.dtype(dtype)
+    if op in ("sum", "any"):
+        return 0
+    if op in ("prod", "all"):
+        return 1
+    mm = getminmax(dtype)
+    return mm[1] if op == "min" else mm[0]
+
+
+def _local_partial_tensor(red_arr, n, op):
+    """This rank's block of the partial array as a flat device tensor of n elements in the accumulator dtype (float64 /
+    int64) - the reduction's identity when the rank holds no part."""
+    import torch
+
+    w = common.worker_num
+    acc_dt = torch.float64 if red_arr.dtype.kind == "f" else torch.int64
+    sv = red_arr.distribution[w]
+    if shardview.is_empty(sv) or red_arr.gid not in RT.shards:
+        return torch.full((n,), _host_identity(op, red_arr.dtype), dtype=acc_dt, device=RT.device)
+    return RT.shards[red_arr.gid].buf[:n].to(acc_dt)
+
+
 def _reduction2b(red_arr, op, dtype, asarray):
-    """Stage 2 of a global reduction: gather one partial per worker and reduce on the host
-    (ramba/ramba.py:5852-5863)."""
+    """Stage 2 of a global reduction.  The reference gathers one partial per worker to the driver and reduces them
+    there (ramba/ramba.py:5852-5863); under SPMD every rank needs the result, so the partials (one element per rank,
+    on the GPUs) are combined by ONE all-reduce and only the scalar comes back to the host."""
     if builtins.all(i == 1 for i in red_arr.shape):
         sl = (0,) * red_arr.ndim if not asarray else (slice(0, 1),) + (0,) * (red_arr.ndim - 1)
         return red_arr[sl]
-    local = np.array(red_arr.asarray())
-    val = _np_reduce(op)(local)
+    if common.num_workers > 1:
+        import torch.distributed as dist
+
+        deferred_op.do_ops()
+        RT.ensure_process_group()
+        t = _local_partial_tensor(red_arr, 1, op)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, _ALLREDUCE_OP[op]))
+        RT.collectives += 1
+        val = t.cpu().numpy()[0]
+        if op in ("all", "any"):
+            val = np.bool_(val != 0)
+    else:
+        local = np.array(red_arr.asarray())
+        val = _np_reduce(op)(local)
     if not asarray:
         return np.sum(val, dtype=dtype)
     return full((1,), val, dtype=dtype)
 
 
+def _split_only_along(red_arr, axis):
+    """True when every rank's block of the partial array spans the kept axes completely (the source array is cut along
+    reduced axes only), so that stage 2 is an element-wise combination of whole partial rows."""
+    for sv in red_arr.distribution:
+        if shardview.is_empty(sv):
+            continue
+        for d in range(red_arr.ndim):
+            if d in axis:
+                if int(sv.size[d]) != 1:
+                    return False
+            elif int(sv.start[d]) != 0 or int(sv.size[d]) != red_arr.shape[d]:
+                return False
+    return True
+
+
 def _reduction2(red_arr, op, redop, dtype, axis, keepdims):
-    """Stage 2 of an axis reduction: fold the per-division partial slices
-    (ramba/ramba.py:5818-5849)."""
+    """Stage 2 of an axis reduction: fold the per-division partial slices (ramba/ramba.py:5818-5849).  When the
+    partial rows live on different ranks and each rank holds whole rows, they are summed by ONE all-reduce (each rank
+    then keeps its own division of the result); otherwise a second fused op over the partial slices does it."""
     nd = red_arr.ndim
     if keepdims:
         sl1 = tuple(slice(None) for _ in range(nd))
@@ -1322,6 +1467,29 @@ def _reduction2(red_arr, op, redop, dtype, axis, keepdims):
     k = [red_arr.shape[a] for a in axis]
     if builtins.all(x == 1 for x in k):
         return red_arr if keepdims else red_arr[sl1]
+    kept_elems = int(np.prod([red_arr.shape[d] for d in range(nd) if d not in axis]))
+    if common.num_workers > 1 and op in _ALLREDUCE_OP and kept_elems <= (1 << 24) and _split_only_along(red_arr, axis):
+        import torch
+        import torch.distributed as dist
+
+        deferred_op.do_ops()
+        RT.ensure_process_group()
+        w = common.worker_num
+        t = _local_partial_tensor(red_arr, kept_elems, op)
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, _ALLREDUCE_OP[op]))
+        RT.collectives += 1
+        RT.bytes_sent += kept_elems * t.element_size()
+        out_shape = tuple(1 if d in axis else red_arr.shape[d] for d in range(nd))
+        arr = ndarray(out_shape, dtype=red_arr.dtype, flex_dist=False)
+        sh = RT.create_array(arr.gid, _local_shape(arr.bdarray.distribution, w), arr.dtype)
+        sv = arr.distribution[w]
+        if not shardview.is_empty(sv):
+            mine = t.view(out_shape)[shardview.to_slice(sv)]
+            n = int(np.prod([int(x) for x in sv.size]))
+            sh.buf[:n].view([int(x) for x in sv.size]).copy_(mine)  # (converts the accumulator dtype back to the array's)
+        arr.bdarray.remote_constructed = True
+        arr.bdarray.flex_dist = False
+        return arr if keepdims else arr[sl1]
     arr = empty_like(red_arr[sl2])
     name = {cabi.RED_ADD: "add", cabi.RED_MUL: "mul", cabi.RED_MIN: "min", cabi.RED_MAX: "max"}[redop]
     expr = None

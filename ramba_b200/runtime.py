@@ -75,6 +75,7 @@ class Runtime:
         self.test_mode = False
         self.launches = 0
         self.bytes_sent = 0
+        self.collectives = 0  # all-gather / all-reduce calls issued
         self.keepalive = None  # staging buffers of the last flush
         self.profile_events = None  # list -> (start, end, n_insns) CUDA events around every launch
 

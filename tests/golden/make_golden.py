@@ -182,6 +182,29 @@ def main():
         env.update({"RAMBA_NON_DIST": "1", "RAMBA_NUM_THREADS": "2", "RAMBA_BIG_DATA": "1",
                     "PYTHONPATH": tmp + ":" + REF, "NUMBA_CACHE_DIR": os.path.join(tmp, "nbcache")})
         only = sys.argv[1:]
+        if only and only[0] == "--add":
+            # `make_golden.py --add case1,case2`: run only these API cases under the reference and merge their outputs
+            # into the existing api_golden.npz (the full regeneration takes minutes)
+            import numpy as onp
+
+            out = os.path.join(HERE, "api_golden.npz")
+            alone = os.path.join(tmp, "alone.npz")
+            env2 = dict(env)
+            env2["RB_GOLDEN_CASES"] = only[1]
+            subprocess.check_call([sys.executable, child, "api", alone], env=env2, cwd=tmp)
+            z, z2 = dict(onp.load(out)), dict(onp.load(alone))
+            status = json.loads(str(z["__status__"]))
+            status.update(json.loads(str(z2["__status__"])))
+            for name in only[1].split(","):
+                for k in [k for k in z if k.startswith(name + "__")]:
+                    del z[k]
+            for k, v in z2.items():
+                if k != "__status__":
+                    z[k] = v
+            z["__status__"] = onp.array(json.dumps(status))
+            onp.savez_compressed(out, **z)
+            print("merged", only[1], "into", out)
+            return
         for mode, name in (("partition", "partition_golden.json"), ("programs", "programs_golden.npz"), ("api", "api_golden.npz")):
             if only and mode not in only:
                 continue

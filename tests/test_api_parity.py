@@ -848,6 +848,16 @@ def where_float_condition(np):  # the condition is tested in its own class befor
     return [_h(np.where(c, ia, ib)), _h(np.where(tiny, f32, f32 * onp.float32(2.0)))]
 
 
+# ---- operands every rank needs in full / partial rows that cross ranks (BASELINE config 5's shape, small)
+@case
+def broadcast_vector_axis_sum(np):
+    M = np.fromfunction(lambda i, j: (i + 3 * j) % 8, (1024, 128)).astype(onp.float32)  # split by rows at 2..8 ranks
+    v = (np.arange(128) % 8).astype(onp.float32)                                       # split into chunks: every rank needs all
+    w = np.arange(128) * 0.5
+    return [_h((M + v).sum(axis=0)), _h(M * v - w), onp.asarray((M * 2.0 + v).sum()), _h((M + v).sum(axis=1)),
+            _h((M * v).prod(axis=0) * 0.0 + (M + 1.0).sum(axis=0))]
+
+
 def _compare(got, exp, name):
     assert len(got) == len(exp), name
     for i, (g, e) in enumerate(zip(got, exp)):

@@ -48,3 +48,5 @@ def test_programs_multirank(world):
     outs = _run(world, "all")
     # the stencil / broadcast / axis-sum programs must really have crossed ranks
     assert any("bytes_sent=0" not in o for _, o in outs)
+    # ... and the stage-2 reductions / operands needed everywhere went through collectives (all-reduce, all-gather)
+    assert all("collectives=0 " not in o for _, o in outs)

@@ -18,6 +18,10 @@ def lib():
         L.chain_f64.restype = None
         L.sum_affine_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double]
         L.sum_affine_f32.restype = ctypes.c_double
+        L.laplace7_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+        L.laplace7_f32.restype = None
+        L.bcast_add_axis0_sum_f32.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64, ctypes.c_int64]
+        L.bcast_add_axis0_sum_f32.restype = None
         L.oracle_num_threads.restype = ctypes.c_int
         L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_set_num_threads.restype = None
@@ -34,6 +38,16 @@ def chain_f64(A, B, C, D, global_start=0, make_A=False):
 def sum_affine_f32(X, mul, add):
     assert X.dtype == np.float32 and X.flags.c_contiguous
     return lib().sum_affine_f32(X.ctypes.data, X.size, mul, add)
+
+
+def laplace7_f32(U, V):
+    assert U.dtype == np.float32 and V.dtype == np.float32 and U.flags.c_contiguous and V.flags.c_contiguous and U.shape == V.shape
+    lib().laplace7_f32(U.ctypes.data, V.ctypes.data, U.shape[0])
+
+
+def bcast_add_axis0_sum_f32(M, v, red):
+    assert M.dtype == np.float32 and v.dtype == np.float32 and red.dtype == np.float32 and M.flags.c_contiguous
+    lib().bcast_add_axis0_sum_f32(M.ctypes.data, v.ctypes.data, red.ctypes.data, M.shape[0], M.shape[1])
 
 
 def num_threads():

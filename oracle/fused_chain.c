@@ -50,5 +50,41 @@ double sum_affine_f32(const float* X, int64_t n, double mul, double add) {
   return acc;
 }
 
+/* laplace7_f32: BASELINE config 4, the optimised kernel the reference generates for
+ *   V[1:-1,1:-1,1:-1] = U[:-2,..] + U[2:,..] + U[..,:-2,..] + U[..,2:,..] + U[..,:-2] + U[..,2:] - 6.0*U[1:-1,..]
+ * (ramba/ramba.py:8146-8188): float32 neighbour sum, float64 `6.0*u` and subtraction, rounded on store. */
+void laplace7_f32(const float* U, float* V, int64_t n) {
+#pragma omp parallel for schedule(static) collapse(2)
+  for (int64_t i = 1; i < n - 1; ++i)
+    for (int64_t j = 1; j < n - 1; ++j) {
+      const float* u = U + (i * n + j) * n;
+      float* v = V + (i * n + j) * n;
+      for (int64_t k = 1; k < n - 1; ++k) {
+        float s = u[k - n * n] + u[k + n * n];
+        s = s + u[k - n];
+        s = s + u[k + n];
+        s = s + u[k - 1];
+        s = s + u[k + 1];
+        v[k] = (float)((double)s - 6.0 * (double)u[k]);
+      }
+    }
+}
+
+/* bcast_add_axis0_sum_f32: BASELINE config 5 stage 1, `red[j] = red[j] + (M[i,j] + v[j])` walked row by row through the
+ * float32 partial array (ramba/ramba.py:8231-8244); columns are split over the threads. */
+void bcast_add_axis0_sum_f32(const float* M, const float* v, float* red, int64_t rows, int64_t cols) {
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < cols; ++j) red[j] = 0.0f;
+#pragma omp parallel
+  {
+    const int nt = omp_get_num_threads(), t = omp_get_thread_num();
+    const int64_t c0 = cols * t / nt, c1 = cols * (t + 1) / nt;
+    for (int64_t i = 0; i < rows; ++i) {
+      const float* m = M + i * cols;
+      for (int64_t j = c0; j < c1; ++j) red[j] = red[j] + (m[j] + v[j]);
+    }
+  }
+}
+
 int oracle_num_threads(void) { return omp_get_max_threads(); }
 void oracle_set_num_threads(int n) { omp_set_num_threads(n); }

@@ -581,15 +581,17 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     ared_views = set()
     # which views are aligned with the iteration box on every worker?
     local_everywhere = []
+    clean_exec = [shardview.clean_range(exec_dist[j]) for j in range(W)]
     for i in range(nviews):
         ok = True
-        for j in range(W):
-            ss = shardview.clean_range(exec_dist[j])
-            if shardview.is_empty(ss):
-                continue
-            if not shardview.is_compat(ss, vdist[i][j]):
-                ok = False
-                break
+        if vdist[i] is not exec_dist:  # (the common case: the operand's distribution IS the op's)
+            for j in range(W):
+                ss = clean_exec[j]
+                if shardview.is_empty(ss):
+                    continue
+                if not shardview.is_compat(ss, vdist[i][j]):
+                    ok = False
+                    break
         local_everywhere.append(ok)
     # parts[i] = list of (box, data_ptr, elem_strides or None(shard-addressed), sv)
     parts = [[] for _ in range(nviews)]
@@ -676,14 +678,15 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     # local parts
     for i in range(nviews):
         sv = vdist[i][w]
-        if shardview.is_compat(subspace, sv):
+        if local_everywhere[i] or shardview.is_compat(subspace, sv):
             parts[i].append((subspace, None, None, sv))
         else:
             part = shardview.intersect(sv, exec_dist[w])
             if not shardview.is_empty(part):
                 parts[i].append((shardview.clean_range(part), None, None, shardview.mapslice_keep(sv, part.start, part.start + part.size)))
     # ranges: every operand has one source inside a range
-    if builtins.all(len(p) == 1 and p[0][3] is not None and shardview.is_compat(p[0][0], subspace) for p in parts):
+    single = builtins.all(len(p) == 1 and p[0][3] is not None and (p[0][0] is subspace or shardview.is_compat(p[0][0], subspace)) for p in parts)
+    if single:
         ranges = [subspace]
     else:
         ranges = shardview.get_range_splits_list([shardview.clean_range(subspace)] + [p[0] for pl in parts for p in pl])
@@ -708,7 +711,8 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                     break
         return False
 
-    ranges = sorted(ranges, key=lambda r: 1 if (pending and _needs_transfer(r)) else 0)  # (stable: local ranges first)
+    if pending:
+        ranges = sorted(ranges, key=lambda r: 1 if _needs_transfer(r) else 0)  # (stable: local ranges first)
     for r in ranges:
         if pending and _needs_transfer(r):
             for wk in pending:
@@ -718,10 +722,13 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         ok = True
         for i in range(nviews):
             src = None
-            for (box, ptr, cst, sv) in parts[i]:
-                if shardview.contains(box, r):
-                    src = (box, ptr, cst, sv)
-                    break
+            if single:
+                src = parts[i][0]
+            else:
+                for (box, ptr, cst, sv) in parts[i]:
+                    if shardview.contains(box, r):
+                        src = (box, ptr, cst, sv)
+                        break
             if src is None:
                 if ared and builtins.any(views[i][0] == rv.gid for (_, rv, _) in ared):
                     src = None

@@ -560,6 +560,42 @@ def _gatherable(vd, exec_dist, bc, vshape, W):
     return n
 
 
+def _ring_receivable(bd_dist, vd, exec_dist, w, W, shard):
+    """True when every remote piece of view distribution `vd` this rank needs lies within `shard.border` elements of its
+    own block (in every dim), i.e. can be received into the ring of the padded block and then be addressed by this
+    rank's own shardview of the view, extended past its box (what LocalNdarray.getborder prepares,
+    ramba/ramba.py:1260-1322, regions from shardview.compute_from_border, ramba/shardview_array.py:1069-1136)."""
+    mine = vd[w]
+    if shardview.is_empty(mine):
+        return False
+    k = len(mine.size)
+    b = shard.border
+    for d in range(k):
+        if int(mine.axis_map[d]) < 0 or int(mine.steps[d]) < 1:
+            return False
+    for peer in range(W):
+        if peer == w:
+            continue
+        part = shardview.intersect(vd[peer], exec_dist[w])
+        if shardview.is_empty(part):
+            continue
+        theirs = vd[peer]
+        for d in range(k):
+            a = int(mine.axis_map[d])
+            st = int(mine.steps[d])
+            if int(theirs.axis_map[d]) != a or int(theirs.steps[d]) != st:
+                return False
+            lo = int(mine.base_offset[a]) + (int(part.start[d]) - int(mine.start[d])) * st  # my block coordinates
+            hi = lo + (int(part.size[d]) - 1) * st
+            if lo < -b or hi > shard.shape[a] - 1 + b:
+                return False
+            # the same element through the owner's addressing: both must name the same global coordinate
+            g_theirs = int(bd_dist[peer].start[a]) + int(theirs.base_offset[a]) + (int(part.start[d]) - int(theirs.start[d])) * st
+            if int(bd_dist[w].start[a]) + lo != g_theirs:
+                return False
+    return True
+
+
 def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     """This worker's share of one flush (RemoteState.run_deferred_ops, ramba/ramba.py:3493-3819)."""
     import torch
@@ -572,7 +608,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         bd = bdarray.get_by_gid(gid)
         sh = RT.shards.get(gid)
         if sh is None:
-            sh = RT.create_array(gid, _local_shape(bd.distribution, w), bd.dtype)
+            sh = RT.create_array(gid, _local_shape(bd.distribution, w), bd.dtype, bd.pad)
         shards.append(sh)
     nviews = len(views)
     vdist = [det.distribution for (_, det) in views]
@@ -595,6 +631,8 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         local_everywhere.append(ok)
     # parts[i] = list of (box, data_ptr, elem_strides or None(shard-addressed), sv)
     parts = [[] for _ in range(nviews)]
+    ring = [False] * nviews  # views whose remote pieces are received into the ring of this rank's padded block
+    post_wait = []           # unpack launches that need the received data: (program, shape, bound views)
     recv_bufs = []
     pending = []  # collectives / transfers in flight: waited for only before the first range that reads what they bring
     if W > 1 and not builtins.all(local_everywhere):
@@ -608,6 +646,8 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             if written[i]:
                 raise ProgramError("fused op writes a view that is not aligned with its iteration space")
             bc = [int(a) < 0 for a in vdist[i][0].axis_map]
+            ring[i] = shards[i].border > 0 and not shardview.is_empty(subspace) and _ring_receivable(
+                bdarray.get_by_gid(views[i][0]).distribution, vdist[i], exec_dist, w, W, shards[i])
             itemsize = np.dtype(views[i][1].dtype).itemsize
             g = _gatherable(vdist[i], exec_dist, bc, views[i][1].shape, W)
             if g is not None:
@@ -622,7 +662,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                 cst, _ = _contig_strides(shp, bc)
                 off, st = RT.bind_view(vdist[i][w], shards[i].strides, part)
                 RT.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
-                          [(shards[i].buf.data_ptr() + off * itemsize, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
+                          [(shards[i].ptr(off), [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
                            (mine.data_ptr(), cst, vcode[i])])
                 full = torch.empty(W * n, dtype=tdt, device=RT.device)
                 pending.append(dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), async_op=True))
@@ -634,7 +674,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                 fst, _ = _contig_strides(fshape, bc)
                 box = shardview.ShardView(np.array([int(subspace.size[d]) if bc[d] else int(vshape[d]) for d in range(len(bc))], dtype=np.int64),
                                           np.array([int(subspace.start[d]) if bc[d] else 0 for d in range(len(bc))], dtype=np.int64))
-                parts[i].append((box, full.data_ptr(), fst, None))
+                parts[i].append((box, full.data_ptr(), fst, None, True))
                 continue
             for peer in range(W):
                 if peer == w:
@@ -648,7 +688,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                         cst, n = _contig_strides(shp, bc)
                         buf = torch.empty(max(n, 1), dtype=torch_dtype(views[i][1].dtype), device=RT.device)
                         off, st = RT.bind_view(vdist[i][w], shards[i].strides, part)
-                        src_ptr = shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize
+                        src_ptr = shards[i].ptr(off)
                         RT.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
                                   [(src_ptr, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
                                    (buf.data_ptr(), cst, vcode[i])])
@@ -664,7 +704,17 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                         buf = torch.empty(max(n, 1), dtype=torch_dtype(views[i][1].dtype), device=RT.device)
                         ops.append(dist.P2POp(dist.irecv, buf.view(torch.uint8), peer))
                         recv_bufs.append(buf)
-                        parts[i].append((shardview.clean_range(part), buf.data_ptr(), cst, None))
+                        pb = shardview.clean_range(part)
+                        if ring[i]:
+                            # getborder (ramba/ramba.py:1260-1322): the neighbour's edge lands in the ring of MY padded
+                            # block, where my own shardview of this view, extended past its box, addresses it
+                            off, st = RT.bind_view(vdist[i][w], shards[i].strides, pb)
+                            post_wait.append((_pack_program(vcode[i], vcode[i]), shp,
+                                              [(buf.data_ptr(), cst, vcode[i]), (shards[i].ptr(off), st, vcode[i])]))
+                            parts[i].append((pb, None, None, vdist[i][w], True))
+                            RT.ring_receives += 1
+                        else:
+                            parts[i].append((pb, buf.data_ptr(), cst, None, True))
         if ops:
             # the pack kernels run on the current stream; NCCL orders its transfers after them.  The transfers are NOT
             # waited for here: ranges whose operands are all local (the interior of a stencil) are launched first and
@@ -679,13 +729,14 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     for i in range(nviews):
         sv = vdist[i][w]
         if local_everywhere[i] or shardview.is_compat(subspace, sv):
-            parts[i].append((subspace, None, None, sv))
+            parts[i].append((subspace, None, None, sv, False))
         else:
             part = shardview.intersect(sv, exec_dist[w])
             if not shardview.is_empty(part):
-                parts[i].append((shardview.clean_range(part), None, None, shardview.mapslice_keep(sv, part.start, part.start + part.size)))
+                parts[i].append((shardview.clean_range(part), None, None,
+                                 sv if ring[i] else shardview.mapslice_keep(sv, part.start, part.start + part.size), False))
     # ranges: every operand has one source inside a range
-    single = builtins.all(len(p) == 1 and p[0][3] is not None and (p[0][0] is subspace or shardview.is_compat(p[0][0], subspace)) for p in parts)
+    single = builtins.all(len(p) == 1 and not p[0][4] and (p[0][0] is subspace or shardview.is_compat(p[0][0], subspace)) for p in parts)
     if single:
         ranges = [subspace]
     else:
@@ -701,12 +752,12 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             i = [j for j, (g, det) in enumerate(views) if g == red_view.gid and shardview.dist_is_eq(det.distribution, red_view.distribution)][0]
             # this worker's element of the partial array: the first element of its (size-1) block
             off, _ = RT.bind_view(vdist[i][w], shards[i].strides, shardview.clean_range(vdist[i][w]))
-            gred_out[slot] = (shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize, vcode[i])
+            gred_out[slot] = (shards[i].ptr(off), vcode[i])
     def _needs_transfer(r):
         for i in range(nviews):
-            for (box, ptr, cst, sv) in parts[i]:
+            for (box, ptr, cst, sv, dep) in parts[i]:
                 if shardview.contains(box, r):
-                    if sv is None:
+                    if dep:
                         return True
                     break
         return False
@@ -718,6 +769,9 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             for wk in pending:
                 wk.wait()  # the launching stream waits for the transfers; the host does not
             pending = []
+            for (pp, pshape, pbound) in post_wait:
+                RT.launch(pp, pshape, [0] * len(pshape), pbound)
+            post_wait = []
         bound = []
         ok = True
         for i in range(nviews):
@@ -725,9 +779,9 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             if single:
                 src = parts[i][0]
             else:
-                for (box, ptr, cst, sv) in parts[i]:
+                for (box, ptr, cst, sv, dep) in parts[i]:
                     if shardview.contains(box, r):
-                        src = (box, ptr, cst, sv)
+                        src = (box, ptr, cst, sv, dep)
                         break
             if src is None:
                 if ared and builtins.any(views[i][0] == rv.gid for (_, rv, _) in ared):
@@ -735,10 +789,10 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                 ok = ok and (src is not None)
                 bound.append(None)
                 continue
-            box, ptr, cst, sv = src
+            box, ptr, cst, sv, dep = src
             if sv is not None:
                 off, st = RT.bind_view(sv, shards[i].strides, r)
-                bound.append((shards[i].buf.data_ptr() + off * shards[i].dtype.itemsize, st, vcode[i], shards[i].bounds))
+                bound.append((shards[i].ptr(off), st, vcode[i], shards[i].bounds))
             else:
                 off = 0
                 for d in range(k):
@@ -789,6 +843,8 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         recv_bufs.append(partials)
     for wk in pending:  # (nothing needed them, e.g. an empty boundary)
         wk.wait()
+    for (pp, pshape, pbound) in post_wait:
+        RT.launch(pp, pshape, [0] * len(pshape), pbound)
     # staging buffers are torch allocations consumed on the launching stream: the caching allocator reuses them in
     # stream order, so no host synchronisation is needed here (the references are kept until the next flush anyway)
     RT.keepalive = recv_bufs
@@ -1417,7 +1473,7 @@ def _local_partial_tensor(red_arr, n, op):
     sv = red_arr.distribution[w]
     if shardview.is_empty(sv) or red_arr.gid not in RT.shards:
         return torch.full((n,), _host_identity(op, red_arr.dtype), dtype=acc_dt, device=RT.device)
-    return RT.shards[red_arr.gid].buf[:n].to(acc_dt)
+    return RT.shards[red_arr.gid].interior().reshape(-1)[:n].to(acc_dt)
 
 
 def _reduction2b(red_arr, op, dtype, asarray):
@@ -1488,12 +1544,12 @@ def _reduction2(red_arr, op, redop, dtype, axis, keepdims):
         RT.bytes_sent += kept_elems * t.element_size()
         out_shape = tuple(1 if d in axis else red_arr.shape[d] for d in range(nd))
         arr = ndarray(out_shape, dtype=red_arr.dtype, flex_dist=False)
-        sh = RT.create_array(arr.gid, _local_shape(arr.bdarray.distribution, w), arr.dtype)
+        sh = RT.create_array(arr.gid, _local_shape(arr.bdarray.distribution, w), arr.dtype, arr.bdarray.pad)
         sv = arr.distribution[w]
         if not shardview.is_empty(sv):
             mine = t.view(out_shape)[shardview.to_slice(sv)]
             n = int(np.prod([int(x) for x in sv.size]))
-            sh.buf[:n].view([int(x) for x in sv.size]).copy_(mine)  # (converts the accumulator dtype back to the array's)
+            sh.interior().copy_(mine)  # (converts the accumulator dtype back to the array's)
         arr.bdarray.remote_constructed = True
         arr.bdarray.flex_dist = False
         return arr if keepdims else arr[sl1]
@@ -1632,7 +1688,7 @@ def _shard_view_tensor(nd, w):
     sh = RT.shards[nd.gid]
     box = shardview.clean_range(sv)
     off, st = RT.bind_view(sv, sh.strides, box)
-    return sh.buf.as_strided([int(x) for x in sv.size], st, off) if builtins.min(st + [0]) >= 0 else None, off, st
+    return sh.buf.as_strided([int(x) for x in sv.size], st, off + sh.origin) if builtins.min(st + [0]) >= 0 else None, off, st
 
 
 def _is_whole_shard(sv, sh):
@@ -1650,10 +1706,10 @@ def _part_to_host(nd, w, out=None, non_blocking=False):
         return np.zeros([0] * nd.ndim, dtype=nd.dtype)
     if nd.gid not in RT.shards:
         bd = nd.bdarray
-        RT.create_array(nd.gid, _local_shape(bd.distribution, w), bd.dtype)
+        RT.create_array(nd.gid, _local_shape(bd.distribution, w), bd.dtype, bd.pad)
     sh = RT.shards[nd.gid]
     shape = [int(x) for x in sv.size]
-    if _is_whole_shard(sv, sh) and nd.dtype != np.bool_:
+    if _is_whole_shard(sv, sh) and sh.border == 0 and nd.dtype != np.bool_:
         n = int(np.prod(shape))
         if out is not None and out.flags.c_contiguous and out.dtype == nd.dtype and out.size == n:
             # straight DMA (pinned `out`: full PCIe rate)
@@ -1666,7 +1722,7 @@ def _part_to_host(nd, w, out=None, non_blocking=False):
     off, st = RT.bind_view(sv, sh.strides, shardview.clean_range(sv))
     code = rb_dtype(nd.dtype)
     RT.launch(_pack_program(code, code), shape, [0] * len(shape),
-              [(sh.buf.data_ptr() + off * sh.dtype.itemsize, st, code), (buf.data_ptr(), cst, code)])
+              [(sh.ptr(off), st, code), (buf.data_ptr(), cst, code)])
     RT.synchronize()
     host = buf[:n].cpu().numpy().reshape(shape)
     if nd.dtype == np.bool_:
@@ -1739,7 +1795,7 @@ def fromarray(x, local_border=0, dtype=None, **kwargs):
     deferred_op.do_ops()
     w = common.worker_num
     sv = new.distribution[w]
-    sh = RT.create_array(new.gid, _local_shape(new.bdarray.distribution, w), new.dtype)
+    sh = RT.create_array(new.gid, _local_shape(new.bdarray.distribution, w), new.dtype, new.bdarray.pad)
     if not shardview.is_empty(sv):
         blk = x[shardview.to_slice(sv)]
         if blk.dtype != new.dtype:
@@ -1749,7 +1805,10 @@ def fromarray(x, local_border=0, dtype=None, **kwargs):
         if new.dtype == np.bool_:
             blk = blk.astype(np.uint8)
         t = torch.from_numpy(blk.reshape(-1))  # a view when x is contiguous: pinned x -> straight DMA
-        sh.buf[: t.numel()].copy_(t, non_blocking=True)
+        if sh.border:
+            sh.interior().copy_(t.view(sh.shape), non_blocking=True)
+        else:
+            sh.buf[: t.numel()].copy_(t, non_blocking=True)
     new.bdarray.remote_constructed = True
     new.bdarray.flex_dist = False
     return new
@@ -1768,7 +1827,7 @@ def fromarray_local(block, shape, dtype=None, **kwargs):
     deferred_op.do_ops()
     w = common.worker_num
     sv = new.distribution[w]
-    sh = RT.create_array(new.gid, _local_shape(new.bdarray.distribution, w), new.dtype)
+    sh = RT.create_array(new.gid, _local_shape(new.bdarray.distribution, w), new.dtype, new.bdarray.pad)
     if not shardview.is_empty(sv):
         if tuple(block.shape) != tuple(int(x) for x in sv.size):
             raise ValueError("fromarray_local: block shape %s != this rank's division %s" % (block.shape, tuple(int(x) for x in sv.size)))
@@ -1778,7 +1837,10 @@ def fromarray_local(block, shape, dtype=None, **kwargs):
         if new.dtype == np.bool_:
             blk = blk.astype(np.uint8)
         t = torch.from_numpy(blk.reshape(-1))
-        sh.buf[: t.numel()].copy_(t, non_blocking=True)
+        if sh.border:
+            sh.interior().copy_(t.view(sh.shape), non_blocking=True)
+        else:
+            sh.buf[: t.numel()].copy_(t, non_blocking=True)
     new.bdarray.remote_constructed = True
     new.bdarray.flex_dist = False
     return new
@@ -1848,7 +1910,7 @@ def _fill_now(nd, value):
     w = common.worker_num
     bd = nd.bdarray
     sv = bd.distribution[w]
-    sh = RT.create_array(nd.gid, _local_shape(bd.distribution, w), bd.dtype)
+    sh = RT.create_array(nd.gid, _local_shape(bd.distribution, w), bd.dtype, bd.pad)
     bd.remote_constructed = True
     bd.flex_dist = False
     if shardview.is_empty(sv):
@@ -1862,7 +1924,7 @@ def _fill_now(nd, value):
         lw = Lowering([code])
         lw.store(0, lw.scalar(value))
         prog = _fill_programs[key] = lw.finish()
-    n = int(np.prod(sh.shape)) if sh.shape else 1
+    n = sh.buf.numel()  # (the ring of a padded block is filled too)
     RT.launch(prog, [n], [0], [(sh.buf.data_ptr(), [1], code)])
 
 
@@ -2210,7 +2272,15 @@ def sstencil(func, *args, out=None, **kwargs):
     lo = tuple(n[0] for n in func.neighborhood)
     hi = tuple(n[1] for n in func.neighborhood)
     res = func.func(*[_RelView(a, lo, hi) if isinstance(a, ndarray) else a for a in args])
-    new = out if out is not None else zeros(shape, dtype=res.dtype if isinstance(res, ndarray) else np.float64)
+    if out is not None:
+        new = out
+    elif arrays[0].local_border > 0:
+        # like the reference: allocated with the divisions and the border of the first argument (ramba/ramba.py:10022-10026)
+        new = create_array_with_divisions(shape, arrays[0].distribution, local_border=arrays[0].local_border,
+                                          dtype=res.dtype if isinstance(res, ndarray) else np.float64)
+        deferred_op.add_op([new, 0], new)
+    else:
+        new = zeros(shape, dtype=res.dtype if isinstance(res, ndarray) else np.float64)
     interior = tuple(slice(-lo[d], shape[d] - hi[d]) for d in range(k))
     new[interior] = res
     return new

@@ -45,23 +45,40 @@ def torch_dtype(dt):
 
 
 class Shard:
-    """This worker's block of one bdarray (LocalNdarray, ramba/ramba.py:1169-1357, without
-    borders)."""
+    """This worker's block of one bdarray (LocalNdarray, ramba/ramba.py:1169-1357).  With `border` > 0 the buffer is the
+    block grown by `border` elements on every side of every dim (`np.empty(dim_lens + 2*border)`,
+    ramba/ramba.py:1208-1214): the ring receives the neighbours' edge elements (getborder,
+    ramba/ramba.py:1260-1322), so that shifted views of the array read ONE buffer with ONE set of strides."""
 
-    __slots__ = ("buf", "shape", "dtype", "strides", "bounds")
+    __slots__ = ("buf", "shape", "dtype", "strides", "bounds", "border", "origin")
 
-    def __init__(self, buf, shape, dtype):
+    def __init__(self, buf, shape, dtype, border=0):
         self.buf = buf
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
+        self.border = int(border)
         st = []
         acc = 1
         for s in reversed(self.shape):
             st.append(acc)
-            acc *= max(1, s)
-        self.strides = tuple(reversed(st))  # elements, C order
+            acc *= max(1, s + 2 * self.border)
+        self.strides = tuple(reversed(st))  # elements, C order over the padded block
+        self.origin = sum(self.border * x for x in self.strides)  # element offset of interior element (0, 0, ...)
         p = buf.data_ptr()
         self.bounds = (p, p + buf.numel() * buf.element_size())  # [alloc_lo, alloc_hi) handed to the C-ABI
+
+    def ptr(self, off=0):
+        """Device address of interior-relative element offset `off`."""
+        return self.buf.data_ptr() + (self.origin + off) * self.dtype.itemsize
+
+    def interior(self):
+        """torch view of the block without its ring (contiguous when border == 0)."""
+        n = 1
+        for x in self.shape:
+            n *= x
+        if self.border == 0:
+            return self.buf[:n].view(self.shape) if self.shape else self.buf[:1]
+        return self.buf.as_strided(self.shape, self.strides, self.origin)
 
 
 class Runtime:
@@ -76,6 +93,7 @@ class Runtime:
         self.launches = 0
         self.bytes_sent = 0
         self.collectives = 0  # all-gather / all-reduce calls issued
+        self.ring_receives = 0  # halo pieces received into the ring of a padded block (getborder)
         self.keepalive = None  # staging buffers of the last flush
         self.profile_events = None  # list -> (start, end, n_insns) CUDA events around every launch
 
@@ -134,15 +152,24 @@ class Runtime:
         self._pg_ready = True
 
     # ---- shard storage --------------------------------------------------------------------
-    def create_array(self, gid, local_shape, dtype):
-        """Allocate this worker's block (uninitialised, like np.empty at ramba/ramba.py:1208-1214)."""
+    def create_array(self, gid, local_shape, dtype, border=0):
+        """Allocate this worker's block (uninitialised, like np.empty at ramba/ramba.py:1208-1214), grown by `border` on
+        every side when the array was created with local_border."""
         if gid in self.shards:
             return self.shards[gid]
         n = 1
         for s in local_shape:
             n *= int(s)
+        if n == 0:
+            border = 0
+        if border:
+            n = 1
+            for s in local_shape:
+                n *= int(s) + 2 * border
         buf = torch.empty(max(n, 1), dtype=torch_dtype(dtype), device=self.device)
-        sh = Shard(buf, local_shape, dtype)
+        if border:
+            buf.zero_()  # the ring of a block at the array's edge is never received: keep it defined
+        sh = Shard(buf, local_shape, dtype, border)
         self.shards[gid] = sh
         return sh
 

@@ -46,7 +46,7 @@ def main():
         from ramba_b200 import _cabi
 
         assert not RT.test_mode and _cabi.launch_count() > 0, "the CUDA library did not run"
-    print("RANK %d/%d launches=%d bytes_sent=%d collectives=%d failures=%s" % (common.worker_num, common.num_workers, RT.launches, RT.bytes_sent, RT.collectives, failures))
+    print("RANK %d/%d launches=%d bytes_sent=%d collectives=%d ring_receives=%d failures=%s" % (common.worker_num, common.num_workers, RT.launches, RT.bytes_sent, RT.collectives, RT.ring_receives, failures))
     sys.stdout.flush()
     import torch.distributed as dist
 

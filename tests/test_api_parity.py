@@ -242,6 +242,45 @@ def sstencil_skeleton(np):
     return [_h(np.sstencil(np.stencil(star), x)), _h(np.stencil(wide)(x, y))]
 
 
+# (module level: the reference's StencilMetadata.compile reads the source and wants an unindented `def`, ramba/ramba.py:468-474)
+def _st_star(a):
+    return 0.25 * (a[-1, 0] + a[1, 0] + a[0, -1] + a[0, 1]) + a[0, 0]
+
+
+def _st_wide(a, b):
+    return a[0, -2] + a[0, 2] - 2.0 * b[0, 0]
+
+
+def _st_diag(a):
+    return a[-2, -2] + a[0, 0] + a[2, 2]
+
+
+@case
+def sstencil_local_border(np):
+    # the reference's sstencil form (ramba/tests/test_distributed_array.py:17-22, README.md:271-299): arrays created with
+    # local_border, a relative-index stencil function, the result allocated like the first argument or given as out=
+    star, wide, diag = _st_star, _st_wide, _st_diag
+    n, m = 130, 140
+    xh = ((onp.arange(n)[:, None] * 7 + onp.arange(m)[None, :] * 3) % 16).astype(onp.float64)
+    yh = ((onp.arange(n)[:, None] + onp.arange(m)[None, :]) % 5).astype(onp.float64)
+    if np is onp:
+        r1 = onp.zeros((n, m))
+        r1[1:-1, 1:-1] = 0.25 * (xh[:-2, 1:-1] + xh[2:, 1:-1] + xh[1:-1, :-2] + xh[1:-1, 2:]) + xh[1:-1, 1:-1]
+        r2 = onp.zeros((n, m))
+        r2[:, 2:-2] = xh[:, :-4] + xh[:, 4:] - 2.0 * yh[:, 2:-2]
+        r3 = onp.zeros((n, m))
+        r3[2:-2, 2:-2] = xh[:-4, :-4] + xh[2:-2, 2:-2] + xh[4:, 4:]
+        r4 = onp.zeros((n, m))
+        r4[1:-1, 1:-1] = 0.25 * (r1[:-2, 1:-1] + r1[2:, 1:-1] + r1[1:-1, :-2] + r1[1:-1, 2:]) + r1[1:-1, 1:-1]
+        return [r1, r2, r3, r4]
+    x = np.fromarray(xh, local_border=2)
+    y = np.fromarray(yh, local_border=2)
+    s1 = np.sstencil(np.stencil(star), x)
+    out = np.zeros((n, m), local_border=2)
+    np.sstencil(np.stencil(star), s1, out=out)  # the result of one sstencil (padded like its argument) feeds the next
+    return [_h(s1), _h(np.sstencil(np.stencil(wide), x, y)), _h(np.sstencil(np.stencil(diag), x)), _h(out)]
+
+
 # ---- apps (TestApps): pi integration, manual matmul via broadcast + axis sum
 @case
 def pi_integration(np):

@@ -50,3 +50,11 @@ def test_programs_multirank(world):
     assert any("bytes_sent=0" not in o for _, o in outs)
     # ... and the stage-2 reductions / operands needed everywhere went through collectives (all-reduce, all-gather)
     assert all("collectives=0 " not in o for _, o in outs)
+
+
+@pytest.mark.timeout(300)
+def test_local_border_halo_goes_into_the_ring():
+    """Arrays created with local_border: the neighbours' edges are received into the ring of the padded block
+    (getborder) and the stencil reads one buffer."""
+    outs = _run(4, "sstencil_local_border")
+    assert all("ring_receives=0 " not in o for _, o in outs), outs

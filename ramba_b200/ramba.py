@@ -1791,7 +1791,7 @@ def fromarray(x, local_border=0, dtype=None, **kwargs):
         dtype = x.dtype
     if x.shape == ():
         return array(x.astype(dtype))
-    new = ndarray(x.shape, dtype=dtype, flex_dist=False, **kwargs)
+    new = ndarray(x.shape, dtype=dtype, flex_dist=False, local_border=local_border, **kwargs)
     deferred_op.do_ops()
     w = common.worker_num
     sv = new.distribution[w]

@@ -21,6 +21,7 @@
  *                               become the `red_*` fields.
  *   rb200_reduce_partials    <- stage 2 of an axis reduction over partial slices,
  *                               ndarray.internal_reduction2_executor, ramba/ramba.py:5818-5849.
+ *   rb200_cumulative         <- RemoteState.scumulative_worker, ramba/ramba.py:3378-3437 (cumsum / scumulative).
  *   rb200_last_error         <- worker exception -> ("ERROR", worker, traceback) reply,
  *                               ramba/ramba.py:3875-3881.
  *
@@ -223,6 +224,16 @@ int64_t rb200_red_scratch_bytes(void);
 /* out[j] = reduce_k partial[k*stride_k + j], j < n  (stage 2 of an axis reduction). */
 int rb200_reduce_partials(void* out, const void* partials, int64_t n, int64_t k, int64_t stride_k,
                           int32_t dtype, int32_t redop, void* stream);
+
+/* Inclusive cumulative scan (cumsum / scumulative with +, *, min, max) of one worker's block, replacing
+ * RemoteState.scumulative_worker (ramba/ramba.py:3378-3437): the block is [n_outer][len][n_inner] elements in C order,
+ * the scan runs along `len`.  dtype: RB200_F64 / F32 (float64 accumulation) or RB200_I64 / I32 (int64 accumulation).
+ * carry_in (optional): one accumulator-class value per sequence (n_outer * n_inner), the total of the blocks that
+ * precede this one along the axis; totals_out (optional): each sequence's inclusive total.  `scratch` must hold
+ * rb200_cumulative_scratch_bytes() bytes.  src == dst is allowed.  One read and one write of every element.         */
+int64_t rb200_cumulative_scratch_bytes(int64_t n_outer, int64_t len, int64_t n_inner);
+int rb200_cumulative(const void* src, void* dst, int32_t dtype, int64_t n_outer, int64_t len, int64_t n_inner,
+                     int32_t redop, const void* carry_in, void* totals_out, void* scratch, void* stream);
 
 /* Thread-local description of the last error returned on this thread.               */
 const char* rb200_last_error(void);

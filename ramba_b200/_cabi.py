@@ -93,6 +93,8 @@ EXPORTS = [
     "rb200_run_deferred_ops",
     "rb200_red_scratch_bytes",
     "rb200_reduce_partials",
+    "rb200_cumulative",
+    "rb200_cumulative_scratch_bytes",
     "rb200_last_error",
     "rb200_abi_version",
     "rb200_launch_count",
@@ -130,6 +132,11 @@ def load():
     lib.rb200_red_scratch_bytes.restype = C.c_int64
     lib.rb200_reduce_partials.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.rb200_reduce_partials.restype = C.c_int
+    lib.rb200_cumulative.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    lib.rb200_cumulative.restype = C.c_int
+    lib.rb200_cumulative_scratch_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+    lib.rb200_cumulative_scratch_bytes.restype = C.c_int64
     lib.rb200_last_error.argtypes = []
     lib.rb200_last_error.restype = C.c_char_p
     lib.rb200_abi_version.argtypes = []
@@ -161,6 +168,18 @@ def reduce_partials(out_ptr, part_ptr, n, k, stride_k, dtype, redop, stream=None
     lib = load()
     check(lib.rb200_reduce_partials(C.c_void_p(out_ptr), C.c_void_p(part_ptr), n, k, stride_k, dtype, redop,
                                     C.c_void_p(stream) if stream else None))
+
+
+def cumulative(src, dst, dtype, n_outer, length, n_inner, redop, carry_in=None, totals_out=None, scratch=None, stream=None):
+    """Inclusive scan of one block [n_outer][length][n_inner] along `length` (device pointers as ints)."""
+    lib = load()
+    check(lib.rb200_cumulative(C.c_void_p(src), C.c_void_p(dst), dtype, n_outer, length, n_inner, redop,
+                               C.c_void_p(carry_in) if carry_in else None, C.c_void_p(totals_out) if totals_out else None,
+                               C.c_void_p(scratch) if scratch else None, C.c_void_p(stream) if stream else None))
+
+
+def cumulative_scratch_bytes(n_outer, length, n_inner):
+    return int(load().rb200_cumulative_scratch_bytes(n_outer, length, n_inner))
 
 
 def red_scratch_bytes():

@@ -514,6 +514,28 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   return 0;
 }
 
+int64_t rb200_cumulative_scratch_bytes(int64_t n_outer, int64_t len, int64_t n_inner) {
+  if (n_outer < 0 || len < 0 || n_inner < 1) return 256;
+  return (int64_t)scan_scratch_bytes(n_outer, len, n_inner);
+}
+
+int rb200_cumulative(const void* src, void* dst, int32_t dtype, int64_t n_outer, int64_t len, int64_t n_inner, int32_t redop, const void* carry_in,
+                     void* totals_out, void* scratch, void* stream_v) {
+  if (n_outer < 0 || len < 0 || n_inner < 1) return fail("cumulative: bad extents");
+  if (redop < RB200_RED_ADD || redop > RB200_RED_MAX) return fail("cumulative: bad operation");
+  if (dtype != RB200_F64 && dtype != RB200_F32 && dtype != RB200_I64 && dtype != RB200_I32) return fail("cumulative: dtype must be float64/float32/int64/int32");
+  if (n_outer == 0 || len == 0) return 0;
+  if (!src || !dst || !scratch) return fail("null pointer");
+  const int sms = sm_count();
+  if (sms <= 0) return fail("no usable CUDA device (libramba_b200 has no CPU path)");
+  bool supported = true;
+  const cudaError_t e = launch_scan(src, dst, dtype, n_outer, len, n_inner, redop, carry_in, totals_out, scratch, sms, (cudaStream_t)stream_v, &supported);
+  if (!supported) return fail("cumulative: unsupported dtype");
+  if (e != cudaSuccess) return fail_cuda("scan kernel launch", e);
+  g_launches.fetch_add(1);
+  return 0;
+}
+
 int rb200_reduce_partials(void* out, const void* partials, int64_t n, int64_t k, int64_t stride_k, int32_t dtype,
                           int32_t redop, void* stream_v) {
   if (!out || !partials) return fail("null pointer");

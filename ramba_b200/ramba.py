@@ -2624,16 +2624,95 @@ def sreduce_index(func, reducer, identity, *args, parallel=True):
     return _sreduce("sreduce_index", func, reducer, identity, args, True)
 
 
+def _scan_native(a, axis, op, dtype):
+    """cumsum / cumprod / running min / max along `axis` with the single-pass scan kernel (rb200_cumulative): every
+    rank scans its own block; when the array is cut along the scan axis the block totals are all-gathered and every rank
+    folds the totals of the blocks before its own into its part (the reference passes boundary values worker to worker,
+    ramba/ramba.py:3378-3437).  Returns None when this layout / dtype is not covered (caller falls back)."""
+    import torch
+
+    out_dtype = np.dtype(dtype) if dtype is not None else a.dtype
+    if out_dtype.kind in "iub" and out_dtype.itemsize < 8:
+        out_dtype = np.dtype(np.int64)  # NumPy: small integers accumulate in the platform integer
+    if out_dtype not in (np.dtype(np.float64), np.dtype(np.float32), np.dtype(np.int64)):
+        return None
+    W, w = common.num_workers, common.worker_num
+    # a whole array in the result dtype, in its own buffer: views / other dtypes are materialised by one fused copy
+    src = a.astype(out_dtype) if (a.dtype != out_dtype or a.base is not None or a.maskarray is not None) else a
+    deferred_op.do_ops()
+    dist = src.bdarray.distribution
+    if src.base is not None or src.distribution is not dist and not shardview.dist_is_eq(src.distribution, dist):
+        return None
+    nd = src.ndim
+    split_axis = builtins.any(not shardview.is_empty(sv) and (int(sv.start[axis]) != 0 or int(sv.size[axis]) != src.shape[axis]) for sv in dist)
+    if split_axis:
+        for sv in dist:  # cut along the scan axis ONLY: every rank's totals cover the same columns
+            if shardview.is_empty(sv):
+                continue
+            if builtins.any(int(sv.start[d]) != 0 or int(sv.size[d]) != src.shape[d] for d in range(nd) if d != axis):
+                return None
+    res = create_array_with_divisions(src.shape, dist, dtype=out_dtype)
+    sh_src = RT.shards.get(src.gid) or RT.create_array(src.gid, _local_shape(dist, w), src.dtype, src.bdarray.pad)
+    sh_res = RT.create_array(res.gid, _local_shape(res.bdarray.distribution, w), res.dtype)
+    if sh_src.border:
+        return None
+    res.bdarray.remote_constructed = True
+    res.bdarray.flex_dist = False
+    lshape = sh_src.shape
+    mine_empty = shardview.is_empty(dist[w])
+    n_outer = int(np.prod(lshape[:axis])) if not mine_empty else 0
+    length = int(lshape[axis]) if not mine_empty else 0
+    n_inner = int(np.prod(lshape[axis + 1:])) if not mine_empty else 1
+    code = rb_dtype(out_dtype)
+    acc_dt = torch.float64 if out_dtype.kind == "f" else torch.int64
+    ncols = int(np.prod([src.shape[d] for d in range(nd) if d != axis]))
+    totals = torch.empty(max(1, ncols), dtype=acc_dt, device=RT.device) if split_axis else None
+    if totals is not None:
+        totals.fill_(_host_identity({cabi.RED_ADD: "sum", cabi.RED_MUL: "prod", cabi.RED_MIN: "min", cabi.RED_MAX: "max"}[op], out_dtype))
+    if not mine_empty:
+        RT.cumulative(sh_src.ptr(0), sh_res.ptr(0), code, n_outer, length, n_inner, op, None, totals.data_ptr() if totals is not None else None)
+    if split_axis and W > 1:
+        import torch.distributed as tdist
+
+        RT.ensure_process_group()
+        allt = torch.empty(W * ncols, dtype=acc_dt, device=RT.device)
+        tdist.all_gather_into_tensor(allt, totals)
+        RT.collectives += 1
+        RT.bytes_sent += ncols * 8 * (W - 1)
+        if not mine_empty:
+            before = [p for p in range(W) if not shardview.is_empty(dist[p]) and int(dist[p].start[axis]) < int(dist[w].start[axis])]
+            if before:
+                stack = allt.view(W, ncols)[before]
+                carry = {cabi.RED_ADD: stack.sum(0), cabi.RED_MUL: stack.prod(0), cabi.RED_MIN: stack.min(0).values, cabi.RED_MAX: stack.max(0).values}[op]
+                carry = carry.contiguous()
+                acc_code = cabi.F64 if acc_dt == torch.float64 else cabi.I64
+                # res[o, l, i] = carry[o, i] (op) res[o, l, i] for every l: one fused op with the carry broadcast along the axis
+                RT.launch(_combine_program(code, acc_code, op), [n_outer, length, n_inner], [0, 0, 0],
+                          [(sh_res.ptr(0), [length * n_inner, n_inner, 1], code, sh_res.bounds), (carry.data_ptr(), [n_inner, 0, 1], acc_code)])
+                RT.keepalive_carry = carry
+    return res
+
+
 def scumulative(local_func, final_func, array, axis=None, dtype=None, out=None):
     """Inclusive scan with a user function (ramba/ramba.py:10057-10116): the reference scans every worker's part with
-    `local_func` and then folds the boundary values in with `final_func`; here `local_func(previous, current)` is
-    applied in log2(n) shifted-slice steps, so it has to be associative (and traceable, like smap functions)."""
+    `local_func` and then folds the boundary values in with `final_func`.  When `local_func` is +, *, min or max
+    (recognised by probing, like sreduce) the single-pass scan kernel runs it; any other traceable associative
+    function is applied in log2(n) shifted-slice steps on the elementwise kernels."""
     array = _as_nd(array)
     if array.ndim == 1 and axis is None:
         axis = 0
     assert isinstance(axis, numbers.Number) and 0 <= axis < array.ndim, "scumulative needs an axis for N-d arrays"
     assert out is None, "scumulative(out=...) is not supported (nor by the reference, ramba/ramba.py:10071-10075)"
     f = _user_function(local_func)
+    try:
+        kind = _classify_reducer(f)
+    except NotImplementedError:
+        kind = None
+    if kind is not None and array.size > 0:
+        op = {"sum": cabi.RED_ADD, "prod": cabi.RED_MUL, "min": cabi.RED_MIN, "max": cabi.RED_MAX}[kind]
+        res = _scan_native(array, int(axis), op, dtype)
+        if res is not None:
+            return res
     cur = array.astype(dtype) if dtype is not None and np.dtype(dtype) != array.dtype else array + 0
     n = array.shape[axis]
     d = 1
@@ -2648,16 +2727,21 @@ def scumulative(local_func, final_func, array, axis=None, dtype=None, out=None):
 
 
 def cumsum(a, axis=None, dtype=None, out=None):
-    """Cumulative sum along `axis` (ramba/ramba.py:9675-9679).  The reference scans each worker's part and
-    then adds the boundary values worker by worker; here it is log2(n) fused shifted-slice additions
-    (Hillis-Steele), which run on the elementwise kernels and cross shards through the ordinary halo
-    exchange.  Integer and exactly representable data agree with NumPy bit for bit; floating-point sums are
-    associated differently (as they are in the reference)."""
+    """Cumulative sum along `axis` (ramba/ramba.py:9675-9679).  The reference scans each worker's part and then adds the
+    boundary values worker by worker; here every rank's block is scanned in ONE pass over HBM by the decoupled-look-back
+    scan kernel (rb200_cumulative) and, when the array is cut along the axis, the block totals travel by one all-gather.
+    Integer and exactly representable data agree with NumPy bit for bit; floating-point sums are associated differently
+    (as they are in the reference).  Layouts the kernel does not cover (2-D block partitions cut along and across the
+    axis) fall back to log2(n) fused shifted-slice additions."""
     a = _as_nd(a)
     if a.ndim == 1 and axis is None:
         axis = 0
     assert isinstance(axis, numbers.Number) and 0 <= axis < a.ndim, "cumsum needs an axis for N-d arrays"
     assert out is None, "cumsum(out=...) is not supported (nor by the reference, ramba/ramba.py:10071-10075)"
+    if a.size > 0:
+        res = _scan_native(a, int(axis), cabi.RED_ADD, dtype)
+        if res is not None:
+            return res
     cur = a.astype(dtype) if dtype is not None and np.dtype(dtype) != a.dtype else a + 0
     n = a.shape[axis]
     d = 1

@@ -87,6 +87,7 @@ class Runtime:
         self._device = None
         self._executor = None
         self._reduce_partials = None
+        self._cumulative = None
         self._red_scratch = None
         self._pg_ready = False
         self.test_mode = False
@@ -109,11 +110,12 @@ class Runtime:
             torch.cuda.set_device(self._device)
         return self._device
 
-    def set_test_executor(self, executor, reduce_partials, device="cpu"):
+    def set_test_executor(self, executor, reduce_partials, device="cpu", cumulative=None):
         """TEST SEAM ONLY: run op lists through a checker (the oracle) on host buffers so that the
         host logic can be exercised without a GPU.  Never used by the product path."""
         self._executor = executor
         self._reduce_partials = reduce_partials
+        self._cumulative = cumulative
         self._device = torch.device(device)
         self.test_mode = True
 
@@ -123,6 +125,7 @@ class Runtime:
         self._device = None
         self._executor = None
         self._reduce_partials = None
+        self._cumulative = None
         self._red_scratch = None
         self.test_mode = False
 
@@ -313,6 +316,20 @@ class Runtime:
             ex(fop, self.stream_handle())
         self.launches += 1
         return fop
+
+    def cumulative(self, src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in=None, totals_out=None):
+        """Inclusive scan of one local block through the C-ABI (rb200_cumulative)."""
+        self.executor()
+        if self.test_mode:
+            if self._cumulative is None:
+                raise RuntimeError("the test executor has no cumulative()")
+            self._cumulative(src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out, None, None)
+        else:
+            nbytes = cabi.cumulative_scratch_bytes(n_outer, length, n_inner)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            cabi.cumulative(src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out, scratch.data_ptr(), self.stream_handle())
+            self.keepalive_scan = scratch
+        self.launches += 1
 
     def synchronize(self):
         if not self.test_mode and self._device is not None:

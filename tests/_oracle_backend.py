@@ -41,4 +41,4 @@ def install():
         _library_accepts(fop)
         return vm.run_deferred_ops(fop, stream)
 
-    RT.set_test_executor(run, vm.reduce_partials, device="cpu")
+    RT.set_test_executor(run, vm.reduce_partials, device="cpu", cumulative=vm.cumulative)

@@ -26,7 +26,7 @@ constexpr int LV = 8;  // elements per thread per tile (256 threads -> 2048 elem
 enum LeanKind { L_ACC = 0, L_REG = 1, L_SCAL = 2, L_STAGED = 3, L_DIRECT = 4, L_NONE = 7 };
 enum LeanOp {
   LO_MOV = 0, LO_ADD, LO_SUB, LO_RSUB, LO_MUL, LO_DIV, LO_NEG, LO_ABS, LO_SQUARE, LO_MIN, LO_MAX,
-  LO_MULADD, LO_MULSUB, LO_MULRSUB, LO_CVT, LO_RED, LO_NUM
+  LO_MULADD, LO_MULSUB, LO_MULRSUB, LO_CVT, LO_RED, LO_CHAIN, LO_NUM
 };
 
 struct LInsn {  // 12 bytes, read from the constant bank
@@ -37,6 +37,14 @@ struct LInsn {  // 12 bytes, read from the constant bank
   unsigned char st_view;  // RB200_NOSTORE: none
   unsigned char red_op;   // LO_RED: rb200_redop; arg a_arg... slot in b_arg
   unsigned char pad[2];
+};
+
+// LO_CHAIN: `acc = (((a op1 s1) op2 s2) ...)` over STAGED operands - a run of add / sub / mul instructions of one class
+// whose left operand is the running value (the neighbour sum of a stencil) executed by ONE dispatch: b_arg = first
+// step in the kernel's chain table, c_arg = number of steps.  Same order, same roundings as the separate instructions.
+enum LeanChainOp { LC_ADD = 0, LC_SUB = 1, LC_RSUB = 2, LC_MUL = 3 };
+struct LChainStep {
+  unsigned char op, staged, pad[2];
 };
 
 struct LDirect {  // a view addressed in global memory: element (z, y, x) at base + z*s0 + y*s1 + x*s2 (elements)
@@ -114,6 +122,27 @@ template <int LOP, class F, bool AACC, class CX> __device__ __forceinline__ void
     if constexpr (LOP == LO_MOV) {
 #pragma unroll
       for (int k = 0; k < LV; ++k) r[k] = a[k];
+    } else if constexpr (LOP == LO_CHAIN) {
+#pragma unroll
+      for (int k = 0; k < LV; ++k) r[k] = a[k];
+#pragma unroll 1
+      for (int s = 0; s < (int)I.c_arg; ++s) {
+        F b[LV];
+        const int cop = cx.template chain_fetch<F>((int)I.b_arg + s, b);
+        if (cop == LC_ADD) {
+#pragma unroll
+          for (int k = 0; k < LV; ++k) r[k] = l_add<F>(r[k], b[k]);
+        } else if (cop == LC_SUB) {
+#pragma unroll
+          for (int k = 0; k < LV; ++k) r[k] = l_sub<F>(r[k], b[k]);
+        } else if (cop == LC_RSUB) {
+#pragma unroll
+          for (int k = 0; k < LV; ++k) r[k] = l_sub<F>(b[k], r[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < LV; ++k) r[k] = l_mul<F>(r[k], b[k]);
+        }
+      }
     } else if constexpr (LOP == LO_NEG) {
 #pragma unroll
       for (int k = 0; k < LV; ++k) r[k] = -a[k];
@@ -193,6 +222,7 @@ template <class CX> __device__ __forceinline__ void lean_dispatch(CX& cx, const 
     RB200_LEAN_CASE(LO_MULRSUB)
     RB200_LEAN_CASE(LO_CVT)
     RB200_LEAN_CASE(LO_RED)
+    RB200_LEAN_CASE(LO_CHAIN)
     default: break;
   }
 }

@@ -103,4 +103,48 @@ static inline void lean_translate(const rb200_fused_op* op, const int* view_kind
   }
 }
 
+// Fuse runs of add / sub / mul instructions whose right operand is a STAGED view and whose left operand is the running
+// value into LO_CHAIN instructions (rb200_lean.cuh).  `insns` is rewritten in place; returns the new instruction count
+// and fills `chain` (at most max_chain steps).
+static inline int lean_fuse_chains(LInsn* insns, int n, LChainStep* chain, int max_chain, int* n_chain_out) {
+  int out = 0, nc = 0;
+  int i = 0;
+  auto chain_op = [](const LInsn& L) -> int {
+    const int lop = L.handler >> 2;
+    return lop == LO_ADD ? LC_ADD : lop == LO_SUB ? LC_SUB : lop == LO_RSUB ? LC_RSUB : lop == LO_MUL ? LC_MUL : -1;
+  };
+  while (i < n) {
+    const LInsn first = insns[i];
+    int j = i;
+    if (chain_op(first) >= 0 && first.b_kind == L_STAGED) {
+      const int cls = (first.handler >> 1) & 1;
+      j = i + 1;
+      while (j < n && insns[j - 1].st_reg == RB200_NOSTORE && insns[j - 1].st_view == RB200_NOSTORE && chain_op(insns[j]) >= 0 &&
+             insns[j].b_kind == L_STAGED && insns[j].a_kind == L_ACC && ((insns[j].handler >> 1) & 1) == cls && nc + (j - i) + 1 <= max_chain && (j - i) < 200)
+        ++j;
+      if (j - i >= 2) {
+        LInsn L = first;
+        L.handler = (unsigned char)(LO_CHAIN * 4 + cls * 2 + (first.a_kind == L_ACC ? 1 : 0));
+        L.b_kind = L_NONE;
+        L.b_arg = (unsigned char)nc;
+        L.c_arg = (unsigned char)(j - i);
+        L.st_reg = insns[j - 1].st_reg;
+        L.st_view = insns[j - 1].st_view;
+        for (int q = i; q < j; ++q) {
+          chain[nc].op = (unsigned char)chain_op(insns[q]);
+          chain[nc].staged = insns[q].b_arg;
+          ++nc;
+        }
+        insns[out++] = L;
+        i = j;
+        continue;
+      }
+    }
+    insns[out++] = first;
+    ++i;
+  }
+  *n_chain_out = nc;
+  return out;
+}
+
 }  // namespace rb200

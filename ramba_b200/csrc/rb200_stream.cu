@@ -127,6 +127,7 @@ struct StreamCtx {
         for (int k = 0; k < LV; ++k) out[k] = LAcc<F>::get(alo[k], ahi[k]);
     }
   }
+  template <class F> __device__ __forceinline__ int chain_fetch(int, F (&)[LV]) { return 0; }  // (no chains in this kernel)
   template <class F> __device__ __forceinline__ void store_reg(int reg, const F (&r)[LV]) {
     const unsigned addr = reg_s + (unsigned)reg * (LV * kThreads * 8);
 #pragma unroll

@@ -37,6 +37,11 @@ namespace rb200 {
 
 constexpr int kTileMaxStaged = RB200_MAX_VIEWS;
 constexpr int kTileMaxRing = 8;
+// tile geometry (compile-time, so that every shared-memory access of an operand is base + immediate): 128 columns x
+// 16 rows of outputs per plane, element k of a thread is 2 rows below element k-1; the staged box is 144 columns wide
+// (halo <= 16 columns in total) and 16 + halo rows high
+constexpr int kTileTX = 128, kTileLogTX = 7, kTileRY = kThreads / kTileTX, kTileTY = LV * kTileRY, kTilePX = 144;
+constexpr int kTileMaxChain = 64;
 
 struct TileStagedOp {
   int dzl;           // plane of the ring relative to the oldest needed plane (0 .. hz)
@@ -45,14 +50,13 @@ struct TileStagedOp {
 
 struct TileParams {
   long long Z, Y, X;        // iteration extents (Z == 1 for 2-D ops)
-  int TX, logTX, RY, TY;    // tile: TX columns x TY rows = 2048 outputs; RY = 256 / TX rows per element step k
   int nxt, nyt, nzc;        // tiles along x, y; chunks along z
   long long ZC;             // planes per work item
   long long n_items;
   // staged group
   int has_group, use_tma, elem;
   int hz_lo, hz, hy_lo, hy, hx_lo, hx;  // halos: lo part and total (lo + hi)
-  int PX, PY, D;                         // plane box (elements) and ring depth
+  int PY, D;                             // rows of the plane box (kTilePX columns) and ring depth
   unsigned plane_bytes;
   const char* gcorner;                   // address of group element (z = -hz_lo, y = -hy_lo, x = -hx_lo)
   long long gs0, gs1;                    // group strides (elements) of z and y; x stride is 1
@@ -66,6 +70,7 @@ struct TileParams {
   int n_insns, n_regs;
   LInsn insns[RB200_MAX_INSNS];
   u64 scal[RB200_MAX_SCALARS];
+  LChainStep chain[kTileMaxChain];
 };
 
 __device__ __forceinline__ void tma_load_3d(unsigned sdst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned mbar) {
@@ -83,7 +88,7 @@ template <class TE> struct TileCtx {
   unsigned ring_s;  // shared-window address of the plane ring
   unsigned reg_s;   // this thread's column of the spill-register file ([reg][k][thread], 8-byte slots)
   unsigned tb0;     // byte offset of this thread's element k = 0 inside a plane (halo included)
-  unsigned kstep;   // byte step between elements k and k+1 inside a plane
+  static constexpr unsigned kstep = (unsigned)(kTileRY * kTilePX * sizeof(TE));  // byte step between elements k and k+1 inside a plane
   int fb;           // ring slot holding plane (z - hz_lo)
   long long z, gy0, gx;
   unsigned valid;
@@ -96,14 +101,14 @@ template <class TE> struct TileCtx {
         const TileStagedOp t = P.staged[arg];
         int slot = fb + t.dzl;
         if (slot >= P.D) slot -= P.D;
-        unsigned addr = ring_s + (unsigned)slot * P.plane_bytes + t.off + tb0;
+        const unsigned addr = ring_s + (unsigned)slot * P.plane_bytes + t.off + tb0;
 #pragma unroll
-        for (int k = 0; k < LV; ++k, addr += kstep) out[k] = (F)lean_lds<TE>(addr);
+        for (int k = 0; k < LV; ++k) out[k] = (F)lean_lds<TE>(addr + k * kstep);
       } break;
       case L_DIRECT: {
         const LDirect& v = P.direct[arg];
         const long long off = z * v.s0 + gy0 * v.s1 + gx * v.s2;
-        const long long step = (long long)P.RY * v.s1;
+        const long long step = (long long)kTileRY * v.s1;
         if (v.dtype == RB200_F32) {
           const float* p = reinterpret_cast<const float*>(v.base) + off;
 #pragma unroll
@@ -130,6 +135,16 @@ template <class TE> struct TileCtx {
         for (int k = 0; k < LV; ++k) out[k] = LAcc<F>::get(alo[k], ahi[k]);
     }
   }
+  template <class F> __device__ __forceinline__ int chain_fetch(int step, F (&out)[LV]) {
+    const LChainStep cs = P.chain[step];
+    const TileStagedOp t = P.staged[cs.staged];
+    int slot = fb + t.dzl;
+    if (slot >= P.D) slot -= P.D;
+    const unsigned addr = ring_s + (unsigned)slot * P.plane_bytes + t.off + tb0;
+#pragma unroll
+    for (int k = 0; k < LV; ++k) out[k] = (F)lean_lds<TE>(addr + k * kstep);
+    return cs.op;
+  }
   template <class F> __device__ __forceinline__ void store_reg(int reg, const F (&r)[LV]) {
     const unsigned addr = reg_s + (unsigned)reg * (LV * kThreads * 8);
 #pragma unroll
@@ -138,7 +153,7 @@ template <class TE> struct TileCtx {
   template <class F> __device__ __forceinline__ void store_view(int arg, const F (&r)[LV]) {
     const LDirect& v = P.direct[arg];
     const long long off = z * v.s0 + gy0 * v.s1 + gx * v.s2;
-    const long long step = (long long)P.RY * v.s1;
+    const long long step = (long long)kTileRY * v.s1;
     if (v.dtype == RB200_F32) {
       float* p = reinterpret_cast<float*>(v.base) + off;
 #pragma unroll
@@ -172,10 +187,9 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
   TileCtx<TE> cx(P);
   cx.ring_s = smem_s;
   cx.reg_s = regs_s + tid * 8u;
-  const int x = (int)(tid & (unsigned)(P.TX - 1));
-  const int yrow = (int)(tid >> P.logTX);
-  cx.tb0 = (unsigned)(((yrow + P.hy_lo) * P.PX + x + P.hx_lo) * (int)sizeof(TE));
-  cx.kstep = (unsigned)(P.RY * P.PX * (int)sizeof(TE));
+  const int x = (int)(tid & (unsigned)(kTileTX - 1));
+  const int yrow = (int)(tid >> kTileLogTX);
+  cx.tb0 = (unsigned)(((yrow + P.hy_lo) * kTilePX + x + P.hx_lo) * (int)sizeof(TE));
   const int hz_hi = P.hz - P.hz_lo;
   unsigned fills = 0;  // planes this CTA has requested so far (slot = fills % D, parity = (fills / D) & 1)
 
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
     const long long r1 = item / P.nxt;
     const int ty = (int)(r1 % P.nyt);
     const long long zc = r1 / P.nyt;
-    const long long x0 = (long long)tx * P.TX, y0 = (long long)ty * P.TY;
+    const long long x0 = (long long)tx * kTileTX, y0 = (long long)ty * kTileTY;
     const long long zb = zc * P.ZC;
     long long ze = zb + P.ZC;
     if (ze > P.Z) ze = P.Z;
@@ -194,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
     if (cx.gx < P.X) {
 #pragma unroll
       for (int k = 0; k < LV; ++k)
-        if (cx.gy0 + (long long)k * P.RY < P.Y) valid |= 1u << k;
+        if (cx.gy0 + (long long)k * kTileRY < P.Y) valid |= 1u << k;
     }
     cx.valid = valid;
 
@@ -205,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
       const unsigned dst = smem_s + slot * P.plane_bytes;
       if (P.use_tma) {
         if (tid == 0) {
-          mbar_expect_tx(bar, (unsigned)(P.PX * P.PY * (int)sizeof(TE)));
+          mbar_expect_tx(bar, (unsigned)(kTilePX * P.PY * (int)sizeof(TE)));
           tma_load_3d(dst, &tmap, (int)x0 + P.tma_shift, (int)y0, (int)pz, bar);
         }
       } else {
@@ -215,9 +229,9 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
         for (int py = warp; py < P.PY; py += kThreads / 32) {
           const long long gy = y0 + py;
           const TE* row = reinterpret_cast<const TE*>(P.gcorner) + pz * P.gs0 + gy * P.gs1 + x0;
-          const unsigned drow = dst + (unsigned)(py * P.PX * (int)sizeof(TE));
+          const unsigned drow = dst + (unsigned)(py * kTilePX * (int)sizeof(TE));
           const bool row_ok = gy < Yh && pz >= 0 && pz < Zh;
-          for (int px = lane; px < P.PX; px += 32) {
+          for (int px = lane; px < kTilePX; px += 32) {
             const TE* src = row + px;
             const bool ok = row_ok && (x0 + px) < Xh && (const char*)src >= P.safe_lo && (const char*)(src + 1) <= P.safe_hi;
             if constexpr (sizeof(TE) == 8) cp_async8(drow + px * 8u, ok ? (const void*)src : (const void*)P.safe_lo, ok);
@@ -329,7 +343,7 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
       }
       const long long dy = floor_div(delta + S(r, 1) / 2, S(r, 1));
       const long long dx = delta - dy * S(r, 1);
-      if (dz < -3 || dz > 3 || dy < -8 || dy > 8 || dx < -16 || dx > 16) continue;
+      if (dz < -3 || dz > 3 || dy < -8 || dy > 8 || dx < -8 || dx > 8) continue;
       ++n;
     }
     if (n > best_n) {
@@ -362,7 +376,7 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
       }
       const long long dy = floor_div(delta + S(r, 1) / 2, S(r, 1));
       const long long dx = delta - dy * S(r, 1);
-      if (dz < -3 || dz > 3 || dy < -8 || dy > 8 || dx < -16 || dx > 16) continue;
+      if (dz < -3 || dz > 3 || dy < -8 || dy > 8 || dx < -8 || dx > 8) continue;
       member[n] = v;
       mdz[n] = dz; mdy[n] = dy; mdx[n] = dx;
       if (dz < lo[0]) lo[0] = dz;
@@ -396,25 +410,18 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
   }
 
   // ---- tile geometry
-  int TX = 128;
-  if (P.X <= 32) TX = 32;
-  else if (P.X <= 64) TX = 64;
-  P.TX = TX;
-  P.logTX = TX == 32 ? 5 : TX == 64 ? 6 : 7;
-  P.RY = kThreads / TX;
-  P.TY = LV * P.RY;
+  const int TX = kTileTX;
   P.nxt = (int)((P.X + TX - 1) / TX);
-  P.nyt = (int)((P.Y + P.TY - 1) / P.TY);
+  P.nyt = (int)((P.Y + kTileTY - 1) / kTileTY);
   if (P.has_group) {
-    const int per16 = 16 / es;
-    P.PX = ((TX + P.hx + per16 - 1) / per16) * per16;
-    P.PY = P.TY + P.hy;
+    if (TX + P.hx > kTilePX) return 1;
+    P.PY = kTileTY + P.hy;
     P.D = P.hz + 2;
-    if (P.D > kTileMaxRing || P.PX > 256 || P.PY > 256) return 1;
-    P.plane_bytes = (unsigned)(((size_t)P.PX * P.PY * es + 127) / 128 * 128);
+    if (P.D > kTileMaxRing || P.PY > 256) return 1;
+    P.plane_bytes = (unsigned)(((size_t)kTilePX * P.PY * es + 127) / 128 * 128);
     for (int j = 0; j < P.n_staged; ++j) {
       P.staged[j].dzl = (int)(mdz[j] + P.hz_lo);
-      P.staged[j].off = (unsigned)(((mdy[j] + P.hy_lo) * P.PX + (mdx[j] + P.hx_lo)) * es);
+      P.staged[j].off = (unsigned)(((mdy[j] + P.hy_lo) * kTilePX + (mdx[j] + P.hx_lo)) * es);
       view_kind[member[j]] = L_STAGED;
       view_arg[member[j]] = j;
     }
@@ -433,6 +440,10 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
   P.n_insns = op->n_insns;
   P.n_regs = op->n_regs;
   lean_translate(op, view_kind, view_arg, store_arg, P.insns);
+  {
+    int n_chain = 0;
+    P.n_insns = lean_fuse_chains(P.insns, P.n_insns, P.chain, kTileMaxChain, &n_chain);
+  }
   for (int i = 0; i < op->n_scalars; ++i) P.scal[i] = op->scalars[i];
 
   const size_t smem = (size_t)P.D * P.plane_bytes + (size_t)P.n_regs * LV * kThreads * 8 + (size_t)P.D * 8 + 16;
@@ -470,7 +481,7 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
     if (!no_tma && enc && aligned && inside && Xh < (1ll << 31)) {
       cuuint64_t gdim[3] = {(cuuint64_t)Xh, (cuuint64_t)Yh, (cuuint64_t)Zh};
       cuuint64_t gstr[2] = {(cuuint64_t)(P.gs1 * es), (cuuint64_t)((nd == 3 ? P.gs0 : P.gs1 * Yh) * es)};
-      cuuint32_t box[3] = {(cuuint32_t)P.PX, (cuuint32_t)P.PY, 1};
+      cuuint32_t box[3] = {(cuuint32_t)kTilePX, (cuuint32_t)P.PY, 1};
       cuuint32_t estr[3] = {1, 1, 1};
       const CUresult rc = enc(&tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)tbase, gdim, gstr, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

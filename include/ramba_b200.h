@@ -235,6 +235,11 @@ int64_t rb200_cumulative_scratch_bytes(int64_t n_outer, int64_t len, int64_t n_i
 int rb200_cumulative(const void* src, void* dst, int32_t dtype, int64_t n_outer, int64_t len, int64_t n_inner,
                      int32_t redop, const void* carry_in, void* totals_out, void* scratch, void* stream);
 
+/* Which kernel rb200_run_deferred_ops would run `op` on and how (staged views, halos, TMA or cp.async loader, ring depth,
+ * lean instructions, CTAs), as one text line in out[0..cap).  Needs no device and touches no pointer: the counterpart
+ * of RAMBA_SHOW_CODE printing the generated kernel (ramba/ramba.py:8266-8284).                                       */
+int rb200_describe_plan(const rb200_fused_op* op, char* out, int64_t cap);
+
 /* Thread-local description of the last error returned on this thread.               */
 const char* rb200_last_error(void);
 

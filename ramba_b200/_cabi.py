@@ -95,6 +95,7 @@ EXPORTS = [
     "rb200_reduce_partials",
     "rb200_cumulative",
     "rb200_cumulative_scratch_bytes",
+    "rb200_describe_plan",
     "rb200_last_error",
     "rb200_abi_version",
     "rb200_launch_count",
@@ -137,6 +138,8 @@ def load():
     lib.rb200_cumulative.restype = C.c_int
     lib.rb200_cumulative_scratch_bytes.argtypes = [C.c_int64, C.c_int64, C.c_int64]
     lib.rb200_cumulative_scratch_bytes.restype = C.c_int64
+    lib.rb200_describe_plan.argtypes = [C.POINTER(FusedOp), C.c_char_p, C.c_int64]
+    lib.rb200_describe_plan.restype = C.c_int
     lib.rb200_last_error.argtypes = []
     lib.rb200_last_error.restype = C.c_char_p
     lib.rb200_abi_version.argtypes = []
@@ -180,6 +183,14 @@ def cumulative(src, dst, dtype, n_outer, length, n_inner, redop, carry_in=None, 
 
 def cumulative_scratch_bytes(n_outer, length, n_inner):
     return int(load().rb200_cumulative_scratch_bytes(n_outer, length, n_inner))
+
+
+def describe_plan(fop):
+    """One text line: the kernel the library would run this fused op on, and how (no device needed)."""
+    lib = load()
+    buf = C.create_string_buffer(600)
+    check(lib.rb200_describe_plan(C.byref(fop), buf, 600))
+    return buf.value.decode()
 
 
 def red_scratch_bytes():

@@ -514,6 +514,24 @@ int rb200_run_deferred_ops(const rb200_fused_op* op, void* stream_v) {
   return 0;
 }
 
+int rb200_describe_plan(const rb200_fused_op* op, char* out, int64_t cap) {
+  if (!op || !out || cap < 2) return fail("describe_plan: null argument");
+  if (op->abi_version != RB200_ABI_VERSION) return fail("ABI version mismatch between caller and libramba_b200");
+  if (op->ndim < 1 || op->ndim > RB200_MAX_DIMS || op->n_views < 0 || op->n_views > RB200_MAX_VIEWS || op->n_insns < 0 ||
+      op->n_insns > RB200_MAX_INSNS || op->n_scalars < 0 || op->n_scalars > RB200_MAX_SCALARS || op->n_reds < 0 || op->n_reds > RB200_MAX_REDS)
+    return fail("describe_plan: malformed fused op");
+  const int sms = 148;  // B200; the plan does not depend on a device being present
+  std::string d;
+  if (!(op->n_axis_red_dims == 0 && describe_stencil_tile(op, sms, &d)) && !describe_stream(op, sms, &d)) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "kernel=general_interpreter form=%s ndim=%d insns=%d views=%d", op->n_axis_red_dims ? "axis_reduce" : "elementwise", op->ndim,
+             op->n_insns, op->n_views);
+    d = buf;
+  }
+  snprintf(out, (size_t)cap, "%s", d.c_str());
+  return 0;
+}
+
 int64_t rb200_cumulative_scratch_bytes(int64_t n_outer, int64_t len, int64_t n_inner) {
   if (n_outer < 0 || len < 0 || n_inner < 1) return 256;
   return (int64_t)scan_scratch_bytes(n_outer, len, n_inner);

@@ -458,6 +458,52 @@ static cudaError_t stream_launch(const StreamParams& P, unsigned blocks, size_t 
   return cudaGetLastError();
 }
 
+// one line for rb200_describe_plan; false: not this kernel's form
+bool describe_stream(const rb200_fused_op* op, int sms, std::string* out) {
+  StreamParams P;
+  memset(&P, 0, sizeof(P));
+  const char* mode = nullptr;
+  long long ctas = 0;
+  if (op->ndim == 1 && op->n_axis_red_dims == 0) {
+    if (!lean_eligible(op, true)) return false;
+    for (int s = 0; s < op->n_reds; ++s)
+      if (op->reds[s].ctype != RB200_T_F64 || (op->reds[s].out_dtype != RB200_F64 && op->reds[s].out_dtype != RB200_F32)) return false;
+    P.mode = 0;
+    P.total = op->itershape[0];
+    P.n_tiles = (P.total + kStreamTile - 1) / kStreamTile;
+    stream_translate(op, P, false, 0);
+    mode = "elementwise";
+    ctas = P.n_tiles < (long long)sms * 2 ? P.n_tiles : (long long)sms * 2;
+  } else if (op->ndim == 2 && op->n_axis_red_dims == 1 && op->n_reds == 1) {
+    if (!lean_eligible(op, true) || op->reds[0].ctype != RB200_T_F64) return false;
+    const long long R = op->itershape[0], C = op->itershape[1];
+    if (C % kStreamTile != 0 || C / kStreamTile > (long long)sms * 2 || R < 2) return false;
+    for (int i = 0; i < op->n_insns; ++i)
+      if (op->insns[i].st_view != RB200_NOSTORE) return false;
+    for (int v = 0; v < op->n_views; ++v)
+      if (op->views[v].stride[1] != 1 || !(op->views[v].stride[0] == C || op->views[v].stride[0] == 0)) return false;
+    P.mode = 1;
+    P.R = R;
+    P.C = C;
+    stream_translate(op, P, true, C);
+    mode = "columns";
+    int eff = (int)(((long long)sms * 2) / (C / kStreamTile));
+    if (op->axis_nsplit > 0 && eff > op->axis_nsplit) eff = op->axis_nsplit;
+    if ((long long)eff > R) eff = (int)R;
+    if (eff < 1) eff = 1;
+    ctas = (long long)eff * (C / kStreamTile);
+  } else {
+    return false;
+  }
+  const size_t smem = stream_smem(P);
+  if (smem == 0) return false;
+  char buf[300];
+  snprintf(buf, sizeof(buf), "kernel=stream mode=%s staged_views=%d ring_depth=%d stage_bytes=%u direct_views=%d hoisted=%d lean_insns=%d reds=%d ctas=%lld smem=%zu",
+           mode, P.n_staged, P.depth, P.stage_bytes, P.n_direct, P.n_hoist, P.n_insns, op->n_reds, ctas, smem);
+  *out = buf;
+  return true;
+}
+
 // mode 0.  0: launched, 1: not of this form, 2: error
 int launch_stream_1d(const rb200_fused_op* op, int sms, int max_red_blocks, cudaStream_t stream, std::string* err) {
   static const bool disabled = getenv("RB200_NO_STREAM_KERNEL") != nullptr;  // debugging aid

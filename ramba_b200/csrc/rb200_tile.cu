@@ -48,6 +48,24 @@ struct TileStagedOp {
   unsigned off;      // byte offset inside a plane: ((dy + hy_lo) * PX + dx + hx_lo) * elem
 };
 
+// ---- the "weighted shifted sum" form (ramba/ramba.py:8146-8188: `acc = U[o1+i] + U[o2+i] + ... ; V[i] = acc - c*U[..]`):
+// an op list that is ONE running value updated by views and scalars, with at most one float32 -> float64 promotion and
+// one store at the end, is flattened into term steps and run by stencil_terms_kernel (no dispatch tree, the running
+// value never leaves registers).  Same operations, same order, same classes, one rounding each.
+enum TermOp {
+  T_LOAD = 0, T_ADD, T_SUB, T_RSUB, T_MUL,  // acc (op) x        (x: a staged or direct view element)
+  T_MULADD, T_MULSUB, T_MULRSUB,            // acc + x*s, acc - x*s, x*s - acc   (product rounded first)
+  T_ADDS, T_SUBS, T_RSUBS, T_MULS,          // acc (op) s        (s: scalar)
+  T_NEG, T_LOADS
+};
+enum TermX { X_NONE = 0, X_STAGED = 1, X_DIRECT = 2 };
+struct TermStep {  // 8 bytes
+  unsigned char op, xkind, xidx, sidx;
+  unsigned short off;  // staged: byte offset of the operand inside a plane
+  unsigned char dzl, pad;
+};
+constexpr int kTileMaxTerms = 48;
+
 struct TileParams {
   long long Z, Y, X;        // iteration extents (Z == 1 for 2-D ops)
   int nxt, nyt, nzc;        // tiles along x, y; chunks along z
@@ -71,6 +89,9 @@ struct TileParams {
   LInsn insns[RB200_MAX_INSNS];
   u64 scal[RB200_MAX_SCALARS];
   LChainStep chain[kTileMaxChain];
+  // term form (n_terms > 0): steps [0, n32) run in float32, steps [n32, n_terms) in float64
+  int n_terms, n32, out_view;
+  TermStep terms[kTileMaxTerms];
 };
 
 __device__ __forceinline__ void tma_load_3d(unsigned sdst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned mbar) {
@@ -87,7 +108,7 @@ template <class TE> struct TileCtx {
   const TileParams& P;
   unsigned ring_s;  // shared-window address of the plane ring
   unsigned reg_s;   // this thread's column of the spill-register file ([reg][k][thread], 8-byte slots)
-  unsigned tb0;     // byte offset of this thread's element k = 0 inside a plane (halo included)
+  unsigned tb0;     // byte offset of this thread's element k = 0 inside a plane, before the operand's own (dy, dx) offset
   static constexpr unsigned kstep = (unsigned)(kTileRY * kTilePX * sizeof(TE));  // byte step between elements k and k+1 inside a plane
   int fb;           // ring slot holding plane (z - hz_lo)
   long long z, gy0, gx;
@@ -189,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
   cx.reg_s = regs_s + tid * 8u;
   const int x = (int)(tid & (unsigned)(kTileTX - 1));
   const int yrow = (int)(tid >> kTileLogTX);
-  cx.tb0 = (unsigned)(((yrow + P.hy_lo) * kTilePX + x + P.hx_lo) * (int)sizeof(TE));
+  cx.tb0 = (unsigned)((yrow * kTilePX + x) * (int)sizeof(TE));  // (the halo offsets are part of every staged operand's `off`)
   const int hz_hi = P.hz - P.hz_lo;
   unsigned fills = 0;  // planes this CTA has requested so far (slot = fills % D, parity = (fills / D) & 1)
 
@@ -251,6 +272,11 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
     for (long long z = zb; z < ze; ++z) {
       if (P.has_group) {
         const unsigned newest = fill0 + (unsigned)(z - zb) + (unsigned)P.hz;  // plane z + hz_hi
+        if (z == zb) {
+          // first plane of an item: the older planes of the prologue have their own barriers, and bulk copies may
+          // complete out of order
+          for (unsigned f = fill0; f < newest; ++f) mbar_wait(mbar_s + 8u * (f % (unsigned)P.D), (f / (unsigned)P.D) & 1u);
+        }
         mbar_wait(mbar_s + 8u * (newest % (unsigned)P.D), (newest / (unsigned)P.D) & 1u);
         __syncthreads();  // plane z - 1 - hz_lo is free now: its slot takes the plane after the newest
         if (z + 1 < ze) request(z + 1 + P.hz);
@@ -265,6 +291,263 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
     }
   }
   (void)hz_hi;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// shared by both kernels: ask for plane `pz` (halo coordinates) of the staged group into ring slot `slot`
+template <class TE>
+__device__ __forceinline__ void tile_request(const TileParams& P, const CUtensorMap* tmap, unsigned smem_s, unsigned mbar_s, unsigned slot, long long x0,
+                                             long long y0, long long pz, unsigned tid) {
+  const unsigned bar = mbar_s + 8u * slot;
+  const unsigned dst = smem_s + slot * P.plane_bytes;
+  if (P.use_tma) {
+    if (tid == 0) {
+      mbar_expect_tx(bar, (unsigned)(kTilePX * P.PY * (int)sizeof(TE)));
+      tma_load_3d(dst, tmap, (int)x0 + P.tma_shift, (int)y0, (int)pz, bar);
+    }
+  } else {
+    // rows of the box by warps, elements by lanes; out-of-range elements are zero-filled
+    const int lane = (int)(tid & 31u), warp = (int)(tid >> 5);
+    const long long Xh = P.X + P.hx, Yh = P.Y + P.hy, Zh = P.Z + P.hz;
+    for (int py = warp; py < P.PY; py += kThreads / 32) {
+      const long long gy = y0 + py;
+      const TE* row = reinterpret_cast<const TE*>(P.gcorner) + pz * P.gs0 + gy * P.gs1 + x0;
+      const unsigned drow = dst + (unsigned)(py * kTilePX * (int)sizeof(TE));
+      const bool row_ok = gy < Yh && pz >= 0 && pz < Zh;
+      for (int px = lane; px < kTilePX; px += 32) {
+        const TE* src = row + px;
+        const bool ok = row_ok && (x0 + px) < Xh && (const char*)src >= P.safe_lo && (const char*)(src + 1) <= P.safe_hi;
+        if constexpr (sizeof(TE) == 8) cp_async8(drow + px * 8u, ok ? (const void*)src : (const void*)P.safe_lo, ok);
+        else cp_async4(drow + px * 4u, ok ? (const void*)src : (const void*)P.safe_lo, ok);
+      }
+    }
+    cp_async_mbar_arrive(bar);
+  }
+}
+
+template <class TE> struct TermCtx {
+  unsigned tb0;            // byte offset of element k = 0 of this thread inside a plane
+  unsigned pa[4];          // shared-window address of the ring slot holding plane (z - hz_lo + d), d = 0..3
+  long long z, gy0, gx;
+  unsigned valid;
+};
+
+template <class TE, class F>
+__device__ __forceinline__ void term_fetch(const TileParams& P, const TermCtx<TE>& cx, const TermStep t, F (&x)[LV]) {
+  constexpr unsigned kstep = (unsigned)(kTileRY * kTilePX * sizeof(TE));
+  if (t.xkind == X_STAGED) {
+    const unsigned base = t.dzl == 0 ? cx.pa[0] : t.dzl == 1 ? cx.pa[1] : t.dzl == 2 ? cx.pa[2] : cx.pa[3];
+    const unsigned addr = base + t.off + cx.tb0;
+#pragma unroll
+    for (int k = 0; k < LV; ++k) x[k] = (F)lean_lds<TE>(addr + k * kstep);
+  } else {
+    const LDirect& v = P.direct[t.xidx];
+    const long long off = cx.z * v.s0 + cx.gy0 * v.s1 + cx.gx * v.s2;
+    const long long step = (long long)kTileRY * v.s1;
+    if (v.dtype == RB200_F32) {
+      const float* p = reinterpret_cast<const float*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<float>(p) : F(0);
+    } else {
+      const double* p = reinterpret_cast<const double*>(v.base) + off;
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<double>(p) : F(0);
+    }
+  }
+}
+
+template <class TE, class F>
+__device__ __forceinline__ void term_steps(const TileParams& P, const TermCtx<TE>& cx, int s0, int s1, F (&acc)[LV]) {
+#pragma unroll 1
+  for (int s = s0; s < s1; ++s) {
+    const TermStep t = P.terms[s];
+    F x[LV];
+    if (t.xkind != X_NONE) term_fetch<TE, F>(P, cx, t, x);
+    const u64 sbits = P.scal[t.sidx];
+    const F sc = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
+    switch (t.op) {
+      case T_LOAD:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = x[k];
+        break;
+      case T_ADD:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], x[k]);
+        break;
+      case T_SUB:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], x[k]);
+        break;
+      case T_RSUB:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(x[k], acc[k]);
+        break;
+      case T_MUL:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_mul<F>(acc[k], x[k]);
+        break;
+      case T_MULADD:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], l_mul<F>(x[k], sc));
+        break;
+      case T_MULSUB:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], l_mul<F>(x[k], sc));
+        break;
+      case T_MULRSUB:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(l_mul<F>(x[k], sc), acc[k]);
+        break;
+      case T_ADDS:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], sc);
+        break;
+      case T_SUBS:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], sc);
+        break;
+      case T_RSUBS:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(sc, acc[k]);
+        break;
+      case T_MULS:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = l_mul<F>(acc[k], sc);
+        break;
+      case T_NEG:
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = -acc[k];
+        break;
+      default:  // T_LOADS
+#pragma unroll
+        for (int k = 0; k < LV; ++k) acc[k] = sc;
+    }
+  }
+}
+
+template <class TE, class F>
+__device__ __forceinline__ void term_store(const TileParams& P, const TermCtx<TE>& cx, const F (&acc)[LV]) {
+  const LDirect& v = P.direct[P.out_view];
+  const long long off = cx.z * v.s0 + cx.gy0 * v.s1 + cx.gx * v.s2;
+  const long long step = (long long)kTileRY * v.s1;
+  if (v.dtype == RB200_F32) {
+    float* p = reinterpret_cast<float*>(v.base) + off;
+    if (cx.valid == (1u << LV) - 1u) {
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step) stg<float>(p, (float)acc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step)
+        if ((cx.valid >> k) & 1u) stg<float>(p, (float)acc[k]);
+    }
+  } else {
+    double* p = reinterpret_cast<double*>(v.base) + off;
+    if (cx.valid == (1u << LV) - 1u) {
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step) stg<double>(p, (double)acc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < LV; ++k, p += step)
+        if ((cx.valid >> k) & 1u) stg<double>(p, (double)acc[k]);
+    }
+  }
+}
+
+template <class TE>
+__global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid_constant__ TileParams P, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const unsigned tid = threadIdx.x;
+  const unsigned mbar_s = smem_s + (unsigned)P.D * P.plane_bytes;  // layout: [ring: D planes][mbarriers: D * 8]
+  if (P.has_group && tid == 0) {
+    for (int s = 0; s < P.D; ++s) mbar_init(mbar_s + 8u * s, P.use_tma ? 1u : (unsigned)kThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  TermCtx<TE> cx;
+  const int x = (int)(tid & (unsigned)(kTileTX - 1));
+  const int yrow = (int)(tid >> kTileLogTX);
+  cx.tb0 = (unsigned)((yrow * kTilePX + x) * (int)sizeof(TE));
+  const int D = P.D, hz = P.hz;
+  int rq = 0;          // ring slot of the next plane to request
+  unsigned par = 0;    // bit s: parity of the next completion to wait for on slot s
+
+  for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+    const int tx = (int)(item % P.nxt);
+    const long long r1 = item / P.nxt;
+    const int ty = (int)(r1 % P.nyt);
+    const long long zc = r1 / P.nyt;
+    const long long x0 = (long long)tx * kTileTX, y0 = (long long)ty * kTileTY;
+    const long long zb = zc * P.ZC;
+    long long ze = zb + P.ZC;
+    if (ze > P.Z) ze = P.Z;
+    cx.gx = x0 + x;
+    cx.gy0 = y0 + yrow;
+    unsigned valid = 0;
+    if (cx.gx < P.X) {
+#pragma unroll
+      for (int k = 0; k < LV; ++k)
+        if (cx.gy0 + (long long)k * kTileRY < P.Y) valid |= 1u << k;
+    }
+    cx.valid = valid;
+    int cur = rq;  // slot of plane (zb - hz_lo)
+    if (P.has_group) {
+      __syncthreads();  // every thread is done with the planes of the previous item
+      for (int p = 0; p <= hz; ++p) {
+        tile_request<TE>(P, &tmap, smem_s, mbar_s, (unsigned)rq, x0, y0, zb + p, tid);
+        rq = rq + 1 == D ? 0 : rq + 1;
+      }
+    }
+    for (long long z = zb; z < ze; ++z) {
+      if (P.has_group) {
+        int sl = cur;
+        if (z == zb) {
+          // first plane of an item: every plane of the prologue has its own barrier (bulk copies may complete out of order)
+          for (int p = 0; p < hz; ++p) {
+            mbar_wait(mbar_s + 8u * (unsigned)sl, (par >> sl) & 1u);
+            par ^= 1u << sl;
+            sl = sl + 1 == D ? 0 : sl + 1;
+          }
+        } else {
+          sl = cur + hz;
+          if (sl >= D) sl -= D;
+        }
+        mbar_wait(mbar_s + 8u * (unsigned)sl, (par >> sl) & 1u);  // the newest plane, z + hz_hi
+        par ^= 1u << sl;
+        __syncthreads();  // plane z - 1 - hz_lo is free now: its slot takes the plane after the newest
+        if (z + 1 < ze) {
+          tile_request<TE>(P, &tmap, smem_s, mbar_s, (unsigned)rq, x0, y0, z + 1 + hz, tid);
+          rq = rq + 1 == D ? 0 : rq + 1;
+        }
+        int q = cur;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          cx.pa[d] = smem_s + (unsigned)q * P.plane_bytes;
+          q = q + 1 == D ? 0 : q + 1;
+        }
+        cur = cur + 1 == D ? 0 : cur + 1;
+      }
+      cx.z = z;
+      if (P.n32 > 0) {
+        float a32[LV];
+        if constexpr (sizeof(TE) == 4) term_steps<TE, float>(P, cx, 0, P.n32, a32);
+        if (P.n_terms > P.n32) {
+          double a64[LV];
+#pragma unroll
+          for (int k = 0; k < LV; ++k) a64[k] = (double)a32[k];
+          term_steps<TE, double>(P, cx, P.n32, P.n_terms, a64);
+          term_store<TE, double>(P, cx, a64);
+        } else {
+          term_store<TE, float>(P, cx, a32);
+        }
+      } else {
+        double a64[LV];
+        term_steps<TE, double>(P, cx, 0, P.n_terms, a64);
+        term_store<TE, double>(P, cx, a64);
+      }
+    }
+  }
 }
 
 // =============================================================================================
@@ -290,16 +573,139 @@ static long long floor_div(long long a, long long b) {  // b > 0
   return q;
 }
 
-// 0: launched, 1: not eligible (caller falls back to the general interpreter), 2: error (*err set)
-int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, std::string* err) {
-  static const bool disabled = getenv("RB200_NO_TILE_KERNEL") != nullptr;  // debugging aid
-  if (disabled) return 1;
+
+// Flatten translated lean instructions into term steps (see TermOp).  false: not of the weighted-shifted-sum form.
+static bool build_terms(TileParams& P, const LInsn* L, int n, bool staged_is_f32) {
+  if (P.n_regs != 0 || n < 1) return false;
+  int nt = 0, cls = -1, n32 = -1;
+  auto push = [&](int op, int kind, int arg, int sidx) -> bool {
+    if (nt >= kTileMaxTerms) return false;
+    TermStep t;
+    memset(&t, 0, sizeof(t));
+    t.op = (unsigned char)op;
+    t.sidx = (unsigned char)sidx;
+    if (kind == L_STAGED) {
+      if (cls == 1 && !staged_is_f32) return false;
+      t.xkind = X_STAGED;
+      t.xidx = (unsigned char)arg;
+      t.dzl = (unsigned char)P.staged[arg].dzl;
+      if (P.staged[arg].off > 0xffffu || P.staged[arg].dzl > 3) return false;
+      t.off = (unsigned short)P.staged[arg].off;
+    } else if (kind == L_DIRECT) {
+      t.xkind = X_DIRECT;
+      t.xidx = (unsigned char)arg;
+    } else {
+      t.xkind = X_NONE;
+    }
+    P.terms[nt++] = t;
+    return true;
+  };
+  auto is_view = [](int k) { return k == L_STAGED || k == L_DIRECT; };
+  // acc (op) operand
+  auto apply = [&](int viewop, int scalop, int kind, int arg) -> bool {
+    if (is_view(kind)) return push(viewop, kind, arg, 0);
+    if (kind == L_SCAL) return push(scalop, L_NONE, 0, arg);
+    return false;
+  };
+  auto load = [&](int kind, int arg) -> bool { return apply(T_LOAD, T_LOADS, kind, arg); };
+  for (int i = 0; i < n; ++i) {
+    const LInsn& I = L[i];
+    const int lop = I.handler >> 2, f32 = (I.handler >> 1) & 1;
+    const bool aacc = (I.handler & 1) != 0;
+    if (I.st_reg != RB200_NOSTORE) return false;
+    if (I.st_view != RB200_NOSTORE && i != n - 1) return false;
+    if (lop == LO_CVT) {
+      if (!aacc || nt == 0) return false;
+      if (f32 == 0) {  // float32 -> float64: the one promotion
+        if (cls != 1 || n32 >= 0) return false;
+        n32 = nt;
+        cls = 0;
+      } else {  // float64 -> float32: only as the last instruction into a float32 view (the store converts)
+        if (i != n - 1 || cls != 0 || I.st_view == RB200_NOSTORE || P.direct[I.st_view].dtype != RB200_F32) return false;
+      }
+      continue;
+    }
+    if (cls < 0) cls = f32;
+    else if (cls != f32) return false;
+    const bool fresh = nt == 0;  // no running value yet: the instruction may start from its own operands
+    switch (lop) {
+      case LO_MOV:
+        if (!aacc && !(fresh && load(I.a_kind, I.a_arg))) return false;
+        break;
+      case LO_NEG:
+        if (!aacc && !(fresh && load(I.a_kind, I.a_arg))) return false;
+        if (!push(T_NEG, L_NONE, 0, 0)) return false;
+        break;
+      case LO_ADD:
+      case LO_SUB:
+      case LO_RSUB:
+      case LO_MUL: {
+        if (!aacc && !(fresh && load(I.a_kind, I.a_arg))) return false;
+        const int vop = lop == LO_ADD ? T_ADD : lop == LO_SUB ? T_SUB : lop == LO_RSUB ? T_RSUB : T_MUL;
+        const int sop = lop == LO_ADD ? T_ADDS : lop == LO_SUB ? T_SUBS : lop == LO_RSUB ? T_RSUBS : T_MULS;
+        if (!apply(vop, sop, I.b_kind, I.b_arg)) return false;
+      } break;
+      case LO_MULADD:
+      case LO_MULSUB:
+      case LO_MULRSUB: {
+        // r = a + p, a - p, p - a  with p = b*c rounded first
+        const int with_view = lop == LO_MULADD ? T_MULADD : lop == LO_MULSUB ? T_MULSUB : T_MULRSUB;
+        if (aacc) {
+          if (is_view(I.b_kind) && I.c_kind == L_SCAL) {
+            if (!push(with_view, I.b_kind, I.b_arg, I.c_arg)) return false;
+          } else if (is_view(I.c_kind) && I.b_kind == L_SCAL) {
+            if (!push(with_view, I.c_kind, I.c_arg, I.b_arg)) return false;
+          } else {
+            return false;
+          }
+          break;
+        }
+        // the running value is (or becomes) the product; then `a` is folded in
+        if (I.b_kind == L_ACC || I.c_kind == L_ACC) {
+          const int ok = I.b_kind == L_ACC ? I.c_kind : I.b_kind, oa = I.b_kind == L_ACC ? I.c_arg : I.b_arg;
+          if (!apply(T_MUL, T_MULS, ok, oa)) return false;
+        } else {
+          if (!fresh) return false;
+          // start from the view factor when there is one (x*s == s*x)
+          const bool bv = is_view(I.b_kind);
+          if (!load(bv ? I.b_kind : I.c_kind, bv ? I.b_arg : I.c_arg)) return false;
+          if (!apply(T_MUL, T_MULS, bv ? I.c_kind : I.b_kind, bv ? I.c_arg : I.b_arg)) return false;
+        }
+        const int vop = lop == LO_MULADD ? T_ADD : lop == LO_MULSUB ? T_RSUB : T_SUB;
+        const int sop = lop == LO_MULADD ? T_ADDS : lop == LO_MULSUB ? T_RSUBS : T_SUBS;
+        if (!apply(vop, sop, I.a_kind, I.a_arg)) return false;
+      } break;
+      default: return false;
+    }
+  }
+  if (L[n - 1].st_view == RB200_NOSTORE || nt == 0) return false;
+  P.out_view = L[n - 1].st_view;
+  P.n_terms = nt;
+  P.n32 = n32 >= 0 ? n32 : (cls == 1 ? nt : 0);
+  // (cls is the FINAL class: an op list that started in float32 and never promoted has n32 == nt)
+  if (n32 < 0 && cls == 1 && !staged_is_f32) return false;
+  return true;
+}
+
+struct TilePlan {
+  TileParams P;
+  size_t smem;
+  long long blocks;
+  // TMA descriptor inputs (valid when tma_ok): base moved down to 16-byte alignment, halo'd extents
+  bool tma_ok;
+  const char* tbase;
+  long long Xh, Yh, Zh;
+  int shift, es, nd;
+};
+
+// 0: planned, 1: not eligible (caller falls back to the general interpreter)
+static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
   if (op->ndim != 2 && op->ndim != 3) return 1;
   if (op->n_reds != 0 || op->n_axis_red_dims != 0) return 1;
   if (!lean_eligible(op, false)) return 1;
   const int nd = op->ndim;
-  TileParams P;
-  memset(&P, 0, sizeof(P));
+  TileParams& P = T.P;
+  memset(&T, 0, sizeof(T));
   P.Z = nd == 3 ? op->itershape[0] : 1;
   P.Y = op->itershape[nd - 2];
   P.X = op->itershape[nd - 1];
@@ -440,13 +846,15 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
   P.n_insns = op->n_insns;
   P.n_regs = op->n_regs;
   lean_translate(op, view_kind, view_arg, store_arg, P.insns);
-  {
+  static const bool no_terms = getenv("RB200_NO_TERMS_KERNEL") != nullptr;  // debugging aid: always the general tile kernel
+  if (no_terms || !build_terms(P, P.insns, P.n_insns, es == 4)) {
+    P.n_terms = 0;
     int n_chain = 0;
     P.n_insns = lean_fuse_chains(P.insns, P.n_insns, P.chain, kTileMaxChain, &n_chain);
   }
   for (int i = 0; i < op->n_scalars; ++i) P.scal[i] = op->scalars[i];
 
-  const size_t smem = (size_t)P.D * P.plane_bytes + (size_t)P.n_regs * LV * kThreads * 8 + (size_t)P.D * 8 + 16;
+  const size_t smem = (size_t)P.D * P.plane_bytes + (P.n_terms > 0 ? 0 : (size_t)P.n_regs * LV * kThreads * 8) + (size_t)P.D * 8 + 16;
   if (smem > 100 * 1024) return 1;  // (two CTAs per SM)
 
   // ---- work items: z chunks so that every CTA of the persistent grid gets several
@@ -461,53 +869,95 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
   P.ZC = ZC;
   P.nzc = (int)((P.Z + ZC - 1) / ZC);
   P.n_items = (long long)P.nzc * xy;
-  long long blocks = P.n_items < grid_cap ? P.n_items : grid_cap;
-
-  // ---- TMA descriptor over the halo'd source box
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
+  T.blocks = P.n_items < grid_cap ? P.n_items : grid_cap;
+  T.smem = smem;
+  T.es = es;
+  T.nd = nd;
+  // ---- can the halo'd source box be described by a TMA tensor map?  (strides multiples of 16 bytes, base moved down
+  // to 16-byte alignment, the whole box inside the shard buffer)
   if (P.has_group) {
-    static const bool no_tma = getenv("RB200_NO_TMA") != nullptr;  // debugging aid: always the cooperative loader
-    EncodeTiledFn enc = encode_tiled_fn();
     const uintptr_t corner = (uintptr_t)P.gcorner;
-    const int shift = (int)((corner & 15u) / (unsigned)es);
-    const char* tbase = P.gcorner - (size_t)shift * es;
-    const long long Xh = P.X + P.hx + shift, Yh = P.Y + P.hy, Zh = P.Z + P.hz;
-    const char* far_end = P.gcorner + ((Zh - 1) * P.gs0 + (Yh - 1) * P.gs1 + (P.X + P.hx)) * es;
+    T.shift = (int)((corner & 15u) / (unsigned)es);
+    T.tbase = P.gcorner - (size_t)T.shift * es;
+    T.Xh = P.X + P.hx + T.shift;
+    T.Yh = P.Y + P.hy;
+    T.Zh = P.Z + P.hz;
+    const char* far_end = P.gcorner + ((T.Zh - 1) * P.gs0 + (T.Yh - 1) * P.gs1 + (P.X + P.hx)) * es;
     const char* alo = (const char*)op->views[best_ref].alloc_lo;
     const char* ahi = (const char*)op->views[best_ref].alloc_hi;
-    const bool aligned = (P.gs1 * es) % 16 == 0 && (nd == 2 || (P.gs0 * es) % 16 == 0) && (corner % (unsigned)es) == 0;
-    const bool inside = tbase >= alo && far_end <= ahi;
-    if (!no_tma && enc && aligned && inside && Xh < (1ll << 31)) {
-      cuuint64_t gdim[3] = {(cuuint64_t)Xh, (cuuint64_t)Yh, (cuuint64_t)Zh};
-      cuuint64_t gstr[2] = {(cuuint64_t)(P.gs1 * es), (cuuint64_t)((nd == 3 ? P.gs0 : P.gs1 * Yh) * es)};
+    const bool aligned = (P.gs1 * es) % 16 == 0 && (nd == 2 || ((P.gs0 * es) % 16 == 0 && P.gs0 > 0)) && (corner % (unsigned)es) == 0;
+    const bool inside = T.tbase >= alo && far_end <= ahi;
+    T.tma_ok = aligned && inside && T.Xh < (1ll << 31);
+  }
+  return 0;
+}
+
+// one line for rb200_describe_plan; false: not this kernel's form
+bool describe_stencil_tile(const rb200_fused_op* op, int sms, std::string* out) {
+  TilePlan T;
+  if (plan_stencil_tile(op, sms, T) != 0) return false;
+  const TileParams& P = T.P;
+  int n_chain_insns = 0, n_chain_steps = 0;
+  for (int i = 0; i < P.n_insns; ++i)
+    if ((P.insns[i].handler >> 2) == LO_CHAIN) {
+      ++n_chain_insns;
+      n_chain_steps += P.insns[i].c_arg;
+    }
+  char buf[400];
+  snprintf(buf, sizeof(buf),
+           "kernel=%s elem=%d box=%lldx%lldx%lld staged_views=%d halo=z%d+%d,y%d+%d,x%d+%d ring=%d loader=%s direct_views=%d lean_insns=%d "
+           "chains=%d chain_steps=%d terms=%d(f32:%d) items=%lld planes_per_item=%lld ctas=%lld smem=%zu",
+           P.n_terms > 0 ? "stencil_terms" : "stencil_tile", T.es, P.Z, P.Y, P.X, P.n_staged, P.hz_lo, P.hz - P.hz_lo, P.hy_lo, P.hy - P.hy_lo, P.hx_lo, P.hx - P.hx_lo, P.D,
+           !P.has_group ? "none" : (T.tma_ok ? "tma" : "cp.async"), P.n_direct, P.n_insns, n_chain_insns, n_chain_steps, P.n_terms, P.n32, P.n_items, P.ZC, T.blocks, T.smem);
+  *out = buf;
+  return true;
+}
+
+// 0: launched, 1: not eligible (caller falls back to the general interpreter), 2: error (*err set)
+int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, std::string* err) {
+  static const bool disabled = getenv("RB200_NO_TILE_KERNEL") != nullptr;  // debugging aid
+  if (disabled) return 1;
+  static TilePlan T;  // (large; launches are issued from one thread per process)
+  if (plan_stencil_tile(op, sms, T) != 0) return 1;
+  TileParams& P = T.P;
+  const int es = T.es, nd = T.nd;
+  const size_t smem = T.smem;
+  const long long blocks = T.blocks;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (P.has_group && T.tma_ok) {
+    static const bool no_tma = getenv("RB200_NO_TMA") != nullptr;  // debugging aid: always the cooperative loader
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!no_tma && enc) {
+      cuuint64_t gdim[3] = {(cuuint64_t)T.Xh, (cuuint64_t)T.Yh, (cuuint64_t)T.Zh};
+      cuuint64_t gstr[2] = {(cuuint64_t)(P.gs1 * es), (cuuint64_t)((nd == 3 ? P.gs0 : P.gs1 * T.Yh) * es)};
       cuuint32_t box[3] = {(cuuint32_t)kTilePX, (cuuint32_t)P.PY, 1};
       cuuint32_t estr[3] = {1, 1, 1};
-      const CUresult rc = enc(&tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)tbase, gdim, gstr, box,
+      const CUresult rc = enc(&tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)T.tbase, gdim, gstr, box,
                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (rc == CUDA_SUCCESS) {
         P.use_tma = 1;
-        P.tma_shift = shift;
+        P.tma_shift = T.shift;
       }
     }
   }
 
   cudaError_t e;
-  if (es == 8) {
-    static bool attr8 = false;
-    if (!attr8) {
-      cudaFuncSetAttribute(stencil_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      attr8 = true;
-    }
-    stencil_tile_kernel<double><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+  static bool attrs = false;
+  if (!attrs) {
+    cudaFuncSetAttribute(stencil_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(stencil_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(stencil_terms_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(stencil_terms_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attrs = true;
+  }
+  if (P.n_terms > 0) {
+    if (es == 8) stencil_terms_kernel<double><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+    else stencil_terms_kernel<float><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
   } else {
-    static bool attr4 = false;
-    if (!attr4) {
-      cudaFuncSetAttribute(stencil_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      attr4 = true;
-    }
-    stencil_tile_kernel<float><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+    if (es == 8) stencil_tile_kernel<double><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+    else stencil_tile_kernel<float><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -7,6 +7,7 @@ import sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 
+PLANS = []     # rb200_describe_plan() of every op list handed to the executor (which kernel the CUDA library would run)
 REJECTED = []  # (message, op list summary) of every op list the CUDA library's validation refused
 
 
@@ -39,6 +40,12 @@ def install():
 
     def run(fop, stream=None):
         _library_accepts(fop)
+        try:
+            from ramba_b200 import _cabi
+
+            PLANS.append(_cabi.describe_plan(fop))
+        except Exception as ex:  # library not built: test_cabi_exports complains about that
+            PLANS.append("unavailable: %s" % (ex,))
         return vm.run_deferred_ops(fop, stream)
 
     RT.set_test_executor(run, vm.reduce_partials, device="cpu", cumulative=vm.cumulative)

@@ -50,19 +50,21 @@ struct TileStagedOp {
 
 // ---- the "weighted shifted sum" form (ramba/ramba.py:8146-8188: `acc = U[o1+i] + U[o2+i] + ... ; V[i] = acc - c*U[..]`):
 // an op list that is ONE running value updated by views and scalars, with at most one float32 -> float64 promotion and
-// one store at the end, is flattened into term steps and run by stencil_terms_kernel (no dispatch tree, the running
-// value never leaves registers).  Same operations, same order, same classes, one rounding each.
-enum TermOp {
-  T_LOAD = 0, T_ADD, T_SUB, T_RSUB, T_MUL,  // acc (op) x        (x: a staged or direct view element)
-  T_MULADD, T_MULSUB, T_MULRSUB,            // acc + x*s, acc - x*s, x*s - acc   (product rounded first)
-  T_ADDS, T_SUBS, T_RSUBS, T_MULS,          // acc (op) s        (s: scalar)
-  T_NEG, T_LOADS
-};
+// one store at the end, is flattened into TERMS and run by stencil_terms_kernel: no dispatch tree, the running value never
+// leaves its registers.  Every term is   p = x*w | x | w   (x: element of a staged or direct view, w: scalar; the product
+// is rounded on its own) followed by   acc = p (first term),  acc = (+-acc) + (+-p),  acc = acc * p   or   acc = -acc.
+// Same operations, same order, same classes, one rounding each as in the op list:  a - b is a + (-b) exactly.
+enum TermKind { TK_SET = 0, TK_ADD = 1, TK_MUL = 2, TK_NEG = 3 };
 enum TermX { X_NONE = 0, X_STAGED = 1, X_DIRECT = 2 };
-struct TermStep {  // 8 bytes
-  unsigned char op, xkind, xidx, sidx;
-  unsigned short off;  // staged: byte offset of the operand inside a plane
-  unsigned char dzl, pad;
+enum TermFlags { TF_W = 1, TF_NEGP = 2, TF_NEGACC = 4 };
+struct TermStep {  // 8 bytes, one constant-bank load
+  unsigned char kind;   // TermKind
+  unsigned char xkind;  // TermX
+  unsigned char xidx;   // staged / direct index
+  unsigned char sidx;   // scalar index (TF_W)
+  unsigned short off;   // staged: byte offset of the operand inside a plane
+  unsigned char dzl;    // staged: plane of the ring
+  unsigned char flags;  // TermFlags
 };
 constexpr int kTileMaxTerms = 48;
 
@@ -362,66 +364,44 @@ __device__ __forceinline__ void term_steps(const TileParams& P, const TermCtx<TE
 #pragma unroll 1
   for (int s = s0; s < s1; ++s) {
     const TermStep t = P.terms[s];
-    F x[LV];
-    if (t.xkind != X_NONE) term_fetch<TE, F>(P, cx, t, x);
-    const u64 sbits = P.scal[t.sidx];
-    const F sc = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
-    switch (t.op) {
-      case T_LOAD:
+    if (t.kind == TK_NEG) {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = x[k];
-        break;
-      case T_ADD:
+      for (int k = 0; k < LV; ++k) acc[k] = -acc[k];
+      continue;
+    }
+    F p[LV];
+    F w = F(0);
+    if (t.flags & TF_W) {
+      const u64 sbits = P.scal[t.sidx];
+      w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
+    }
+    if (t.xkind != X_NONE) {
+      term_fetch<TE, F>(P, cx, t, p);
+      if (t.flags & TF_W) {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], x[k]);
-        break;
-      case T_SUB:
+        for (int k = 0; k < LV; ++k) p[k] = l_mul<F>(p[k], w);
+      }
+    } else {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], x[k]);
-        break;
-      case T_RSUB:
+      for (int k = 0; k < LV; ++k) p[k] = w;
+    }
+    if (t.kind == TK_ADD) {
+      if (t.flags & TF_NEGP) {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(x[k], acc[k]);
-        break;
-      case T_MUL:
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], p[k]);
+      } else if (t.flags & TF_NEGACC) {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_mul<F>(acc[k], x[k]);
-        break;
-      case T_MULADD:
+        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(p[k], acc[k]);
+      } else {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], l_mul<F>(x[k], sc));
-        break;
-      case T_MULSUB:
+        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], p[k]);
+      }
+    } else if (t.kind == TK_MUL) {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], l_mul<F>(x[k], sc));
-        break;
-      case T_MULRSUB:
+      for (int k = 0; k < LV; ++k) acc[k] = l_mul<F>(acc[k], p[k]);
+    } else {  // TK_SET
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(l_mul<F>(x[k], sc), acc[k]);
-        break;
-      case T_ADDS:
-#pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], sc);
-        break;
-      case T_SUBS:
-#pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], sc);
-        break;
-      case T_RSUBS:
-#pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(sc, acc[k]);
-        break;
-      case T_MULS:
-#pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_mul<F>(acc[k], sc);
-        break;
-      case T_NEG:
-#pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = -acc[k];
-        break;
-      default:  // T_LOADS
-#pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = sc;
+      for (int k = 0; k < LV; ++k) acc[k] = p[k];
     }
   }
 }
@@ -574,40 +554,49 @@ static long long floor_div(long long a, long long b) {  // b > 0
 }
 
 
-// Flatten translated lean instructions into term steps (see TermOp).  false: not of the weighted-shifted-sum form.
+// Flatten translated lean instructions into terms (see TermStep).  false: not of the weighted-shifted-sum form.
 static bool build_terms(TileParams& P, const LInsn* L, int n, bool staged_is_f32) {
   if (P.n_regs != 0 || n < 1) return false;
   int nt = 0, cls = -1, n32 = -1;
-  auto push = [&](int op, int kind, int arg, int sidx) -> bool {
+  auto is_view = [](int k) { return k == L_STAGED || k == L_DIRECT; };
+  // one term: p from (view operand, scalar operand) - either may be absent (kind L_NONE) but not both
+  auto push = [&](int kind, int vkind, int varg, int skind, int sarg, int flags) -> bool {
     if (nt >= kTileMaxTerms) return false;
     TermStep t;
     memset(&t, 0, sizeof(t));
-    t.op = (unsigned char)op;
-    t.sidx = (unsigned char)sidx;
-    if (kind == L_STAGED) {
-      if (cls == 1 && !staged_is_f32) return false;
-      t.xkind = X_STAGED;
-      t.xidx = (unsigned char)arg;
-      t.dzl = (unsigned char)P.staged[arg].dzl;
-      if (P.staged[arg].off > 0xffffu || P.staged[arg].dzl > 3) return false;
-      t.off = (unsigned short)P.staged[arg].off;
-    } else if (kind == L_DIRECT) {
-      t.xkind = X_DIRECT;
-      t.xidx = (unsigned char)arg;
-    } else {
-      t.xkind = X_NONE;
+    t.kind = (unsigned char)kind;
+    t.flags = (unsigned char)flags;
+    if (kind != TK_NEG) {
+      if (vkind == L_STAGED) {
+        if (cls == 1 && !staged_is_f32) return false;
+        if (P.staged[varg].off > 0xffffu || P.staged[varg].dzl > 3) return false;
+        t.xkind = X_STAGED;
+        t.xidx = (unsigned char)varg;
+        t.dzl = (unsigned char)P.staged[varg].dzl;
+        t.off = (unsigned short)P.staged[varg].off;
+      } else if (vkind == L_DIRECT) {
+        t.xkind = X_DIRECT;
+        t.xidx = (unsigned char)varg;
+      } else if (vkind != L_NONE) {
+        return false;
+      }
+      if (skind == L_SCAL) {
+        t.flags |= TF_W;
+        t.sidx = (unsigned char)sarg;
+      } else if (skind != L_NONE) {
+        return false;
+      }
+      if (t.xkind == X_NONE && !(t.flags & TF_W)) return false;
     }
     P.terms[nt++] = t;
     return true;
   };
-  auto is_view = [](int k) { return k == L_STAGED || k == L_DIRECT; };
-  // acc (op) operand
-  auto apply = [&](int viewop, int scalop, int kind, int arg) -> bool {
-    if (is_view(kind)) return push(viewop, kind, arg, 0);
-    if (kind == L_SCAL) return push(scalop, L_NONE, 0, arg);
+  // p = one operand (view or scalar)
+  auto one = [&](int kind, int okind, int oarg, int flags) -> bool {
+    if (is_view(okind)) return push(kind, okind, oarg, L_NONE, 0, flags);
+    if (okind == L_SCAL) return push(kind, L_NONE, 0, L_SCAL, oarg, flags);
     return false;
   };
-  auto load = [&](int kind, int arg) -> bool { return apply(T_LOAD, T_LOADS, kind, arg); };
   for (int i = 0; i < n; ++i) {
     const LInsn& I = L[i];
     const int lop = I.handler >> 2, f32 = (I.handler >> 1) & 1;
@@ -630,50 +619,53 @@ static bool build_terms(TileParams& P, const LInsn* L, int n, bool staged_is_f32
     const bool fresh = nt == 0;  // no running value yet: the instruction may start from its own operands
     switch (lop) {
       case LO_MOV:
-        if (!aacc && !(fresh && load(I.a_kind, I.a_arg))) return false;
+        if (!aacc && !(fresh && one(TK_SET, I.a_kind, I.a_arg, 0))) return false;
         break;
       case LO_NEG:
-        if (!aacc && !(fresh && load(I.a_kind, I.a_arg))) return false;
-        if (!push(T_NEG, L_NONE, 0, 0)) return false;
+        if (!aacc && !(fresh && one(TK_SET, I.a_kind, I.a_arg, 0))) return false;
+        if (!push(TK_NEG, L_NONE, 0, L_NONE, 0, 0)) return false;
         break;
       case LO_ADD:
       case LO_SUB:
       case LO_RSUB:
       case LO_MUL: {
-        if (!aacc && !(fresh && load(I.a_kind, I.a_arg))) return false;
-        const int vop = lop == LO_ADD ? T_ADD : lop == LO_SUB ? T_SUB : lop == LO_RSUB ? T_RSUB : T_MUL;
-        const int sop = lop == LO_ADD ? T_ADDS : lop == LO_SUB ? T_SUBS : lop == LO_RSUB ? T_RSUBS : T_MULS;
-        if (!apply(vop, sop, I.b_kind, I.b_arg)) return false;
+        if (!aacc && !(fresh && one(TK_SET, I.a_kind, I.a_arg, 0))) return false;
+        const int kind = lop == LO_MUL ? TK_MUL : TK_ADD;
+        const int fl = lop == LO_SUB ? TF_NEGP : lop == LO_RSUB ? TF_NEGACC : 0;
+        if (!one(kind, I.b_kind, I.b_arg, fl)) return false;
       } break;
       case LO_MULADD:
       case LO_MULSUB:
       case LO_MULRSUB: {
         // r = a + p, a - p, p - a  with p = b*c rounded first
-        const int with_view = lop == LO_MULADD ? T_MULADD : lop == LO_MULSUB ? T_MULSUB : T_MULRSUB;
+        const int fl = lop == LO_MULADD ? 0 : lop == LO_MULSUB ? TF_NEGP : TF_NEGACC;
         if (aacc) {
           if (is_view(I.b_kind) && I.c_kind == L_SCAL) {
-            if (!push(with_view, I.b_kind, I.b_arg, I.c_arg)) return false;
+            if (!push(TK_ADD, I.b_kind, I.b_arg, L_SCAL, I.c_arg, fl)) return false;
           } else if (is_view(I.c_kind) && I.b_kind == L_SCAL) {
-            if (!push(with_view, I.c_kind, I.c_arg, I.b_arg)) return false;
+            if (!push(TK_ADD, I.c_kind, I.c_arg, L_SCAL, I.b_arg, fl)) return false;
           } else {
             return false;
           }
           break;
         }
-        // the running value is (or becomes) the product; then `a` is folded in
+        // the running value is (or becomes) the product; then `a` is folded in: a + p, a - p (= -p + a), p - a
         if (I.b_kind == L_ACC || I.c_kind == L_ACC) {
           const int ok = I.b_kind == L_ACC ? I.c_kind : I.b_kind, oa = I.b_kind == L_ACC ? I.c_arg : I.b_arg;
-          if (!apply(T_MUL, T_MULS, ok, oa)) return false;
+          if (!one(TK_MUL, ok, oa, 0)) return false;
         } else {
           if (!fresh) return false;
-          // start from the view factor when there is one (x*s == s*x)
-          const bool bv = is_view(I.b_kind);
-          if (!load(bv ? I.b_kind : I.c_kind, bv ? I.b_arg : I.c_arg)) return false;
-          if (!apply(T_MUL, T_MULS, bv ? I.c_kind : I.b_kind, bv ? I.c_arg : I.b_arg)) return false;
+          if (is_view(I.b_kind) && I.c_kind == L_SCAL) {
+            if (!push(TK_SET, I.b_kind, I.b_arg, L_SCAL, I.c_arg, 0)) return false;
+          } else if (is_view(I.c_kind) && I.b_kind == L_SCAL) {
+            if (!push(TK_SET, I.c_kind, I.c_arg, L_SCAL, I.b_arg, 0)) return false;
+          } else {
+            if (!one(TK_SET, I.b_kind, I.b_arg, 0) || !one(TK_MUL, I.c_kind, I.c_arg, 0)) return false;
+          }
         }
-        const int vop = lop == LO_MULADD ? T_ADD : lop == LO_MULSUB ? T_RSUB : T_SUB;
-        const int sop = lop == LO_MULADD ? T_ADDS : lop == LO_MULSUB ? T_RSUBS : T_SUBS;
-        if (!apply(vop, sop, I.a_kind, I.a_arg)) return false;
+        // now acc = p;  MULADD: a + p -> acc + a;  MULSUB: a - p -> (-acc) + a;  MULRSUB: p - a -> acc - a
+        const int fl2 = lop == LO_MULADD ? 0 : lop == LO_MULSUB ? TF_NEGACC : TF_NEGP;
+        if (!one(TK_ADD, I.a_kind, I.a_arg, fl2)) return false;
       } break;
       default: return false;
     }
@@ -682,7 +674,6 @@ static bool build_terms(TileParams& P, const LInsn* L, int n, bool staged_is_f32
   P.out_view = L[n - 1].st_view;
   P.n_terms = nt;
   P.n32 = n32 >= 0 ? n32 : (cls == 1 ? nt : 0);
-  // (cls is the FINAL class: an op list that started in float32 and never promoted has n32 == nt)
   if (n32 < 0 && cls == 1 && !staged_is_f32) return false;
   return true;
 }

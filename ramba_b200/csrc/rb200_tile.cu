@@ -93,7 +93,9 @@ struct TileParams {
   LChainStep chain[kTileMaxChain];
   // term form (n_terms > 0): steps [0, n32) run in float32, steps [n32, n_terms) in float64
   int n_terms, n32, out_view;
+  int tv;  // elements per thread per plane of this launch (8, or 16 for the term kernel on float32 tiles): tile rows = tv * 2
   TermStep terms[kTileMaxTerms];
+  unsigned char term_run[kTileMaxTerms];  // > 0: this and the next term_run-1 terms are plain `acc (+|-)= staged x` of one sign
 };
 
 __device__ __forceinline__ void tma_load_3d(unsigned sdst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned mbar) {
@@ -328,21 +330,20 @@ __device__ __forceinline__ void tile_request(const TileParams& P, const CUtensor
   }
 }
 
-template <class TE> struct TermCtx {
-  unsigned tb0;            // byte offset of element k = 0 of this thread inside a plane
-  unsigned pa[4];          // shared-window address of the ring slot holding plane (z - hz_lo + d), d = 0..3
+template <class TE, int TV> struct TermCtx {
+  unsigned tb0;      // byte offset of element k = 0 of this thread inside a plane
+  unsigned table_s;  // shared-window address of the per-plane operand table (one 32-bit plane address per term)
   long long z, gy0, gx;
   unsigned valid;
 };
 
-template <class TE, class F>
-__device__ __forceinline__ void term_fetch(const TileParams& P, const TermCtx<TE>& cx, const TermStep t, F (&x)[LV]) {
+template <class TE, int TV, class F>
+__device__ __forceinline__ void term_fetch(const TileParams& P, const TermCtx<TE, TV>& cx, const TermStep t, int s, F (&x)[TV]) {
   constexpr unsigned kstep = (unsigned)(kTileRY * kTilePX * sizeof(TE));
   if (t.xkind == X_STAGED) {
-    const unsigned base = t.dzl == 0 ? cx.pa[0] : t.dzl == 1 ? cx.pa[1] : t.dzl == 2 ? cx.pa[2] : cx.pa[3];
-    const unsigned addr = base + t.off + cx.tb0;
+    const unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
 #pragma unroll
-    for (int k = 0; k < LV; ++k) x[k] = (F)lean_lds<TE>(addr + k * kstep);
+    for (int k = 0; k < TV; ++k) x[k] = (F)lean_lds<TE>(addr + k * kstep);
   } else {
     const LDirect& v = P.direct[t.xidx];
     const long long off = cx.z * v.s0 + cx.gy0 * v.s1 + cx.gx * v.s2;
@@ -350,115 +351,153 @@ __device__ __forceinline__ void term_fetch(const TileParams& P, const TermCtx<TE
     if (v.dtype == RB200_F32) {
       const float* p = reinterpret_cast<const float*>(v.base) + off;
 #pragma unroll
-      for (int k = 0; k < LV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<float>(p) : F(0);
+      for (int k = 0; k < TV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<float>(p) : F(0);
     } else {
       const double* p = reinterpret_cast<const double*>(v.base) + off;
 #pragma unroll
-      for (int k = 0; k < LV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<double>(p) : F(0);
+      for (int k = 0; k < TV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<double>(p) : F(0);
     }
   }
 }
 
-template <class TE, class F>
-__device__ __forceinline__ void term_steps(const TileParams& P, const TermCtx<TE>& cx, int s0, int s1, F (&acc)[LV]) {
+template <class TE, int TV, class F>
+__device__ __forceinline__ void term_steps(const TileParams& P, const TermCtx<TE, TV>& cx, int s0, int s1, F (&acc)[TV]) {
+  constexpr unsigned kstep = (unsigned)(kTileRY * kTilePX * sizeof(TE));
+  int s = s0;
 #pragma unroll 1
-  for (int s = s0; s < s1; ++s) {
+  while (s < s1) {
+    const int run = P.term_run[s];
+    if (run > 0) {
+      // the neighbour sum: `run` consecutive terms acc = acc (+|-) x over staged operands, nothing to decode per term
+      // but the operand's plane address (one broadcast shared-memory load)
+      const bool neg = (P.terms[s].flags & TF_NEGP) != 0;
+      const int e = s + run;
+      if (!neg) {
+#pragma unroll 1
+        for (; s < e; ++s) {
+          const unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
+#pragma unroll
+          for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], (F)lean_lds<TE>(addr + k * kstep));
+        }
+      } else {
+#pragma unroll 1
+        for (; s < e; ++s) {
+          const unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
+#pragma unroll
+          for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], (F)lean_lds<TE>(addr + k * kstep));
+        }
+      }
+      continue;
+    }
     const TermStep t = P.terms[s];
     if (t.kind == TK_NEG) {
 #pragma unroll
-      for (int k = 0; k < LV; ++k) acc[k] = -acc[k];
+      for (int k = 0; k < TV; ++k) acc[k] = -acc[k];
+      ++s;
       continue;
     }
-    F p[LV];
-    F w = F(0);
-    if (t.flags & TF_W) {
-      const u64 sbits = P.scal[t.sidx];
-      w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
-    }
+    F p[TV];
     if (t.xkind != X_NONE) {
-      term_fetch<TE, F>(P, cx, t, p);
+      term_fetch<TE, TV, F>(P, cx, t, s, p);
       if (t.flags & TF_W) {
+        const u64 sbits = P.scal[t.sidx];
+        const F w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
 #pragma unroll
-        for (int k = 0; k < LV; ++k) p[k] = l_mul<F>(p[k], w);
+        for (int k = 0; k < TV; ++k) p[k] = l_mul<F>(p[k], w);
       }
     } else {
+      const u64 sbits = P.scal[t.sidx];
+      const F w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
 #pragma unroll
-      for (int k = 0; k < LV; ++k) p[k] = w;
+      for (int k = 0; k < TV; ++k) p[k] = w;
     }
     if (t.kind == TK_ADD) {
       if (t.flags & TF_NEGP) {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(acc[k], p[k]);
+        for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], p[k]);
       } else if (t.flags & TF_NEGACC) {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_sub<F>(p[k], acc[k]);
+        for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(p[k], acc[k]);
       } else {
 #pragma unroll
-        for (int k = 0; k < LV; ++k) acc[k] = l_add<F>(acc[k], p[k]);
+        for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], p[k]);
       }
     } else if (t.kind == TK_MUL) {
 #pragma unroll
-      for (int k = 0; k < LV; ++k) acc[k] = l_mul<F>(acc[k], p[k]);
+      for (int k = 0; k < TV; ++k) acc[k] = l_mul<F>(acc[k], p[k]);
     } else {  // TK_SET
 #pragma unroll
-      for (int k = 0; k < LV; ++k) acc[k] = p[k];
+      for (int k = 0; k < TV; ++k) acc[k] = p[k];
     }
+    ++s;
   }
 }
 
-template <class TE, class F>
-__device__ __forceinline__ void term_store(const TileParams& P, const TermCtx<TE>& cx, const F (&acc)[LV]) {
+template <class TE, int TV, class F>
+__device__ __forceinline__ void term_store(const TileParams& P, const TermCtx<TE, TV>& cx, const F (&acc)[TV]) {
   const LDirect& v = P.direct[P.out_view];
   const long long off = cx.z * v.s0 + cx.gy0 * v.s1 + cx.gx * v.s2;
   const long long step = (long long)kTileRY * v.s1;
   if (v.dtype == RB200_F32) {
     float* p = reinterpret_cast<float*>(v.base) + off;
-    if (cx.valid == (1u << LV) - 1u) {
+    if (cx.valid == (1u << TV) - 1u) {
 #pragma unroll
-      for (int k = 0; k < LV; ++k, p += step) stg<float>(p, (float)acc[k]);
+      for (int k = 0; k < TV; ++k, p += step) stg<float>(p, (float)acc[k]);
     } else {
 #pragma unroll
-      for (int k = 0; k < LV; ++k, p += step)
+      for (int k = 0; k < TV; ++k, p += step)
         if ((cx.valid >> k) & 1u) stg<float>(p, (float)acc[k]);
     }
   } else {
     double* p = reinterpret_cast<double*>(v.base) + off;
-    if (cx.valid == (1u << LV) - 1u) {
+    if (cx.valid == (1u << TV) - 1u) {
 #pragma unroll
-      for (int k = 0; k < LV; ++k, p += step) stg<double>(p, (double)acc[k]);
+      for (int k = 0; k < TV; ++k, p += step) stg<double>(p, (double)acc[k]);
     } else {
 #pragma unroll
-      for (int k = 0; k < LV; ++k, p += step)
+      for (int k = 0; k < TV; ++k, p += step)
         if ((cx.valid >> k) & 1u) stg<double>(p, (double)acc[k]);
     }
   }
 }
 
-template <class TE>
+// TV elements per thread per plane: tile = 128 columns x 2*TV rows
+template <class TE, int TV>
 __global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid_constant__ TileParams P, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
   const unsigned tid = threadIdx.x;
-  const unsigned mbar_s = smem_s + (unsigned)P.D * P.plane_bytes;  // layout: [ring: D planes][mbarriers: D * 8]
+  // layout: [ring: D planes][operand table, double buffered by plane parity: 2 * kTileMaxTerms * 4][mbarriers: D * 8]
+  const unsigned table_s = smem_s + (unsigned)P.D * P.plane_bytes;
+  const unsigned mbar_s = table_s + 2u * kTileMaxTerms * 4u;
   if (P.has_group && tid == 0) {
     for (int s = 0; s < P.D; ++s) mbar_init(mbar_s + 8u * s, P.use_tma ? 1u : (unsigned)kThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  TermCtx<TE> cx;
+  TermCtx<TE, TV> cx;
+  cx.table_s = table_s;
   const int x = (int)(tid & (unsigned)(kTileTX - 1));
   const int yrow = (int)(tid >> kTileLogTX);
   cx.tb0 = (unsigned)((yrow * kTilePX + x) * (int)sizeof(TE));
   const int D = P.D, hz = P.hz;
-  int rq = 0;          // ring slot of the next plane to request
-  unsigned par = 0;    // bit s: parity of the next completion to wait for on slot s
+  constexpr int TY = TV * kTileRY;
+  int rq = 0;        // ring slot of the next plane to request
+  unsigned par = 0;  // bit s: parity of the next completion to wait for on slot s
+  // this thread's entry of the operand table (threads 0 .. n_terms-1): static part
+  unsigned my_off = 0;
+  int my_dzl = -1;
+  if ((int)tid < P.n_terms && P.terms[tid].xkind == X_STAGED) {
+    my_off = P.terms[tid].off;
+    my_dzl = P.terms[tid].dzl;
+  }
 
   for (long long item = blockIdx.x; item < P.n_items; item += gridDim.x) {
     const int tx = (int)(item % P.nxt);
     const long long r1 = item / P.nxt;
     const int ty = (int)(r1 % P.nyt);
     const long long zc = r1 / P.nyt;
-    const long long x0 = (long long)tx * kTileTX, y0 = (long long)ty * kTileTY;
+    const long long x0 = (long long)tx * kTileTX, y0 = (long long)ty * TY;
     const long long zb = zc * P.ZC;
     long long ze = zb + P.ZC;
     if (ze > P.Z) ze = P.Z;
@@ -467,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid
     unsigned valid = 0;
     if (cx.gx < P.X) {
 #pragma unroll
-      for (int k = 0; k < LV; ++k)
+      for (int k = 0; k < TV; ++k)
         if (cx.gy0 + (long long)k * kTileRY < P.Y) valid |= 1u << k;
     }
     cx.valid = valid;
@@ -495,36 +534,41 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid
         }
         mbar_wait(mbar_s + 8u * (unsigned)sl, (par >> sl) & 1u);  // the newest plane, z + hz_hi
         par ^= 1u << sl;
-        __syncthreads();  // plane z - 1 - hz_lo is free now: its slot takes the plane after the newest
+        if (my_dzl >= 0) {  // where this plane's copy of my term's operand starts
+          int q = cur + my_dzl;
+          if (q >= D) q -= D;
+          // (two tables: a thread that is still computing plane z - 1 reads the other one)
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(table_s + ((unsigned)z & 1u) * (kTileMaxTerms * 4u) + 4u * tid),
+                       "r"(smem_s + (unsigned)q * P.plane_bytes + my_off)
+                       : "memory");
+        }
+        __syncthreads();  // plane z - 1 - hz_lo is free now: its slot takes the plane after the newest; the table is visible
         if (z + 1 < ze) {
           tile_request<TE>(P, &tmap, smem_s, mbar_s, (unsigned)rq, x0, y0, z + 1 + hz, tid);
           rq = rq + 1 == D ? 0 : rq + 1;
         }
-        int q = cur;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          cx.pa[d] = smem_s + (unsigned)q * P.plane_bytes;
-          q = q + 1 == D ? 0 : q + 1;
-        }
         cur = cur + 1 == D ? 0 : cur + 1;
       }
       cx.z = z;
+      cx.table_s = table_s + ((unsigned)z & 1u) * (kTileMaxTerms * 4u);
       if (P.n32 > 0) {
-        float a32[LV];
-        if constexpr (sizeof(TE) == 4) term_steps<TE, float>(P, cx, 0, P.n32, a32);
-        if (P.n_terms > P.n32) {
-          double a64[LV];
+        if constexpr (sizeof(TE) == 4) {
+          float a32[TV];
+          term_steps<TE, TV, float>(P, cx, 0, P.n32, a32);
+          if (P.n_terms > P.n32) {
+            double a64[TV];
 #pragma unroll
-          for (int k = 0; k < LV; ++k) a64[k] = (double)a32[k];
-          term_steps<TE, double>(P, cx, P.n32, P.n_terms, a64);
-          term_store<TE, double>(P, cx, a64);
-        } else {
-          term_store<TE, float>(P, cx, a32);
+            for (int k = 0; k < TV; ++k) a64[k] = (double)a32[k];
+            term_steps<TE, TV, double>(P, cx, P.n32, P.n_terms, a64);
+            term_store<TE, TV, double>(P, cx, a64);
+          } else {
+            term_store<TE, TV, float>(P, cx, a32);
+          }
         }
       } else {
-        double a64[LV];
-        term_steps<TE, double>(P, cx, 0, P.n_terms, a64);
-        term_store<TE, double>(P, cx, a64);
+        double a64[TV];
+        term_steps<TE, TV, double>(P, cx, 0, P.n_terms, a64);
+        term_store<TE, TV, double>(P, cx, a64);
       }
     }
   }
@@ -806,16 +850,11 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
     P.safe_hi = shi;
   }
 
-  // ---- tile geometry
-  const int TX = kTileTX;
-  P.nxt = (int)((P.X + TX - 1) / TX);
-  P.nyt = (int)((P.Y + kTileTY - 1) / kTileTY);
+  // ---- staged operands: plane of the ring and byte offset inside a plane (rows of kTilePX elements)
   if (P.has_group) {
-    if (TX + P.hx > kTilePX) return 1;
-    P.PY = kTileTY + P.hy;
+    if (kTileTX + P.hx > kTilePX) return 1;
     P.D = P.hz + 2;
-    if (P.D > kTileMaxRing || P.PY > 256) return 1;
-    P.plane_bytes = (unsigned)(((size_t)kTilePX * P.PY * es + 127) / 128 * 128);
+    if (P.D > kTileMaxRing || P.hz > 3) return 1;
     for (int j = 0; j < P.n_staged; ++j) {
       P.staged[j].dzl = (int)(mdz[j] + P.hz_lo);
       P.staged[j].off = (unsigned)(((mdy[j] + P.hy_lo) * kTilePX + (mdx[j] + P.hx_lo)) * es);
@@ -838,14 +877,43 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
   P.n_regs = op->n_regs;
   lean_translate(op, view_kind, view_arg, store_arg, P.insns);
   static const bool no_terms = getenv("RB200_NO_TERMS_KERNEL") != nullptr;  // debugging aid: always the general tile kernel
+  P.tv = LV;
   if (no_terms || !build_terms(P, P.insns, P.n_insns, es == 4)) {
     P.n_terms = 0;
     int n_chain = 0;
     P.n_insns = lean_fuse_chains(P.insns, P.n_insns, P.chain, kTileMaxChain, &n_chain);
+  } else {
+    // runs of plain `acc (+|-)= staged x` terms of one sign (the neighbour sum): the kernel walks them without decoding
+    for (int i = 0; i < P.n_terms;) {
+      auto plain = [&](int q) {
+        const TermStep& t = P.terms[q];
+        return t.kind == TK_ADD && t.xkind == X_STAGED && (t.flags & ~TF_NEGP) == 0;
+      };
+      if (!plain(i)) {
+        ++i;
+        continue;
+      }
+      int j = i + 1;
+      while (j < P.n_terms && plain(j) && P.terms[j].flags == P.terms[i].flags && (j < P.n32) == (i < P.n32) && j - i < 250) ++j;
+      P.term_run[i] = (unsigned char)(j - i);
+      i = j;
+    }
+    // float32 tiles: 16 elements per thread (tile of 32 rows) halve the per-term and per-plane fixed cost per element
+    static const bool tv8 = getenv("RB200_TERMS_TV8") != nullptr;  // debugging aid
+    if (es == 4 && !tv8) P.tv = 16;
   }
   for (int i = 0; i < op->n_scalars; ++i) P.scal[i] = op->scalars[i];
 
-  const size_t smem = (size_t)P.D * P.plane_bytes + (P.n_terms > 0 ? 0 : (size_t)P.n_regs * LV * kThreads * 8) + (size_t)P.D * 8 + 16;
+  // ---- tile geometry: 128 columns x (2 * tv) rows
+  const int TX = kTileTX, TYr = P.tv * kTileRY;
+  P.nxt = (int)((P.X + TX - 1) / TX);
+  P.nyt = (int)((P.Y + TYr - 1) / TYr);
+  if (P.has_group) {
+    P.PY = TYr + P.hy;
+    if (P.PY > 256) return 1;
+    P.plane_bytes = (unsigned)(((size_t)kTilePX * P.PY * es + 127) / 128 * 128);
+  }
+  const size_t smem = (size_t)P.D * P.plane_bytes + (P.n_terms > 0 ? (size_t)2 * kTileMaxTerms * 4 : (size_t)P.n_regs * LV * kThreads * 8) + (size_t)P.D * 8 + 16;
   if (smem > 100 * 1024) return 1;  // (two CTAs per SM)
 
   // ---- work items: z chunks so that every CTA of the persistent grid gets several
@@ -897,9 +965,9 @@ bool describe_stencil_tile(const rb200_fused_op* op, int sms, std::string* out) 
   char buf[400];
   snprintf(buf, sizeof(buf),
            "kernel=%s elem=%d box=%lldx%lldx%lld staged_views=%d halo=z%d+%d,y%d+%d,x%d+%d ring=%d loader=%s direct_views=%d lean_insns=%d "
-           "chains=%d chain_steps=%d terms=%d(f32:%d) items=%lld planes_per_item=%lld ctas=%lld smem=%zu",
+           "chains=%d chain_steps=%d terms=%d(f32:%d) tile=128x%d items=%lld planes_per_item=%lld ctas=%lld smem=%zu",
            P.n_terms > 0 ? "stencil_terms" : "stencil_tile", T.es, P.Z, P.Y, P.X, P.n_staged, P.hz_lo, P.hz - P.hz_lo, P.hy_lo, P.hy - P.hy_lo, P.hx_lo, P.hx - P.hx_lo, P.D,
-           !P.has_group ? "none" : (T.tma_ok ? "tma" : "cp.async"), P.n_direct, P.n_insns, n_chain_insns, n_chain_steps, P.n_terms, P.n32, P.n_items, P.ZC, T.blocks, T.smem);
+           !P.has_group ? "none" : (T.tma_ok ? "tma" : "cp.async"), P.n_direct, P.n_insns, n_chain_insns, n_chain_steps, P.n_terms, P.n32, P.tv * kTileRY, P.n_items, P.ZC, T.blocks, T.smem);
   *out = buf;
   return true;
 }
@@ -939,13 +1007,15 @@ int launch_stencil_tile(const rb200_fused_op* op, int sms, cudaStream_t stream, 
   if (!attrs) {
     cudaFuncSetAttribute(stencil_tile_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaFuncSetAttribute(stencil_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(stencil_terms_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(stencil_terms_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(stencil_terms_kernel<double, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(stencil_terms_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(stencil_terms_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     attrs = true;
   }
   if (P.n_terms > 0) {
-    if (es == 8) stencil_terms_kernel<double><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
-    else stencil_terms_kernel<float><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+    if (es == 8) stencil_terms_kernel<double, 8><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+    else if (P.tv == 16) stencil_terms_kernel<float, 16><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
+    else stencil_terms_kernel<float, 8><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
   } else {
     if (es == 8) stencil_tile_kernel<double><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);
     else stencil_tile_kernel<float><<<(unsigned)blocks, kThreads, smem, stream>>>(P, tmap);

@@ -42,6 +42,7 @@ constexpr int kTileMaxRing = 8;
 // (halo <= 16 columns in total) and 16 + halo rows high
 constexpr int kTileTX = 128, kTileLogTX = 7, kTileRY = kThreads / kTileTX, kTileTY = LV * kTileRY, kTilePX = 144;
 constexpr int kTileMaxChain = 64;
+constexpr int kTilePrefetch = 2;  // planes requested ahead of the one being computed (1 when the ring would not fit)
 
 struct TileStagedOp {
   int dzl;           // plane of the ring relative to the oldest needed plane (0 .. hz)
@@ -76,7 +77,7 @@ struct TileParams {
   // staged group
   int has_group, use_tma, elem;
   int hz_lo, hz, hy_lo, hy, hx_lo, hx;  // halos: lo part and total (lo + hi)
-  int PY, D;                             // rows of the plane box (kTilePX columns) and ring depth
+  int PY, D, prefetch;                   // rows of the plane box (kTilePX columns), ring depth, planes requested ahead
   unsigned plane_bytes;
   const char* gcorner;                   // address of group element (z = -hz_lo, y = -hy_lo, x = -hx_lo)
   long long gs0, gs1;                    // group strides (elements) of z and y; x stride is 1
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
     unsigned fill0 = fills;  // fill index of plane zb (halo coordinate zb)
     if (P.has_group) {
       __syncthreads();  // every thread is done with the planes of the previous item
-      for (int p = 0; p <= P.hz; ++p) request(zb + p);
+      for (int p = 0; p < P.hz + P.prefetch && p < (int)(ze - zb) + P.hz; ++p) request(zb + p);
     }
     for (long long z = zb; z < ze; ++z) {
       if (P.has_group) {
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_tile_kernel(const __grid_
         }
         mbar_wait(mbar_s + 8u * (newest % (unsigned)P.D), (newest / (unsigned)P.D) & 1u);
         __syncthreads();  // plane z - 1 - hz_lo is free now: its slot takes the plane after the newest
-        if (z + 1 < ze) request(z + 1 + P.hz);
+        if (z + P.prefetch < ze) request(z + P.hz + P.prefetch);
         cx.fb = (int)((fill0 + (unsigned)(z - zb)) % (unsigned)P.D);
       }
       cx.z = z;
@@ -372,20 +373,32 @@ __device__ __forceinline__ void term_steps(const TileParams& P, const TermCtx<TE
       // but the operand's plane address (one broadcast shared-memory load)
       const bool neg = (P.terms[s].flags & TF_NEGP) != 0;
       const int e = s + run;
-      if (!neg) {
-#pragma unroll 1
-        for (; s < e; ++s) {
-          const unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
+      // (the next operand's address and values are fetched before the current ones are added: the loads of term j+1
+      // overlap the additions of term j)
+      unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
+      TE xv[TV];
 #pragma unroll
-          for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], (F)lean_lds<TE>(addr + k * kstep));
-        }
-      } else {
+      for (int k = 0; k < TV; ++k) xv[k] = lean_lds<TE>(addr + k * kstep);
 #pragma unroll 1
-        for (; s < e; ++s) {
-          const unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
+      for (; s < e; ++s) {
+        TE xn[TV];
+        if (s + 1 < e) {
+          addr = lds32(cx.table_s + 4u * (unsigned)(s + 1)) + cx.tb0;
 #pragma unroll
-          for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], (F)lean_lds<TE>(addr + k * kstep));
+          for (int k = 0; k < TV; ++k) xn[k] = lean_lds<TE>(addr + k * kstep);
+        } else {
+#pragma unroll
+          for (int k = 0; k < TV; ++k) xn[k] = TE(0);
         }
+        if (!neg) {
+#pragma unroll
+          for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], (F)xv[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], (F)xv[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < TV; ++k) xv[k] = xn[k];
       }
       continue;
     }
@@ -437,26 +450,28 @@ template <class TE, int TV, class F>
 __device__ __forceinline__ void term_store(const TileParams& P, const TermCtx<TE, TV>& cx, const F (&acc)[TV]) {
   const LDirect& v = P.direct[P.out_view];
   const long long off = cx.z * v.s0 + cx.gy0 * v.s1 + cx.gx * v.s2;
-  const long long step = (long long)kTileRY * v.s1;
+  const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
   if (v.dtype == RB200_F32) {
-    float* p = reinterpret_cast<float*>(v.base) + off;
-    if (cx.valid == (1u << TV) - 1u) {
+    char* p = v.base + off * 4;
+    const long long step = (long long)kTileRY * v.s1 * 4;  // bytes
+    if (full) {
 #pragma unroll
-      for (int k = 0; k < TV; ++k, p += step) stg<float>(p, (float)acc[k]);
+      for (int k = 0; k < TV; ++k, p += step) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < TV; ++k, p += step)
-        if ((cx.valid >> k) & 1u) stg<float>(p, (float)acc[k]);
+        if ((cx.valid >> k) & 1u) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
     }
   } else {
-    double* p = reinterpret_cast<double*>(v.base) + off;
-    if (cx.valid == (1u << TV) - 1u) {
+    char* p = v.base + off * 8;
+    const long long step = (long long)kTileRY * v.s1 * 8;
+    if (full) {
 #pragma unroll
-      for (int k = 0; k < TV; ++k, p += step) stg<double>(p, (double)acc[k]);
+      for (int k = 0; k < TV; ++k, p += step) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < TV; ++k, p += step)
-        if ((cx.valid >> k) & 1u) stg<double>(p, (double)acc[k]);
+        if ((cx.valid >> k) & 1u) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
     }
   }
 }
@@ -513,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid
     int cur = rq;  // slot of plane (zb - hz_lo)
     if (P.has_group) {
       __syncthreads();  // every thread is done with the planes of the previous item
-      for (int p = 0; p <= hz; ++p) {
+      for (int p = 0; p < hz + P.prefetch && p < (int)(ze - zb) + hz; ++p) {
         tile_request<TE>(P, &tmap, smem_s, mbar_s, (unsigned)rq, x0, y0, zb + p, tid);
         rq = rq + 1 == D ? 0 : rq + 1;
       }
@@ -543,8 +558,8 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid
                        : "memory");
         }
         __syncthreads();  // plane z - 1 - hz_lo is free now: its slot takes the plane after the newest; the table is visible
-        if (z + 1 < ze) {
-          tile_request<TE>(P, &tmap, smem_s, mbar_s, (unsigned)rq, x0, y0, z + 1 + hz, tid);
+        if (z + P.prefetch < ze) {
+          tile_request<TE>(P, &tmap, smem_s, mbar_s, (unsigned)rq, x0, y0, z + hz + P.prefetch, tid);
           rq = rq + 1 == D ? 0 : rq + 1;
         }
         cur = cur + 1 == D ? 0 : cur + 1;
@@ -853,8 +868,7 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
   // ---- staged operands: plane of the ring and byte offset inside a plane (rows of kTilePX elements)
   if (P.has_group) {
     if (kTileTX + P.hx > kTilePX) return 1;
-    P.D = P.hz + 2;
-    if (P.D > kTileMaxRing || P.hz > 3) return 1;
+    if (P.hz > 3) return 1;
     for (int j = 0; j < P.n_staged; ++j) {
       P.staged[j].dzl = (int)(mdz[j] + P.hz_lo);
       P.staged[j].off = (unsigned)(((mdy[j] + P.hy_lo) * kTilePX + (mdx[j] + P.hx_lo)) * es);
@@ -908,12 +922,18 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
   const int TX = kTileTX, TYr = P.tv * kTileRY;
   P.nxt = (int)((P.X + TX - 1) / TX);
   P.nyt = (int)((P.Y + TYr - 1) / TYr);
+  const size_t other = (P.n_terms > 0 ? (size_t)2 * kTileMaxTerms * 4 : (size_t)P.n_regs * LV * kThreads * 8) + kTileMaxRing * 8 + 16;
   if (P.has_group) {
     P.PY = TYr + P.hy;
     if (P.PY > 256) return 1;
     P.plane_bytes = (unsigned)(((size_t)kTilePX * P.PY * es + 127) / 128 * 128);
+    // ring = planes in use (hz + 1) + planes in flight; two in flight when that still leaves room for two CTAs per SM
+    P.prefetch = kTilePrefetch;
+    while (P.prefetch > 1 && (size_t)(P.hz + 1 + P.prefetch) * P.plane_bytes + other > 100 * 1024) --P.prefetch;
+    P.D = P.hz + 1 + P.prefetch;
+    if (P.D > kTileMaxRing) return 1;
   }
-  const size_t smem = (size_t)P.D * P.plane_bytes + (P.n_terms > 0 ? (size_t)2 * kTileMaxTerms * 4 : (size_t)P.n_regs * LV * kThreads * 8) + (size_t)P.D * 8 + 16;
+  const size_t smem = (size_t)P.D * P.plane_bytes + other;
   if (smem > 100 * 1024) return 1;  // (two CTAs per SM)
 
   // ---- work items: z chunks so that every CTA of the persistent grid gets several

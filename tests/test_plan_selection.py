@@ -33,7 +33,7 @@ def test_laplacian_runs_on_the_term_kernel_with_tma(plans):
     rb.sync()
     d = _last(plans, "kernel=stencil_terms")
     # (halos are counted from the first staged view, U[:-2, 1:-1, 1:-1]: two planes ahead, one row / column either side)
-    assert d["staged_views"] == "7" and d["halo"] == "z0+2,y1+1,x1+1" and d["loader"] == "tma" and d["ring"] == "4"
+    assert d["staged_views"] == "7" and d["halo"] == "z0+2,y1+1,x1+1" and d["loader"] == "tma" and d["ring"] == "5"
     assert d["terms"] == "7(f32:6)" and d["direct_views"] == "1"
 
 

@@ -94,6 +94,7 @@ struct TileParams {
   LChainStep chain[kTileMaxChain];
   // term form (n_terms > 0): steps [0, n32) run in float32, steps [n32, n_terms) in float64
   int n_terms, n32, out_view;
+  int fast_tail;  // the float64 phase is exactly one `acc (+|-) w*x` term over a staged operand
   int tv;  // elements per thread per plane of this launch (8, or 16 for the term kernel on float32 tiles): tile rows = tv * 2
   TermStep terms[kTileMaxTerms];
   unsigned char term_run[kTileMaxTerms];  // > 0: this and the next term_run-1 terms are plain `acc (+|-)= staged x` of one sign
@@ -373,32 +374,20 @@ __device__ __forceinline__ void term_steps(const TileParams& P, const TermCtx<TE
       // but the operand's plane address (one broadcast shared-memory load)
       const bool neg = (P.terms[s].flags & TF_NEGP) != 0;
       const int e = s + run;
-      // (the next operand's address and values are fetched before the current ones are added: the loads of term j+1
-      // overlap the additions of term j)
-      unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
-      TE xv[TV];
-#pragma unroll
-      for (int k = 0; k < TV; ++k) xv[k] = lean_lds<TE>(addr + k * kstep);
+      if (!neg) {
 #pragma unroll 1
-      for (; s < e; ++s) {
-        TE xn[TV];
-        if (s + 1 < e) {
-          addr = lds32(cx.table_s + 4u * (unsigned)(s + 1)) + cx.tb0;
+        for (; s < e; ++s) {
+          const unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
 #pragma unroll
-          for (int k = 0; k < TV; ++k) xn[k] = lean_lds<TE>(addr + k * kstep);
-        } else {
-#pragma unroll
-          for (int k = 0; k < TV; ++k) xn[k] = TE(0);
+          for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], (F)lean_lds<TE>(addr + k * kstep));
         }
-        if (!neg) {
+      } else {
+#pragma unroll 1
+        for (; s < e; ++s) {
+          const unsigned addr = lds32(cx.table_s + 4u * (unsigned)s) + cx.tb0;
 #pragma unroll
-          for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], (F)xv[k]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], (F)xv[k]);
+          for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], (F)lean_lds<TE>(addr + k * kstep));
         }
-#pragma unroll
-        for (int k = 0; k < TV; ++k) xv[k] = xn[k];
       }
       continue;
     }
@@ -446,39 +435,37 @@ __device__ __forceinline__ void term_steps(const TileParams& P, const TermCtx<TE
   }
 }
 
-template <class TE, int TV, class F>
-__device__ __forceinline__ void term_store(const TileParams& P, const TermCtx<TE, TV>& cx, const F (&acc)[TV]) {
-  const LDirect& v = P.direct[P.out_view];
-  const long long off = cx.z * v.s0 + cx.gy0 * v.s1 + cx.gx * v.s2;
-  const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
-  if (v.dtype == RB200_F32) {
-    char* p = v.base + off * 4;
-    const long long step = (long long)kTileRY * v.s1 * 4;  // bytes
+// store the thread's TV results: `p` = address of element k = 0 in the output view, `step` = bytes between elements k and k+1
+template <int TV, class F>
+__device__ __forceinline__ void term_store(char* p, long long step, int dtype, unsigned valid, const F (&acc)[TV]) {
+  const bool full = valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
+  if (dtype == RB200_F32) {
     if (full) {
 #pragma unroll
       for (int k = 0; k < TV; ++k, p += step) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < TV; ++k, p += step)
-        if ((cx.valid >> k) & 1u) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
+        if ((valid >> k) & 1u) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
     }
   } else {
-    char* p = v.base + off * 8;
-    const long long step = (long long)kTileRY * v.s1 * 8;
     if (full) {
 #pragma unroll
       for (int k = 0; k < TV; ++k, p += step) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < TV; ++k, p += step)
-        if ((cx.valid >> k) & 1u) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
+        if ((valid >> k) & 1u) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
     }
   }
 }
 
 // TV elements per thread per plane: tile = 128 columns x 2*TV rows
 template <class TE, int TV>
-__global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid_constant__ TileParams P, const __grid_constant__ CUtensorMap tmap) {
+#ifndef RB200_TERMS_MINB
+#define RB200_TERMS_MINB 3
+#endif
+__global__ void __launch_bounds__(kThreads, (TV == 8 && sizeof(TE) == 4) ? RB200_TERMS_MINB : 2) stencil_terms_kernel(const __grid_constant__ TileParams P, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
   const unsigned tid = threadIdx.x;
@@ -525,6 +512,11 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid
         if (cx.gy0 + (long long)k * kTileRY < P.Y) valid |= 1u << k;
     }
     cx.valid = valid;
+    // output: address of this thread's element k = 0 of plane zb, advanced by one plane per iteration
+    const LDirect& ov = P.direct[P.out_view];
+    const int oes = ov.dtype == RB200_F64 ? 8 : 4;
+    char* optr = ov.base + (zb * ov.s0 + cx.gy0 * ov.s1 + cx.gx * ov.s2) * oes;
+    const long long ostep = (long long)kTileRY * ov.s1 * oes, oplane = ov.s0 * oes;
     int cur = rq;  // slot of plane (zb - hz_lo)
     if (P.has_group) {
       __syncthreads();  // every thread is done with the planes of the previous item
@@ -568,23 +560,42 @@ __global__ void __launch_bounds__(kThreads, 2) stencil_terms_kernel(const __grid
       cx.table_s = table_s + ((unsigned)z & 1u) * (kTileMaxTerms * 4u);
       if (P.n32 > 0) {
         if constexpr (sizeof(TE) == 4) {
+          constexpr unsigned kstep = (unsigned)(kTileRY * kTilePX * sizeof(TE));
           float a32[TV];
           term_steps<TE, TV, float>(P, cx, 0, P.n32, a32);
-          if (P.n_terms > P.n32) {
+          if (P.fast_tail) {
+            // the usual end of a stencil: ONE weighted staged term in float64 (`acc -+ w*x`), then the store
+            const TermStep t = P.terms[P.n32];
+            const double w = __longlong_as_double((long long)P.scal[t.sidx]);
+            const unsigned addr = lds32(cx.table_s + 4u * (unsigned)P.n32) + cx.tb0;
+            double r[TV];
+            if (t.flags & TF_NEGP) {
+#pragma unroll
+              for (int k = 0; k < TV; ++k) r[k] = __dsub_rn((double)a32[k], __dmul_rn((double)lean_lds<TE>(addr + k * kstep), w));
+            } else if (t.flags & TF_NEGACC) {
+#pragma unroll
+              for (int k = 0; k < TV; ++k) r[k] = __dsub_rn(__dmul_rn((double)lean_lds<TE>(addr + k * kstep), w), (double)a32[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < TV; ++k) r[k] = __dadd_rn((double)a32[k], __dmul_rn((double)lean_lds<TE>(addr + k * kstep), w));
+            }
+            term_store<TV, double>(optr, ostep, ov.dtype, cx.valid, r);
+          } else if (P.n_terms > P.n32) {
             double a64[TV];
 #pragma unroll
             for (int k = 0; k < TV; ++k) a64[k] = (double)a32[k];
             term_steps<TE, TV, double>(P, cx, P.n32, P.n_terms, a64);
-            term_store<TE, TV, double>(P, cx, a64);
+            term_store<TV, double>(optr, ostep, ov.dtype, cx.valid, a64);
           } else {
-            term_store<TE, TV, float>(P, cx, a32);
+            term_store<TV, float>(optr, ostep, ov.dtype, cx.valid, a32);
           }
         }
       } else {
         double a64[TV];
         term_steps<TE, TV, double>(P, cx, 0, P.n_terms, a64);
-        term_store<TE, TV, double>(P, cx, a64);
+        term_store<TV, double>(optr, ostep, ov.dtype, cx.valid, a64);
       }
+      optr += oplane;
     }
   }
 }
@@ -912,9 +923,13 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
       P.term_run[i] = (unsigned char)(j - i);
       i = j;
     }
+    if (P.n32 > 0 && P.n_terms == P.n32 + 1) {
+      const TermStep& t = P.terms[P.n32];
+      P.fast_tail = t.kind == TK_ADD && t.xkind == X_STAGED && (t.flags & TF_W) != 0 ? 1 : 0;
+    }
     // float32 tiles: 16 elements per thread (tile of 32 rows) halve the per-term and per-plane fixed cost per element
-    static const bool tv8 = getenv("RB200_TERMS_TV8") != nullptr;  // debugging aid
-    if (es == 4 && !tv8) P.tv = 16;
+    static const bool tv8 = getenv("RB200_TERMS_TV16") != nullptr;  // debugging aid: 16 elements per thread, 2 CTAs per SM
+    if (es == 4 && tv8) P.tv = 16;  // (measured: 8 elements per thread at 3 CTAs per SM beat 16 at 2: 2.18 vs 2.39 ms on 1024^3)
   }
   for (int i = 0; i < op->n_scalars; ++i) P.scal[i] = op->scalars[i];
 
@@ -928,7 +943,8 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
     if (P.PY > 256) return 1;
     P.plane_bytes = (unsigned)(((size_t)kTilePX * P.PY * es + 127) / 128 * 128);
     // ring = planes in use (hz + 1) + planes in flight; two in flight when that still leaves room for two CTAs per SM
-    P.prefetch = kTilePrefetch;
+    static const int pf_env = getenv("RB200_TILE_PREFETCH") ? atoi(getenv("RB200_TILE_PREFETCH")) : 0;  // debugging aid
+    P.prefetch = pf_env >= 1 && pf_env <= 4 ? pf_env : kTilePrefetch;
     while (P.prefetch > 1 && (size_t)(P.hz + 1 + P.prefetch) * P.plane_bytes + other > 100 * 1024) --P.prefetch;
     P.D = P.hz + 1 + P.prefetch;
     if (P.D > kTileMaxRing) return 1;
@@ -937,7 +953,7 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
   if (smem > 100 * 1024) return 1;  // (two CTAs per SM)
 
   // ---- work items: z chunks so that every CTA of the persistent grid gets several
-  const long long grid_cap = (long long)sms * 2;
+  const long long grid_cap = (long long)sms * ((P.n_terms > 0 && P.tv == 8 && es == 4 && smem <= (220 * 1024) / RB200_TERMS_MINB - 1024) ? RB200_TERMS_MINB : 2);
   const long long xy = (long long)P.nxt * P.nyt;
   long long want_chunks = (grid_cap * 6 + xy - 1) / xy;
   if (want_chunks < 1) want_chunks = 1;

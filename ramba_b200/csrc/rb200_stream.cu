@@ -26,6 +26,7 @@
 #include "rb200_launch.h"
 #include "rb200_lean.cuh"
 #include "rb200_lean_plan.h"
+#include "rb200_terms.h"
 
 namespace rb200 {
 
@@ -63,7 +64,13 @@ struct StreamParams {
   KRed reds[RB200_MAX_REDS];
   u64* red_partials;
   unsigned int* red_counter;
+  // term form (n_terms > 0, stream_terms_kernel): tile = tv * 256 elements; steps [0, n32) in float32, the rest in float64
+  int tv, n_terms, n32;
+  int n_thoist;                      // column mode: row-broadcast operands copied once per CTA into shared memory
+  int thoist_direct[kStreamMaxStaged];
+  TermStep terms[kMaxTerms];
 };
+constexpr int X_HOIST = 3;  // TermStep.xkind of the streaming kernel: element of a hoisted (row-broadcast) operand
 
 struct StreamCtx {
   const StreamParams& P;
@@ -171,6 +178,70 @@ struct StreamCtx {
     }
   }
 };
+
+// global reductions of a CTA's float64 accumulators: thread -> warp -> CTA -> per-CTA partial -> last CTA (fixed order,
+// deterministic per grid); red[0,..] = red[0,..] (op) acc (ramba/ramba.py:5805-5806)
+__device__ __forceinline__ void stream_finish_reductions(const StreamParams& P, const double (&racc)[RB200_MAX_REDS]) {
+  // ---- global reductions: thread -> warp -> CTA -> per-CTA partial -> last CTA (fixed order, deterministic per grid)
+  if (P.n_reds > 0) {
+    __shared__ u64 wpart[RB200_MAX_REDS][kThreads / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s = 0; s < P.n_reds; ++s) {
+      const int op = P.reds[s].op;
+      double mine = 0.0;
+#pragma unroll
+      for (int q = 0; q < RB200_MAX_REDS; ++q)
+        if (q == s) mine = racc[q];
+      u64 v = CT<double>::bits(mine);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, RB200_T_F64, v, __shfl_down_sync(0xffffffffu, v, o));
+      if (lane == 0) wpart[s][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < P.n_reds; ++s) {
+        const int op = P.reds[s].op;
+        u64 v = wpart[s][0];
+        for (int q = 1; q < kThreads / 32; ++q) v = red_combine_bits(op, RB200_T_F64, v, wpart[s][q]);
+        P.red_partials[(long long)s * gridDim.x + blockIdx.x] = v;
+      }
+      __threadfence();
+      const unsigned prev = atomicAdd(P.red_counter, 1u);
+      is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      for (int s = 0; s < P.n_reds; ++s) {
+        const int op = P.reds[s].op;
+        u64 v = red_identity_bits(op, RB200_T_F64);
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads)
+          v = red_combine_bits(op, RB200_T_F64, v, __ldcg(&P.red_partials[(long long)s * gridDim.x + b]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, RB200_T_F64, v, __shfl_down_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if (lane == 0) wpart[s][warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          v = wpart[s][0];
+          for (int q = 1; q < kThreads / 32; ++q) v = red_combine_bits(op, RB200_T_F64, v, wpart[s][q]);
+          // red[0,..] = red[0,..] (op) acc  (ramba/ramba.py:5805-5806), rounded to the partial array's dtype on store
+          const double vd = CT<double>::get(v);
+          void* out = P.reds[s].out;
+          if (P.reds[s].out_dtype == RB200_F64) {
+            double* o = (double*)out;
+            *o = red_combine<double>(op, *o, vd);
+          } else {
+            float* o = (float*)out;
+            *o = (float)red_combine<double>(op, (double)*o, vd);
+          }
+        }
+      }
+      if (threadIdx.x == 0) *P.red_counter = 0u;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const __grid_constant__ StreamParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -291,65 +362,292 @@ __global__ void __launch_bounds__(kThreads, 2) stream_kernel(const __grid_consta
     for (int k = 0; k < LV; ++k) P.red_partials[split * P.C + col0 + tid + (long long)k * kThreads] = CT<double>::bits(cx.cacc[k]);
     return;
   }
-  // ---- global reductions: thread -> warp -> CTA -> per-CTA partial -> last CTA (fixed order, deterministic per grid)
-  if (P.n_reds > 0) {
-    __shared__ u64 wpart[RB200_MAX_REDS][kThreads / 32];
-    __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int s = 0; s < P.n_reds; ++s) {
-      const int op = P.reds[s].op;
-      double mine = 0.0;
+  stream_finish_reductions(P, cx.racc);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// The term form of the same op lists (rb200_terms.h): one running value per element, no dispatch tree.
+// TV elements per thread per tile (tile = TV * 256 elements; element k of thread t is k*256 + t).
+template <int TV> struct STermCtx {
+  unsigned stage_s, hoist_s, tid;
+  bool staged_ok;
+  long long row, e0;
+  unsigned valid;
+  double racc[RB200_MAX_REDS];
+  double cacc[TV];
+};
+
+template <int TV, class F>
+__device__ __forceinline__ void sterm_fetch(const StreamParams& P, const STermCtx<TV>& cx, const TermStep t, F (&x)[TV]) {
+  int dview = t.xidx;
+  if (t.xkind == X_STAGED) {
+    const StreamStaged& sv = P.staged[t.xidx];
+    if (cx.staged_ok) {
+      if (sv.es == 4) {
+        const unsigned addr = cx.stage_s + sv.off + cx.tid * 4u;
 #pragma unroll
-      for (int q = 0; q < RB200_MAX_REDS; ++q)
-        if (q == s) mine = cx.racc[q];
-      u64 v = CT<double>::bits(mine);
+        for (int k = 0; k < TV; ++k) x[k] = (F)lean_lds<float>(addr + k * kThreads * 4);
+      } else {
+        const unsigned addr = cx.stage_s + sv.off + cx.tid * 8u;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, RB200_T_F64, v, __shfl_down_sync(0xffffffffu, v, o));
-      if (lane == 0) wpart[s][warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int s = 0; s < P.n_reds; ++s) {
-        const int op = P.reds[s].op;
-        u64 v = wpart[s][0];
-        for (int q = 1; q < kThreads / 32; ++q) v = red_combine_bits(op, RB200_T_F64, v, wpart[s][q]);
-        P.red_partials[(long long)s * gridDim.x + blockIdx.x] = v;
+        for (int k = 0; k < TV; ++k) x[k] = (F)lean_lds<double>(addr + k * kThreads * 8);
       }
-      __threadfence();
-      const unsigned prev = atomicAdd(P.red_counter, 1u);
-      is_last = (prev == gridDim.x - 1);
+      return;
     }
-    __syncthreads();
-    if (is_last) {
-      __threadfence();
-      for (int s = 0; s < P.n_reds; ++s) {
-        const int op = P.reds[s].op;
-        u64 v = red_identity_bits(op, RB200_T_F64);
-        for (unsigned b = threadIdx.x; b < gridDim.x; b += kThreads)
-          v = red_combine_bits(op, RB200_T_F64, v, __ldcg(&P.red_partials[(long long)s * gridDim.x + b]));
+    dview = sv.dview;  // ragged last tile: read directly
+  } else if (t.xkind == X_HOIST) {
+    // row-broadcast operand: this CTA's columns were copied to shared memory once
+    const unsigned base = cx.hoist_s + (unsigned)t.xidx * (TV * kThreads * 8);
+    if (P.direct[P.thoist_direct[t.xidx]].dtype == RB200_F32) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = red_combine_bits(op, RB200_T_F64, v, __shfl_down_sync(0xffffffffu, v, o));
-        __syncthreads();
-        if (lane == 0) wpart[s][warp] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          v = wpart[s][0];
-          for (int q = 1; q < kThreads / 32; ++q) v = red_combine_bits(op, RB200_T_F64, v, wpart[s][q]);
-          // red[0,..] = red[0,..] (op) acc  (ramba/ramba.py:5805-5806), rounded to the partial array's dtype on store
-          const double vd = CT<double>::get(v);
-          void* out = P.reds[s].out;
-          if (P.reds[s].out_dtype == RB200_F64) {
-            double* o = (double*)out;
-            *o = red_combine<double>(op, *o, vd);
+      for (int k = 0; k < TV; ++k) x[k] = (F)lean_lds<float>(base + cx.tid * 4u + k * kThreads * 4);
+    } else {
+#pragma unroll
+      for (int k = 0; k < TV; ++k) x[k] = (F)lean_lds<double>(base + cx.tid * 8u + k * kThreads * 8);
+    }
+    return;
+  }
+  const LDirect& v = P.direct[dview];
+  const long long off = cx.row * v.s1 + cx.e0 * v.s2;
+  const long long step = (long long)kThreads * v.s2;
+  if (v.dtype == RB200_F32) {
+    const float* p = reinterpret_cast<const float*>(v.base) + off;
+#pragma unroll
+    for (int k = 0; k < TV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<float>(p) : F(0);
+  } else {
+    const double* p = reinterpret_cast<const double*>(v.base) + off;
+#pragma unroll
+    for (int k = 0; k < TV; ++k, p += step) x[k] = ((cx.valid >> k) & 1u) ? (F)ldg<double>(p) : F(0);
+  }
+}
+
+template <int TV, class F>
+__device__ __forceinline__ void sterm_steps(const StreamParams& P, STermCtx<TV>& cx, int s0, int s1, F (&acc)[TV]) {
+#pragma unroll 1
+  for (int s = s0; s < s1; ++s) {
+    const TermStep t = P.terms[s];
+    if (t.kind >= TK_NEG) {
+      if (t.kind == TK_NEG) {
+#pragma unroll
+        for (int k = 0; k < TV; ++k) acc[k] = -acc[k];
+      } else if (t.kind == TK_ROUND32) {
+        // the value a float32 temporary would hold
+#pragma unroll
+        for (int k = 0; k < TV; ++k) acc[k] = (F)(float)acc[k];
+      } else if (t.kind == TK_STORE) {
+        const LDirect& v = P.direct[t.xidx];
+        const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
+        if (v.dtype == RB200_F32) {
+          char* p = v.base + (cx.row * v.s1 + cx.e0 * v.s2) * 4;
+          const long long step = (long long)kThreads * v.s2 * 4;
+          if (full) {
+#pragma unroll
+            for (int k = 0; k < TV; ++k, p += step) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
           } else {
-            float* o = (float*)out;
-            *o = (float)red_combine<double>(op, (double)*o, vd);
+#pragma unroll
+            for (int k = 0; k < TV; ++k, p += step)
+              if ((cx.valid >> k) & 1u) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
+          }
+        } else {
+          char* p = v.base + (cx.row * v.s1 + cx.e0 * v.s2) * 8;
+          const long long step = (long long)kThreads * v.s2 * 8;
+          if (full) {
+#pragma unroll
+            for (int k = 0; k < TV; ++k, p += step) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < TV; ++k, p += step)
+              if ((cx.valid >> k) & 1u) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
           }
         }
+      } else if constexpr (sizeof(F) == 8) {  // TK_RED (float64 phase only)
+        const int rop = t.dzl;
+        if (P.mode == 1) {
+#pragma unroll
+          for (int k = 0; k < TV; ++k) cx.cacc[k] = red_combine<double>(rop, cx.cacc[k], acc[k]);
+        } else {
+          double x[TV];
+          const double ident = CT<double>::get(red_identity_bits(rop, RB200_T_F64));
+          const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
+#pragma unroll
+          for (int k = 0; k < TV; ++k) x[k] = (full || ((cx.valid >> k) & 1u)) ? acc[k] : ident;
+#pragma unroll
+          for (int w = TV / 2; w > 0; w >>= 1) {
+#pragma unroll
+            for (int k = 0; k < w; ++k) x[k] = red_combine<double>(rop, x[k], x[k + w]);
+          }
+#pragma unroll
+          for (int q = 0; q < RB200_MAX_REDS; ++q)
+            if (q == (int)t.sidx) cx.racc[q] = red_combine<double>(rop, cx.racc[q], x[0]);
+        }
       }
-      if (threadIdx.x == 0) *P.red_counter = 0u;
+      continue;
+    }
+    F p[TV];
+    if (t.xkind != X_NONE) {
+      sterm_fetch<TV, F>(P, cx, t, p);
+      if (t.flags & TF_W) {
+        const u64 sbits = P.scal[t.sidx];
+        const F w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
+#pragma unroll
+        for (int k = 0; k < TV; ++k) p[k] = l_mul<F>(p[k], w);
+      }
+    } else {
+      const u64 sbits = P.scal[t.sidx];
+      const F w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
+#pragma unroll
+      for (int k = 0; k < TV; ++k) p[k] = w;
+    }
+    if (t.kind == TK_ADD) {
+      if (t.flags & TF_NEGP) {
+#pragma unroll
+        for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], p[k]);
+      } else if (t.flags & TF_NEGACC) {
+#pragma unroll
+        for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(p[k], acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], p[k]);
+      }
+    } else if (t.kind == TK_MUL) {
+#pragma unroll
+      for (int k = 0; k < TV; ++k) acc[k] = l_mul<F>(acc[k], p[k]);
+    } else {  // TK_SET
+#pragma unroll
+      for (int k = 0; k < TV; ++k) acc[k] = p[k];
     }
   }
+}
+
+template <int TV>
+__global__ void __launch_bounds__(kThreads, 2) stream_terms_kernel(const __grid_constant__ StreamParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const unsigned tid = threadIdx.x;
+  constexpr int TILE = TV * kThreads;
+  // layout: [ring: depth stages][hoisted operands: n_thoist * TILE * 8][mbarriers]
+  const unsigned hoist_s = smem_s + (unsigned)P.depth * P.stage_bytes;
+  const unsigned mbar_s = hoist_s + (unsigned)P.n_thoist * (TILE * 8);
+  if (P.n_staged > 0 && tid == 0) {
+    for (int s = 0; s < P.depth; ++s) mbar_init(mbar_s + 8u * s, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  STermCtx<TV> cx;
+  cx.tid = tid;
+  cx.hoist_s = hoist_s;
+#pragma unroll
+  for (int s = 0; s < RB200_MAX_REDS; ++s) cx.racc[s] = 0.0;
+  for (int s = 0; s < P.n_reds; ++s) {
+    const double ident = CT<double>::get(red_identity_bits(P.reds[s].op, RB200_T_F64));
+#pragma unroll
+    for (int q = 0; q < RB200_MAX_REDS; ++q)
+      if (q == s) cx.racc[q] = ident;
+  }
+  long long n_it, base0, step_it;  // element offset of tile `it` = base0 + it * step_it
+  long long split = 0, col0 = 0, r0 = 0;
+  if (P.mode == 0) {
+    n_it = (P.n_tiles - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+    base0 = (long long)blockIdx.x * TILE;
+    step_it = (long long)gridDim.x * TILE;
+    cx.row = 0;
+  } else {
+    split = blockIdx.x / (unsigned)P.n_chunks;
+    const long long chunk = blockIdx.x - split * P.n_chunks;
+    col0 = chunk * TILE;
+    r0 = split * P.rows_per_split;
+    long long r1 = r0 + P.rows_per_split;
+    if (r1 > P.R) r1 = P.R;
+    n_it = r1 > r0 ? r1 - r0 : 0;
+    base0 = r0 * P.C + col0;
+    step_it = P.C;
+    const double ident = CT<double>::get(red_identity_bits(P.reds[0].op, RB200_T_F64));
+#pragma unroll
+    for (int k = 0; k < TV; ++k) cx.cacc[k] = ident;
+    cx.e0 = col0 + tid;
+    cx.valid = TV == 32 ? 0xffffffffu : (1u << TV) - 1u;
+    cx.row = 0;
+    // operands broadcast over the rows: this CTA's columns once into shared memory (natural element order)
+    for (int h = 0; h < P.n_thoist; ++h) {
+      const LDirect& v = P.direct[P.thoist_direct[h]];
+      const unsigned dst = hoist_s + (unsigned)h * (TILE * 8);
+      if (v.dtype == RB200_F32) {
+        const float* p = reinterpret_cast<const float*>(v.base) + col0;
+        for (int e = (int)tid; e < TILE; e += kThreads) lean_sts<float>(dst + (unsigned)e * 4u, ldg<float>(p + e));
+      } else {
+        const double* p = reinterpret_cast<const double*>(v.base) + col0;
+        for (int e = (int)tid; e < TILE; e += kThreads) lean_sts<double>(dst + (unsigned)e * 8u, ldg<double>(p + e));
+      }
+    }
+  }
+  __syncthreads();
+
+  auto tile_full = [&](long long it) -> bool { return P.mode == 1 || base0 + it * step_it + TILE <= P.total; };
+  auto issue = [&](long long it) {
+    if (tid != 0) return;
+    const unsigned slot = (unsigned)(it % P.depth);
+    const unsigned bar = mbar_s + 8u * slot;
+    const unsigned dst = smem_s + slot * P.stage_bytes;
+    const long long eoff = base0 + it * step_it;
+    mbar_expect_tx(bar, P.stage_bytes);
+    for (int j = 0; j < P.n_staged; ++j)
+      bulk_g2s(dst + P.staged[j].off, P.staged[j].base + eoff * P.staged[j].es, (unsigned)(TILE * P.staged[j].es), bar);
+  };
+  if (P.n_staged > 0) {
+    for (long long it = 0; it < P.depth - 1 && it < n_it; ++it)
+      if (tile_full(it)) issue(it);
+  }
+  int slot = 0;
+  unsigned par = 0;
+  for (long long it = 0; it < n_it; ++it) {
+    const bool full = tile_full(it);
+    if (P.n_staged > 0) {
+      __syncthreads();  // everyone is done with tile it-1: its stage takes tile it + depth - 1
+      const long long nx = it + P.depth - 1;
+      if (nx < n_it && tile_full(nx)) issue(nx);
+      if (full) {
+        mbar_wait(mbar_s + 8u * (unsigned)slot, (par >> slot) & 1u);
+        par ^= 1u << slot;
+      }
+    }
+    cx.staged_ok = full && P.n_staged > 0;
+    cx.stage_s = smem_s + (unsigned)slot * P.stage_bytes;
+    slot = slot + 1 >= P.depth ? 0 : slot + 1;
+    if (P.mode == 0) {
+      const long long e = base0 + it * step_it + tid;
+      cx.e0 = e;
+      unsigned valid = TV == 32 ? 0xffffffffu : (1u << TV) - 1u;
+      if (!full) {
+        valid = 0;
+#pragma unroll
+        for (int k = 0; k < TV; ++k)
+          if (e + (long long)k * kThreads < P.total) valid |= 1u << k;
+      }
+      cx.valid = valid;
+    } else {
+      cx.row = r0 + it;
+    }
+    if (P.n32 > 0) {
+      float a32[TV];
+      sterm_steps<TV, float>(P, cx, 0, P.n32, a32);
+      if (P.n_terms > P.n32) {
+        double a64[TV];
+#pragma unroll
+        for (int k = 0; k < TV; ++k) a64[k] = (double)a32[k];
+        sterm_steps<TV, double>(P, cx, P.n32, P.n_terms, a64);
+      }
+    } else {
+      double a64[TV];
+      sterm_steps<TV, double>(P, cx, 0, P.n_terms, a64);
+    }
+  }
+
+  if (P.mode == 1) {
+#pragma unroll
+    for (int k = 0; k < TV; ++k) P.red_partials[split * P.C + col0 + tid + (long long)k * kThreads] = CT<double>::bits(cx.cacc[k]);
+    return;
+  }
+  stream_finish_reductions(P, cx.racc);
 }
 
 // =============================================================================================
@@ -399,8 +697,11 @@ static bool stream_translate(const rb200_fused_op* op, StreamParams& P, bool col
   P.n_regs = op->n_regs;
   lean_translate(op, view_kind, view_arg, store_arg, P.insns);
   for (int i = 0; i < op->n_scalars; ++i) P.scal[i] = op->scalars[i];
-  if (column_mode) {
-    // row-broadcast operands fetched in ONE class move into the register file
+  return true;
+}
+
+// lean kernel, column mode: row-broadcast operands fetched in ONE class move into the register file
+static void stream_hoist_lean(StreamParams& P) {
     for (int dv = 0; dv < P.n_direct && P.n_hoist < kStreamMaxStaged; ++dv) {
       if (P.direct[dv].s1 != 0 || P.direct[dv].s2 != 1) continue;
       int cls = -1;
@@ -431,11 +732,21 @@ static bool stream_translate(const rb200_fused_op* op, StreamParams& P, bool col
       }
     }
   }
-  return true;
+
+// byte offsets of the staged views inside a stage for tiles of tv * 256 elements
+static void stream_layout(StreamParams& P) {
+  unsigned off = 0;
+  for (int j = 0; j < P.n_staged; ++j) {
+    P.staged[j].off = off;
+    off += (unsigned)(P.tv * kThreads * P.staged[j].es);
+  }
+  P.stage_bytes = off;
 }
 
+// shared-memory budget: ring depth from what is left after the register file / hoisted operands.  0: does not fit.
 static size_t stream_smem(StreamParams& P) {
-  const size_t regs = (size_t)(P.n_regs + P.n_hoist) * LV * kThreads * 8;
+  const size_t tile = (size_t)P.tv * kThreads;
+  const size_t regs = P.n_terms > 0 ? (size_t)P.n_thoist * tile * 8 : (size_t)(P.n_regs + P.n_hoist) * LV * kThreads * 8;
   const size_t budget = 100 * 1024;
   if (regs + 1024 > budget) return 0;
   int depth = 0;
@@ -445,61 +756,152 @@ static size_t stream_smem(StreamParams& P) {
     if (depth < 2) return 0;
   }
   P.depth = depth;
-  return (size_t)depth * P.stage_bytes + regs + (size_t)depth * 8 + 16;
+  return (size_t)depth * P.stage_bytes + regs + (size_t)(depth > 0 ? depth : 1) * 8 + 16;
+}
+
+struct StreamPlan {
+  StreamParams P;
+  size_t smem;
+  long long blocks;
+  int eff;  // column mode: splits actually written
+};
+
+// 0: planned, 1: not of this kernel's form
+static int stream_plan(const rb200_fused_op* op, int sms, int max_red_blocks, int n_split, StreamPlan& T) {
+  StreamParams& P = T.P;
+  memset(&T, 0, sizeof(T));
+  const bool column = op->n_axis_red_dims != 0;
+  if (!column) {
+    if (op->ndim != 1) return 1;
+    if (!lean_eligible(op, true)) return 1;
+    for (int s = 0; s < op->n_reds; ++s) {
+      if (op->reds[s].ctype != RB200_T_F64) return 1;
+      if (op->reds[s].out_dtype != RB200_F64 && op->reds[s].out_dtype != RB200_F32) return 1;
+    }
+    P.mode = 0;
+    P.total = op->itershape[0];
+  } else {
+    if (op->ndim != 2 || op->n_axis_red_dims != 1 || op->n_reds != 1) return 1;
+    if (!lean_eligible(op, true)) return 1;
+    if (op->reds[0].ctype != RB200_T_F64) return 1;
+    const long long R = op->itershape[0], C = op->itershape[1];
+    if (C % (LV * kThreads) != 0 || R < 2) return 1;
+    for (int i = 0; i < op->n_insns; ++i)
+      if (op->insns[i].st_view != RB200_NOSTORE) return 1;
+    for (int v = 0; v < op->n_views; ++v) {
+      const rb200_view& vw = op->views[v];
+      if (vw.stride[1] != 1 || !(vw.stride[0] == C || vw.stride[0] == 0)) return 1;
+    }
+    P.mode = 1;
+    P.R = R;
+    P.C = C;
+    P.total = R * C;
+  }
+  P.tv = LV;
+  stream_translate(op, P, column, P.C);
+  // ---- the term form first
+  static const bool no_terms = getenv("RB200_NO_TERMS_KERNEL") != nullptr;  // debugging aid
+  TermBuild tb;
+  tb.n_regs = P.n_regs;
+  tb.direct = P.direct;
+  tb.stream = true;
+  tb.staged_fill = [](void*, int, int, TermStep*) -> bool { return true; };
+  tb.ctx = nullptr;
+  int out_view = -1;
+  bool all_f32 = true;
+  for (int v = 0; v < op->n_views; ++v)
+    if (op->views[v].dtype != RB200_F32) all_f32 = false;
+  if (!no_terms && build_terms(tb, P.insns, P.n_insns, P.terms, kMaxTerms, &P.n_terms, &P.n32, &out_view)) {
+    static const bool tv8 = getenv("RB200_STREAM_TV8") != nullptr;  // debugging aid
+    if (all_f32 && !tv8 && (!column || P.C % (16 * kThreads) == 0)) P.tv = 16;
+    stream_layout(P);
+    if (column) {
+      // row-broadcast direct operands: one copy per CTA in shared memory
+      for (int i = 0; i < P.n_terms; ++i) {
+        TermStep& t = P.terms[i];
+        if (t.xkind != X_DIRECT || P.direct[t.xidx].s1 != 0 || P.direct[t.xidx].s2 != 1) continue;
+        int h = -1;
+        for (int q = 0; q < P.n_thoist; ++q)
+          if (P.thoist_direct[q] == t.xidx) h = q;
+        if (h < 0 && P.n_thoist < kStreamMaxStaged) {
+          h = P.n_thoist++;
+          P.thoist_direct[h] = t.xidx;
+        }
+        if (h >= 0) {
+          t.xkind = X_HOIST;
+          t.xidx = (unsigned char)h;
+        }
+      }
+    }
+  } else {
+    P.n_terms = 0;
+    if (column) stream_hoist_lean(P);
+  }
+  T.smem = stream_smem(P);
+  if (T.smem == 0) return 1;
+  const long long tile = (long long)P.tv * kThreads;
+  P.n_reds = op->n_reds;
+  for (int s = 0; s < op->n_reds; ++s) {
+    P.reds[s].op = op->reds[s].op;
+    P.reds[s].ctype = op->reds[s].ctype;
+    P.reds[s].out = op->reds[s].out;
+    P.reds[s].out_dtype = op->reds[s].out_dtype;
+  }
+  if (!column) {
+    P.n_tiles = (P.total + tile - 1) / tile;
+    if (op->n_reds > 0) {
+      P.red_counter = (unsigned int*)op->red_scratch;
+      P.red_partials = (u64*)((char*)op->red_scratch + 256);
+    }
+    long long blocks = P.n_tiles;
+    long long cap = (long long)sms * 2;
+    if (op->n_reds > 0 && cap > max_red_blocks) cap = max_red_blocks;
+    if (blocks > cap) blocks = cap;
+    T.blocks = blocks;
+  } else {
+    P.n_chunks = (int)(P.C / tile);
+    if (P.n_chunks > sms * 2) return 1;
+    int eff = (int)(((long long)sms * 2) / P.n_chunks);
+    if (n_split > 0 && eff > n_split) eff = n_split;
+    if ((long long)eff > P.R) eff = (int)P.R;
+    if (eff < 1) eff = 1;
+    P.n_split = eff;
+    P.rows_per_split = (P.R + eff - 1) / eff;
+    P.red_partials = (u64*)op->red_scratch;
+    T.eff = eff;
+    T.blocks = (long long)eff * P.n_chunks;
+  }
+  return 0;
 }
 
 static cudaError_t stream_launch(const StreamParams& P, unsigned blocks, size_t smem, cudaStream_t stream) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024);
+    cudaFuncSetAttribute(stream_terms_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024);
+    cudaFuncSetAttribute(stream_terms_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024);
     attr = true;
   }
-  stream_kernel<<<blocks, kThreads, smem, stream>>>(P);
+  if (P.n_terms > 0) {
+    if (P.tv == 16) stream_terms_kernel<16><<<blocks, kThreads, smem, stream>>>(P);
+    else stream_terms_kernel<8><<<blocks, kThreads, smem, stream>>>(P);
+  } else {
+    stream_kernel<<<blocks, kThreads, smem, stream>>>(P);
+  }
   return cudaGetLastError();
 }
 
 // one line for rb200_describe_plan; false: not this kernel's form
 bool describe_stream(const rb200_fused_op* op, int sms, std::string* out) {
-  StreamParams P;
-  memset(&P, 0, sizeof(P));
-  const char* mode = nullptr;
-  long long ctas = 0;
-  if (op->ndim == 1 && op->n_axis_red_dims == 0) {
-    if (!lean_eligible(op, true)) return false;
-    for (int s = 0; s < op->n_reds; ++s)
-      if (op->reds[s].ctype != RB200_T_F64 || (op->reds[s].out_dtype != RB200_F64 && op->reds[s].out_dtype != RB200_F32)) return false;
-    P.mode = 0;
-    P.total = op->itershape[0];
-    P.n_tiles = (P.total + kStreamTile - 1) / kStreamTile;
-    stream_translate(op, P, false, 0);
-    mode = "elementwise";
-    ctas = P.n_tiles < (long long)sms * 2 ? P.n_tiles : (long long)sms * 2;
-  } else if (op->ndim == 2 && op->n_axis_red_dims == 1 && op->n_reds == 1) {
-    if (!lean_eligible(op, true) || op->reds[0].ctype != RB200_T_F64) return false;
-    const long long R = op->itershape[0], C = op->itershape[1];
-    if (C % kStreamTile != 0 || C / kStreamTile > (long long)sms * 2 || R < 2) return false;
-    for (int i = 0; i < op->n_insns; ++i)
-      if (op->insns[i].st_view != RB200_NOSTORE) return false;
-    for (int v = 0; v < op->n_views; ++v)
-      if (op->views[v].stride[1] != 1 || !(op->views[v].stride[0] == C || op->views[v].stride[0] == 0)) return false;
-    P.mode = 1;
-    P.R = R;
-    P.C = C;
-    stream_translate(op, P, true, C);
-    mode = "columns";
-    int eff = (int)(((long long)sms * 2) / (C / kStreamTile));
-    if (op->axis_nsplit > 0 && eff > op->axis_nsplit) eff = op->axis_nsplit;
-    if ((long long)eff > R) eff = (int)R;
-    if (eff < 1) eff = 1;
-    ctas = (long long)eff * (C / kStreamTile);
-  } else {
-    return false;
-  }
-  const size_t smem = stream_smem(P);
-  if (smem == 0) return false;
-  char buf[300];
-  snprintf(buf, sizeof(buf), "kernel=stream mode=%s staged_views=%d ring_depth=%d stage_bytes=%u direct_views=%d hoisted=%d lean_insns=%d reds=%d ctas=%lld smem=%zu",
-           mode, P.n_staged, P.depth, P.stage_bytes, P.n_direct, P.n_hoist, P.n_insns, op->n_reds, ctas, smem);
+  static StreamPlan T;
+  if (stream_plan(op, sms, 4096, op->axis_nsplit, T) != 0) return false;
+  const StreamParams& P = T.P;
+  char buf[320];
+  snprintf(buf, sizeof(buf),
+           "kernel=%s mode=%s staged_views=%d ring_depth=%d stage_bytes=%u direct_views=%d hoisted=%d lean_insns=%d terms=%d(f32:%d) tile=%d reds=%d "
+           "ctas=%lld smem=%zu",
+           P.n_terms > 0 ? "stream_terms" : "stream", P.mode == 0 ? "elementwise" : "columns", P.n_staged, P.depth, P.stage_bytes, P.n_direct,
+           P.n_terms > 0 ? P.n_thoist : P.n_hoist, P.n_insns, P.n_terms, P.n32, P.tv * kThreads, op->n_reds, T.blocks, T.smem);
   *out = buf;
   return true;
 }
@@ -509,40 +911,16 @@ int launch_stream_1d(const rb200_fused_op* op, int sms, int max_red_blocks, cuda
   static const bool disabled = getenv("RB200_NO_STREAM_KERNEL") != nullptr;  // debugging aid
   if (disabled) return 1;
   if (op->ndim != 1 || op->n_axis_red_dims != 0) return 1;
-  if (!lean_eligible(op, true)) return 1;
-  for (int s = 0; s < op->n_reds; ++s) {
-    if (op->reds[s].ctype != RB200_T_F64) return 1;
-    if (op->reds[s].out_dtype != RB200_F64 && op->reds[s].out_dtype != RB200_F32) return 1;
+  for (int s = 0; s < op->n_reds; ++s)
     if (!op->reds[s].out) return 1;
-  }
-  StreamParams P;
-  memset(&P, 0, sizeof(P));
-  P.mode = 0;
-  P.total = op->itershape[0];
-  P.n_tiles = (P.total + kStreamTile - 1) / kStreamTile;
-  stream_translate(op, P, false, 0);
-  const size_t smem = stream_smem(P);
-  if (smem == 0) return 1;
-  P.n_reds = op->n_reds;
-  if (op->n_reds > 0) {
-    if (!op->red_scratch) return 1;
-    P.red_counter = (unsigned int*)op->red_scratch;
-    P.red_partials = (u64*)((char*)op->red_scratch + 256);
-    for (int s = 0; s < op->n_reds; ++s) {
-      P.reds[s].op = op->reds[s].op;
-      P.reds[s].ctype = op->reds[s].ctype;
-      P.reds[s].out = op->reds[s].out;
-      P.reds[s].out_dtype = op->reds[s].out_dtype;
-    }
-  }
-  long long blocks = P.n_tiles;
-  long long cap = (long long)sms * 2;
-  if (op->n_reds > 0 && cap > max_red_blocks) cap = max_red_blocks;
-  if (blocks > cap) blocks = cap;
-  const cudaError_t e = stream_launch(P, (unsigned)blocks, smem, stream);
+  if (op->n_reds > 0 && !op->red_scratch) return 1;
+  static StreamPlan T;  // (large; launches are issued from one thread per process)
+  if (stream_plan(op, sms, max_red_blocks, 0, T) != 0) return 1;
+  const cudaError_t e = stream_launch(T.P, (unsigned)T.blocks, T.smem, stream);
   if (e != cudaSuccess) {
     char buf[200];
-    snprintf(buf, sizeof(buf), "stream_kernel launch (blocks=%lld smem=%zu staged=%d depth=%d): %s", blocks, smem, P.n_staged, P.depth, cudaGetErrorString(e));
+    snprintf(buf, sizeof(buf), "stream kernel launch (blocks=%lld smem=%zu staged=%d depth=%d terms=%d): %s", T.blocks, T.smem, T.P.n_staged, T.P.depth,
+             T.P.n_terms, cudaGetErrorString(e));
     *err = buf;
     return 2;
   }
@@ -554,46 +932,18 @@ int launch_stream_1d(const rb200_fused_op* op, int sms, int max_red_blocks, cuda
 int launch_stream_columns(const rb200_fused_op* op, int sms, int n_split, cudaStream_t stream, int* n_split_eff_out, std::string* err) {
   static const bool disabled = getenv("RB200_NO_STREAM_KERNEL") != nullptr;
   if (disabled) return 1;
-  if (op->ndim != 2 || op->n_axis_red_dims != 1 || op->n_reds != 1) return 1;
-  if (!lean_eligible(op, true)) return 1;
-  if (op->reds[0].ctype != RB200_T_F64 || !op->red_scratch) return 1;
-  const long long R = op->itershape[0], C = op->itershape[1];
-  if (C % kStreamTile != 0 || C / kStreamTile > (long long)sms * 2 || R < 2) return 1;
-  for (int i = 0; i < op->n_insns; ++i)
-    if (op->insns[i].st_view != RB200_NOSTORE) return 1;
-  for (int v = 0; v < op->n_views; ++v) {
-    const rb200_view& vw = op->views[v];
-    if (vw.stride[1] != 1 || !(vw.stride[0] == C || vw.stride[0] == 0)) return 1;
-  }
-  StreamParams P;
-  memset(&P, 0, sizeof(P));
-  P.mode = 1;
-  P.R = R;
-  P.C = C;
-  P.total = R * C;
-  stream_translate(op, P, true, C);
-  const size_t smem = stream_smem(P);
-  if (smem == 0) return 1;
-  P.n_chunks = (int)(C / kStreamTile);
-  int eff = (int)(((long long)sms * 2) / P.n_chunks);
-  if (eff > n_split) eff = n_split;
-  if ((long long)eff > R) eff = (int)R;
-  if (eff < 1) eff = 1;
-  P.n_split = eff;
-  P.rows_per_split = (R + eff - 1) / eff;
-  P.n_reds = 1;
-  P.reds[0].op = op->reds[0].op;
-  P.reds[0].ctype = op->reds[0].ctype;
-  P.red_partials = (u64*)op->red_scratch;
-  const cudaError_t e = stream_launch(P, (unsigned)(eff * P.n_chunks), smem, stream);
+  if (op->ndim != 2 || op->n_axis_red_dims != 1 || op->n_reds != 1 || !op->red_scratch) return 1;
+  static StreamPlan T;
+  if (stream_plan(op, sms, 4096, n_split, T) != 0) return 1;
+  const cudaError_t e = stream_launch(T.P, (unsigned)T.blocks, T.smem, stream);
   if (e != cudaSuccess) {
     char buf[200];
-    snprintf(buf, sizeof(buf), "stream_kernel (columns) launch (blocks=%d smem=%zu staged=%d depth=%d): %s", eff * P.n_chunks, smem, P.n_staged, P.depth,
-             cudaGetErrorString(e));
+    snprintf(buf, sizeof(buf), "stream kernel (columns) launch (blocks=%lld smem=%zu staged=%d depth=%d terms=%d): %s", T.blocks, T.smem, T.P.n_staged,
+             T.P.depth, T.P.n_terms, cudaGetErrorString(e));
     *err = buf;
     return 2;
   }
-  *n_split_eff_out = eff;
+  *n_split_eff_out = T.eff;
   return 0;
 }
 

@@ -32,6 +32,7 @@
 #include "rb200_launch.h"
 #include "rb200_lean.cuh"
 #include "rb200_lean_plan.h"
+#include "rb200_terms.h"
 
 namespace rb200 {
 
@@ -49,25 +50,7 @@ struct TileStagedOp {
   unsigned off;      // byte offset inside a plane: ((dy + hy_lo) * PX + dx + hx_lo) * elem
 };
 
-// ---- the "weighted shifted sum" form (ramba/ramba.py:8146-8188: `acc = U[o1+i] + U[o2+i] + ... ; V[i] = acc - c*U[..]`):
-// an op list that is ONE running value updated by views and scalars, with at most one float32 -> float64 promotion and
-// one store at the end, is flattened into TERMS and run by stencil_terms_kernel: no dispatch tree, the running value never
-// leaves its registers.  Every term is   p = x*w | x | w   (x: element of a staged or direct view, w: scalar; the product
-// is rounded on its own) followed by   acc = p (first term),  acc = (+-acc) + (+-p),  acc = acc * p   or   acc = -acc.
-// Same operations, same order, same classes, one rounding each as in the op list:  a - b is a + (-b) exactly.
-enum TermKind { TK_SET = 0, TK_ADD = 1, TK_MUL = 2, TK_NEG = 3 };
-enum TermX { X_NONE = 0, X_STAGED = 1, X_DIRECT = 2 };
-enum TermFlags { TF_W = 1, TF_NEGP = 2, TF_NEGACC = 4 };
-struct TermStep {  // 8 bytes, one constant-bank load
-  unsigned char kind;   // TermKind
-  unsigned char xkind;  // TermX
-  unsigned char xidx;   // staged / direct index
-  unsigned char sidx;   // scalar index (TF_W)
-  unsigned short off;   // staged: byte offset of the operand inside a plane
-  unsigned char dzl;    // staged: plane of the ring
-  unsigned char flags;  // TermFlags
-};
-constexpr int kTileMaxTerms = 48;
+constexpr int kTileMaxTerms = kMaxTerms;
 
 struct TileParams {
   long long Z, Y, X;        // iteration extents (Z == 1 for 2-D ops)
@@ -624,130 +607,6 @@ static long long floor_div(long long a, long long b) {  // b > 0
 }
 
 
-// Flatten translated lean instructions into terms (see TermStep).  false: not of the weighted-shifted-sum form.
-static bool build_terms(TileParams& P, const LInsn* L, int n, bool staged_is_f32) {
-  if (P.n_regs != 0 || n < 1) return false;
-  int nt = 0, cls = -1, n32 = -1;
-  auto is_view = [](int k) { return k == L_STAGED || k == L_DIRECT; };
-  // one term: p from (view operand, scalar operand) - either may be absent (kind L_NONE) but not both
-  auto push = [&](int kind, int vkind, int varg, int skind, int sarg, int flags) -> bool {
-    if (nt >= kTileMaxTerms) return false;
-    TermStep t;
-    memset(&t, 0, sizeof(t));
-    t.kind = (unsigned char)kind;
-    t.flags = (unsigned char)flags;
-    if (kind != TK_NEG) {
-      if (vkind == L_STAGED) {
-        if (cls == 1 && !staged_is_f32) return false;
-        if (P.staged[varg].off > 0xffffu || P.staged[varg].dzl > 3) return false;
-        t.xkind = X_STAGED;
-        t.xidx = (unsigned char)varg;
-        t.dzl = (unsigned char)P.staged[varg].dzl;
-        t.off = (unsigned short)P.staged[varg].off;
-      } else if (vkind == L_DIRECT) {
-        t.xkind = X_DIRECT;
-        t.xidx = (unsigned char)varg;
-      } else if (vkind != L_NONE) {
-        return false;
-      }
-      if (skind == L_SCAL) {
-        t.flags |= TF_W;
-        t.sidx = (unsigned char)sarg;
-      } else if (skind != L_NONE) {
-        return false;
-      }
-      if (t.xkind == X_NONE && !(t.flags & TF_W)) return false;
-    }
-    P.terms[nt++] = t;
-    return true;
-  };
-  // p = one operand (view or scalar)
-  auto one = [&](int kind, int okind, int oarg, int flags) -> bool {
-    if (is_view(okind)) return push(kind, okind, oarg, L_NONE, 0, flags);
-    if (okind == L_SCAL) return push(kind, L_NONE, 0, L_SCAL, oarg, flags);
-    return false;
-  };
-  for (int i = 0; i < n; ++i) {
-    const LInsn& I = L[i];
-    const int lop = I.handler >> 2, f32 = (I.handler >> 1) & 1;
-    const bool aacc = (I.handler & 1) != 0;
-    if (I.st_reg != RB200_NOSTORE) return false;
-    if (I.st_view != RB200_NOSTORE && i != n - 1) return false;
-    if (lop == LO_CVT) {
-      if (!aacc || nt == 0) return false;
-      if (f32 == 0) {  // float32 -> float64: the one promotion
-        if (cls != 1 || n32 >= 0) return false;
-        n32 = nt;
-        cls = 0;
-      } else {  // float64 -> float32: only as the last instruction into a float32 view (the store converts)
-        if (i != n - 1 || cls != 0 || I.st_view == RB200_NOSTORE || P.direct[I.st_view].dtype != RB200_F32) return false;
-      }
-      continue;
-    }
-    if (cls < 0) cls = f32;
-    else if (cls != f32) return false;
-    const bool fresh = nt == 0;  // no running value yet: the instruction may start from its own operands
-    switch (lop) {
-      case LO_MOV:
-        if (!aacc && !(fresh && one(TK_SET, I.a_kind, I.a_arg, 0))) return false;
-        break;
-      case LO_NEG:
-        if (!aacc && !(fresh && one(TK_SET, I.a_kind, I.a_arg, 0))) return false;
-        if (!push(TK_NEG, L_NONE, 0, L_NONE, 0, 0)) return false;
-        break;
-      case LO_ADD:
-      case LO_SUB:
-      case LO_RSUB:
-      case LO_MUL: {
-        if (!aacc && !(fresh && one(TK_SET, I.a_kind, I.a_arg, 0))) return false;
-        const int kind = lop == LO_MUL ? TK_MUL : TK_ADD;
-        const int fl = lop == LO_SUB ? TF_NEGP : lop == LO_RSUB ? TF_NEGACC : 0;
-        if (!one(kind, I.b_kind, I.b_arg, fl)) return false;
-      } break;
-      case LO_MULADD:
-      case LO_MULSUB:
-      case LO_MULRSUB: {
-        // r = a + p, a - p, p - a  with p = b*c rounded first
-        const int fl = lop == LO_MULADD ? 0 : lop == LO_MULSUB ? TF_NEGP : TF_NEGACC;
-        if (aacc) {
-          if (is_view(I.b_kind) && I.c_kind == L_SCAL) {
-            if (!push(TK_ADD, I.b_kind, I.b_arg, L_SCAL, I.c_arg, fl)) return false;
-          } else if (is_view(I.c_kind) && I.b_kind == L_SCAL) {
-            if (!push(TK_ADD, I.c_kind, I.c_arg, L_SCAL, I.b_arg, fl)) return false;
-          } else {
-            return false;
-          }
-          break;
-        }
-        // the running value is (or becomes) the product; then `a` is folded in: a + p, a - p (= -p + a), p - a
-        if (I.b_kind == L_ACC || I.c_kind == L_ACC) {
-          const int ok = I.b_kind == L_ACC ? I.c_kind : I.b_kind, oa = I.b_kind == L_ACC ? I.c_arg : I.b_arg;
-          if (!one(TK_MUL, ok, oa, 0)) return false;
-        } else {
-          if (!fresh) return false;
-          if (is_view(I.b_kind) && I.c_kind == L_SCAL) {
-            if (!push(TK_SET, I.b_kind, I.b_arg, L_SCAL, I.c_arg, 0)) return false;
-          } else if (is_view(I.c_kind) && I.b_kind == L_SCAL) {
-            if (!push(TK_SET, I.c_kind, I.c_arg, L_SCAL, I.b_arg, 0)) return false;
-          } else {
-            if (!one(TK_SET, I.b_kind, I.b_arg, 0) || !one(TK_MUL, I.c_kind, I.c_arg, 0)) return false;
-          }
-        }
-        // now acc = p;  MULADD: a + p -> acc + a;  MULSUB: a - p -> (-acc) + a;  MULRSUB: p - a -> acc - a
-        const int fl2 = lop == LO_MULADD ? 0 : lop == LO_MULSUB ? TF_NEGACC : TF_NEGP;
-        if (!one(TK_ADD, I.a_kind, I.a_arg, fl2)) return false;
-      } break;
-      default: return false;
-    }
-  }
-  if (L[n - 1].st_view == RB200_NOSTORE || nt == 0) return false;
-  P.out_view = L[n - 1].st_view;
-  P.n_terms = nt;
-  P.n32 = n32 >= 0 ? n32 : (cls == 1 ? nt : 0);
-  if (n32 < 0 && cls == 1 && !staged_is_f32) return false;
-  return true;
-}
-
 struct TilePlan {
   TileParams P;
   size_t smem;
@@ -903,7 +762,21 @@ static int plan_stencil_tile(const rb200_fused_op* op, int sms, TilePlan& T) {
   lean_translate(op, view_kind, view_arg, store_arg, P.insns);
   static const bool no_terms = getenv("RB200_NO_TERMS_KERNEL") != nullptr;  // debugging aid: always the general tile kernel
   P.tv = LV;
-  if (no_terms || !build_terms(P, P.insns, P.n_insns, es == 4)) {
+  TermBuild tb;
+  tb.n_regs = P.n_regs;
+  tb.direct = P.direct;
+  tb.stream = false;
+  tb.staged_fill = [](void* ctx, int arg, int cls_f32, TermStep* t) -> bool {
+    const TileParams* Q = (const TileParams*)ctx;
+    if (cls_f32 && Q->elem != 4) return false;
+    if (Q->staged[arg].off > 0xffffu || Q->staged[arg].dzl > 3) return false;
+    t->dzl = (unsigned char)Q->staged[arg].dzl;
+    t->off = (unsigned short)Q->staged[arg].off;
+    return true;
+  };
+  tb.ctx = &P;
+  P.elem = es;
+  if (no_terms || !build_terms(tb, P.insns, P.n_insns, P.terms, kTileMaxTerms, &P.n_terms, &P.n32, &P.out_view)) {
     P.n_terms = 0;
     int n_chain = 0;
     P.n_insns = lean_fuse_chains(P.insns, P.n_insns, P.chain, kTileMaxChain, &n_chain);

@@ -56,13 +56,13 @@ def test_streaming_kernel_forms(plans):
     rb.sync()
     del plans[:]
     s = (X * 2.0 + 1.0).sum()
-    d = _last(plans, "kernel=stream mode=elementwise")
+    d = _last(plans, "kernel=stream_terms mode=elementwise")
     assert d["staged_views"] == "1" and d["reds"] == "1" and int(d["ring_depth"]) >= 4
     assert float(s) == 3.0 * 64 * 4096
     del plans[:]
     r = (X + v).sum(axis=0)
     rb.sync()
-    d = _last(plans, "kernel=stream mode=columns")
+    d = _last(plans, "kernel=stream_terms mode=columns")
     assert d["staged_views"] == "1" and d["hoisted"] == "1"
     assert onp.array_equal(r.asarray(), onp.full(4096, 128.0, dtype=onp.float32))
 

@@ -374,9 +374,17 @@ template <int TV> struct STermCtx {
   bool staged_ok;
   long long row, e0;
   unsigned valid;
-  double racc[RB200_MAX_REDS];
-  double cacc[TV];
 };
+
+// in-place arithmetic: the running value keeps its registers across the term loop (no copies at the loop's merge points)
+__device__ __forceinline__ void ip_add(double& a, double b) { asm("add.rn.f64 %0, %0, %1;" : "+d"(a) : "d"(b)); }
+__device__ __forceinline__ void ip_sub(double& a, double b) { asm("sub.rn.f64 %0, %0, %1;" : "+d"(a) : "d"(b)); }
+__device__ __forceinline__ void ip_rsub(double& a, double b) { asm("sub.rn.f64 %0, %1, %0;" : "+d"(a) : "d"(b)); }
+__device__ __forceinline__ void ip_mul(double& a, double b) { asm("mul.rn.f64 %0, %0, %1;" : "+d"(a) : "d"(b)); }
+__device__ __forceinline__ void ip_add(float& a, float b) { asm("add.rn.f32 %0, %0, %1;" : "+f"(a) : "f"(b)); }
+__device__ __forceinline__ void ip_sub(float& a, float b) { asm("sub.rn.f32 %0, %0, %1;" : "+f"(a) : "f"(b)); }
+__device__ __forceinline__ void ip_rsub(float& a, float b) { asm("sub.rn.f32 %0, %1, %0;" : "+f"(a) : "f"(b)); }
+__device__ __forceinline__ void ip_mul(float& a, float b) { asm("mul.rn.f32 %0, %0, %1;" : "+f"(a) : "f"(b)); }
 
 template <int TV, class F>
 __device__ __forceinline__ void sterm_fetch(const StreamParams& P, const STermCtx<TV>& cx, const TermStep t, F (&x)[TV]) {
@@ -422,8 +430,89 @@ __device__ __forceinline__ void sterm_fetch(const StreamParams& P, const STermCt
   }
 }
 
+template <int TV, class F> __device__ __forceinline__ void sterm_store(const StreamParams& P, const STermCtx<TV>& cx, int dview, const F (&acc)[TV]) {
+  const LDirect& v = P.direct[dview];
+  const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
+  if (v.dtype == RB200_F32) {
+    char* p = v.base + (cx.row * v.s1 + cx.e0 * v.s2) * 4;
+    const long long step = (long long)kThreads * v.s2 * 4;
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < TV; ++k, p += step) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < TV; ++k, p += step)
+        if ((cx.valid >> k) & 1u) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
+    }
+  } else {
+    char* p = v.base + (cx.row * v.s1 + cx.e0 * v.s2) * 8;
+    const long long step = (long long)kThreads * v.s2 * 8;
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < TV; ++k, p += step) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < TV; ++k, p += step)
+        if ((cx.valid >> k) & 1u) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
+    }
+  }
+}
+
+// fold the thread's TV values into the accumulators of a reduction (float64 phase)
+template <int TV>
+__device__ __forceinline__ void sterm_reduce(const StreamParams& P, const STermCtx<TV>& cx, const TermStep t, const double (&acc)[TV], double (&cacc)[TV],
+                                             double (&racc)[RB200_MAX_REDS]) {
+  const int rop = t.dzl;
+  if (P.mode == 1) {  // column accumulators, one per element of the thread
+    if (rop == RB200_RED_ADD) {
+#pragma unroll
+      for (int k = 0; k < TV; ++k) ip_add(cacc[k], acc[k]);
+    } else if (rop == RB200_RED_MUL) {
+#pragma unroll
+      for (int k = 0; k < TV; ++k) ip_mul(cacc[k], acc[k]);
+    } else if (rop == RB200_RED_MIN) {
+#pragma unroll
+      for (int k = 0; k < TV; ++k) cacc[k] = acc[k] < cacc[k] ? acc[k] : cacc[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < TV; ++k) cacc[k] = acc[k] > cacc[k] ? acc[k] : cacc[k];
+    }
+    return;
+  }
+  double x[TV];
+  const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < TV; ++k) x[k] = acc[k];
+  } else {
+    const double ident = CT<double>::get(red_identity_bits(rop, RB200_T_F64));
+#pragma unroll
+    for (int k = 0; k < TV; ++k) x[k] = ((cx.valid >> k) & 1u) ? acc[k] : ident;
+  }
+  double r;
+  if (rop == RB200_RED_ADD) {
+#pragma unroll
+    for (int w = TV / 2; w > 0; w /= 2) {
+#pragma unroll
+      for (int k = 0; k < w; ++k) x[k] = __dadd_rn(x[k], x[k + w]);
+    }
+    r = x[0];
+  } else {
+#pragma unroll
+    for (int w = TV / 2; w > 0; w /= 2) {
+#pragma unroll
+      for (int k = 0; k < w; ++k) x[k] = red_combine<double>(rop, x[k], x[k + w]);
+    }
+    r = x[0];
+  }
+#pragma unroll
+  for (int q = 0; q < RB200_MAX_REDS; ++q)
+    if (q == (int)t.sidx) racc[q] = red_combine<double>(rop, racc[q], r);
+}
+
 template <int TV, class F>
-__device__ __forceinline__ void sterm_steps(const StreamParams& P, STermCtx<TV>& cx, int s0, int s1, F (&acc)[TV]) {
+__device__ __forceinline__ void sterm_steps(const StreamParams& P, const STermCtx<TV>& cx, int s0, int s1, F (&acc)[TV], double (&cacc)[TV],
+                                            double (&racc)[RB200_MAX_REDS]) {
 #pragma unroll 1
   for (int s = s0; s < s1; ++s) {
     const TermStep t = P.terms[s];
@@ -432,96 +521,76 @@ __device__ __forceinline__ void sterm_steps(const StreamParams& P, STermCtx<TV>&
 #pragma unroll
         for (int k = 0; k < TV; ++k) acc[k] = -acc[k];
       } else if (t.kind == TK_ROUND32) {
-        // the value a float32 temporary would hold
 #pragma unroll
-        for (int k = 0; k < TV; ++k) acc[k] = (F)(float)acc[k];
+        for (int k = 0; k < TV; ++k) acc[k] = (F)(float)acc[k];  // the value a float32 temporary would hold
       } else if (t.kind == TK_STORE) {
-        const LDirect& v = P.direct[t.xidx];
-        const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
-        if (v.dtype == RB200_F32) {
-          char* p = v.base + (cx.row * v.s1 + cx.e0 * v.s2) * 4;
-          const long long step = (long long)kThreads * v.s2 * 4;
-          if (full) {
+        sterm_store<TV, F>(P, cx, t.xidx, acc);
+      } else if constexpr (sizeof(F) == 8) {
+        sterm_reduce<TV>(P, cx, t, acc, cacc, racc);
+      }
+      continue;
+    }
+    F w = F(0);
+    if (t.flags & TF_W) {
+      const u64 sbits = P.scal[t.sidx];
+      w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
+    }
+    if (t.kind == TK_SET) {  // straight into the running value
+      if (t.xkind != X_NONE) {
+        sterm_fetch<TV, F>(P, cx, t, acc);
+        if (t.flags & TF_W) {
 #pragma unroll
-            for (int k = 0; k < TV; ++k, p += step) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < TV; ++k, p += step)
-              if ((cx.valid >> k) & 1u) stg<float>(reinterpret_cast<float*>(p), (float)acc[k]);
-          }
-        } else {
-          char* p = v.base + (cx.row * v.s1 + cx.e0 * v.s2) * 8;
-          const long long step = (long long)kThreads * v.s2 * 8;
-          if (full) {
-#pragma unroll
-            for (int k = 0; k < TV; ++k, p += step) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < TV; ++k, p += step)
-              if ((cx.valid >> k) & 1u) stg<double>(reinterpret_cast<double*>(p), (double)acc[k]);
-          }
+          for (int k = 0; k < TV; ++k) ip_mul(acc[k], w);
         }
-      } else if constexpr (sizeof(F) == 8) {  // TK_RED (float64 phase only)
-        const int rop = t.dzl;
-        if (P.mode == 1) {
+      } else {
 #pragma unroll
-          for (int k = 0; k < TV; ++k) cx.cacc[k] = red_combine<double>(rop, cx.cacc[k], acc[k]);
-        } else {
-          double x[TV];
-          const double ident = CT<double>::get(red_identity_bits(rop, RB200_T_F64));
-          const bool full = cx.valid == (TV == 32 ? 0xffffffffu : (1u << TV) - 1u);
+        for (int k = 0; k < TV; ++k) acc[k] = w;
+      }
+      continue;
+    }
+    if (t.xkind == X_NONE) {  // acc (op) scalar
+      if (t.kind == TK_MUL) {
 #pragma unroll
-          for (int k = 0; k < TV; ++k) x[k] = (full || ((cx.valid >> k) & 1u)) ? acc[k] : ident;
+        for (int k = 0; k < TV; ++k) ip_mul(acc[k], w);
+      } else if (t.flags & TF_NEGP) {
 #pragma unroll
-          for (int w = TV / 2; w > 0; w >>= 1) {
+        for (int k = 0; k < TV; ++k) ip_sub(acc[k], w);
+      } else if (t.flags & TF_NEGACC) {
 #pragma unroll
-            for (int k = 0; k < w; ++k) x[k] = red_combine<double>(rop, x[k], x[k + w]);
-          }
+        for (int k = 0; k < TV; ++k) ip_rsub(acc[k], w);
+      } else {
 #pragma unroll
-          for (int q = 0; q < RB200_MAX_REDS; ++q)
-            if (q == (int)t.sidx) cx.racc[q] = red_combine<double>(rop, cx.racc[q], x[0]);
-        }
+        for (int k = 0; k < TV; ++k) ip_add(acc[k], w);
       }
       continue;
     }
     F p[TV];
-    if (t.xkind != X_NONE) {
-      sterm_fetch<TV, F>(P, cx, t, p);
-      if (t.flags & TF_W) {
-        const u64 sbits = P.scal[t.sidx];
-        const F w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
+    sterm_fetch<TV, F>(P, cx, t, p);
+    if (t.flags & TF_W) {
 #pragma unroll
-        for (int k = 0; k < TV; ++k) p[k] = l_mul<F>(p[k], w);
-      }
-    } else {
-      const u64 sbits = P.scal[t.sidx];
-      const F w = sizeof(F) == 8 ? (F)__longlong_as_double((long long)sbits) : (F)__uint_as_float((unsigned)sbits);
-#pragma unroll
-      for (int k = 0; k < TV; ++k) p[k] = w;
+      for (int k = 0; k < TV; ++k) ip_mul(p[k], w);
     }
-    if (t.kind == TK_ADD) {
-      if (t.flags & TF_NEGP) {
+    if (t.kind == TK_MUL) {
 #pragma unroll
-        for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(acc[k], p[k]);
-      } else if (t.flags & TF_NEGACC) {
+      for (int k = 0; k < TV; ++k) ip_mul(acc[k], p[k]);
+    } else if (t.flags & TF_NEGP) {
 #pragma unroll
-        for (int k = 0; k < TV; ++k) acc[k] = l_sub<F>(p[k], acc[k]);
-      } else {
+      for (int k = 0; k < TV; ++k) ip_sub(acc[k], p[k]);
+    } else if (t.flags & TF_NEGACC) {
 #pragma unroll
-        for (int k = 0; k < TV; ++k) acc[k] = l_add<F>(acc[k], p[k]);
-      }
-    } else if (t.kind == TK_MUL) {
+      for (int k = 0; k < TV; ++k) ip_rsub(acc[k], p[k]);
+    } else {
 #pragma unroll
-      for (int k = 0; k < TV; ++k) acc[k] = l_mul<F>(acc[k], p[k]);
-    } else {  // TK_SET
-#pragma unroll
-      for (int k = 0; k < TV; ++k) acc[k] = p[k];
+      for (int k = 0; k < TV; ++k) ip_add(acc[k], p[k]);
     }
   }
 }
 
+#ifndef RB200_STREAM_MINB8
+#define RB200_STREAM_MINB8 3
+#endif
 template <int TV>
-__global__ void __launch_bounds__(kThreads, 2) stream_terms_kernel(const __grid_constant__ StreamParams P) {
+__global__ void __launch_bounds__(kThreads, TV == 8 ? RB200_STREAM_MINB8 : 2) stream_terms_kernel(const __grid_constant__ StreamParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem_raw);
   const unsigned tid = threadIdx.x;
@@ -536,14 +605,18 @@ __global__ void __launch_bounds__(kThreads, 2) stream_terms_kernel(const __grid_
   STermCtx<TV> cx;
   cx.tid = tid;
   cx.hoist_s = hoist_s;
+  double racc[RB200_MAX_REDS];
+  double cacc[TV];
 #pragma unroll
-  for (int s = 0; s < RB200_MAX_REDS; ++s) cx.racc[s] = 0.0;
+  for (int s = 0; s < RB200_MAX_REDS; ++s) racc[s] = 0.0;
   for (int s = 0; s < P.n_reds; ++s) {
     const double ident = CT<double>::get(red_identity_bits(P.reds[s].op, RB200_T_F64));
 #pragma unroll
     for (int q = 0; q < RB200_MAX_REDS; ++q)
-      if (q == s) cx.racc[q] = ident;
+      if (q == s) racc[q] = ident;
   }
+#pragma unroll
+  for (int k = 0; k < TV; ++k) cacc[k] = 0.0;
   long long n_it, base0, step_it;  // element offset of tile `it` = base0 + it * step_it
   long long split = 0, col0 = 0, r0 = 0;
   if (P.mode == 0) {
@@ -563,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 2) stream_terms_kernel(const __grid_
     step_it = P.C;
     const double ident = CT<double>::get(red_identity_bits(P.reds[0].op, RB200_T_F64));
 #pragma unroll
-    for (int k = 0; k < TV; ++k) cx.cacc[k] = ident;
+    for (int k = 0; k < TV; ++k) cacc[k] = ident;
     cx.e0 = col0 + tid;
     cx.valid = TV == 32 ? 0xffffffffu : (1u << TV) - 1u;
     cx.row = 0;
@@ -583,19 +656,21 @@ __global__ void __launch_bounds__(kThreads, 2) stream_terms_kernel(const __grid_
   __syncthreads();
 
   auto tile_full = [&](long long it) -> bool { return P.mode == 1 || base0 + it * step_it + TILE <= P.total; };
-  auto issue = [&](long long it) {
+  auto issue = [&](long long it, int slot) {
     if (tid != 0) return;
-    const unsigned slot = (unsigned)(it % P.depth);
-    const unsigned bar = mbar_s + 8u * slot;
-    const unsigned dst = smem_s + slot * P.stage_bytes;
+    const unsigned bar = mbar_s + 8u * (unsigned)slot;
+    const unsigned dst = smem_s + (unsigned)slot * P.stage_bytes;
     const long long eoff = base0 + it * step_it;
     mbar_expect_tx(bar, P.stage_bytes);
     for (int j = 0; j < P.n_staged; ++j)
       bulk_g2s(dst + P.staged[j].off, P.staged[j].base + eoff * P.staged[j].es, (unsigned)(TILE * P.staged[j].es), bar);
   };
+  int islot = 0;  // ring slot of the next tile to request
   if (P.n_staged > 0) {
-    for (long long it = 0; it < P.depth - 1 && it < n_it; ++it)
-      if (tile_full(it)) issue(it);
+    for (long long it = 0; it < P.depth - 1 && it < n_it; ++it) {
+      if (tile_full(it)) issue(it, islot);
+      islot = islot + 1 >= P.depth ? 0 : islot + 1;
+    }
   }
   int slot = 0;
   unsigned par = 0;
@@ -604,7 +679,10 @@ __global__ void __launch_bounds__(kThreads, 2) stream_terms_kernel(const __grid_
     if (P.n_staged > 0) {
       __syncthreads();  // everyone is done with tile it-1: its stage takes tile it + depth - 1
       const long long nx = it + P.depth - 1;
-      if (nx < n_it && tile_full(nx)) issue(nx);
+      if (nx < n_it) {
+        if (tile_full(nx)) issue(nx, islot);
+        islot = islot + 1 >= P.depth ? 0 : islot + 1;
+      }
       if (full) {
         mbar_wait(mbar_s + 8u * (unsigned)slot, (par >> slot) & 1u);
         par ^= 1u << slot;
@@ -629,25 +707,25 @@ __global__ void __launch_bounds__(kThreads, 2) stream_terms_kernel(const __grid_
     }
     if (P.n32 > 0) {
       float a32[TV];
-      sterm_steps<TV, float>(P, cx, 0, P.n32, a32);
+      sterm_steps<TV, float>(P, cx, 0, P.n32, a32, cacc, racc);
       if (P.n_terms > P.n32) {
         double a64[TV];
 #pragma unroll
         for (int k = 0; k < TV; ++k) a64[k] = (double)a32[k];
-        sterm_steps<TV, double>(P, cx, P.n32, P.n_terms, a64);
+        sterm_steps<TV, double>(P, cx, P.n32, P.n_terms, a64, cacc, racc);
       }
     } else {
       double a64[TV];
-      sterm_steps<TV, double>(P, cx, 0, P.n_terms, a64);
+      sterm_steps<TV, double>(P, cx, 0, P.n_terms, a64, cacc, racc);
     }
   }
 
   if (P.mode == 1) {
 #pragma unroll
-    for (int k = 0; k < TV; ++k) P.red_partials[split * P.C + col0 + tid + (long long)k * kThreads] = CT<double>::bits(cx.cacc[k]);
+    for (int k = 0; k < TV; ++k) P.red_partials[split * P.C + col0 + tid + (long long)k * kThreads] = CT<double>::bits(cacc[k]);
     return;
   }
-  stream_finish_reductions(P, cx.racc);
+  stream_finish_reductions(P, racc);
 }
 
 // =============================================================================================
@@ -747,7 +825,7 @@ static void stream_layout(StreamParams& P) {
 static size_t stream_smem(StreamParams& P) {
   const size_t tile = (size_t)P.tv * kThreads;
   const size_t regs = P.n_terms > 0 ? (size_t)P.n_thoist * tile * 8 : (size_t)(P.n_regs + P.n_hoist) * LV * kThreads * 8;
-  const size_t budget = 100 * 1024;
+  const size_t budget = (P.n_terms > 0 && P.tv == 8) ? 70 * 1024 : 100 * 1024;  // (term kernel, 8 per thread: 3 CTAs per SM)
   if (regs + 1024 > budget) return 0;
   int depth = 0;
   if (P.n_staged > 0) {
@@ -812,8 +890,8 @@ static int stream_plan(const rb200_fused_op* op, int sms, int max_red_blocks, in
   for (int v = 0; v < op->n_views; ++v)
     if (op->views[v].dtype != RB200_F32) all_f32 = false;
   if (!no_terms && build_terms(tb, P.insns, P.n_insns, P.terms, kMaxTerms, &P.n_terms, &P.n32, &out_view)) {
-    static const bool tv8 = getenv("RB200_STREAM_TV8") != nullptr;  // debugging aid
-    if (all_f32 && !tv8 && (!column || P.C % (16 * kThreads) == 0)) P.tv = 16;
+    static const bool tv8 = getenv("RB200_STREAM_TV16") != nullptr;  // debugging aid: 16 elements per thread
+    if (all_f32 && tv8 && (!column || P.C % (16 * kThreads) == 0)) P.tv = 16;  // (16 per thread spills: 8 per thread at 3 CTAs per SM is the default)
     stream_layout(P);
     if (column) {
       // row-broadcast direct operands: one copy per CTA in shared memory
@@ -854,14 +932,15 @@ static int stream_plan(const rb200_fused_op* op, int sms, int max_red_blocks, in
       P.red_partials = (u64*)((char*)op->red_scratch + 256);
     }
     long long blocks = P.n_tiles;
-    long long cap = (long long)sms * 2;
+    long long cap = (long long)sms * ((P.n_terms > 0 && P.tv == 8 && T.smem <= 72 * 1024) ? RB200_STREAM_MINB8 : 2);
     if (op->n_reds > 0 && cap > max_red_blocks) cap = max_red_blocks;
     if (blocks > cap) blocks = cap;
     T.blocks = blocks;
   } else {
     P.n_chunks = (int)(P.C / tile);
-    if (P.n_chunks > sms * 2) return 1;
-    int eff = (int)(((long long)sms * 2) / P.n_chunks);
+    const int per_sm = (P.n_terms > 0 && P.tv == 8 && T.smem <= 72 * 1024) ? RB200_STREAM_MINB8 : 2;
+    if (P.n_chunks > sms * per_sm) return 1;
+    int eff = (int)(((long long)sms * per_sm) / P.n_chunks);
     if (n_split > 0 && eff > n_split) eff = n_split;
     if ((long long)eff > P.R) eff = (int)P.R;
     if (eff < 1) eff = 1;

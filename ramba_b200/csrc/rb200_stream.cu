@@ -27,10 +27,13 @@
 #include "rb200_lean.cuh"
 #include "rb200_lean_plan.h"
 #include "rb200_terms.h"
+#include "rb200_mapred.h"
 
 namespace rb200 {
 
 constexpr int kStreamMaxStaged = 4;
+
+
 constexpr int kStreamTile = LV * kThreads;  // 2048
 
 struct StreamStaged {
@@ -511,11 +514,9 @@ __device__ __forceinline__ void sterm_reduce(const StreamParams& P, const STermC
 }
 
 template <int TV, class F>
-__device__ __forceinline__ void sterm_steps(const StreamParams& P, const STermCtx<TV>& cx, int s0, int s1, F (&acc)[TV], double (&cacc)[TV],
-                                            double (&racc)[RB200_MAX_REDS]) {
-#pragma unroll 1
-  for (int s = s0; s < s1; ++s) {
-    const TermStep t = P.terms[s];
+__device__ __forceinline__ void sterm_step(const StreamParams& P, const STermCtx<TV>& cx, const TermStep t, F (&acc)[TV], double (&cacc)[TV],
+                                           double (&racc)[RB200_MAX_REDS]) {
+  {
     if (t.kind >= TK_NEG) {
       if (t.kind == TK_NEG) {
 #pragma unroll
@@ -528,7 +529,7 @@ __device__ __forceinline__ void sterm_steps(const StreamParams& P, const STermCt
       } else if constexpr (sizeof(F) == 8) {
         sterm_reduce<TV>(P, cx, t, acc, cacc, racc);
       }
-      continue;
+      return;
     }
     F w = F(0);
     if (t.flags & TF_W) {
@@ -546,7 +547,7 @@ __device__ __forceinline__ void sterm_steps(const StreamParams& P, const STermCt
 #pragma unroll
         for (int k = 0; k < TV; ++k) acc[k] = w;
       }
-      continue;
+      return;
     }
     if (t.xkind == X_NONE) {  // acc (op) scalar
       if (t.kind == TK_MUL) {
@@ -562,7 +563,7 @@ __device__ __forceinline__ void sterm_steps(const StreamParams& P, const STermCt
 #pragma unroll
         for (int k = 0; k < TV; ++k) ip_add(acc[k], w);
       }
-      continue;
+      return;
     }
     F p[TV];
     sterm_fetch<TV, F>(P, cx, t, p);
@@ -584,6 +585,19 @@ __device__ __forceinline__ void sterm_steps(const StreamParams& P, const STermCt
       for (int k = 0; k < TV; ++k) ip_add(acc[k], p[k]);
     }
   }
+}
+
+// the first kUnrolledSteps steps are unrolled: their descriptors sit at fixed constant-bank addresses, so the compiler
+// loads and decodes them ONCE, outside the loop over tiles
+constexpr int kUnrolledSteps = 6;
+template <int TV, class F>
+__device__ __forceinline__ void sterm_steps(const StreamParams& P, const STermCtx<TV>& cx, int s0, int s1, F (&acc)[TV], double (&cacc)[TV],
+                                            double (&racc)[RB200_MAX_REDS]) {
+#pragma unroll
+  for (int u = 0; u < kUnrolledSteps; ++u)
+    if (s0 + u < s1) sterm_step<TV, F>(P, cx, P.terms[s0 + u], acc, cacc, racc);
+#pragma unroll 1
+  for (int s = s0 + kUnrolledSteps; s < s1; ++s) sterm_step<TV, F>(P, cx, P.terms[s], acc, cacc, racc);
 }
 
 #ifndef RB200_STREAM_MINB8
@@ -842,6 +856,8 @@ struct StreamPlan {
   size_t smem;
   long long blocks;
   int eff;  // column mode: splits actually written
+  bool use_mr;  // the map + reduce kernels of rb200_mapred.cu run this op list
+  MrParams mr;
 };
 
 // 0: planned, 1: not of this kernel's form
@@ -890,6 +906,63 @@ static int stream_plan(const rb200_fused_op* op, int sms, int max_red_blocks, in
   for (int v = 0; v < op->n_views; ++v)
     if (op->views[v].dtype != RB200_F32) all_f32 = false;
   if (!no_terms && build_terms(tb, P.insns, P.n_insns, P.terms, kMaxTerms, &P.n_terms, &P.n32, &out_view)) {
+    // ---- one contiguous source, scalar map, one reduction: the map + reduce kernels (no staging, no interpretation)
+    static const bool no_mr = getenv("RB200_NO_MAPRED_KERNEL") != nullptr;  // debugging aid
+    auto src_of = [](void* ctx, const TermStep& t) -> MrSource {
+      const StreamParams* Q = (const StreamParams*)ctx;
+      MrSource r = {nullptr, 0, false};
+      const LDirect* d = nullptr;
+      if (t.xkind == X_STAGED) d = &Q->direct[Q->staged[t.xidx].dview];
+      else if (t.xkind == X_DIRECT) d = &Q->direct[t.xidx];
+      if (!d || d->s2 != 1) return r;
+      if (Q->mode == 1 && !(d->s1 == Q->C || d->s1 == 0)) return r;
+      r.base = d->base;
+      r.f32 = d->dtype == RB200_F32;
+      r.row_broadcast = Q->mode == 1 && d->s1 == 0;
+      return r;
+    };
+    if (!no_mr && op->n_reds == 1 && mapred_try(P.mode, P.terms, P.n_terms, P.n32, P.scal, src_of, &P, &T.mr) == 0) {
+      MrParams& M = T.mr;
+      const int vec = M.src_f32 ? 4 : 2;
+      bool ok = true;
+      if (!column) {
+        M.total = P.total;
+        M.red.op = op->reds[0].op;
+        M.red.ctype = op->reds[0].ctype;
+        M.red.out = op->reds[0].out;
+        M.red.out_dtype = op->reds[0].out_dtype;
+        M.red_counter = (unsigned int*)op->red_scratch;
+        M.red_partials = (u64*)((char*)op->red_scratch + 256);
+        long long blocks = (P.total / (vec * 4) + kThreads - 1) / kThreads;
+        long long cap = (long long)sms * 8;
+        if (cap > max_red_blocks) cap = max_red_blocks;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        T.blocks = blocks;
+      } else {
+        const long long chunk = (long long)kThreads * vec;
+        if (P.C % chunk != 0 || (P.C * (M.src_f32 ? 4 : 8)) % 16 != 0) ok = false;
+        if (ok) {
+          M.R = P.R;
+          M.C = P.C;
+          M.n_chunks = (int)(P.C / chunk);
+          int eff = (int)(((long long)sms * 8) / M.n_chunks);
+          if (n_split > 0 && eff > n_split) eff = n_split;
+          if ((long long)eff > P.R) eff = (int)P.R;
+          if (eff < 1) eff = 1;
+          M.n_split = eff;
+          M.rows_per_split = (P.R + eff - 1) / eff;
+          M.red_partials = (u64*)op->red_scratch;
+          T.eff = eff;
+          T.blocks = (long long)eff * M.n_chunks;
+        }
+      }
+      if (ok) {
+        T.use_mr = true;
+        T.smem = 0;
+        return 0;
+      }
+    }
     static const bool tv8 = getenv("RB200_STREAM_TV16") != nullptr;  // debugging aid: 16 elements per thread
     if (all_f32 && tv8 && (!column || P.C % (16 * kThreads) == 0)) P.tv = 16;  // (16 per thread spills: 8 per thread at 3 CTAs per SM is the default)
     stream_layout(P);
@@ -976,6 +1049,12 @@ bool describe_stream(const rb200_fused_op* op, int sms, std::string* out) {
   if (stream_plan(op, sms, 4096, op->axis_nsplit, T) != 0) return false;
   const StreamParams& P = T.P;
   char buf[320];
+  if (T.use_mr) {
+    snprintf(buf, sizeof(buf), "kernel=mapred mode=%s source=%s ops=%d(f32:%d) broadcast_operand=%d reduction=%d loads=128bit ctas=%lld", P.mode == 0 ? "global" : "columns",
+             T.mr.src_f32 ? "f32" : "f64", T.mr.n32 + T.mr.n64, T.mr.n32, T.mr.vsrc ? 1 : 0, T.mr.redop, T.blocks);
+    *out = buf;
+    return true;
+  }
   snprintf(buf, sizeof(buf),
            "kernel=%s mode=%s staged_views=%d ring_depth=%d stage_bytes=%u direct_views=%d hoisted=%d lean_insns=%d terms=%d(f32:%d) tile=%d reds=%d "
            "ctas=%lld smem=%zu",
@@ -995,7 +1074,7 @@ int launch_stream_1d(const rb200_fused_op* op, int sms, int max_red_blocks, cuda
   if (op->n_reds > 0 && !op->red_scratch) return 1;
   static StreamPlan T;  // (large; launches are issued from one thread per process)
   if (stream_plan(op, sms, max_red_blocks, 0, T) != 0) return 1;
-  const cudaError_t e = stream_launch(T.P, (unsigned)T.blocks, T.smem, stream);
+  const cudaError_t e = T.use_mr ? mapred_launch(T.mr, (unsigned)T.blocks, stream) : stream_launch(T.P, (unsigned)T.blocks, T.smem, stream);
   if (e != cudaSuccess) {
     char buf[200];
     snprintf(buf, sizeof(buf), "stream kernel launch (blocks=%lld smem=%zu staged=%d depth=%d terms=%d): %s", T.blocks, T.smem, T.P.n_staged, T.P.depth,
@@ -1014,7 +1093,7 @@ int launch_stream_columns(const rb200_fused_op* op, int sms, int n_split, cudaSt
   if (op->ndim != 2 || op->n_axis_red_dims != 1 || op->n_reds != 1 || !op->red_scratch) return 1;
   static StreamPlan T;
   if (stream_plan(op, sms, 4096, n_split, T) != 0) return 1;
-  const cudaError_t e = stream_launch(T.P, (unsigned)T.blocks, T.smem, stream);
+  const cudaError_t e = T.use_mr ? mapred_launch(T.mr, (unsigned)T.blocks, stream) : stream_launch(T.P, (unsigned)T.blocks, T.smem, stream);
   if (e != cudaSuccess) {
     char buf[200];
     snprintf(buf, sizeof(buf), "stream kernel (columns) launch (blocks=%lld smem=%zu staged=%d depth=%d terms=%d): %s", T.blocks, T.smem, T.P.n_staged,

@@ -48,23 +48,35 @@ def test_odd_rows_use_the_cooperative_loader(plans):
     assert _last(plans, "kernel=stencil_terms")["loader"] == "cp.async"
 
 
-def test_streaming_kernel_forms(plans):
+def test_map_reduce_and_streaming_forms(plans):
     import ramba_b200 as rb
 
     X = rb.fromarray(onp.ones((64, 4096), dtype=onp.float32))
+    Y = rb.fromarray(onp.ones((64, 4096), dtype=onp.float32) * 2)
     v = rb.fromarray(onp.ones(4096, dtype=onp.float32))
     rb.sync()
     del plans[:]
-    s = (X * 2.0 + 1.0).sum()
-    d = _last(plans, "kernel=stream_terms mode=elementwise")
-    assert d["staged_views"] == "1" and d["reds"] == "1" and int(d["ring_depth"]) >= 4
+    s = (X * 2.0 + 1.0).sum()  # one source, scalar map, global sum: the map + reduce kernel
+    d = _last(plans, "kernel=mapred mode=global")
+    assert d["source"] == "f32" and d["ops"] == "3(f32:0)" and d["loads"] == "128bit"
     assert float(s) == 3.0 * 64 * 4096
     del plans[:]
-    r = (X + v).sum(axis=0)
+    r = (X + v).sum(axis=0)  # row-split matrix + row-broadcast vector, column sums
     rb.sync()
-    d = _last(plans, "kernel=stream_terms mode=columns")
-    assert d["staged_views"] == "1" and d["hoisted"] == "1"
+    d = _last(plans, "kernel=mapred mode=columns")
+    assert d["broadcast_operand"] == "1" and d["ops"] == "1(f32:1)"
     assert onp.array_equal(r.asarray(), onp.full(4096, 128.0, dtype=onp.float32))
+    del plans[:]
+    t = (X * Y - 0.5).sum()  # two sources: the streaming term kernel (staged ring)
+    d = _last(plans, "kernel=stream_terms mode=elementwise")
+    assert d["staged_views"] == "2" and d["reds"] == "1" and int(d["ring_depth"]) >= 3
+    assert float(t) == 1.5 * 64 * 4096
+    del plans[:]
+    Z = X * 3.0 - Y  # elementwise with a store
+    rb.sync()
+    d = _last(plans, "kernel=stream_terms mode=elementwise")
+    assert d["staged_views"] == "2" and d["reds"] == "0"
+    assert Z is not None
 
 
 def test_everything_else_stays_on_the_general_interpreter(plans):

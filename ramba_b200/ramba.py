@@ -42,6 +42,12 @@ def _new_gid():
 
 
 def shapeToInt(shape):
+    if type(shape) is tuple:
+        for x in shape:
+            if type(x) is not int:
+                break
+        else:
+            return shape
     if isinstance(shape, numbers.Integral):
         return (int(shape),)
     return tuple(int(x) if isinstance(x, numbers.Integral) else x for x in shape)
@@ -965,7 +971,7 @@ def _slice_len(s):
 
 
 class ndarray:
-    __slots__ = ("base", "bdarray", "shape", "distribution", "local_border", "readonly", "maskarray", "__weakref__")
+    __slots__ = ("base", "bdarray", "shape", "distribution", "local_border", "readonly", "maskarray", "_slices", "__weakref__")
     __array_priority__ = 20.0
 
     def __init__(self, shape, dtype=None, *, base=None, distribution=None, local_border=0, flex_dist=True,
@@ -987,6 +993,7 @@ class ndarray:
         self.local_border = local_border
         self.readonly = readonly
         self.maskarray = maskarray
+        self._slices = None  # index -> (shape, distribution) of slice views taken so far
 
     def __del__(self):
         try:
@@ -1230,14 +1237,29 @@ class ndarray:
             cindex = canonical_index(index, self.shape)
             deferred_op.do_ops()
             return getitem_global(self, tuple(s.start for s in cindex))
-        cindex = canonical_index(index, self.shape)
         if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
             deferred_op.do_ops()
-        dim_shapes = tuple(_slice_len(x) for x in cindex)
-        sdist = shardview.slice_distribution(cindex, self.distribution)
-        axismap = [i for i in range(len(dim_shapes)) if i >= len(index) or isinstance(index[i], slice)]
-        if len(axismap) < len(dim_shapes):
-            dim_shapes, sdist = shardview.remap_axis(dim_shapes, sdist, axismap)
+        # the partition of a slice view is a pure function of (this view's distribution, the index): computed once per
+        # array and index - an iterative program takes the same slices every step (ramba/ramba.py:6548-6579 recomputes)
+        try:
+            key = tuple((i.start, i.stop, i.step) if type(i) is slice else ("i", int(i)) for i in index)
+            hit = self._slices.get(key) if self._slices is not None else None
+        except TypeError:
+            key, hit = None, None
+        if hit is None:
+            cindex = canonical_index(index, self.shape)
+            dim_shapes = tuple(_slice_len(x) for x in cindex)
+            sdist = shardview.slice_distribution(cindex, self.distribution)
+            axismap = [i for i in range(len(dim_shapes)) if i >= len(index) or isinstance(index[i], slice)]
+            if len(axismap) < len(dim_shapes):
+                dim_shapes, sdist = shardview.remap_axis(dim_shapes, sdist, axismap)
+            hit = (dim_shapes, sdist)
+            if key is not None:
+                if self._slices is None:
+                    self._slices = {}
+                if len(self._slices) < 64:
+                    self._slices[key] = hit
+        dim_shapes, sdist = hit
         return ndarray(dim_shapes, base=self, distribution=sdist, local_border=0, readonly=self.readonly)
 
     def __setitem__(self, index, value):

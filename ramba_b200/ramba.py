@@ -637,6 +637,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         local_everywhere.append(ok)
     # parts[i] = list of (box, data_ptr, elem_strides or None(shard-addressed), sv)
     parts = [[] for _ in range(nviews)]
+    gathered = set()         # views served whole by an all-gathered buffer
     ring = [False] * nviews  # views whose remote pieces are received into the ring of this rank's padded block
     post_wait = []           # unpack launches that need the received data: (program, shape, bound views)
     recv_bufs = []
@@ -681,6 +682,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                 box = shardview.ShardView(np.array([int(subspace.size[d]) if bc[d] else int(vshape[d]) for d in range(len(bc))], dtype=np.int64),
                                           np.array([int(subspace.start[d]) if bc[d] else 0 for d in range(len(bc))], dtype=np.int64))
                 parts[i].append((box, full.data_ptr(), fst, None, True))
+                gathered.add(i)
                 continue
             for peer in range(W):
                 if peer == w:
@@ -733,6 +735,8 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         return
     # local parts
     for i in range(nviews):
+        if i in gathered:
+            continue
         sv = vdist[i][w]
         if local_everywhere[i] or shardview.is_compat(subspace, sv):
             parts[i].append((subspace, None, None, sv, False))

@@ -16,6 +16,7 @@ never touch HBM (they are register temporaries), live ones are read/written in p
 own division on its own GPU through ramba_b200.runtime.
 """
 import builtins
+import os
 import numbers
 import weakref
 
@@ -149,6 +150,23 @@ def _walk_operands(x, out):
     else:
         out.append(x)
     return out
+
+
+_lower_cache = {}
+_VERIFY_LOWER_CACHE = bool(int(os.environ.get("RB200_VERIFY_LOWER_CACHE", "0")))
+
+
+def _check_same_lowering(a, b):
+    """RB200_VERIFY_LOWER_CACHE=1: every memoised lowering is recomputed and must be identical."""
+    if a[0] != b[0]:
+        raise AssertionError("lowering memo: %r vs %r" % (a[0], b[0]))
+    if a[0] == "limit":
+        return
+    pa, pb = a[1], b[1]
+    same = (pa.insns == pb.insns and pa.scalars == pb.scalars and pa.n_regs == pb.n_regs and pa.reds == pb.reds
+            and pa.view_written == pb.view_written and pa.uses_iota == pb.uses_iota and a[2] == b[2] and a[3] == b[3])
+    if not same:
+        raise AssertionError("lowering memo returned a different op list for the same structural key")
 
 
 class deferred_op:
@@ -356,13 +374,20 @@ class deferred_op:
         add_time("run_deferred_ops", timer() - t1)
 
     def _lower(self, statements, live_gids):
-        # view table
+        """Statements -> (view table, op list, global reductions, axis reductions).  The op list depends only on the
+        STRUCTURE of the statements (operators, which operand is which view / temporary / dead array, view dtypes and
+        aliasing, scalar values), not on the arrays themselves, so it is memoised on that structure: the second and
+        later iterations of a loop skip typing, lowering and register allocation (the reference gets the same effect
+        from Numba's compile cache keyed by the generated source, ramba/ramba.py:8247-8265)."""
         views = []  # (gid, details)
         vindex = {}
+        reads = {}
+        gid_ids = {}
+        tmp_ids = {}
+        elide = self.elide_gids
 
         def view_of(nd):
-            key = nd.gid
-            lst = vindex.setdefault(key, [])
+            lst = vindex.setdefault(nd.gid, [])
             for (dist, idx) in lst:
                 if dist is nd.distribution or shardview.dist_is_eq(dist, nd.distribution):
                     return idx
@@ -371,29 +396,75 @@ class deferred_op:
             lst.append((nd.distribution, idx))
             return idx
 
-        # count reads per view for CSE; register views in first-use order
-        reads = {}
-
-        def count_reads(x):
-            for o in _walk_operands(x, []):
-                if isinstance(o, ArrRef) and o.shape != () and o.gid in live_gids:
-                    i = view_of(o)
+        def key_of(x):
+            """Structural key of an expression; registers views in first-use order and counts their reads."""
+            if isinstance(x, E):
+                return (x.op, x.imm) + tuple([key_of(a) for a in x.args])
+            if isinstance(x, ArrRef):
+                if x.shape == ():
+                    return ("s", type(x.value), repr(x.value))
+                if x.gid in live_gids:
+                    i = view_of(x)
                     reads[i] = reads.get(i, 0) + 1
+                    return ("v", i)
+                return ("d", gid_ids.setdefault(x.gid, len(gid_ids)))
+            if isinstance(x, TempVar):
+                return ("t", tmp_ids.setdefault(x, len(tmp_ids)))
+            if isinstance(x, Iota):
+                return ("i", x.dim)
+            if isinstance(x, np.ndarray) and x.shape == ():
+                x = x.item()
+            return ("s", type(x), repr(x))
 
+        skeys = []
         for st in statements:
             if st[0] == "assign":
-                count_reads(st[2])
-                if st[3] is not None:
-                    count_reads(st[3])
-                if isinstance(st[1], ArrRef) and st[1].gid in live_gids:
-                    view_of(st[1])
+                ek = key_of(st[2])
+                mk = key_of(st[3]) if st[3] is not None else None
+                dst = st[1]
+                if isinstance(dst, TempVar):
+                    dk = ("t", tmp_ids.setdefault(dst, len(tmp_ids)))
+                elif dst.gid in live_gids:
+                    dk = ("v", view_of(dst))
+                elif dst.gid in elide:
+                    dk = ("e", gid_ids.setdefault(dst.gid, len(gid_ids)), rb_dtype(dst.dtype))
+                else:
+                    dk = ("d", gid_ids.setdefault(dst.gid, len(gid_ids)))
+                skeys.append(("assign", dk, ek, mk))
             else:
-                count_reads(st[2])
-                view_of(st[3])
+                ek = key_of(st[2])
+                skeys.append((st[0], st[1], ek, view_of(st[3])))
         if len(views) > cabi.MAX_VIEWS:
             raise ProgramLimit("fused op touches %d array views (max %d)" % (len(views), cabi.MAX_VIEWS))
         if not views or not statements:
             return None
+        vcodes = tuple([rb_dtype(det.dtype) for (_, det) in views])
+        alias = {}
+        key = (vcodes, tuple([alias.setdefault(g, len(alias)) for (g, _) in views]), tuple(skeys))
+        hit = _lower_cache.get(key)
+        if hit is None or _VERIFY_LOWER_CACHE:
+            try:
+                fresh = self._lower_uncached(statements, live_gids, views, vindex, reads)
+            except ProgramLimit as e:
+                fresh = ("limit", str(e))
+            if hit is not None:
+                _check_same_lowering(hit, fresh)
+            if len(_lower_cache) >= 1024:
+                _lower_cache.clear()
+            hit = _lower_cache[key] = fresh
+        if hit[0] == "limit":
+            raise ProgramLimit(hit[1])
+        _, prog, gslots, aslots = hit
+        gred = [(slot, statements[si][3]) for (slot, si) in gslots]
+        ared = [(slot, statements[si][3], statements[si][1]) for (slot, si) in aslots]
+        return views, prog, gred, ared
+
+    def _lower_uncached(self, statements, live_gids, views, vindex, reads):
+        def view_of(nd):
+            for (dist, idx) in vindex[nd.gid]:
+                if dist is nd.distribution or shardview.dist_is_eq(dist, nd.distribution):
+                    return idx
+            raise ProgramError("internal: view not registered")
 
         lw = Lowering([rb_dtype(det.dtype) for (_, det) in views])
         lw.view_gids = [g for (g, _) in views]
@@ -416,9 +487,9 @@ class deferred_op:
                 return lw.scalar(o.item())
             return lw.scalar(o)
 
-        gred = []  # (slot, red_view)
-        ared = []
-        for st in statements:
+        gslots = []  # (slot, statement index)
+        aslots = []
+        for si, st in enumerate(statements):
             if st[0] == "assign":
                 _, dst, expr, mask = st
                 tv = lw.build(expr, resolve)
@@ -434,15 +505,10 @@ class deferred_op:
                 else:
                     dead_values[dst.gid] = tv
             elif st[0] == "gred":
-                _, redop, expr, red_view = st
-                slot = lw.reduce(redop, lw.build(expr, resolve))
-                gred.append((slot, red_view))
+                gslots.append((lw.reduce(st[1], lw.build(st[2], resolve)), si))
             else:
-                _, redop, expr, red_view = st
-                slot = lw.reduce(redop, lw.build(expr, resolve))
-                ared.append((slot, red_view, redop))
-        prog = lw.finish()
-        return views, prog, gred, ared
+                aslots.append((lw.reduce(st[1], lw.build(st[2], resolve)), si))
+        return ("ok", lw.finish(), gslots, aslots)
 
     def _finish(self, live_gids):
         for g in self.delete_gids:

@@ -335,7 +335,7 @@ class Chain:
 class AffineSum:
     """config 3"""
     config = 3
-    kernel = "stream_kernel (lean machine, staged ring, fp64 accumulators)"
+    kernel = "mapred_global_kernel<float> (128-bit loads, 4 in flight, scalar op chain, fp64 accumulation)"
 
     def __init__(self, rb, W, n_total, args):
         import numpy as np
@@ -367,7 +367,7 @@ class AffineSum:
 class Laplacian:
     """config 4"""
     config = 4
-    kernel = "stencil_tile_kernel<float> (TMA-staged halo planes, lean machine)"
+    kernel = "stencil_terms_kernel<float,8> (halo planes staged by TMA tensor copies, weighted-term form)"
 
     def __init__(self, rb, W, n_total, args):
         import numpy as np
@@ -415,7 +415,7 @@ class Laplacian:
 class BcastAxisSum:
     """config 5"""
     config = 5
-    kernel = "stream_kernel, column form (lean machine, staged rows, 8 column accumulators per thread)"
+    kernel = "mapred_columns_kernel<float,8> (128-bit loads, broadcast row operand, 8 fp64 column accumulators per thread)"
 
     def __init__(self, rb, W, n_total, args):
         import numpy as np

@@ -5,7 +5,7 @@
 # into gpurun_out/; profiles/summarise.py (run in the build container) turns them into the committed summaries.
 set -x
 mkdir -p gpurun_out
-declare -A KERN=( [2]="vm_elementwise_kernel" [3]="stream_" [4]="stencil_t" [5]="stream_" )
+declare -A KERN=( [2]="vm_elementwise_kernel" [3]="mapred_global" [4]="stencil_t" [5]="mapred_columns" )
 for c in ${CONFIGS:-2 3 4 5}; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_launches_cfg$c.csv \
       python benchmarks/one_config.py --config $c --steps 4 > gpurun_out/r02_launches_cfg$c.log 2>&1

@@ -34,6 +34,8 @@ def raw_rows(rep):
 def main():
     traffic = {}
     sha = None
+    if "--sass-only" in sys.argv:  # (the library changed after the last capture: refresh the SASS evidence only)
+        return sass_mnemonics()
     p = os.path.join(GO, "r02_lib.sha256")
     if os.path.exists(p):
         sha = open(p).read().split()[0]
@@ -73,6 +75,10 @@ def main():
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
         print(json.dumps(traffic, indent=1))
+    sass_mnemonics()
+
+
+def sass_mnemonics():
     so = os.path.join(ROOT, "ramba_b200", "lib", "libramba_b200.so")
     sass = subprocess.run(["cuobjdump", "-sass", so], stdout=subprocess.PIPE, text=True).stdout
     counts, fn = {}, None
@@ -81,11 +87,14 @@ def main():
         if m:
             fn = m.group(1)
             continue
-        m = re.search(r"\b(UTMALDG\S*|UBLKCP\S*|LDGSTS\S*|SYNCS\S*|ARRIVES\S*)", line)
+        m = re.search(r"\b(UTMALDG\S*|UBLKCP\S*|LDGSTS\S*|SYNCS\S*|ARRIVES\S*|LDG\.E\.128\S*)", line)
         if m and fn:
             counts[(fn, m.group(1))] = counts.get((fn, m.group(1)), 0) + 1
     with open(os.path.join(ROOT, "profiles", "r02_sass_mnemonics.txt"), "w") as f:
-        f.write("# cuobjdump -sass ramba_b200/lib/libramba_b200.so: async-copy / TMA / mbarrier mnemonics per kernel (count)\n")
+        import hashlib
+
+        f.write("# cuobjdump -sass ramba_b200/lib/libramba_b200.so (sha256 %s):\n# async-copy / TMA / mbarrier / 128-bit load mnemonics per kernel (count)\n"
+                % hashlib.sha256(open(so, "rb").read()).hexdigest())
         for (fn, mn), n in sorted(counts.items()):
             dem = subprocess.run(["c++filt", fn], stdout=subprocess.PIPE, text=True).stdout.strip()
             f.write("%-28s %4d  %s\n" % (mn, n, dem[:150]))

@@ -668,6 +668,79 @@ def _ring_receivable(bd_dist, vd, exec_dist, w, W, shard):
     return True
 
 
+_plan_cache = {}
+_PLAN_GENERAL = object()  # this flush needs the general path (exchange, several ranges, nothing to do on this rank)
+_VERIFY_PLAN_CACHE = bool(int(os.environ.get("RB200_VERIFY_PLAN_CACHE", "0")))
+
+
+def _remember_plan(pkey, fop, shards, bound, gred_out, gred_src):
+    """Keep the bound op list of a single-range, all-local flush as a template: the struct bytes, and for every pointer
+    in it the shard it points into and the byte offset from that shard's interior origin."""
+    import ctypes
+
+    vpatch = []
+    for v, b in enumerate(bound):
+        if len(b) < 4 or b[3] is None:
+            return  # (an operand that is not shard-addressed: not a plain local flush)
+        vpatch.append(b[0] - shards[v].ptr(0))
+    rpatch = []
+    if gred_out:
+        for slot, g in enumerate(gred_out):
+            if g is None or slot not in gred_src:
+                return
+            v = gred_src[slot]
+            rpatch.append((slot, v, g[0] - shards[v].ptr(0)))
+    if len(_plan_cache) >= 1024:
+        _plan_cache.clear()
+    _plan_cache[pkey] = (ctypes.string_at(ctypes.addressof(fop), ctypes.sizeof(fop)), vpatch, rpatch)
+
+
+def _run_planned(plan, shards, verify_prog, views, exec_dist, gred):
+    template, vpatch, rpatch = plan
+    fop = cabi.FusedOp.from_buffer_copy(template)
+    fv = fop.views
+    for v, off in enumerate(vpatch):
+        sh = shards[v]
+        one = fv[v]
+        one.base = sh.ptr(0) + off
+        one.alloc_lo, one.alloc_hi = sh.bounds
+    for (slot, v, off) in rpatch:
+        fop.reds[slot].out = shards[v].ptr(0) + off
+    if fop.n_reds:
+        fop.red_scratch = RT.red_scratch().data_ptr()
+    if verify_prog is not None:
+        _verify_plan(fop, verify_prog, views, exec_dist, gred)
+    RT.submit(fop)
+
+
+def _verify_plan(fop, prog, views, exec_dist, gred):
+    """RB200_VERIFY_PLAN_CACHE=1: rebuild the bound op list the long way (without submitting it) and compare bytes."""
+    import ctypes
+
+    saved = dict(_plan_cache)
+    _plan_cache.clear()
+    captured = []
+    orig = RT.submit
+    RT.submit = lambda f: captured.append(f) or f
+    try:
+        _plan_cache_disabled.append(1)
+        run_deferred_ops("verify", views, prog, exec_dist, gred, [], None)
+    finally:
+        _plan_cache_disabled.pop()
+        RT.submit = orig
+        _plan_cache.clear()
+        _plan_cache.update(saved)
+    if len(captured) != 1:
+        raise AssertionError("flush-plan memo: the general path issues %d launches for a memoised single-range flush" % len(captured))
+    a = ctypes.string_at(ctypes.addressof(fop), ctypes.sizeof(fop))
+    b = ctypes.string_at(ctypes.addressof(captured[0]), ctypes.sizeof(captured[0]))
+    if a != b:
+        raise AssertionError("flush-plan memo: the patched template differs from a freshly bound op list")
+
+
+_plan_cache_disabled = []
+
+
 def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     """This worker's share of one flush (RemoteState.run_deferred_ops, ramba/ramba.py:3493-3819)."""
     import torch
@@ -684,6 +757,19 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         shards.append(sh)
     nviews = len(views)
     vdist = [det.distribution for (_, det) in views]
+    # ---- flush-plan memo: a flush whose operands are all local on every rank and that runs as ONE range without axis
+    # reductions is, apart from the buffer addresses, a function of (op list, distributions, shard layouts): the bound
+    # rb200_fused_op of the first execution is kept as a template and later executions only patch pointers into a copy
+    pkey = None
+    if not ared and not _plan_cache_disabled:
+        pkey = (prog, w, W, tuple([sv.key() for sv in exec_dist]), tuple([tuple([sv.key() for sv in vd]) for vd in vdist]),
+                tuple([(sh.shape, sh.border) for sh in shards]))
+        plan = _plan_cache.get(pkey)
+        if plan is not None and plan is not _PLAN_GENERAL:
+            _run_planned(plan, shards, prog if _VERIFY_PLAN_CACHE else None, views, exec_dist, gred)
+            return
+        if plan is _PLAN_GENERAL:
+            pkey = None
     vcode = [rb_dtype(det.dtype) for (_, det) in views]
     written = [bool(prog.view_written.get(i)) for i in range(nviews)]
     ared_views = set()
@@ -798,6 +884,8 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         for wk in pending:
             wk.wait()
         RT.keepalive = recv_bufs
+        if pkey is not None:
+            _plan_cache[pkey] = _PLAN_GENERAL
         return
     # local parts
     for i in range(nviews):
@@ -822,6 +910,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     red_axes = list(red_axes) if red_axes else []
     order = red_axes + [d for d in range(k) if d not in red_axes]
     gred_out = None
+    gred_src = {}
     if gred:
         gred_out = [None] * len(prog.reds)
         for (slot, red_view) in gred:
@@ -829,6 +918,7 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
             # this worker's element of the partial array: the first element of its (size-1) block
             off, _ = RT.bind_view(vdist[i][w], shards[i].strides, shardview.clean_range(vdist[i][w]))
             gred_out[slot] = (shards[i].ptr(off), vcode[i])
+            gred_src[slot] = i
     def _needs_transfer(r):
         for i in range(nviews):
             for (box, ptr, cst, sv, dep) in parts[i]:
@@ -879,7 +969,13 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         shape_r = [int(x) for x in r.size]
         gs = [int(x) for x in r.start]
         if not ared:
-            RT.launch(prog, shape_r, gs, bound, reds=gred_out, worker_num=w, num_workers=W)
+            fop = RT.launch(prog, shape_r, gs, bound, reds=gred_out, worker_num=w, num_workers=W)
+            if pkey is not None:
+                if single and not pending and not post_wait and not recv_bufs and len(ranges) == 1:
+                    _remember_plan(pkey, fop, shards, bound, gred_out, gred_src)
+                else:
+                    _plan_cache[pkey] = _PLAN_GENERAL
+                pkey = None
             continue
         # ---- axis reduction: stage 1 into per-split partials, then fold into the partial array
         shape_p = [shape_r[d] for d in order]

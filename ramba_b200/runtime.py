@@ -215,7 +215,7 @@ class Runtime:
 
     # ---- launching ----------------------------------------------------------------------------
     def launch(self, program, rng_shape, gstart, bound_views, reds=None, n_axis_red=0, axis_nsplit=1,
-               axis_partials=None, worker_num=0, num_workers=1):
+               axis_partials=None, worker_num=0, num_workers=1, submit=True):
         """Bind `program` to one range and call the C-ABI.
         bound_views: list of (data_ptr, elem strides per iteration dim, rb dtype)."""
         ndim = len(rng_shape)
@@ -304,6 +304,12 @@ class Runtime:
                 fop.red_scratch = axis_partials
             else:
                 fop.red_scratch = self.red_scratch().data_ptr()
+        if not submit:
+            return fop
+        return self.submit(fop)
+
+    def submit(self, fop):
+        """Hand one bound op list to the C-ABI on the current stream."""
         ex = self.executor()
         if self.profile_events is not None and not self.test_mode:
             e0 = torch.cuda.Event(enable_timing=True)

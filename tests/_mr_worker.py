@@ -67,6 +67,10 @@ def main():
         from ramba_b200 import _cabi
 
         assert not RT.test_mode and _cabi.launch_count() > 0, "the CUDA library did not run"
+    if MODE == "oracle" and os.environ.get("RB200_DUMP_PLANS"):
+        # debugging aid: which kernel of the CUDA library every op list of this rank would have got
+        with open("%s.%d" % (os.environ["RB200_DUMP_PLANS"], common.worker_num), "w") as f:
+            f.write("\n".join(_oracle_backend.PLANS) + "\n")
     print("RANK %d/%d launches=%d bytes_sent=%d collectives=%d ring_receives=%d failures=%s" % (common.worker_num, common.num_workers, RT.launches, RT.bytes_sent, RT.collectives, RT.ring_receives, failures))
     sys.stdout.flush()
     import torch.distributed as dist

@@ -41,6 +41,7 @@ def test_repeated_step_skips_lowering(oracle_engine, monkeypatch):
         return orig(self, *a, **k)
 
     monkeypatch.setattr(ramba.deferred_op, "_lower_uncached", counted)
+    monkeypatch.setattr(ramba, "_VERIFY_LOWER_CACHE", False)  # (the verification mode lowers every time by design)
     ramba._lower_cache.clear()
     A = rb.arange(1000) / 1000.0
     rb.sync()
@@ -126,3 +127,69 @@ def test_dtypes_are_part_of_the_key(verified_memo):
         got = (rb.fromarray(x) * 3 + 1).asarray()
         exp = x * 3 + 1
         assert got.dtype == exp.dtype and onp.array_equal(got, exp)
+
+
+# ---- the flush-plan memo (ramba.py::run_deferred_ops): bound op lists of single-range, all-local flushes are templates
+@pytest.fixture
+def verified_plans(oracle_engine, monkeypatch):
+    from ramba_b200 import ramba
+
+    monkeypatch.setattr(ramba, "_VERIFY_PLAN_CACHE", True)
+    ramba._plan_cache.clear()
+    return ramba
+
+
+def test_repeated_flush_is_served_by_the_plan_memo(verified_plans, monkeypatch):
+    import ramba_b200 as rb
+
+    planned = []
+    orig = verified_plans._run_planned
+
+    def counted(*a, **k):
+        planned.append(1)
+        return orig(*a, **k)
+
+    monkeypatch.setattr(verified_plans, "_run_planned", counted)
+    x = onp.arange(5000, dtype=onp.float64) / 7.0
+    A = rb.fromarray(x)
+    U = rb.fromarray(onp.arange(20 * 30 * 40, dtype=onp.float32).reshape(20, 30, 40) % 17)
+    V = rb.zeros((20, 30, 40), dtype=onp.float32)
+    rb.sync()
+    for it in range(4):
+        planned.clear()
+        B = rb.sin(A)
+        D = B * B + rb.cos(A) ** 2
+        rb.sync()
+        V[1:-1, 1:-1, 1:-1] = (U[:-2, 1:-1, 1:-1] + U[2:, 1:-1, 1:-1] + U[1:-1, :-2, 1:-1] + U[1:-1, 2:, 1:-1]
+                               + U[1:-1, 1:-1, :-2] + U[1:-1, 1:-1, 2:] - 6.0 * U[1:-1, 1:-1, 1:-1])
+        rb.sync()
+        s = float((A * 2.0 + 1.0).sum())  # a global reduction: the reduction output pointer is patched as well
+        assert len(planned) == (0 if it == 0 else 3), (it, len(planned))
+        assert onp.allclose(D.asarray(), 1.0)
+        assert s == float((x * 2.0 + 1.0).sum())
+    u = onp.asarray(U.asarray())
+    e = onp.zeros_like(u)
+    e[1:-1, 1:-1, 1:-1] = (u[:-2, 1:-1, 1:-1] + u[2:, 1:-1, 1:-1] + u[1:-1, :-2, 1:-1] + u[1:-1, 2:, 1:-1] + u[1:-1, 1:-1, :-2]
+                          + u[1:-1, 1:-1, 2:] - 6.0 * u[1:-1, 1:-1, 1:-1])
+    assert onp.array_equal(V.asarray(), e)
+
+
+def test_plan_memo_executes_once_and_follows_the_buffers(verified_plans):
+    import ramba_b200 as rb
+
+    a = rb.fromarray(onp.zeros(1000))
+    for it in range(5):
+        a += 1.0  # in place: a flush executed twice (or against a stale buffer) would show
+        rb.sync()
+    assert onp.array_equal(a.asarray(), onp.full(1000, 5.0))
+    outs = []
+    for it in range(4):  # fresh result buffers every iteration, all alive at the end
+        outs.append(a * float(2) + 1.0)
+        rb.sync()
+    for o in outs:
+        assert onp.array_equal(o.asarray(), onp.full(1000, 11.0))
+    # same op list over another layout: different template
+    b = rb.fromarray(onp.ones((10, 100)))
+    c = b[:, 1:] * 2.0 + 1.0
+    d = b[:, :-1] * 2.0 + 1.0
+    assert onp.array_equal(c.asarray(), onp.full((10, 99), 3.0)) and onp.array_equal(d.asarray(), onp.full((10, 99), 3.0))

@@ -1,4 +1,4 @@
-"""N>1 path on CPU: world_size 2 and 4 over gloo.  Every rank runs the same driver program (SPMD),
+"""N>1 path on CPU: world sizes 2, 3, 4 and 8 over gloo.  Every rank runs the same driver program (SPMD),
 owns one division of every array, exchanges operand pieces that cross ranks (halo planes, broadcast
 operands, reduction partials) and must reproduce NumPy exactly."""
 import os
@@ -43,7 +43,7 @@ def _run(world, names):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_programs_multirank(world):
     outs = _run(world, "all")
     # the stencil / broadcast / axis-sum programs must really have crossed ranks

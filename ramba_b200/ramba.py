@@ -1075,6 +1075,10 @@ def numpy_broadcast_shape(a, b):
     sa, sb = shp(a), shp(b)
     if (isinstance(a, numbers.Number) or sa == ()) and (isinstance(b, numbers.Number) or sb == ()):
         return None
+    if sa == sb or sb == ():  # (the common cases: same shape, array with scalar)
+        return sa
+    if sa == ():
+        return sb
     return tuple(np.broadcast_shapes(sa, sb))
 
 

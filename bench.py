@@ -539,7 +539,7 @@ def chain_e2e(rb, W, n_per_gpu, steps):
     # The step is issued in chunks on two CUDA streams so that the upload of one chunk overlaps the download of the
     # previous one (PCIe is full duplex); every byte of A goes host->device and every byte of D device->host inside
     # the timed region.
-    n_chunks = 8
+    n_chunks = 16  # (pipeline fill + drain = 2 chunk transfers: 1/8 of the step at 16 chunks)
     bounds = [n_per_gpu * c // n_chunks for c in range(n_chunks + 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
@@ -580,7 +580,7 @@ def chain_e2e(rb, W, n_per_gpu, steps):
     assert abs(float(hD_np[12345]) - 1.0) < 1e-15
     return {"value": n_per_gpu * W * 32 * steps / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n_per_gpu * 8 * W,
             "d2h_bytes_per_step": n_per_gpu * 8 * W, "ms_per_step": dt / steps * 1e3, "steps": steps,
-            "what": "A in pinned host memory -> fromarray (H2D) -> sin/cos/mul/add fused kernel -> D.asarray(out=pinned) (D2H); 8 chunks on 2 CUDA streams so that H2D and D2H overlap"}
+            "what": "A in pinned host memory -> fromarray (H2D) -> sin/cos/mul/add fused kernel -> D.asarray(out=pinned) (D2H); %d chunks on 2 CUDA streams so that H2D and D2H overlap" % n_chunks}
 
 
 def generic_e2e(wl, rb, W, steps):

@@ -122,6 +122,28 @@ def overlaps(a, b):
     return bool(np.all(((s1 <= s2) & (s2 < e1)) | ((s2 <= s1) & (s1 < e2))))
 
 
+_MEMO_MAX = 1 << 14
+
+
+def _memo2(fn):
+    """Memoise a pure function of two shardviews on their keys (shardviews are immutable once in use; a flush asks the
+    same geometric questions every iteration of a loop)."""
+    cache = {}
+
+    def wrapped(a, b):
+        k = (a.key(), b.key())
+        r = cache.get(k, cache)
+        if r is cache:
+            if len(cache) >= _MEMO_MAX:
+                cache.clear()
+            r = cache[k] = fn(a, b)
+        return r
+
+    wrapped.__name__, wrapped.__doc__, wrapped.cache = fn.__name__, fn.__doc__, cache
+    return wrapped
+
+
+@_memo2
 def contains(a, b):
     return (not is_empty(b)) and bool(np.all((a.start <= b.start) & (_stop(b) <= _stop(a))))
 
@@ -143,12 +165,21 @@ def _is_clean(sv):
     return k[2] == ident[0] and k[3] == ident[1] and k[4] == ident[2]
 
 
+_clean_cache = {}
+
+
 def clean_range(sv):
     """Just the box: drop offset, axis map and steps (ramba/shardview_array.py:207-208).
     An already clean shardview is returned as is (shardviews are immutable once in use)."""
     if _is_clean(sv):
         return sv
-    return ShardView(sv.size, sv.start)
+    k = sv.key()
+    r = _clean_cache.get(k)
+    if r is None:
+        if len(_clean_cache) >= _MEMO_MAX:
+            _clean_cache.clear()
+        r = _clean_cache[k] = ShardView(sv.size, sv.start)
+    return r
 
 
 # ---- index -> buffer coordinates
@@ -259,6 +290,19 @@ def mapsv(sv, box):
 
 def mapslice_keep(sv, lo, hi):
     """sv restricted to global indices [lo, hi) per dim, WITHOUT re-basing the coordinates."""
+    key = (sv.key(), tuple(np.asarray(lo).tolist()), tuple(np.asarray(hi).tolist()))
+    r = _keep_cache.get(key)
+    if r is None:
+        if len(_keep_cache) >= _MEMO_MAX:
+            _keep_cache.clear()
+        r = _keep_cache[key] = _mapslice_keep(sv, lo, hi)
+    return r
+
+
+_keep_cache = {}
+
+
+def _mapslice_keep(sv, lo, hi):
     k = len(sv.size)
     s = np.maximum(sv.start, lo)
     e = np.minimum(_stop(sv), hi)
@@ -269,6 +313,7 @@ def mapslice_keep(sv, lo, hi):
     return ShardView(e - s, s, np.minimum(b0, b1), sv.axis_map, sv.steps)
 
 
+@_memo2
 def intersect(a, b):
     """Box of `a` clipped to the box of `b` (ramba/shardview_array.py:530-538)."""
     s = np.minimum(np.maximum(b.start, a.start), _stop(a))
@@ -473,6 +518,21 @@ def get_range_splits_list(svl):
     """Cut the space covered by the boxes in `svl` along every box boundary: the cartesian product
     of per-axis intervals between consecutive boundaries (ramba/shardview_array.py:697-720).
     Inside one resulting range every operand piece is either wholly present or absent."""
+    key = tuple([s.key()[:2] for s in svl])
+    hit = _splits_cache.get(key)
+    if hit is not None:
+        return list(hit)
+    out = _range_splits(svl)
+    if len(_splits_cache) >= 4096:
+        _splits_cache.clear()
+    _splits_cache[key] = tuple(out)
+    return out
+
+
+_splits_cache = {}
+
+
+def _range_splits(svl):
     k = len(svl[0].size)
     cuts = []
     for d in range(k):

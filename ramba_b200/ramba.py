@@ -448,10 +448,11 @@ class deferred_op:
             except ProgramLimit as e:
                 fresh = ("limit", str(e))
             if hit is not None:
-                _check_same_lowering(hit, fresh)
-            if len(_lower_cache) >= 1024:
-                _lower_cache.clear()
-            hit = _lower_cache[key] = fresh
+                _check_same_lowering(hit, fresh)  # (verification mode; the memoised object stays, it keys the plan memo)
+            else:
+                if len(_lower_cache) >= 1024:
+                    _lower_cache.clear()
+                hit = _lower_cache[key] = fresh
         if hit[0] == "limit":
             raise ProgramLimit(hit[1])
         _, prog, gslots, aslots = hit

@@ -1674,6 +1674,10 @@ def _reduction2b(red_arr, op, dtype, asarray):
     there (ramba/ramba.py:5852-5863); under SPMD every rank needs the result, so the partials (one element per rank,
     on the GPUs) are combined by ONE all-reduce and only the scalar comes back to the host."""
     if builtins.all(i == 1 for i in red_arr.shape):
+        if not asarray and common.num_workers == 1:
+            # one rank, one partial: read it straight from the shard (same value and type as indexing the array)
+            deferred_op.do_ops()
+            return _part_to_host(red_arr, 0).reshape(-1)[0]
         sl = (0,) * red_arr.ndim if not asarray else (slice(0, 1),) + (0,) * (red_arr.ndim - 1)
         return red_arr[sl]
     if common.num_workers > 1:

@@ -1027,9 +1027,15 @@ def _remap_iota(prog, order):
     """Iteration dims were permuted to `order`: point IOTA operands at the new positions."""
     if not prog.uses_iota:
         return prog
+    memo = prog.__dict__.setdefault("_remapped", {})
+    hit = memo.get(tuple(order))
+    if hit is not None:
+        return hit  # (one object per permutation: it keys the launch memo)
     import copy
 
     p = copy.copy(prog)
+    p.__dict__.pop("_remapped", None)
+    p.__dict__.pop("_packed", None)
     inv = {d: i for i, d in enumerate(order)}
     p.insns = []
     for f in prog.insns:
@@ -1039,6 +1045,7 @@ def _remap_iota(prog, order):
                 g[nm + "_idx"] = inv[g[nm + "_idx"]]
         p.insns.append(g)
     p.uses_iota = {inv[d] for d in prog.uses_iota}
+    memo[tuple(order)] = p
     return p
 
 

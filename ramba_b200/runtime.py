@@ -17,6 +17,7 @@ every rank runs the driver and calls its own runtime directly.
 PyTorch is used for device memory, streams and torch.distributed only.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -218,6 +219,41 @@ class Runtime:
                axis_partials=None, worker_num=0, num_workers=1, submit=True):
         """Bind `program` to one range and call the C-ABI.
         bound_views: list of (data_ptr, elem strides per iteration dim, rb dtype)."""
+        # ---- launch memo: everything in the bound struct except the addresses is a function of (op list, range, strides)
+        key = (program, tuple([int(s) for s in rng_shape]), tuple([int(g) for g in gstart]),
+               tuple([(tuple(bv[1]), bv[2], len(bv) > 3 and bv[3] is not None) for bv in bound_views]),
+               None if reds is None else tuple([None if r is None else r[1] for r in reds]),
+               n_axis_red, axis_nsplit, worker_num, num_workers)
+        tpl = _launch_cache.get(key)
+        if tpl is not None:
+            fop = cabi.FusedOp.from_buffer_copy(tpl)
+            fv = fop.views
+            for v, bv in enumerate(bound_views):
+                one = fv[v]
+                one.base = bv[0]
+                if len(bv) > 3 and bv[3] is not None:
+                    one.alloc_lo, one.alloc_hi = bv[3]
+            if program.reds:
+                if reds is not None:
+                    for sl, r in enumerate(reds):
+                        if r is not None:
+                            fop.reds[sl].out = r[0]
+                fop.red_scratch = axis_partials if n_axis_red else self.red_scratch().data_ptr()
+            if _VERIFY_LAUNCH_CACHE:
+                fresh = self._build(program, rng_shape, gstart, bound_views, reds, n_axis_red, axis_nsplit, axis_partials, worker_num, num_workers)
+                if ctypes.string_at(ctypes.addressof(fop), ctypes.sizeof(fop)) != ctypes.string_at(ctypes.addressof(fresh), ctypes.sizeof(fresh)):
+                    raise AssertionError("launch memo: the patched template differs from a freshly bound op list")
+        else:
+            fop = self._build(program, rng_shape, gstart, bound_views, reds, n_axis_red, axis_nsplit, axis_partials, worker_num, num_workers)
+            if len(_launch_cache) >= 4096:
+                _launch_cache.clear()
+            _launch_cache[key] = ctypes.string_at(ctypes.addressof(fop), ctypes.sizeof(fop))
+        if not submit:
+            return fop
+        return self.submit(fop)
+
+    def _build(self, program, rng_shape, gstart, bound_views, reds, n_axis_red, axis_nsplit, axis_partials, worker_num, num_workers):
+        """Fill one rb200_fused_op from scratch (collapse / merge the iteration dims, copy the op list, bind the views)."""
         ndim = len(rng_shape)
         dims = list(range(ndim))
         shape = [int(s) for s in rng_shape]
@@ -304,9 +340,7 @@ class Runtime:
                 fop.red_scratch = axis_partials
             else:
                 fop.red_scratch = self.red_scratch().data_ptr()
-        if not submit:
-            return fop
-        return self.submit(fop)
+        return fop
 
     def submit(self, fop):
         """Hand one bound op list to the C-ABI on the current stream."""
@@ -341,5 +375,8 @@ class Runtime:
         if not self.test_mode and self._device is not None:
             torch.cuda.synchronize(self._device)
 
+
+_launch_cache = {}
+_VERIFY_LAUNCH_CACHE = bool(int(os.environ.get("RB200_VERIFY_PLAN_CACHE", "0")))
 
 RT = Runtime()

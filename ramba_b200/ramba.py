@@ -184,6 +184,8 @@ class deferred_op:
         self.delete_gids = []
         self.read_arrs = []
         self.write_arrs = []
+        self.read_gids = set()   # (gids of read_arrs / write_arrs: the alias checks look at the lists only on a gid match)
+        self.write_gids = set()
         self.use_gids = {}  # gid -> ([(view index within gid, details)], bd_shape, bd_distribution, pad, flex)
         self.preconstructed_gids = {}
         self.statements = []
@@ -244,7 +246,7 @@ class deferred_op:
             cls.do_ops()
         cur = cls.ramba_deferred_ops
         # alias check 1: reads/writes a shifted version of an array written earlier in this op
-        if cur is not None and builtins.any(
+        if cur is not None and cur.write_gids and builtins.any(o.gid in cur.write_gids for o in operands) and builtins.any(
             o.gid == wgid and wdist is not None and not shardview.dist_is_eq(wdist, o.distribution)
             for o in operands for (wgid, wdist) in cur.write_arrs
         ):
@@ -254,7 +256,7 @@ class deferred_op:
         if write_array is not None and isinstance(dst, ndarray) and (
             builtins.any(o is not dst and o.gid == write_array.gid and not shardview.dist_is_eq(o.distribution, write_array.distribution)
                          for o in operands)
-            or (cur is not None and builtins.any(
+            or (cur is not None and write_array.gid in cur.read_gids and builtins.any(
                 rgid == write_array.gid and rdist is not None and not shardview.dist_is_eq(rdist, write_array.distribution)
                 for (rgid, rdist) in cur.read_arrs))
         ):
@@ -275,10 +277,12 @@ class deferred_op:
             operands = [mask] + operands
         if write_array is not None and isinstance(dst, ndarray):
             cur.write_arrs.append((write_array.gid, None if write_array.bdarray.flex_dist else write_array.distribution))
+            cur.write_gids.add(write_array.gid)
         for x in operands:
             if x.shape == ():
                 continue
             cur.read_arrs.append((x.gid, None if x.bdarray.flex_dist else x.distribution))
+            cur.read_gids.add(x.gid)
             cur.add_gid(x)
         expr = _detach(expr)
         if axis_reduce is not None:

@@ -343,6 +343,8 @@ def clean_dist(dist):
 
 
 def compatible_distributions(d1, d2):
+    if d1 is d2:
+        return True
     if len(d1) != len(d2):
         return False
     for a, b in zip(d1, d2):

@@ -23,6 +23,11 @@ from ramba_b200.runtime import RT  # noqa: E402
 
 def main():
     names = sys.argv[1].split(",")
+    # a rank that dies or deadlocks leaves the others waiting in a collective: every rank dumps its Python stack and exits
+    # after WATCHDOG seconds, so that a hang shows up as a failed test with the place it hung at, not as a timeout
+    import faulthandler
+
+    faulthandler.dump_traceback_later(int(os.environ.get("RB200_MR_WATCHDOG", "240")), exit=True)
     RT.ensure_process_group()
     failures = []
     import test_api_parity
@@ -52,7 +57,15 @@ def main():
     for prog in progs + loose:
         if prog.__name__ not in names and names != ["all"]:
             continue
-        got = prog(rb)
+        if os.environ.get("RB200_MR_TRACE"):
+            print("RANK %d: %s" % (common.worker_num, prog.__name__), flush=True)
+        try:
+            got = prog(rb)
+        except BaseException:
+            import traceback
+
+            print("RANK %d failed in %s:\n%s" % (common.worker_num, prog.__name__, traceback.format_exc()), flush=True)
+            os._exit(3)  # (the other ranks are released by their watchdogs)
         exp = prog(onp)
         for i, (g, e) in enumerate(zip(got, exp)):
             g, e = onp.asarray(g), onp.asarray(e)
@@ -76,6 +89,7 @@ def main():
     import torch.distributed as dist
 
     dist.barrier()
+    faulthandler.cancel_dump_traceback_later()
     dist.destroy_process_group()
     sys.exit(1 if failures else 0)
 

@@ -37,7 +37,7 @@ def test_programs_multigpu(world):
     for r in range(world):
         env = dict(os.environ)
         env.update({"RANK": str(r), "WORLD_SIZE": str(world), "LOCAL_RANK": str(r), "MASTER_ADDR": "127.0.0.1",
-                    "MASTER_PORT": str(port)})
+                    "MASTER_PORT": str(port), "RB200_MR_TRACE": "1"})
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_mr_worker.py"), "all", "cuda"], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []

@@ -246,8 +246,28 @@ def cpu_baseline_entry(config, n, steps=5, warmup=1):
     ts, threads, kind, what = cpu_arm(config, n, steps, warmup)
     best, med = min(ts), sorted(ts)[len(ts) // 2]
     byt = CONFIG_UNITS[config][0](int(n))
-    return {"value": byt / med / 1e9, "best": byt / best / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
-            "sample": what + "; median of %d steps (best also given), first (JIT) iteration excluded" % len(ts)}
+    out = {"value": byt / med / 1e9, "best": byt / best / 1e9, "unit": "GB/s", "cores": threads, "kind": kind,
+           "sample": what + "; median of %d steps (best also given), first (JIT) iteration excluded" % len(ts)}
+    if config == 2:
+        out["numpy_1thread"] = numpy_single_thread()
+    return out
+
+
+def numpy_single_thread(n=20_000_000, steps=3):
+    """sample/test-numpy.py of the reference (the README's NumPy column): the same chain in plain NumPy on one host
+    thread, on a bounded sample."""
+    import numpy as np
+
+    A = np.arange(n) / 1000.0
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        B = np.sin(A)
+        C = np.cos(A)
+        D = B * B + C ** 2
+        ts.append(time.perf_counter() - t0)
+    assert abs(float(D[12345]) - 1.0) < 1e-15
+    return {"value": 32.0 * n / sorted(ts)[len(ts) // 2] / 1e9, "unit": "GB/s", "sample": "%d elements, median of %d steps" % (n, steps)}
 
 
 def host_ram_free():

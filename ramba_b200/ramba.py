@@ -214,24 +214,29 @@ class deferred_op:
 
     # ---- adding statements --------------------------------------------------------------
     @classmethod
-    def add_op(cls, oplist, write_array, imports=(), axis_reduce=None, precode=(), postcode=()):
+    def add_op(cls, oplist, write_array, imports=(), axis_reduce=None, precode=(), postcode=(), elide=None):
         """oplist = [dst, expr]: `dst = expr` for every index of the iteration space.  dst is an
         ndarray or a temp_var; expr is an E tree over ndarrays, scalars, temp_vars and Iota.
         Global reductions pass precode=[tmp, init] and postcode=[red_array_view, redop-name]
         (ramba/ramba.py:5798-5807); axis reductions pass axis_reduce=(axes, red_view)
-        (ramba/ramba.py:5809-5814)."""
+        (ramba/ramba.py:5809-5814).  `elide` names the gid of an operand that nobody can observe once the
+        calling API function returns (the temporary of `(X*2.0 + 1.0).sum()`): it is treated as dead in the flush
+        that holds this statement, provided the statement that writes it is part of the SAME fused op."""
         t0 = timer()
         dst, expr = oplist[0], oplist[1]
         operands = ([dst] if isinstance(dst, ndarray) else []) + [o for o in _walk_operands(expr, []) if isinstance(o, ndarray)]
         arr = write_array if write_array is not None else next((o for o in operands if isinstance(o, ndarray)), None)
         assert arr is not None, "Deferred op with no ndarray parameter"
         shape, distribution = arr.shape, arr.distribution
+        # the partition of `arr` can still follow the op's only if arr is a whole array that no flush has touched: a VIEW of
+        # a flexible array was cut from the partition the array had then and does not move when the array is pinned
+        fixed = arr.bdarray.remote_constructed or not arr.bdarray.flex_dist or arr.base is not None
         cur = cls.ramba_deferred_ops
         if cur is not None and (
             cur.shape != shape
             or (
                 not shardview.compatible_distributions(cur.distribution, distribution)
-                and (arr.bdarray.remote_constructed or not arr.bdarray.flex_dist)
+                and fixed
                 and not cur.flex_dist
             )
             or len(cur.statements) >= cls.max_statements
@@ -266,11 +271,15 @@ class deferred_op:
             cls.add_op([write_array, tmp_array], write_array)
             return
         if cls.ramba_deferred_ops is None:
-            cls.ramba_deferred_ops = cls(shape, distribution, arr.bdarray.flex_dist)
+            cls.ramba_deferred_ops = cls(shape, distribution, not fixed)
         cur = cls.ramba_deferred_ops
-        if not arr.bdarray.flex_dist:
+        if fixed and (cur.flex_dist or not arr.bdarray.flex_dist):
             cur.distribution = distribution
             cur.flex_dist = False
+        if elide is not None and elide in cur.write_gids and bdarray.valid_gid(elide) \
+                and not bdarray.get_by_gid(elide).remote_constructed:
+            # (decided HERE, after admission: a flush forced by this very statement must still materialise the operand)
+            cur.elide_gids.add(elide)
         mask = None
         if write_array is not None and isinstance(dst, ndarray) and write_array.maskarray is not None:
             mask = write_array.maskarray
@@ -523,6 +532,246 @@ class deferred_op:
                 bd = bdarray.get_by_gid(k)
                 bd.remote_constructed = True
                 bd.flex_dist = False
+
+
+# =============================================================================================
+# the lazy DAG in front of the fuser (ramba/ramba.py:4387-5293)
+# =============================================================================================
+NO_DAG = bool(int(os.environ.get("RAMBA_NO_DAG", "0")))  # the reference's switch (ramba/common.py): statements go straight to the fuser
+
+
+class DAG:
+    """One node per deferred STATEMENT (`dst = expr`, a reduction, a fill).  The reference builds one node per API call
+    and runs the call's executor when the node is materialised (DAG.add ramba/ramba.py:4512-4548, DAGapi 5160-5293);
+    here an API call computes its result's shape / dtype / distribution at once (all metadata, nothing on the GPU) and
+    what is deferred is exactly the part the reference's executors end in: the `deferred_op.add_op` of the statement.
+
+      * dependencies are tracked per bdarray (gid): a node depends on the last pending writer of everything it reads
+        (RAW), and a writer on the last pending writer (WAW) and on every pending reader since (WAR) - what the
+        reference gets from `ndarray.dag` / `bdarray.dag` and the in-place rule of DAG.add (4527-4539);
+      * `instantiate(arr)` walks the backward dependencies of arr's last writer depth first, same-shaped branches
+        first (depth_first_traverse, 4792-4838), hands the statements to the fuser in that order and flushes;
+        `execute_all` (sync) starts from every node nothing depends on, oldest first, grouped by shape (5025-5060) -
+        so interleaved chains over different shapes fuse per shape instead of flushing at every change;
+      * a node whose output nobody can observe is never executed (DAG.execute's `soutput is None`, 4854-4856): the
+        destination of an out-of-place statement is held weakly; when the last handle dies the node is dropped together
+        with the handles it holds, which may drop the nodes that produced those, and so on;
+      * nodes hold their operands strongly until they are executed (like the reference's `args`), so whether a
+        temporary is materialised is still decided by handle liveness at flush time;
+      * while a node executes, API calls made by the executor run inline (`DAG.in_evaluate`), and RAMBA_NO_DAG=1
+        makes every call inline."""
+
+    __slots__ = ("seq_no", "expr", "dst", "out_ref", "write_array", "kw", "shape", "backward_deps", "forward_deps",
+                 "executed", "rgids", "wgids", "__weakref__")
+    pending = {}       # seq_no -> node, in program order
+    last_writer = {}   # gid -> pending node that writes the array last
+    readers = {}       # gid -> pending nodes that read it since
+    in_evaluate = 0
+    dag_count = 0
+    executed_count = 0
+    pruned_count = 0
+    max_pending = 4096
+
+    @classmethod
+    def add(cls, oplist, write_array, imports=(), axis_reduce=None, precode=(), postcode=(), elide=None):
+        """Same signature as deferred_op.add_op (the operator seam, ramba/ramba.py:8383-8385)."""
+        if NO_DAG or cls.in_evaluate:
+            deferred_op.add_op(oplist, write_array, imports, axis_reduce, precode, postcode, elide)
+            return
+        dst, expr = oplist[0], oplist[1]
+        reads = [o for o in _walk_operands(expr, []) if isinstance(o, ndarray) and o.shape != ()]
+        node = object.__new__(cls)
+        node.seq_no = cls.dag_count
+        cls.dag_count += 1
+        node.expr = expr
+        node.kw = (imports, axis_reduce, precode, postcode, elide)
+        node.executed = False
+        node.forward_deps = set()
+        arr = write_array if write_array is not None else (dst if isinstance(dst, ndarray) else (reads[0] if reads else None))
+        node.shape = arr.shape if arr is not None else None
+        wg = []
+        if write_array is not None:
+            wg.append(write_array.gid)
+            if write_array.maskarray is not None:
+                reads.append(write_array.maskarray)
+        if isinstance(dst, ndarray) and dst is not write_array:
+            wg.append(dst.gid)
+        if axis_reduce is not None:
+            wg.append(axis_reduce[1].gid)
+        if precode:
+            wg.append(postcode[0].gid)
+        rg = [o.gid for o in reads]
+        # the destination of an out-of-place statement is the only way to observe it: hold it weakly
+        if isinstance(dst, ndarray) and dst is write_array and dst.base is None and dst.maskarray is None \
+                and axis_reduce is None and not precode and dst.gid not in rg:
+            node.dst = None
+            node.write_array = None
+            node.out_ref = weakref.ref(dst, node._output_died)
+        else:
+            node.dst = dst
+            node.write_array = write_array
+            node.out_ref = None
+        deps = []
+        lw, rd = cls.last_writer, cls.readers
+        for g in rg:
+            d = lw.get(g)
+            if d is not None and d not in deps:
+                deps.append(d)
+        for g in wg:
+            d = lw.get(g)
+            if d is not None and d not in deps:
+                deps.append(d)
+            for d in rd.get(g, ()):
+                if d not in deps:
+                    deps.append(d)
+        for d in deps:
+            d.forward_deps.add(node)
+        node.backward_deps = deps
+        node.rgids = rg
+        node.wgids = wg
+        for g in rg:
+            rd.setdefault(g, []).append(node)
+        for g in wg:
+            lw[g] = node
+            rd.pop(g, None)
+        cls.pending[node.seq_no] = node
+        if len(cls.pending) >= cls.max_pending:
+            cls.execute_all()
+
+    # ---- pruning ---------------------------------------------------------------------------
+    def _output_died(self, _ref=None):
+        """Weakref callback: the last handle of this node's (out-of-place) destination is gone."""
+        if self.executed or DAG.in_evaluate:
+            return  # (during an evaluation the execution loop skips it)
+        if not self.forward_deps:
+            self._retire(False)
+
+    def _retire(self, ran):
+        """Take the node out of the graph (executed or pruned) and let go of its operands."""
+        self.executed = True
+        cls = DAG
+        cls.pending.pop(self.seq_no, None)
+        for d in self.backward_deps:
+            d.forward_deps.discard(self)
+        for f in self.forward_deps:
+            try:
+                f.backward_deps.remove(self)
+            except ValueError:
+                pass
+        lw, rd = cls.last_writer, cls.readers
+        for g in self.wgids:
+            if lw.get(g) is self:
+                del lw[g]
+        for g in self.rgids:
+            lst = rd.get(g)
+            if lst is not None:
+                try:
+                    lst.remove(self)
+                except ValueError:
+                    pass
+                if not lst:
+                    del rd[g]
+        if ran:
+            cls.executed_count += 1
+        else:
+            cls.pruned_count += 1
+        self.backward_deps = ()
+        self.forward_deps = ()
+        self.out_ref = None
+        self.kw = None
+        # last: dropping the operands may end other arrays' lives (and prune their producers through the callback above)
+        self.expr = None
+        self.dst = None
+        self.write_array = None
+
+    def _execute(self):
+        """Hand the statement to the fuser (DAG.execute, ramba/ramba.py:4846-4872)."""
+        dst, wa = self.dst, self.write_array
+        if self.out_ref is not None:
+            dst = wa = self.out_ref()
+            if dst is None:
+                self._retire(False)  # nobody can observe the result
+                return
+        imports, axis_reduce, precode, postcode, elide = self.kw
+        expr = self.expr
+        self._retire(True)
+        deferred_op.add_op([dst, expr], wa, imports, axis_reduce, precode, postcode, elide)
+
+    # ---- materialisation -------------------------------------------------------------------
+    @classmethod
+    def _run(cls, roots):
+        """Depth-first over the backward dependencies of `roots` (same-shaped branches first), then execute in that
+        order (depth_first_traverse + the loop of instantiate_dag_node, ramba/ramba.py:4792-4838, 5007-5012)."""
+        order = []
+        seen = set()
+        for root in roots:
+            if root.executed or root in seen:
+                continue
+            seen.add(root)
+            stack = [(root, iter(cls._ordered_deps(root)))]
+            while stack:
+                n, it = stack[-1]
+                for d in it:
+                    if d not in seen and not d.executed:
+                        seen.add(d)
+                        stack.append((d, iter(cls._ordered_deps(d))))
+                        break
+                else:
+                    order.append(n)
+                    stack.pop()
+        cls.in_evaluate += 1
+        try:
+            for n in order:
+                if not n.executed:
+                    n._execute()
+        finally:
+            cls.in_evaluate -= 1
+
+    @staticmethod
+    def _ordered_deps(node):
+        deps = node.backward_deps
+        if len(deps) < 2:
+            return deps
+        shp = node.shape
+        return [d for d in deps if d.shape == shp] + [d for d in deps if d.shape != shp]
+
+    @classmethod
+    def instantiate(cls, arr=None):
+        """Make `arr` real: run what it depends on, then flush (DAG.instantiate, ramba/ramba.py:4840-4852)."""
+        if cls.pending and isinstance(arr, ndarray):
+            node = cls.last_writer.get(arr.gid)
+            if node is not None:
+                cls._run([node])
+        deferred_op.do_ops()
+
+    @classmethod
+    def execute_all(cls, do_ops=False):
+        """Run every pending node: start from the ones nothing depends on, oldest first, grouped by output shape
+        (DAG.execute_all, ramba/ramba.py:5025-5060)."""
+        if cls.pending:
+            by_shape = {}
+            for n in cls.pending.values():
+                if not n.forward_deps:
+                    by_shape.setdefault(n.shape, []).append(n)
+            cls._run([n for lst in by_shape.values() for n in lst])
+            if cls.pending:  # (nodes retired by the run may have left others without dependants)
+                cls._run(list(cls.pending.values()))
+        if do_ops:
+            deferred_op.do_ops()
+
+    @classmethod
+    def reset(cls):
+        """Forget every pending node without executing it (tests)."""
+        for n in list(cls.pending.values()):
+            n._retire(False)
+        cls.pending.clear()
+        cls.last_writer.clear()
+        cls.readers.clear()
+        cls.in_evaluate = 0
+        deferred_op.ramba_deferred_ops = None
+
+
+RT.on_reset.append(DAG.reset)
 
 
 def format_program(prog, views, shape):
@@ -1211,7 +1460,7 @@ class ndarray:
         return ndarray_details(self)
 
     def instantiate(self):
-        deferred_op.do_ops()
+        DAG.instantiate(self)
         return self
 
     # ---- host round trip (ramba/ramba.py:5735-5765)
@@ -1222,7 +1471,7 @@ class ndarray:
         caller synchronises before reading `out` (lets transfers of different streams overlap)."""
         if self.shape == ():
             return self.distribution
-        deferred_op.do_ops()
+        DAG.instantiate(self)
         return gather_to_host(self, out=out, non_blocking=non_blocking)
 
     def __array__(self, dtype=None, copy=None):
@@ -1273,7 +1522,7 @@ class ndarray:
             raise ValueError("Non-broadcastable.")
         bd = [i < new_dims or (shape[i] != 1 and self.shape[i - new_dims] == 1) for i in range(len(shape))]
         if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
-            deferred_op.do_ops()
+            DAG.instantiate(self)
         return ndarray(shape, base=self, distribution=shardview.broadcast(self.distribution, bd, shape),
                        local_border=0, readonly=True)
 
@@ -1284,7 +1533,7 @@ class ndarray:
         return not builtins.any(a > 1 and b > 1 and a != b for a, b in zip(shape[new_dims:], self.shape))
 
     def array_unaryop(self, op, optext, reduction=False, dtype=None, axis=None, keepdims=False, redop=None, initval=0,
-                      asarray=False):
+                      asarray=False, elide=None):
         if dtype is None:
             dtype = self.dtype
         elif isinstance(dtype, str) and dtype == "float":
@@ -1292,9 +1541,9 @@ class ndarray:
         dtype = np.dtype(dtype)
         if not reduction:
             new = create_array_with_divisions(self.shape, self.distribution, dtype=dtype)
-            deferred_op.add_op([new, E(optext, self)], new)
+            DAG.add([new, E(optext, self)], new)
             return new
-        return self._reduction(op, redop, dtype, axis, keepdims, initval, asarray)
+        return self._reduction(op, redop, dtype, axis, keepdims, initval, asarray, elide)
 
     def array_binop(self, rhs, op, optext, inplace=False, reverse=False, dtype=None):
         if isinstance(rhs, np.ndarray):
@@ -1321,17 +1570,17 @@ class ndarray:
             if self.readonly:
                 raise ValueError("assignment destination is read-only")
             assert self.shape == new_shape, "non-broadcastable output operand"
-            deferred_op.add_op([self, E(optext, self, rhsview)], self)
+            DAG.add([self, E(optext, self, rhsview)], self)
             return self
         new = empty(new_shape, dtype=new_dtype)
         if reverse:
-            deferred_op.add_op([new, E(optext, rhsview, selfview)], new)
+            DAG.add([new, E(optext, rhsview, selfview)], new)
         else:
-            deferred_op.add_op([new, E(optext, selfview, rhsview)], new)
+            DAG.add([new, E(optext, selfview, rhsview)], new)
         return new
 
     # ---- reductions (ramba/ramba.py:5789-5937)
-    def _reduction(self, op, redop, dtype, axis, keepdims, initval, asarray):
+    def _reduction(self, op, redop, dtype, axis, keepdims, initval, asarray, elide=None):
         if axis is not None:
             if isinstance(axis, numbers.Number):
                 axis = [axis]
@@ -1351,13 +1600,13 @@ class ndarray:
             red_bcast = ndarray(self.shape, base=red_arr, distribution=bdist, local_border=0, readonly=False)
             tmp = deferred_op.get_temp_var()
             src = self
-            deferred_op.add_op([tmp, self if self.maskarray is None else E("where", self.maskarray, self, _identity_scalar(redop, dtype))],
-                               red_bcast, precode=[tmp, initval], postcode=[red_bcast, redop])
+            DAG.add([tmp, self if self.maskarray is None else E("where", self.maskarray, self, _identity_scalar(redop, dtype))],
+                               red_bcast, precode=[tmp, initval], postcode=[red_bcast, redop], elide=elide)
             return _reduction2b(red_arr, op, dtype, asarray)
         dsz, dist, bdist = shardview.reduce_axes(self.shape, self.distribution, axis)
         red_arr = full(dsz, initval, dtype=dtype, distribution=dist, no_defer=True)
         red_bcast = ndarray(self.shape, base=red_arr, distribution=bdist, local_border=0, readonly=False)
-        deferred_op.add_op([red_bcast, self], red_bcast, axis_reduce=(axis, red_bcast), postcode=[red_bcast, redop])
+        DAG.add([red_bcast, self], red_bcast, axis_reduce=(axis, red_bcast), postcode=[red_bcast, redop], elide=elide)
         return _reduction2(red_arr, op, redop, dtype, axis, keepdims is True)
 
     def mean(self, axis=None, dtype=None, **kwargs):
@@ -1417,10 +1666,10 @@ class ndarray:
             return self.distribution[()]
         if builtins.all(isinstance(i, numbers.Integral) for i in index) and len(index) == self.ndim:
             cindex = canonical_index(index, self.shape)
-            deferred_op.do_ops()
+            DAG.instantiate(self)
             return getitem_global(self, tuple(s.start for s in cindex))
         if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
-            deferred_op.do_ops()
+            DAG.instantiate(self)
         # the partition of a slice view is a pure function of (this view's distribution, the index): computed once per
         # array and index - an iterative program takes the same slices every step (ramba/ramba.py:6548-6579 recomputes)
         try:
@@ -1469,23 +1718,23 @@ class ndarray:
             if value.size == 1:
                 value = value.reshape(())
         if isinstance(value, (numbers.Number, np.generic)) or (isinstance(value, np.ndarray) and value.shape == ()):
-            deferred_op.add_op([view, value if not isinstance(value, np.ndarray) else value.item()], view)
+            DAG.add([view, value if not isinstance(value, np.ndarray) else value.item()], view)
             return
         if isinstance(value, np.ndarray):
             value = fromarray(value)
         if value.shape == ():
-            deferred_op.add_op([view, value.distribution.item()], view)
+            DAG.add([view, value.distribution.item()], view)
             return
         if not value.broadcastable_to(view.shape):
             raise ValueError("could not broadcast input array from shape %s into shape %s" % (value.shape, view.shape))
         if value.shape != view.shape:
             value = value.broadcast_to(view.shape)
         if not (view.gid == value.gid and shardview.dist_is_eq(view.distribution, value.distribution)):
-            deferred_op.add_op([view, value], view)
+            DAG.add([view, value], view)
 
     def remapped_axis(self, newmap):
         if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
-            deferred_op.do_ops()
+            DAG.instantiate(self)
         newshape, newdist = shardview.remap_axis(self.shape, self.distribution, newmap)
         return ndarray(newshape, base=self, distribution=newdist, local_border=0, readonly=self.readonly)
 
@@ -1496,7 +1745,7 @@ class ndarray:
         if len(set(axes)) != len(axes):
             raise ValueError("repeated axis")
         if self.bdarray.flex_dist or not self.bdarray.remote_constructed:
-            deferred_op.do_ops()
+            DAG.instantiate(self)
         newshape, newdist = shardview.expand_unit_dims(self.shape, self.distribution, axes)
         return ndarray(newshape, base=self, distribution=newdist, local_border=0, readonly=True)
 
@@ -1552,12 +1801,12 @@ class ndarray:
         if dtype == self.dtype:
             return globals()["copy"](self) if copy else self
         new = create_array_with_divisions(self.shape, self.distribution, dtype=dtype)
-        deferred_op.add_op([new, self], new)
+        DAG.add([new, self], new)
         return new
 
     def clip(self, a_min, a_max, out=None):
         new = out if out is not None else create_array_with_divisions(self.shape, self.distribution, dtype=self.dtype)
-        deferred_op.add_op([new, E("min", a_max, E("max", self, a_min))], new)
+        DAG.add([new, E("min", a_max, E("max", self, a_min))], new)
         return new
 
     def allclose(self, other, rtol=1e-5, atol=1e-8, equal_nan=False):
@@ -1687,14 +1936,14 @@ def _reduction2b(red_arr, op, dtype, asarray):
     if builtins.all(i == 1 for i in red_arr.shape):
         if not asarray and common.num_workers == 1:
             # one rank, one partial: read it straight from the shard (same value and type as indexing the array)
-            deferred_op.do_ops()
+            DAG.instantiate(red_arr)
             return _part_to_host(red_arr, 0).reshape(-1)[0]
         sl = (0,) * red_arr.ndim if not asarray else (slice(0, 1),) + (0,) * (red_arr.ndim - 1)
         return red_arr[sl]
     if common.num_workers > 1:
         import torch.distributed as dist
 
-        deferred_op.do_ops()
+        DAG.instantiate(red_arr)
         RT.ensure_process_group()
         t = _local_partial_tensor(red_arr, 1, op)
         dist.all_reduce(t, op=getattr(dist.ReduceOp, _ALLREDUCE_OP[op]))
@@ -1743,7 +1992,7 @@ def _reduction2(red_arr, op, redop, dtype, axis, keepdims):
         import torch
         import torch.distributed as dist
 
-        deferred_op.do_ops()
+        DAG.instantiate(red_arr)
         RT.ensure_process_group()
         w = common.worker_num
         t = _local_partial_tensor(red_arr, kept_elems, op)
@@ -1775,7 +2024,7 @@ def _reduction2(red_arr, op, redop, dtype, axis, keepdims):
                 sl.append(slice(None))
         piece = red_arr[tuple(sl)]
         expr = piece if expr is None else E(name, expr, piece)
-    deferred_op.add_op([arr, expr], arr)
+    DAG.add([arr, expr], arr)
     return arr[sl1]
 
 
@@ -1846,11 +2095,12 @@ def _make_reduction(name, redop, init, dtype=None):
         # reduction flushes INSIDE the call, while the caller's expression still holds the temporary, so the reference
         # materialises it (ramba/ramba.py:8123-8127 looks at handle liveness only); here a temporary whose only
         # reference is the pending call is treated as already dead and never touches HBM.
+        elide = None
         if _sys_getrefcount(self) <= _TEMP_REFCOUNT and self.base is None and self.bdarray.nrefs == 1 \
-                and not self.bdarray.remote_constructed and deferred_op.ramba_deferred_ops is not None:
-            deferred_op.ramba_deferred_ops.elide_gids.add(self.gid)
+                and not self.bdarray.remote_constructed:
+            elide = self.gid  # (add_op honours it only if the statement writing the temporary shares the fused op)
         return self.array_unaryop(name, None, reduction=True, dtype=dtype, axis=axis, keepdims=keepdims, redop=redop,
-                                  initval=init, asarray=asarray)
+                                  initval=init, asarray=asarray, elide=elide)
 
     _method.__name__ = name
     return _method
@@ -2056,7 +2306,7 @@ def fromarray_local(block, shape, dtype=None, **kwargs):
 
 def local_block_to_host(nd, out=None, non_blocking=False):
     """SPMD extension: this rank's block of `nd` as a host array (no gather)."""
-    deferred_op.do_ops()
+    DAG.instantiate(nd)
     return _part_to_host(nd, common.worker_num, out=out, non_blocking=non_blocking)
 
 
@@ -2106,7 +2356,7 @@ def create_array(shape, filler, local_border=0, dtype=None, distribution=None, n
         # the producers of a reduction stay fused with it (ramba/ramba.py:5918, 8603-8627)
         _fill_now(new, filler)
         return new
-    deferred_op.add_op([new, filler], new)
+    DAG.add([new, filler], new)
     return new
 
 
@@ -2187,7 +2437,7 @@ def full_like(other, v, dtype=None, **kwargs):
 
 def copy(arr, local_border=0):
     new = create_array_with_divisions(arr.shape, arr.distribution, dtype=arr.dtype)
-    deferred_op.add_op([new, arr], new)
+    DAG.add([new, arr], new)
     return new
 
 
@@ -2206,7 +2456,7 @@ def arange(start, stop=None, step=None, dtype=None, *, like=None, local_border=0
         expr = E("add", start, Iota(0))
     else:
         expr = E("add", start, E("mul", step, Iota(0)))
-    deferred_op.add_op([res, expr], res)
+    DAG.add([res, expr], res)
     return res
 
 
@@ -2230,7 +2480,7 @@ def fromfunction(function, shape, dtype=None, **kwargs):
     idx = []
     for d in range(len(shape)):
         a = empty(shape, dtype=np.int64)
-        deferred_op.add_op([a, Iota(d)], a)
+        DAG.add([a, Iota(d)], a)
         idx.append(a)
     out = function(*idx)
     if not isinstance(out, ndarray):
@@ -2357,7 +2607,7 @@ def where(cond, a=None, b=None):
 
     adt = a.dtype if isinstance(a, ndarray) else np.asarray(a).dtype
     new = empty(shape, dtype=adt)
-    deferred_op.add_op([new, E("where", view(cond), view(a), view(b))], new)
+    DAG.add([new, E("where", view(cond), view(a), view(b))], new)
     return new
 
 
@@ -2486,7 +2736,7 @@ def sstencil(func, *args, out=None, **kwargs):
         # like the reference: allocated with the divisions and the border of the first argument (ramba/ramba.py:10022-10026)
         new = create_array_with_divisions(shape, arrays[0].distribution, local_border=arrays[0].local_border,
                                           dtype=res.dtype if isinstance(res, ndarray) else np.float64)
-        deferred_op.add_op([new, 0], new)
+        DAG.add([new, 0], new)
     else:
         new = zeros(shape, dtype=res.dtype if isinstance(res, ndarray) else np.float64)
     interior = tuple(slice(-lo[d], shape[d] - hi[d]) for d in range(k))
@@ -2748,7 +2998,7 @@ def _index_arrays(shape):
     idx = []
     for d in range(len(shape)):
         a = empty(shape, dtype=np.int64)
-        deferred_op.add_op([a, Iota(d)], a)
+        DAG.add([a, Iota(d)], a)
         idx.append(a)
     return idx
 
@@ -2847,7 +3097,7 @@ def _scan_native(a, axis, op, dtype):
     W, w = common.num_workers, common.worker_num
     # a whole array in the result dtype, in its own buffer: views / other dtypes are materialised by one fused copy
     src = a.astype(out_dtype) if (a.dtype != out_dtype or a.base is not None or a.maskarray is not None) else a
-    deferred_op.do_ops()
+    DAG.instantiate(src)
     dist = src.bdarray.distribution
     if src.base is not None or src.distribution is not dist and not shardview.dist_is_eq(src.distribution, dist):
         return None
@@ -2966,6 +3216,7 @@ def cumsum(a, axis=None, dtype=None, out=None):
 def sync():
     """Flush pending fused ops and wait for this rank's GPU (ramba/ramba.py:9843-9849)."""
     t0 = timer()
+    DAG.execute_all()
     deferred_op.do_ops()
     RT.synchronize()
     add_time("sync", timer() - t0)

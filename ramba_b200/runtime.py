@@ -98,6 +98,7 @@ class Runtime:
         self.ring_receives = 0  # halo pieces received into the ring of a padded block (getborder)
         self.keepalive = None  # staging buffers of the last flush
         self.profile_events = None  # list -> (start, end, n_insns) CUDA events around every launch
+        self.on_reset = []  # the engine registers what else must be forgotten with the shards (pending DAG nodes, fused op)
 
     # ---- device / process group ---------------------------------------------------------
     @property
@@ -122,6 +123,8 @@ class Runtime:
 
     def reset(self):
         """Forget every shard and go back to the product configuration (CUDA executor)."""
+        for hook in self.on_reset:
+            hook()
         self.shards.clear()
         self._device = None
         self._executor = None

@@ -36,6 +36,5 @@ def gpu_engine():
     ramba.deferred_op.ramba_deferred_ops = None
     RT.reset()
     yield
-    ramba.deferred_op.do_ops()
-    RT.synchronize()
+    ramba.sync()
     RT.reset()

@@ -1,0 +1,175 @@
+"""The lazy DAG in front of the fuser (ramba_b200/ramba.py::DAG; reference: ramba/ramba.py:4387-5293).
+
+What a user of the reference's default (DAG) mode can observe, checked on the oracle executor:
+results nobody can observe are never computed, materialising one array runs only what it depends on, interleaved chains
+over different shapes fuse per shape, and every reordering respects read-after-write / write-after-read /
+write-after-write on the arrays (views included).  RAMBA_NO_DAG behaviour (statements go straight to the fuser) must give
+the same values."""
+import numpy as onp
+import pytest
+
+import _random_programs
+
+
+@pytest.fixture
+def eng(oracle_engine):
+    import ramba_b200 as rb
+    from ramba_b200 import ramba
+    from ramba_b200.runtime import RT
+
+    return rb, ramba, RT
+
+
+def test_statements_wait_in_the_dag_until_something_is_read(eng):
+    rb, ramba, RT = eng
+    a = rb.arange(1000) * 2.0
+    b = a + 1.0
+    assert len(ramba.DAG.pending) == 3 and ramba.deferred_op.ramba_deferred_ops is None and RT.launches == 0
+    assert onp.array_equal(b.asarray(), onp.arange(1000) * 2.0 + 1.0)
+    assert not ramba.DAG.pending and RT.launches == 1
+
+
+def test_unobservable_results_are_never_computed(eng):
+    rb, ramba, RT = eng
+    x = rb.fromarray(onp.arange(5000, dtype=onp.float64))
+    y = rb.fromarray(onp.arange(300, dtype=onp.float64))
+    rb.sync()
+    l0, p0 = RT.launches, ramba.DAG.pruned_count
+    rb.sin(y)                 # result dropped at once
+    t = y * 3.0
+    u = t + 1.0               # t is held by u's node only
+    del t, u                  # -> both nodes go, cascading through the operand the second one held
+    z = x * 2.0
+    assert len(ramba.DAG.pending) == 1 and ramba.DAG.pruned_count - p0 == 3
+    assert onp.array_equal(z.asarray(), onp.arange(5000) * 2.0)
+    assert RT.launches - l0 == 1   # (no launch over the 300-element shape)
+
+
+def test_materialising_one_array_runs_only_its_dependencies(eng):
+    rb, ramba, RT = eng
+    x = rb.fromarray(onp.arange(4000, dtype=onp.float64))
+    y = rb.fromarray(onp.arange(700, dtype=onp.float64))
+    rb.sync()
+    a = x + 1.0
+    b = y * 2.0
+    c = a * a
+    l0 = RT.launches
+    assert onp.array_equal(c.asarray(), (onp.arange(4000) + 1.0) ** 2)
+    assert RT.launches - l0 == 1 and len(ramba.DAG.pending) == 1   # b's statement is still waiting
+    assert onp.array_equal(b.asarray(), onp.arange(700) * 2.0)
+    assert not ramba.DAG.pending
+
+
+def test_interleaved_chains_fuse_per_shape(eng, monkeypatch):
+    rb, ramba, RT = eng
+    xs, ys = onp.arange(3000, dtype=onp.float64), onp.arange(900, dtype=onp.float64)
+
+    def program():
+        x, y = rb.fromarray(xs), rb.fromarray(ys)
+        rb.sync()
+        l0 = RT.launches
+        outs = []
+        for i in range(4):   # alternate between the two shapes
+            x = x * 1.5 + float(i)
+            y = y - float(i)
+            outs += [x, y]
+        rb.sync()
+        return RT.launches - l0, [o.asarray() for o in outs]
+
+    n_dag, got = program()
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    n_nodag, exp = program()
+    assert n_dag == 2 and n_nodag == 8   # one fused op per shape vs a flush at every change of shape
+    for g, e in zip(got, exp):
+        assert onp.array_equal(g, e)
+    ex, ey = xs.copy(), ys.copy()
+    for i in range(4):
+        ex = ex * 1.5 + float(i)
+        ey = ey - float(i)
+    assert onp.array_equal(got[-2], ex) and onp.array_equal(got[-1], ey)
+
+
+def test_reordering_respects_hazards_on_arrays_and_views(eng):
+    rb, ramba, RT = eng
+
+    def program(np, arr):
+        a = arr(onp.arange(100, dtype=onp.float64))
+        b = arr(onp.arange(50, dtype=onp.float64))
+        c = a + 1.0              # reads a
+        d = b * 2.0
+        a += 10.0                # write after read: c must see the old a
+        e = a + c                # read after write: the new a
+        b[10:20] = 7.0           # view write
+        f = b + d
+        v = a[5:55]              # view of a, same shape as b
+        g = v * b
+        a[5:55] = g + 1.0        # write through another view after the read through v
+        h = a.sum()
+        b *= 0.5
+        i = (b + f).sum()
+        return [x if isinstance(x, (float, onp.floating)) else onp.asarray(x.asarray() if hasattr(x, "asarray") else x)
+                for x in (c, d, e, f, g, a, b, h, i)]
+
+    got = program(rb, rb.fromarray)
+    exp = program(onp, lambda x: x.copy())
+    for k, (g, e) in enumerate(zip(got, exp)):
+        assert onp.array_equal(onp.asarray(g), onp.asarray(e)), k
+
+
+def test_in_place_updates_of_a_dead_handle_still_reach_the_views_base(eng):
+    rb, ramba, RT = eng
+    a = rb.zeros(200)
+    v = a[50:150]
+    v += 3.0
+    del v                        # the view handle is gone, the statement is not: `a` observes it
+    a[0:10] = 1.0
+    e = onp.zeros(200)
+    e[50:150] += 3.0
+    e[0:10] = 1.0
+    assert onp.array_equal(a.asarray(), e)
+
+
+def test_reduction_temporary_is_elided_only_inside_one_fused_op(eng):
+    """`(X*2.0 + 1.0).sum()` never stores its temporary - unless the statement limit cuts the fused op between the
+    temporary and the reduction (then it must be stored: the second op reads it back)."""
+    rb, ramba, RT = eng
+    x = onp.arange(1000, dtype=onp.float32) % 7
+    expect = float((x * 2.0 + 1.0).sum())
+    for nodag in (False, True):
+        ramba.NO_DAG = nodag
+        try:
+            for nfill in range(34, 42):
+                X = rb.fromarray(x)
+                keep = [X * float(i) for i in range(nfill)]
+                assert float((X * 2.0 + 1.0).sum()) == expect, (nodag, nfill)
+                del keep
+        finally:
+            ramba.NO_DAG = False
+
+
+def test_long_dependency_chains_need_no_recursion(eng):
+    rb, ramba, RT = eng
+    a = rb.zeros(256)
+    for _ in range(3000):
+        a = a + 1.0
+    assert onp.array_equal(a.asarray(), onp.full(256, 3000.0))
+    assert not ramba.DAG.pending
+
+
+def test_pending_graph_is_bounded(eng, monkeypatch):
+    rb, ramba, RT = eng
+    monkeypatch.setattr(ramba.DAG, "max_pending", 64)
+    keep = [rb.arange(128) * float(i) for i in range(200)]
+    assert len(ramba.DAG.pending) < 2 * 64
+    for i in (0, 63, 64, 199):
+        assert onp.array_equal(keep[i].asarray(), onp.arange(128) * float(i))
+
+
+@pytest.mark.parametrize("case", _random_programs.CASES[:20], ids=lambda f: f.__name__)
+def test_same_values_with_and_without_the_dag(eng, case, monkeypatch):
+    rb, ramba, RT = eng
+    got = case(rb)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    exp = case(rb)
+    for g, e in zip(got, exp):
+        assert onp.array_equal(onp.asarray(g), onp.asarray(e), equal_nan=True)

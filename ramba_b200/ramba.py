@@ -88,7 +88,7 @@ class bdarray:
             if shape == ():
                 distribution = np.zeros((), dtype=dtype)
             elif distribution is None:
-                distribution = shardview.default_distribution(shape, **kwargs)
+                distribution = shardview.default_distribution(shape, **kwargs) if kwargs else shardview.default_distribution_of(shape)
             else:
                 # a new array: same boxes, fresh buffer coordinates
                 distribution = shardview.clean_dist(distribution)
@@ -135,12 +135,32 @@ class ArrRef:
         self.value = nd.distribution.item() if nd.shape == () else None
 
 
+def _ref_of(nd):
+    """The ArrRef of a handle (one per handle: a handle's shape, partition and buffer never change; 0-d arrays hold a
+    mutable value and get a fresh one every time)."""
+    if nd.shape == ():
+        return ArrRef(nd)
+    r = nd._ref
+    if r is None:
+        r = nd._ref = ArrRef(nd)
+    return r
+
+
 def _detach(x):
-    if isinstance(x, ndarray):
-        return ArrRef(x)
     if isinstance(x, E):
         return E(x.op, *[_detach(a) for a in x.args], imm=x.imm)
+    if isinstance(x, ndarray):
+        return _ref_of(x)
     return x
+
+
+def _array_operands(x, out):
+    """The non-0-d arrays an expression reads, in order of appearance."""
+    if isinstance(x, E):
+        for a in x.args:
+            _array_operands(a, out)
+    elif isinstance(x, ndarray) and x.shape != ():
+        out.append(x)
 
 
 def _walk_operands(x, out):
@@ -200,80 +220,97 @@ class deferred_op:
         return cls.temp_var()
 
     def add_gid(self, nd):
-        gid = nd.gid
-        bd = nd.bdarray
-        if gid not in self.use_gids:
-            self.use_gids[gid] = ([], bd.shape, bd.distribution, bd.pad, bd.flex_dist and not bd.remote_constructed)
+        gid = nd.bdarray.gid
+        ent = self.use_gids.get(gid)
+        if ent is None:
+            bd = nd.bdarray
+            ent = self.use_gids[gid] = ([], bd.shape, bd.distribution, bd.pad, bd.flex_dist and not bd.remote_constructed)
             self.keepalives.add(bd)
-        for det in self.use_gids[gid][0]:
-            if det.distribution is nd.distribution or shardview.dist_is_eq(det.distribution, nd.distribution):
+        ndist = nd.distribution
+        for det in ent[0]:
+            if det.distribution is ndist or shardview.dist_is_eq(det.distribution, ndist):
                 return
-        self.use_gids[gid][0].append(ArrRef(nd))
-        if bd.remote_constructed:
+        ent[0].append(_ref_of(nd))
+        if nd.bdarray.remote_constructed:
             self.preconstructed_gids[gid] = True
 
     # ---- adding statements --------------------------------------------------------------
     @classmethod
-    def add_op(cls, oplist, write_array, imports=(), axis_reduce=None, precode=(), postcode=(), elide=None):
+    def add_op(cls, oplist, write_array, imports=(), axis_reduce=None, precode=(), postcode=(), elide=None, _reads=None):
         """oplist = [dst, expr]: `dst = expr` for every index of the iteration space.  dst is an
         ndarray or a temp_var; expr is an E tree over ndarrays, scalars, temp_vars and Iota.
         Global reductions pass precode=[tmp, init] and postcode=[red_array_view, redop-name]
         (ramba/ramba.py:5798-5807); axis reductions pass axis_reduce=(axes, red_view)
         (ramba/ramba.py:5809-5814).  `elide` names the gid of an operand that nobody can observe once the
         calling API function returns (the temporary of `(X*2.0 + 1.0).sum()`): it is treated as dead in the flush
-        that holds this statement, provided the statement that writes it is part of the SAME fused op."""
+        that holds this statement, provided the statement that writes it is part of the SAME fused op.
+        `_reads`: the non-0-d array operands of expr when the caller (the DAG node) has walked it already."""
         t0 = timer()
         dst, expr = oplist[0], oplist[1]
-        operands = ([dst] if isinstance(dst, ndarray) else []) + [o for o in _walk_operands(expr, []) if isinstance(o, ndarray)]
-        arr = write_array if write_array is not None else next((o for o in operands if isinstance(o, ndarray)), None)
+        dst_nd = isinstance(dst, ndarray)
+        if _reads is None:
+            _reads = []
+            _array_operands(expr, _reads)
+        operands = [dst] + _reads if dst_nd and dst.shape != () else _reads
+        arr = write_array
+        if arr is None:
+            arr = dst if dst_nd else next((o for o in _walk_operands(expr, []) if isinstance(o, ndarray)), None)
         assert arr is not None, "Deferred op with no ndarray parameter"
         shape, distribution = arr.shape, arr.distribution
+        abd = arr.bdarray
         # the partition of `arr` can still follow the op's only if arr is a whole array that no flush has touched: a VIEW of
         # a flexible array was cut from the partition the array had then and does not move when the array is pinned
-        fixed = arr.bdarray.remote_constructed or not arr.bdarray.flex_dist or arr.base is not None
+        fixed = abd.remote_constructed or not abd.flex_dist or arr.base is not None
         cur = cls.ramba_deferred_ops
-        if cur is not None and (
-            cur.shape != shape
-            or (
-                not shardview.compatible_distributions(cur.distribution, distribution)
-                and fixed
-                and not cur.flex_dist
-            )
-            or len(cur.statements) >= cls.max_statements
-        ):
-            cls.do_ops()
-        cur = cls.ramba_deferred_ops
-        # reductions on an axis must agree (ramba/ramba.py:8425-8432)
-        if cur is not None and axis_reduce is not None and cur.axis_reductions and cur.axis_reductions[0][0] != list(axis_reduce[0]):
-            cls.do_ops()
-        if cur is not None and axis_reduce is None and cur.axis_reductions:
-            # a plain statement after an axis reduction would run once per reduced element
-            cls.do_ops()
-        cur = cls.ramba_deferred_ops
+        if cur is not None:
+            if (cur.shape != shape
+                    or (fixed and not cur.flex_dist and not shardview.compatible_distributions(cur.distribution, distribution))
+                    or len(cur.statements) >= cls.max_statements):
+                cls.do_ops()
+                cur = None
+            elif cur.axis_reductions and (axis_reduce is None or cur.axis_reductions[0][0] != list(axis_reduce[0])):
+                # reductions on an axis must agree (ramba/ramba.py:8425-8432); a plain statement after an axis reduction
+                # would run once per reduced element
+                cls.do_ops()
+                cur = None
         # alias check 1: reads/writes a shifted version of an array written earlier in this op
-        if cur is not None and cur.write_gids and builtins.any(o.gid in cur.write_gids for o in operands) and builtins.any(
-            o.gid == wgid and wdist is not None and not shardview.dist_is_eq(wdist, o.distribution)
-            for o in operands for (wgid, wdist) in cur.write_arrs
-        ):
-            cls.do_ops()
-        cur = cls.ramba_deferred_ops
+        if cur is not None and cur.write_gids:
+            wg = cur.write_gids
+            hit = False
+            for o in operands:
+                if o.bdarray.gid in wg:
+                    og, od = o.bdarray.gid, o.distribution
+                    for (wgid, wdist) in cur.write_arrs:
+                        if wgid == og and wdist is not None and not shardview.dist_is_eq(wdist, od):
+                            hit = True
+                            break
+                    if hit:
+                        break
+            if hit:
+                cls.do_ops()
+                cur = None
         # alias check 2: writes an array that is also read through a different view
-        if write_array is not None and isinstance(dst, ndarray) and (
-            builtins.any(o is not dst and o.gid == write_array.gid and not shardview.dist_is_eq(o.distribution, write_array.distribution)
-                         for o in operands)
-            or (cur is not None and write_array.gid in cur.read_gids and builtins.any(
-                rgid == write_array.gid and rdist is not None and not shardview.dist_is_eq(rdist, write_array.distribution)
-                for (rgid, rdist) in cur.read_arrs))
-        ):
-            tmp_array = empty_like(write_array)
-            cls.add_op([tmp_array, expr], tmp_array, imports)
-            cls.do_ops()
-            cls.add_op([write_array, tmp_array], write_array)
-            return
-        if cls.ramba_deferred_ops is None:
-            cls.ramba_deferred_ops = cls(shape, distribution, not fixed)
-        cur = cls.ramba_deferred_ops
-        if fixed and (cur.flex_dist or not arr.bdarray.flex_dist):
+        if write_array is not None and dst_nd:
+            wgid, wdist = write_array.bdarray.gid, write_array.distribution
+            hit = False
+            for o in operands:
+                if o is not dst and o.bdarray.gid == wgid and not shardview.dist_is_eq(o.distribution, wdist):
+                    hit = True
+                    break
+            if not hit and cur is not None and wgid in cur.read_gids:
+                for (rgid, rdist) in cur.read_arrs:
+                    if rgid == wgid and rdist is not None and not shardview.dist_is_eq(rdist, wdist):
+                        hit = True
+                        break
+            if hit:
+                tmp_array = empty_like(write_array)
+                cls.add_op([tmp_array, expr], tmp_array, imports)
+                cls.do_ops()
+                cls.add_op([write_array, tmp_array], write_array)
+                return
+        if cur is None:
+            cur = cls.ramba_deferred_ops = cls(shape, distribution, not fixed)
+        if fixed and (cur.flex_dist or not abd.flex_dist):
             cur.distribution = distribution
             cur.flex_dist = False
         if elide is not None and elide in cur.write_gids and bdarray.valid_gid(elide) \
@@ -281,17 +318,18 @@ class deferred_op:
             # (decided HERE, after admission: a flush forced by this very statement must still materialise the operand)
             cur.elide_gids.add(elide)
         mask = None
-        if write_array is not None and isinstance(dst, ndarray) and write_array.maskarray is not None:
-            mask = write_array.maskarray
-            operands = [mask] + operands
-        if write_array is not None and isinstance(dst, ndarray):
-            cur.write_arrs.append((write_array.gid, None if write_array.bdarray.flex_dist else write_array.distribution))
-            cur.write_gids.add(write_array.gid)
+        if write_array is not None and dst_nd:
+            if write_array.maskarray is not None:
+                mask = write_array.maskarray
+                operands = [mask] + operands
+            wbd = write_array.bdarray
+            cur.write_arrs.append((wbd.gid, None if wbd.flex_dist else write_array.distribution))
+            cur.write_gids.add(wbd.gid)
+        read_arrs, read_gids = cur.read_arrs, cur.read_gids
         for x in operands:
-            if x.shape == ():
-                continue
-            cur.read_arrs.append((x.gid, None if x.bdarray.flex_dist else x.distribution))
-            cur.read_gids.add(x.gid)
+            xbd = x.bdarray
+            read_arrs.append((xbd.gid, None if xbd.flex_dist else x.distribution))
+            read_gids.add(xbd.gid)
             cur.add_gid(x)
         expr = _detach(expr)
         if axis_reduce is not None:
@@ -561,7 +599,7 @@ class DAG:
       * while a node executes, API calls made by the executor run inline (`DAG.in_evaluate`), and RAMBA_NO_DAG=1
         makes every call inline."""
 
-    __slots__ = ("seq_no", "expr", "dst", "out_ref", "write_array", "kw", "shape", "backward_deps", "forward_deps",
+    __slots__ = ("seq_no", "expr", "reads", "dst", "out_ref", "write_array", "kw", "shape", "backward_deps", "forward_deps",
                  "executed", "rgids", "wgids", "__weakref__")
     pending = {}       # seq_no -> node, in program order
     last_writer = {}   # gid -> pending node that writes the array last
@@ -579,31 +617,38 @@ class DAG:
             deferred_op.add_op(oplist, write_array, imports, axis_reduce, precode, postcode, elide)
             return
         dst, expr = oplist[0], oplist[1]
-        reads = [o for o in _walk_operands(expr, []) if isinstance(o, ndarray) and o.shape != ()]
+        reads = []
+        _array_operands(expr, reads)
         node = object.__new__(cls)
-        node.seq_no = cls.dag_count
-        cls.dag_count += 1
+        seq = node.seq_no = cls.dag_count
+        cls.dag_count = seq + 1
         node.expr = expr
+        node.reads = reads
         node.kw = (imports, axis_reduce, precode, postcode, elide)
         node.executed = False
         node.forward_deps = set()
-        arr = write_array if write_array is not None else (dst if isinstance(dst, ndarray) else (reads[0] if reads else None))
+        dst_nd = isinstance(dst, ndarray)
+        arr = write_array if write_array is not None else (dst if dst_nd else (reads[0] if reads else None))
         node.shape = arr.shape if arr is not None else None
-        wg = []
+        rg = [o.bdarray.gid for o in reads]
+        plain = axis_reduce is None and not precode
         if write_array is not None:
-            wg.append(write_array.gid)
+            wgid = write_array.bdarray.gid
+            wg = [wgid]
             if write_array.maskarray is not None:
-                reads.append(write_array.maskarray)
-        if isinstance(dst, ndarray) and dst is not write_array:
+                rg.append(write_array.maskarray.gid)
+        else:
+            wgid = None
+            wg = []
+        if dst_nd and dst is not write_array:
             wg.append(dst.gid)
-        if axis_reduce is not None:
-            wg.append(axis_reduce[1].gid)
-        if precode:
-            wg.append(postcode[0].gid)
-        rg = [o.gid for o in reads]
+        if not plain:
+            if axis_reduce is not None:
+                wg.append(axis_reduce[1].gid)
+            if precode:
+                wg.append(postcode[0].gid)
         # the destination of an out-of-place statement is the only way to observe it: hold it weakly
-        if isinstance(dst, ndarray) and dst is write_array and dst.base is None and dst.maskarray is None \
-                and axis_reduce is None and not precode and dst.gid not in rg:
+        if plain and dst is write_array and dst_nd and dst.base is None and dst.maskarray is None and wgid not in rg:
             node.dst = None
             node.write_array = None
             node.out_ref = weakref.ref(dst, node._output_died)
@@ -611,29 +656,37 @@ class DAG:
             node.dst = dst
             node.write_array = write_array
             node.out_ref = None
-        deps = []
         lw, rd = cls.last_writer, cls.readers
-        for g in rg:
-            d = lw.get(g)
-            if d is not None and d not in deps:
-                deps.append(d)
-        for g in wg:
-            d = lw.get(g)
-            if d is not None and d not in deps:
-                deps.append(d)
-            for d in rd.get(g, ()):
-                if d not in deps:
+        deps = []
+        if lw:
+            for g in rg:
+                d = lw.get(g)
+                if d is not None and d not in deps:
                     deps.append(d)
+            for g in wg:
+                d = lw.get(g)
+                if d is not None and d not in deps:
+                    deps.append(d)
+        if rd:
+            for g in wg:
+                lst = rd.pop(g, None)
+                if lst:
+                    for d in lst:
+                        if d not in deps:
+                            deps.append(d)
         for d in deps:
             d.forward_deps.add(node)
         node.backward_deps = deps
         node.rgids = rg
         node.wgids = wg
         for g in rg:
-            rd.setdefault(g, []).append(node)
+            lst = rd.get(g)
+            if lst is None:
+                rd[g] = [node]
+            else:
+                lst.append(node)
         for g in wg:
             lw[g] = node
-            rd.pop(g, None)
         cls.pending[node.seq_no] = node
         if len(cls.pending) >= cls.max_pending:
             cls.execute_all()
@@ -681,6 +734,7 @@ class DAG:
         self.kw = None
         # last: dropping the operands may end other arrays' lives (and prune their producers through the callback above)
         self.expr = None
+        self.reads = None
         self.dst = None
         self.write_array = None
 
@@ -693,9 +747,9 @@ class DAG:
                 self._retire(False)  # nobody can observe the result
                 return
         imports, axis_reduce, precode, postcode, elide = self.kw
-        expr = self.expr
+        expr, reads = self.expr, self.reads
         self._retire(True)
-        deferred_op.add_op([dst, expr], wa, imports, axis_reduce, precode, postcode, elide)
+        deferred_op.add_op([dst, expr], wa, imports, axis_reduce, precode, postcode, elide, reads)
 
     # ---- materialisation -------------------------------------------------------------------
     @classmethod
@@ -1402,7 +1456,7 @@ def _slice_len(s):
 
 
 class ndarray:
-    __slots__ = ("base", "bdarray", "shape", "distribution", "local_border", "readonly", "maskarray", "_slices", "__weakref__")
+    __slots__ = ("base", "bdarray", "shape", "distribution", "local_border", "readonly", "maskarray", "_slices", "_ref", "__weakref__")
     __array_priority__ = 20.0
 
     def __init__(self, shape, dtype=None, *, base=None, distribution=None, local_border=0, flex_dist=True,
@@ -1425,6 +1479,7 @@ class ndarray:
         self.readonly = readonly
         self.maskarray = maskarray
         self._slices = None  # index -> (shape, distribution) of slice views taken so far
+        self._ref = None     # what statements remember about this handle (ArrRef), made on first use
 
     def __del__(self):
         try:
@@ -2221,8 +2276,7 @@ def gather_to_host(nd, out=None, non_blocking=False):
             t = torch.from_numpy(host.view(np.uint8).reshape(-1))
         else:
             t = torch.empty(nbytes, dtype=torch.uint8)
-        if not RT.test_mode:
-            t = t.to(RT.device)
+        t = t.to(RT.device)
         dist.broadcast(t, src=i)
         part = t.cpu().numpy().view(store_dt).reshape(shape)
         if nd.dtype == np.bool_:
@@ -2334,9 +2388,8 @@ def asarray(x, dtype=None, **kwargs):
 # creation (ramba/ramba.py:8563-8991)
 # =============================================================================================
 def create_array_with_divisions(shape, divisions, local_border=0, dtype=None):
-    new = ndarray(shape, dtype=dtype, distribution=None, local_border=local_border, flex_dist=False)
-    new.bdarray.distribution[:] = shardview.clean_dist(divisions)
-    return new
+    # (a new array given a partition gets the same boxes with fresh buffer coordinates: assign_bdarray cleans it)
+    return ndarray(shape, dtype=dtype, distribution=divisions, local_border=local_border, flex_dist=False)
 
 
 def create_array(shape, filler, local_border=0, dtype=None, distribution=None, no_defer=False, **kwargs):

@@ -53,18 +53,25 @@ class Shard:
 
     __slots__ = ("buf", "shape", "dtype", "strides", "bounds", "border", "origin")
 
+    _layouts = {}  # (shape, border) -> (strides, origin): a pure function, asked for every new result array
+
     def __init__(self, buf, shape, dtype, border=0):
         self.buf = buf
-        self.shape = tuple(int(s) for s in shape)
+        shape = self.shape = tuple([int(s) for s in shape])
         self.dtype = np.dtype(dtype)
-        self.border = int(border)
-        st = []
-        acc = 1
-        for s in reversed(self.shape):
-            st.append(acc)
-            acc *= max(1, s + 2 * self.border)
-        self.strides = tuple(reversed(st))  # elements, C order over the padded block
-        self.origin = sum(self.border * x for x in self.strides)  # element offset of interior element (0, 0, ...)
+        border = self.border = int(border)
+        lay = Shard._layouts.get((shape, border))
+        if lay is None:
+            st = []
+            acc = 1
+            for s in reversed(shape):
+                st.append(acc)
+                acc *= max(1, s + 2 * border)
+            strides = tuple(reversed(st))  # elements, C order over the padded block
+            if len(Shard._layouts) >= 4096:
+                Shard._layouts.clear()
+            lay = Shard._layouts[(shape, border)] = (strides, sum(border * x for x in strides))
+        self.strides, self.origin = lay  # origin: element offset of interior element (0, 0, ...)
         p = buf.data_ptr()
         self.bounds = (p, p + buf.numel() * buf.element_size())  # [alloc_lo, alloc_hi) handed to the C-ABI
 
@@ -82,16 +89,58 @@ class Shard:
         return self.buf.as_strided(self.shape, self.strides, self.origin)
 
 
+class CudaBackend:
+    """Where op lists run: libramba_b200.so on this process's GPU, NCCL between the processes.  It is the only backend the
+    package has; `Runtime.backend` is an attribute so that the test package can put its own object there (the oracle on
+    host buffers, tests/_oracle_backend.py) - nothing in the product refers to, constructs or imports another one."""
+
+    name = "cuda"
+    dist_backend = "nccl"
+    timing = True  # CUDA events around launches (bench.py's per-kernel times)
+
+    def __init__(self):
+        cabi.load()  # raises if the library is missing: there is no fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "ramba_b200 needs a CUDA device (B200, sm_100a): torch.cuda.is_available() is False and "
+                "there is no CPU execution path")
+        self.device = torch.device("cuda", common.local_rank)
+        torch.cuda.set_device(self.device)
+        self.run = cabi.run_deferred_ops
+        self.reduce_partials = cabi.reduce_partials
+
+    def stream_handle(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def red_scratch_bytes(self):
+        return cabi.red_scratch_bytes()
+
+    def cumulative(self, src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out):
+        """rb200_cumulative on the current stream; returns the scratch buffer (the caller keeps it alive)."""
+        nbytes = cabi.cumulative_scratch_bytes(n_outer, length, n_inner)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        cabi.cumulative(src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out, scratch.data_ptr(),
+                        self.stream_handle())
+        return scratch
+
+    def init_process_group(self):
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=self.device)
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+    def events(self):
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
 class Runtime:
     def __init__(self):
         self.shards = {}
-        self._device = None
-        self._executor = None
-        self._reduce_partials = None
-        self._cumulative = None
+        self.backend = None  # CudaBackend(), made at first use
         self._red_scratch = None
         self._pg_ready = False
-        self.test_mode = False
         self.launches = 0
         self.bytes_sent = 0
         self.collectives = 0  # all-gather / all-reduce calls issued
@@ -100,50 +149,38 @@ class Runtime:
         self.profile_events = None  # list -> (start, end, n_insns) CUDA events around every launch
         self.on_reset = []  # the engine registers what else must be forgotten with the shards (pending DAG nodes, fused op)
 
-    # ---- device / process group ---------------------------------------------------------
+    # ---- backend / device / process group --------------------------------------------------
+    def be(self):
+        b = self.backend
+        if b is None:
+            b = self.backend = CudaBackend()
+        return b
+
     @property
     def device(self):
-        if self._device is None:
-            if not torch.cuda.is_available():
-                raise RuntimeError(
-                    "ramba_b200 needs a CUDA device (B200, sm_100a): torch.cuda.is_available() is False and "
-                    "there is no CPU execution path")
-            self._device = torch.device("cuda", common.local_rank)
-            torch.cuda.set_device(self._device)
-        return self._device
+        return self.be().device
 
-    def set_test_executor(self, executor, reduce_partials, device="cpu", cumulative=None):
-        """TEST SEAM ONLY: run op lists through a checker (the oracle) on host buffers so that the
-        host logic can be exercised without a GPU.  Never used by the product path."""
-        self._executor = executor
-        self._reduce_partials = reduce_partials
-        self._cumulative = cumulative
-        self._device = torch.device(device)
-        self.test_mode = True
+    @property
+    def is_cuda(self):
+        """True when op lists go to the CUDA library (always, outside the test package)."""
+        return isinstance(self.be(), CudaBackend)
 
     def reset(self):
-        """Forget every shard and go back to the product configuration (CUDA executor)."""
+        """Forget every shard (and whatever the engine registered in on_reset); the next use builds the CUDA backend."""
         for hook in self.on_reset:
             hook()
         self.shards.clear()
-        self._device = None
-        self._executor = None
-        self._reduce_partials = None
-        self._cumulative = None
+        self.backend = None
         self._red_scratch = None
-        self.test_mode = False
 
     def executor(self):
-        if self._executor is None:
-            cabi.load()  # raises if the library is missing
-            self._executor = cabi.run_deferred_ops
-            self._reduce_partials = cabi.reduce_partials
-        return self._executor
+        return self.be().run
+
+    def _reduce_partials(self, *args):
+        return self.be().reduce_partials(*args)
 
     def stream_handle(self):
-        if self.test_mode:
-            return None
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return self.be().stream_handle()
 
     def ensure_process_group(self):
         if common.num_workers <= 1 or self._pg_ready:
@@ -151,11 +188,7 @@ class Runtime:
         import torch.distributed as dist
 
         if not dist.is_initialized():
-            backend = "gloo" if self.test_mode else "nccl"
-            if backend == "nccl":
-                dist.init_process_group(backend, device_id=self.device)
-            else:
-                dist.init_process_group(backend)
+            self.be().init_process_group()
         self._pg_ready = True
 
     # ---- shard storage --------------------------------------------------------------------
@@ -185,7 +218,7 @@ class Runtime:
 
     def red_scratch(self):
         if self._red_scratch is None:
-            nbytes = 256 + 8 * cabi.MAX_REDS * 4096 if self.test_mode else cabi.red_scratch_bytes()
+            nbytes = self.be().red_scratch_bytes()
             self._red_scratch = torch.zeros(nbytes // 8 + 1, dtype=torch.int64, device=self.device)
         return self._red_scratch
 
@@ -347,36 +380,26 @@ class Runtime:
 
     def submit(self, fop):
         """Hand one bound op list to the C-ABI on the current stream."""
-        ex = self.executor()
-        if self.profile_events is not None and not self.test_mode:
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
+        be = self.backend or self.be()
+        if self.profile_events is not None and be.timing:
+            e0, e1 = be.events()
             e0.record()
-            ex(fop, self.stream_handle())
+            be.run(fop, be.stream_handle())
             e1.record()
             self.profile_events.append((e0, e1, fop.n_insns))
         else:
-            ex(fop, self.stream_handle())
+            be.run(fop, be.stream_handle())
         self.launches += 1
         return fop
 
     def cumulative(self, src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in=None, totals_out=None):
         """Inclusive scan of one local block through the C-ABI (rb200_cumulative)."""
-        self.executor()
-        if self.test_mode:
-            if self._cumulative is None:
-                raise RuntimeError("the test executor has no cumulative()")
-            self._cumulative(src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out, None, None)
-        else:
-            nbytes = cabi.cumulative_scratch_bytes(n_outer, length, n_inner)
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            cabi.cumulative(src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out, scratch.data_ptr(), self.stream_handle())
-            self.keepalive_scan = scratch
+        self.keepalive_scan = self.be().cumulative(src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out)
         self.launches += 1
 
     def synchronize(self):
-        if not self.test_mode and self._device is not None:
-            torch.cuda.synchronize(self._device)
+        if self.backend is not None:
+            self.backend.synchronize()
 
 
 _launch_cache = {}

@@ -412,6 +412,20 @@ def default_distribution(size, dims_do_not_distribute=(), dist_dims=None, num_wo
     return out
 
 
+_plain_dist_cache = {}
+
+
+def default_distribution_of(shape):
+    """default_distribution(shape) for a shape that is a tuple of ints already and no options (every result array)."""
+    ck = (shape, common.num_workers)
+    hit = _plain_dist_cache.get(ck)
+    if hit is None:
+        if len(_plain_dist_cache) >= 4096:
+            _plain_dist_cache.clear()
+        hit = _plain_dist_cache[ck] = tuple(default_distribution(shape))
+    return list(hit)
+
+
 def _default_distribution(size, dims_do_not_distribute, dist_dims, W):
     k = len(size)
     if isinstance(dist_dims, int):

@@ -79,7 +79,7 @@ def main():
     if MODE == "cuda":
         from ramba_b200 import _cabi
 
-        assert not RT.test_mode and _cabi.launch_count() > 0, "the CUDA library did not run"
+        assert RT.is_cuda and _cabi.launch_count() > 0, "the CUDA library did not run"
     if MODE == "oracle" and os.environ.get("RB200_DUMP_PLANS"):
         # debugging aid: which kernel of the CUDA library every op list of this rank would have got
         with open("%s.%d" % (os.environ["RB200_DUMP_PLANS"], common.worker_num), "w") as f:

@@ -34,11 +34,23 @@ def _library_accepts(fop):
         raise AssertionError("libramba_b200 would reject this op list: " + msg)
 
 
-def install():
-    from oracle import vm
-    from ramba_b200.runtime import RT
+class OracleBackend:
+    """Stands where ramba_b200.runtime.CudaBackend does: op lists are evaluated by the NumPy oracle on host buffers, ranks
+    talk over gloo.  Lives in the test package; the product has no reference to it."""
 
-    def run(fop, stream=None):
+    name = "oracle"
+    dist_backend = "gloo"
+    timing = False
+
+    def __init__(self):
+        import torch
+        from oracle import vm
+
+        self.device = torch.device("cpu")
+        self.reduce_partials = vm.reduce_partials
+        self._vm = vm
+
+    def run(self, fop, stream=None):
         _library_accepts(fop)
         try:
             from ramba_b200 import _cabi
@@ -46,6 +58,30 @@ def install():
             PLANS.append(_cabi.describe_plan(fop))
         except Exception as ex:  # library not built: test_cabi_exports complains about that
             PLANS.append("unavailable: %s" % (ex,))
-        return vm.run_deferred_ops(fop, stream)
+        return self._vm.run_deferred_ops(fop, stream)
 
-    RT.set_test_executor(run, vm.reduce_partials, device="cpu", cumulative=vm.cumulative)
+    def stream_handle(self):
+        return None
+
+    def red_scratch_bytes(self):
+        from ramba_b200 import _cabi
+
+        return 256 + 8 * _cabi.MAX_REDS * 4096
+
+    def cumulative(self, src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out):
+        self._vm.cumulative(src_ptr, dst_ptr, code, n_outer, length, n_inner, redop, carry_in, totals_out, None, None)
+        return None
+
+    def init_process_group(self):
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")
+
+    def synchronize(self):
+        pass
+
+
+def install():
+    from ramba_b200.runtime import RT
+
+    RT.backend = OracleBackend()

@@ -925,5 +925,5 @@ def test_run_both_cuda(gpu_engine, f):
 
     before = _cabi.launch_count()
     got = f(rb)
-    assert not RT.test_mode and _cabi.launch_count() > before
+    assert RT.is_cuda and _cabi.launch_count() > before
     _compare(got, f(onp), f.__name__)

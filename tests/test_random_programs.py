@@ -29,7 +29,7 @@ def test_random_program_cuda(gpu_engine, f):
 
     before, before_rt = _cabi.launch_count(), RT.launches
     got = f(rb)
-    assert not RT.test_mode
+    assert RT.is_cuda
     # a seed may draw only empty slices: then there is nothing to launch (RT.launches counts the op lists the
     # engine handed to its executor); whenever the engine did launch, the CUDA library must have run them
     if RT.launches > before_rt:

@@ -63,5 +63,5 @@ def test_scan_cuda(gpu_engine, big):
 
     before = _cabi.launch_count()
     got = scans(rb, big)
-    assert not RT.test_mode and _cabi.launch_count() > before
+    assert RT.is_cuda and _cabi.launch_count() > before
     _check(got, scans(onp, big))

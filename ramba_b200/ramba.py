@@ -589,9 +589,9 @@ class DAG:
         reference gets from `ndarray.dag` / `bdarray.dag` and the in-place rule of DAG.add (4527-4539);
       * `instantiate(arr)` walks the backward dependencies of arr's last writer depth first, same-shaped branches
         first (depth_first_traverse, 4792-4838), hands the statements to the fuser in that order and flushes;
-        `execute_all` (sync) starts from every node nothing depends on, oldest first, grouped by shape (5025-5060) -
+        `execute_all` (sync) starts from every node nothing depends on, oldest first, grouped by shape (5080-5105) -
         so interleaved chains over different shapes fuse per shape instead of flushing at every change;
-      * a node whose output nobody can observe is never executed (DAG.execute's `soutput is None`, 4854-4856): the
+      * a node whose output nobody can observe is never executed (DAG.execute's `soutput is None`, 4846-4849): the
         destination of an out-of-place statement is held weakly; when the last handle dies the node is dropped together
         with the handles it holds, which may drop the nodes that produced those, and so on;
       * nodes hold their operands strongly until they are executed (like the reference's `args`), so whether a
@@ -791,7 +791,7 @@ class DAG:
 
     @classmethod
     def instantiate(cls, arr=None):
-        """Make `arr` real: run what it depends on, then flush (DAG.instantiate, ramba/ramba.py:4840-4852)."""
+        """Make `arr` real: run what it depends on, then flush (DAG.instantiate, ramba/ramba.py:4833-4844)."""
         if cls.pending and isinstance(arr, ndarray):
             node = cls.last_writer.get(arr.gid)
             if node is not None:
@@ -801,7 +801,7 @@ class DAG:
     @classmethod
     def execute_all(cls, do_ops=False):
         """Run every pending node: start from the ones nothing depends on, oldest first, grouped by output shape
-        (DAG.execute_all, ramba/ramba.py:5025-5060)."""
+        (DAG.execute_all, ramba/ramba.py:5080-5105)."""
         if cls.pending:
             by_shape = {}
             for n in cls.pending.values():

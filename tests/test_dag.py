@@ -174,3 +174,36 @@ def test_same_values_with_and_without_the_dag(eng, case, monkeypatch):
     exp = case(rb)
     for g, e in zip(got, exp):
         assert onp.array_equal(onp.asarray(g), onp.asarray(e), equal_nan=True)
+
+
+def test_baseline_programs_lower_to_the_same_op_lists_with_and_without_the_dag(eng, monkeypatch, capsys):
+    """The measured kernels are chosen from the op list: the DAG must hand the fuser the BASELINE programs (bench.py's
+    configs 2-5, here at reduced size) in an order that lowers to the identical op lists and kernel plans."""
+    import types
+
+    import _oracle_backend
+    import bench
+    from ramba_b200 import common
+
+    rb, ramba, RT = eng
+    monkeypatch.setattr(common, "debug_showcode", True)
+    scales = {2: 1, 3: 1 / 64, 4: 1 / 16, 5: 1 / 512}
+
+    def run_all():
+        capsys.readouterr()
+        _oracle_backend.PLANS.clear()
+        for cfg in (2, 3, 4, 5):
+            wl = bench.CLASSES[cfg](rb, 1, 1 << 14, types.SimpleNamespace(scale=scales[cfg]))
+            wl.step()
+            wl.step()
+            assert wl.check(), cfg
+        code = capsys.readouterr().out
+        # gids differ from run to run: compare the op lists, not the array numbering
+        code = "\n".join(line for line in code.splitlines() if ": gid " not in line)
+        return code, list(_oracle_backend.PLANS)
+
+    code_dag, plans_dag = run_all()
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    code_nodag, plans_nodag = run_all()
+    assert plans_dag == plans_nodag
+    assert code_dag == code_nodag and "SINCOS" in code_dag

@@ -2228,7 +2228,11 @@ def _part_to_host(nd, w, out=None, non_blocking=False):
             # straight DMA (pinned `out`: full PCIe rate)
             torch.from_numpy(out.reshape(-1)).copy_(sh.buf[:n], non_blocking=non_blocking)
             return out.reshape(shape)
-        return sh.buf[:n].cpu().numpy().reshape(shape)
+        t = sh.buf[:n]
+        host = t.cpu()
+        if host.data_ptr() == t.data_ptr():
+            host = host.clone()  # (a host-resident shard: the caller gets a copy, never an alias of the live block)
+        return host.numpy().reshape(shape)
     bc = [int(a) < 0 for a in sv.axis_map]
     cst, n = _contig_strides(shape, [False] * len(shape))
     buf = torch.empty(max(n, 1), dtype=torch_dtype(nd.dtype), device=RT.device)

@@ -12,11 +12,12 @@ import _random_programs
 
 
 @pytest.fixture
-def eng(oracle_engine):
+def eng(oracle_engine, monkeypatch):
     import ramba_b200 as rb
     from ramba_b200 import ramba
     from ramba_b200.runtime import RT
 
+    monkeypatch.setattr(ramba, "NO_DAG", False)  # (whatever RAMBA_NO_DAG says: these tests are about the DAG)
     return rb, ramba, RT
 
 
@@ -207,3 +208,40 @@ def test_baseline_programs_lower_to_the_same_op_lists_with_and_without_the_dag(e
     code_nodag, plans_nodag = run_all()
     assert plans_dag == plans_nodag
     assert code_dag == code_nodag and "SINCOS" in code_dag
+
+
+def _same(got, exp, name):
+    assert len(got) == len(exp), name
+    for i, (g, e) in enumerate(zip(got, exp)):
+        g, e = onp.asarray(g), onp.asarray(e)
+        assert g.shape == e.shape and onp.array_equal(g, e), "%s[%d]" % (name, i)
+
+
+@pytest.mark.parametrize("chunk", range(10))
+def test_fuzzed_programs_match_numpy(eng, chunk, monkeypatch):
+    """tests/_dag_fuzz.py: long stretches of pending statements over three shapes with in-place updates, live views,
+    rebinding, del and partial reads - bit-identical to NumPy in program order, with the DAG and without."""
+    import _dag_fuzz
+
+    rb, ramba, RT = eng
+    for f in _dag_fuzz.CASES[chunk * 30:(chunk + 1) * 30]:
+        exp = f(onp)
+        _same(f(rb), exp, f.__name__)
+        assert not ramba.DAG.in_evaluate
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in _dag_fuzz.CASES[chunk * 30:chunk * 30 + 6]:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", range(4))
+def test_fuzzed_programs_cuda(gpu_engine, chunk):
+    import _dag_fuzz
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    for f in _dag_fuzz.CASES[chunk * 15:(chunk + 1) * 15]:
+        _same(f(rb), f(onp), f.__name__)
+    assert RT.is_cuda and _cabi.launch_count() > before

@@ -1,0 +1,29 @@
+"""-m gpu leg of the DAG fuzzer (tests/_dag_fuzz.py) through the CUDA library.  Collected last on purpose: it was added
+after the round's GPU budget was spent, so its first run on a B200 is the driver's; under `pytest -x` it must not stand
+in front of the tests that have been seen green.  Elementwise results are compared exactly; reductions may be
+summed in another order on the GPU, so everything is compared with a tolerance far below what a mis-ordered or dropped
+statement would change (values are small multiples of powers of two)."""
+import numpy as onp
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, exp, name):
+    assert len(got) == len(exp), name
+    for i, (g, e) in enumerate(zip(got, exp)):
+        g, e = onp.asarray(g), onp.asarray(e)
+        assert g.shape == e.shape and onp.allclose(g, e, rtol=1e-12, atol=1e-9), "%s[%d]" % (name, i)
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_fuzzed_programs_cuda(gpu_engine, chunk):
+    import _dag_fuzz
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    for f in _dag_fuzz.CASES[chunk * 15:(chunk + 1) * 15]:
+        _close(f(rb), f(onp), f.__name__)
+    assert RT.is_cuda and _cabi.launch_count() > before

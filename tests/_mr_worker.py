@@ -76,7 +76,7 @@ def main():
                 tol = 1e-5 if e.dtype == onp.float32 else 1e-12
                 ok = g.shape == e.shape and g.dtype == e.dtype and (onp.allclose(g, e, rtol=tol, atol=tol) if e.dtype.kind == "f" else onp.array_equal(g, e))
             else:
-                ok = g.shape == e.shape and (onp.allclose(g, e, rtol=1e-13, atol=1e-12 if prog.__name__.startswith("random_program") else 1e-15) if e.dtype.kind == "f" else onp.array_equal(g, e))
+                ok = g.shape == e.shape and (onp.allclose(g, e, rtol=1e-13, atol=1e-12 if prog.__name__.startswith(("random_program", "dag_program")) else 1e-15) if e.dtype.kind == "f" else onp.array_equal(g, e))
             if not ok:
                 failures.append("%s[%d]" % (prog.__name__, i))
     if MODE == "cuda":

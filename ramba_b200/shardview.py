@@ -364,8 +364,32 @@ def dist_has_neg_step(dist):
     return bool(np.any((d0.axis_map >= 0) & (d0.steps < 0)))
 
 
+_dist_fn_cache = {}
+
+
+def _dist_key(dist):
+    return tuple([s.key() for s in dist])
+
+
+def _memo_dist(tag, dist, args, compute):
+    """Memoise a pure function of (a distribution, hashable arguments) that returns distributions: shardviews are
+    immutable once in use, so the cached objects are shared; the LIST is copied (callers may own and re-point it).
+    An iterative program slices / broadcasts / reduces fresh arrays with the same partitions every step."""
+    try:
+        key = (tag, _dist_key(dist), args)
+        hit = _dist_fn_cache.get(key)
+    except TypeError:
+        return compute()
+    if hit is None:
+        if len(_dist_fn_cache) >= _MEMO_MAX:
+            _dist_fn_cache.clear()
+        hit = _dist_fn_cache[key] = compute()
+    return hit
+
+
 def slice_distribution(sl, dist):
-    return [mapslice(s, sl) for s in dist]
+    args = tuple([(x.start, x.stop, x.step) for x in sl])
+    return list(_memo_dist("slice", dist, args, lambda: tuple([mapslice(s, sl) for s in dist])))
 
 
 def find_index(dist, index):
@@ -447,6 +471,11 @@ def make_uni_dist(size, node=0, num_workers=None):
 def broadcast(distribution, broadcasted_dims, size):
     """Distribution of `distribution`'s array viewed at shape `size`: broadcast dims get
     axis_map -1 and every worker 'holds' their full extent (ramba/shardview_array.py:978-1017)."""
+    args = (tuple([bool(b) for b in broadcasted_dims]), tuple([int(x) for x in size]))
+    return list(_memo_dist("bcast", distribution, args, lambda: tuple(_broadcast(distribution, broadcasted_dims, size))))
+
+
+def _broadcast(distribution, broadcasted_dims, size):
     old_k = len(distribution[0].size)
     new_dims = len(size) - old_k
     k = len(size)
@@ -468,6 +497,12 @@ def expand_unit_dims(size, distribution, axes):
     """Distribution of the same array viewed with unit dims inserted at positions `axes` of the NEW shape
     (no storage behind them: axis_map -1, like a broadcast dim of extent 1).  The reference gets there through
     reshape (ramba/ramba.py:9438-9453, 9125-9238)."""
+    args = (tuple([int(x) for x in size]), tuple([int(a) for a in axes]))
+    new_size, out = _memo_dist("expand", distribution, args, lambda: _expand_unit_dims(size, distribution, axes))
+    return new_size, list(out)
+
+
+def _expand_unit_dims(size, distribution, axes):
     k = len(size) + len(axes)
     old_pos = [j for j in range(k) if j not in axes]
     d0 = distribution[0]
@@ -490,6 +525,12 @@ def expand_unit_dims(size, distribution, axes):
 
 def remap_axis(size, distribution, newmap):
     """Re-order / drop axes (transpose family, ramba/shardview_array.py:1024-1042)."""
+    args = (tuple([int(x) for x in size]), tuple([int(a) for a in newmap]))
+    new_size, out = _memo_dist("remap", distribution, args, lambda: _remap_axis(size, distribution, newmap))
+    return new_size, list(out)
+
+
+def _remap_axis(size, distribution, newmap):
     old = distribution[0].axis_map
     amap = np.array([old[i] for i in newmap], dtype=I64)
     new_size = tuple(size[i] for i in newmap)
@@ -505,6 +546,12 @@ def reduce_axes(size, dist, axes):
     (ramba/shardview_array.py:1046-1066): the partial array keeps ONE element per division along
     every reduced axis (shape rsz, distribution rdist); bdist views it back at the source's shape
     with the reduced axes broadcast."""
+    args = (tuple([int(x) for x in size]), tuple([int(a) for a in axes]))
+    rsz, rdist, bdist = _memo_dist("reduce", dist, args, lambda: _reduce_axes(size, dist, axes))
+    return rsz, list(rdist), list(bdist)
+
+
+def _reduce_axes(size, dist, axes):
     rdist = [ShardView(s.size, s.start) for s in dist]  # fresh objects: they are edited below
     bdist = [ShardView(s.size, s.start) for s in dist]
     rsz = list(size)

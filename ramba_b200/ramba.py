@@ -977,7 +977,6 @@ def _ring_receivable(bd_dist, vd, exec_dist, w, W, shard):
 
 
 _plan_cache = {}
-_PLAN_GENERAL = object()  # this flush needs the general path (exchange, several ranges, nothing to do on this rank)
 _VERIFY_PLAN_CACHE = bool(int(os.environ.get("RB200_VERIFY_PLAN_CACHE", "0")))
 
 
@@ -1000,7 +999,7 @@ def _remember_plan(pkey, fop, shards, bound, gred_out, gred_src):
             rpatch.append((slot, v, g[0] - shards[v].ptr(0)))
     if len(_plan_cache) >= 1024:
         _plan_cache.clear()
-    _plan_cache[pkey] = (ctypes.string_at(ctypes.addressof(fop), ctypes.sizeof(fop)), vpatch, rpatch)
+    _plan_cache[pkey] = ("single", ctypes.string_at(ctypes.addressof(fop), ctypes.sizeof(fop)), vpatch, rpatch)
 
 
 def _run_planned(plan, shards, verify_prog, views, exec_dist, gred):
@@ -1049,6 +1048,167 @@ def _verify_plan(fop, prog, views, exec_dist, gred):
 _plan_cache_disabled = []
 
 
+class _FlushTape:
+    """Everything a flush of the general path does to the GPU and to the other ranks, as it is done AND as a script:
+    buffer allocations, launches (the bound rb200_fused_op with its pointers replaced by (resource, byte offset) pairs:
+    a resource is the shard of one of the flush's views or one of the buffers the flush allocated), the all-gather,
+    the grouped sends / receives, the points where the launching stream waits for them, the fold of axis partials.
+    A later flush with the same key (op list, partitions of the op and of every operand, shard layouts) replays the
+    script instead of planning again: pack -> P2P -> interior ranges -> wait -> boundary ranges becomes a loop over
+    prepared structs (`_replay_tape`).  RB200_VERIFY_PLAN_CACHE=1: every hit plans again and the new script must be
+    identical to the memoised one."""
+
+    def __init__(self, shards):
+        self.shards = shards
+        self.actions = []
+        self.buffers = []
+        self.counts = [0, 0, 0]  # bytes sent, collectives, ring receives
+
+    # ---- resources
+    def _resolve(self, p):
+        """Device address -> (0, view index, byte offset from that shard's interior origin) | (1, buffer slot, offset)."""
+        if not p:
+            return None
+        for i, sh in enumerate(self.shards):
+            lo, hi = sh.bounds
+            if lo <= p < hi:
+                return (0, i, p - sh.ptr(0))
+        for k, b in enumerate(self.buffers):
+            lo = b.data_ptr()
+            if lo <= p < lo + builtins.max(1, b.numel() * b.element_size()):
+                return (1, k, p - lo)
+        if p == RT.red_scratch().data_ptr():
+            return (2, 0, 0)
+        raise ProgramError("internal: a bound pointer belongs to no shard or buffer of this flush")
+
+    def empty(self, n, dtype):
+        import torch
+
+        t = torch.empty(n, dtype=dtype, device=RT.device)
+        self.actions.append(("alloc", int(n), dtype))
+        self.buffers.append(t)
+        return t
+
+    def launch(self, *args, **kw):
+        fop = RT.launch(*args, submit=False, **kw)
+        patches = []
+        for v in range(fop.n_views):
+            one = fop.views[v]
+            patches.append((self._resolve(one.base), one.alloc_lo is not None and one.alloc_lo != 0))
+            one.base = 0
+            one.alloc_lo = 0
+            one.alloc_hi = 0
+        rp = []
+        for sl in range(fop.n_reds):
+            rp.append(self._resolve(fop.reds[sl].out))
+            fop.reds[sl].out = 0
+        scratch = self._resolve(fop.red_scratch)
+        fop.red_scratch = 0
+        import ctypes
+
+        self.actions.append(("launch", ctypes.string_at(ctypes.addressof(fop), ctypes.sizeof(fop)), tuple(patches), tuple(rp), scratch))
+        _submit_patched(self.actions[-1], self.shards, self.buffers)
+
+    def all_gather(self, full, mine):
+        import torch
+        import torch.distributed as dist
+
+        self.actions.append(("allgather", self._slot(full), self._slot(mine)))
+        return dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), async_op=True)
+
+    def _slot(self, t):
+        for k, b in enumerate(self.buffers):
+            if b is t:
+                return k
+        raise ProgramError("internal: a transfer buffer the flush did not allocate")
+
+    def p2p(self, ops):
+        """ops: [(is_send, buffer, peer)] -> the works of ONE grouped launch."""
+        import torch
+        import torch.distributed as dist
+
+        self.actions.append(("p2p", tuple([(bool(s), self._slot(b), int(peer)) for (s, b, peer) in ops])))
+        return dist.batch_isend_irecv([dist.P2POp(dist.isend if s else dist.irecv, b.view(torch.uint8), peer) for (s, b, peer) in ops])
+
+    def wait(self, works):
+        if works:
+            self.actions.append(("wait",))
+            for wk in works:
+                wk.wait()  # the launching stream waits for the transfers; the host does not
+
+    def reduce_partials(self, out_ptr, in_ptr, n, k, stride_k, code, rop):
+        self.actions.append(("fold", self._resolve(out_ptr), self._resolve(in_ptr), int(n), int(k), int(stride_k), int(code), int(rop)))
+        RT._reduce_partials(out_ptr, in_ptr, n, k, stride_k, code, rop, RT.stream_handle())
+
+    def finish(self):
+        RT.bytes_sent += self.counts[0]
+        RT.collectives += self.counts[1]
+        RT.ring_receives += self.counts[2]
+        RT.keepalive = self.buffers  # consumed on the launching stream; kept until the next flush
+        return (tuple(self.actions), tuple(self.counts))
+
+
+def _addr(res, shards, bufs):
+    kind, idx, off = res
+    if kind == 0:
+        return shards[idx].ptr(0) + off
+    if kind == 1:
+        return bufs[idx].data_ptr() + off
+    return RT.red_scratch().data_ptr()
+
+
+def _submit_patched(action, shards, bufs):
+    _, template, patches, rp, scratch = action
+    fop = cabi.FusedOp.from_buffer_copy(template)
+    fv = fop.views
+    for v, (res, bounded) in enumerate(patches):
+        one = fv[v]
+        one.base = _addr(res, shards, bufs)
+        if bounded:
+            one.alloc_lo, one.alloc_hi = shards[res[1]].bounds
+    for sl, res in enumerate(rp):
+        if res is not None:
+            fop.reds[sl].out = _addr(res, shards, bufs)
+    if scratch is not None:
+        fop.red_scratch = _addr(scratch, shards, bufs)
+    RT.submit(fop)
+
+
+def _replay_tape(script, shards):
+    """Run a memoised flush script against this flush's shards (see _FlushTape)."""
+    import torch
+    import torch.distributed as dist
+
+    actions, counts = script
+    bufs = []
+    works = []
+    dev = RT.device
+    for a in actions:
+        k = a[0]
+        if k == "launch":
+            _submit_patched(a, shards, bufs)
+        elif k == "alloc":
+            bufs.append(torch.empty(a[1], dtype=a[2], device=dev))
+        elif k == "p2p":
+            works += dist.batch_isend_irecv([dist.P2POp(dist.isend if s else dist.irecv, bufs[b].view(torch.uint8), peer) for (s, b, peer) in a[1]])
+        elif k == "wait":
+            for wk in works:
+                wk.wait()
+            works = []
+        elif k == "allgather":
+            works.append(dist.all_gather_into_tensor(bufs[a[1]].view(torch.uint8), bufs[a[2]].view(torch.uint8), async_op=True))
+        else:  # fold
+            RT._reduce_partials(_addr(a[1], shards, bufs), _addr(a[2], shards, bufs), a[3], a[4], a[5], a[6], a[7], RT.stream_handle())
+    for wk in works:
+        wk.wait()
+    RT.bytes_sent += counts[0]
+    RT.collectives += counts[1]
+    RT.ring_receives += counts[2]
+    RT.keepalive = bufs
+
+
+
+
 def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     """This worker's share of one flush (RemoteState.run_deferred_ops, ramba/ramba.py:3493-3819)."""
     import torch
@@ -1068,16 +1228,36 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     # ---- flush-plan memo: a flush whose operands are all local on every rank and that runs as ONE range without axis
     # reductions is, apart from the buffer addresses, a function of (op list, distributions, shard layouts): the bound
     # rb200_fused_op of the first execution is kept as a template and later executions only patch pointers into a copy
+    # Every other flush (several ranges, pieces exchanged with other ranks, an all-gathered operand, axis reductions) is
+    # recorded as a script of allocations / launches / transfers / waits with symbolic addresses (_FlushTape) and replayed.
     pkey = None
-    if not ared and not _plan_cache_disabled:
+    verify_script = None
+    if not _plan_cache_disabled:
         pkey = (prog, w, W, tuple([sv.key() for sv in exec_dist]), tuple([tuple([sv.key() for sv in vd]) for vd in vdist]),
-                tuple([(sh.shape, sh.border) for sh in shards]))
+                tuple([(sh.shape, sh.border) for sh in shards]), tuple(red_axes) if red_axes else (),
+                # (what the ring of a padded block can receive depends on the partition of the whole array)
+                tuple([tuple([sv.key() for sv in bdarray.get_by_gid(g).distribution]) if sh.border else None
+                       for (g, _), sh in zip(views, shards)]) if W > 1 else ())
         plan = _plan_cache.get(pkey)
-        if plan is not None and plan is not _PLAN_GENERAL:
-            _run_planned(plan, shards, prog if _VERIFY_PLAN_CACHE else None, views, exec_dist, gred)
-            return
-        if plan is _PLAN_GENERAL:
-            pkey = None
+        if plan is not None:
+            if plan[0] == "single":
+                _run_planned(plan[1:], shards, prog if _VERIFY_PLAN_CACHE else None, views, exec_dist, gred)
+                return
+            if not _VERIFY_PLAN_CACHE:
+                _replay_tape(plan[1], shards)
+                return
+            verify_script = plan[1]
+    tape = _FlushTape(shards)
+
+    def _done():
+        script = tape.finish()
+        if verify_script is not None:
+            if script != verify_script:
+                raise AssertionError("flush-script memo: planning the same flush again gives a different script")
+        elif pkey is not None:
+            if len(_plan_cache) >= 1024:
+                _plan_cache.clear()
+            _plan_cache[pkey] = ("tape", script)
     vcode = [rb_dtype(det.dtype) for (_, det) in views]
     written = [bool(prog.view_written.get(i)) for i in range(nviews)]
     ared_views = set()
@@ -1100,7 +1280,6 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
     gathered = set()         # views served whole by an all-gathered buffer
     ring = [False] * nviews  # views whose remote pieces are received into the ring of this rank's padded block
     post_wait = []           # unpack launches that need the received data: (program, shape, bound views)
-    recv_bufs = []
     pending = []  # collectives / transfers in flight: waited for only before the first range that reads what they bring
     if W > 1 and not builtins.all(local_everywhere):
         RT.ensure_process_group()
@@ -1123,19 +1302,18 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                 # (the reference ships W*(W-1) pickled pieces, ramba/ramba.py:3646-3693)
                 n = g
                 tdt = torch_dtype(views[i][1].dtype)
-                mine = torch.empty(n, dtype=tdt, device=RT.device)
+                mine = tape.empty(n, tdt)
                 part = shardview.clean_range(vdist[i][w])
                 shp = [1 if bc[d] else int(part.size[d]) for d in range(len(bc))]
                 cst, _ = _contig_strides(shp, bc)
                 off, st = RT.bind_view(vdist[i][w], shards[i].strides, part)
-                RT.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
-                          [(shards[i].ptr(off), [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
-                           (mine.data_ptr(), cst, vcode[i])])
-                full = torch.empty(W * n, dtype=tdt, device=RT.device)
-                pending.append(dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), async_op=True))
-                recv_bufs += [full, mine]
-                RT.bytes_sent += n * itemsize * (W - 1)
-                RT.collectives += 1
+                tape.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
+                            [(shards[i].ptr(off), [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
+                             (mine.data_ptr(), cst, vcode[i])])
+                full = tape.empty(W * n, tdt)
+                pending.append(tape.all_gather(full, mine))
+                tape.counts[0] += n * itemsize * (W - 1)
+                tape.counts[1] += 1
                 vshape = views[i][1].shape
                 fshape = [1 if bc[d] else int(vshape[d]) for d in range(len(bc))]
                 fst, _ = _contig_strides(fshape, bc)
@@ -1154,24 +1332,22 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                     if not shardview.is_empty(part):
                         shp = [1 if bc[d] else int(part.size[d]) for d in range(len(bc))]
                         cst, n = _contig_strides(shp, bc)
-                        buf = torch.empty(max(n, 1), dtype=torch_dtype(views[i][1].dtype), device=RT.device)
+                        buf = tape.empty(max(n, 1), torch_dtype(views[i][1].dtype))
                         off, st = RT.bind_view(vdist[i][w], shards[i].strides, part)
                         src_ptr = shards[i].ptr(off)
-                        RT.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
-                                  [(src_ptr, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
-                                   (buf.data_ptr(), cst, vcode[i])])
-                        ops.append(dist.P2POp(dist.isend, buf.view(torch.uint8), peer))
-                        recv_bufs.append(buf)
-                        RT.bytes_sent += buf.numel() * buf.element_size()
+                        tape.launch(_pack_program(vcode[i], vcode[i]), shp, [0] * len(shp),
+                                    [(src_ptr, [0 if bc[d] else st[d] for d in range(len(bc))], vcode[i]),
+                                     (buf.data_ptr(), cst, vcode[i])])
+                        ops.append((True, buf, peer))
+                        tape.counts[0] += buf.numel() * buf.element_size()
                 # what I need from `peer`
                 if not shardview.is_empty(subspace) and not shardview.is_compat(subspace, vdist[i][w]):
                     part = shardview.intersect(vdist[i][peer], exec_dist[w])
                     if not shardview.is_empty(part):
                         shp = [1 if bc[d] else int(part.size[d]) for d in range(len(bc))]
                         cst, n = _contig_strides(shp, bc)
-                        buf = torch.empty(max(n, 1), dtype=torch_dtype(views[i][1].dtype), device=RT.device)
-                        ops.append(dist.P2POp(dist.irecv, buf.view(torch.uint8), peer))
-                        recv_bufs.append(buf)
+                        buf = tape.empty(max(n, 1), torch_dtype(views[i][1].dtype))
+                        ops.append((False, buf, peer))
                         pb = shardview.clean_range(part)
                         if ring[i]:
                             # getborder (ramba/ramba.py:1260-1322): the neighbour's edge lands in the ring of MY padded
@@ -1180,20 +1356,17 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
                             post_wait.append((_pack_program(vcode[i], vcode[i]), shp,
                                               [(buf.data_ptr(), cst, vcode[i]), (shards[i].ptr(off), st, vcode[i])]))
                             parts[i].append((pb, None, None, vdist[i][w], True))
-                            RT.ring_receives += 1
+                            tape.counts[2] += 1
                         else:
                             parts[i].append((pb, buf.data_ptr(), cst, None, True))
         if ops:
             # the pack kernels run on the current stream; NCCL orders its transfers after them.  The transfers are NOT
             # waited for here: ranges whose operands are all local (the interior of a stencil) are launched first and
             # overlap with them (the reference sends, then blocks in the receive loop, ramba/ramba.py:3646-3693)
-            pending += dist.batch_isend_irecv(ops)
+            pending += tape.p2p(ops)
     if shardview.is_empty(subspace):
-        for wk in pending:
-            wk.wait()
-        RT.keepalive = recv_bufs
-        if pkey is not None:
-            _plan_cache[pkey] = _PLAN_GENERAL
+        tape.wait(pending)
+        _done()
         return
     # local parts
     for i in range(nviews):
@@ -1240,11 +1413,10 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         ranges = sorted(ranges, key=lambda r: 1 if _needs_transfer(r) else 0)  # (stable: local ranges first)
     for r in ranges:
         if pending and _needs_transfer(r):
-            for wk in pending:
-                wk.wait()  # the launching stream waits for the transfers; the host does not
+            tape.wait(pending)  # the launching stream waits for the transfers; the host does not
             pending = []
             for (pp, pshape, pbound) in post_wait:
-                RT.launch(pp, pshape, [0] * len(pshape), pbound)
+                tape.launch(pp, pshape, [0] * len(pshape), pbound)
             post_wait = []
         bound = []
         ok = True
@@ -1277,13 +1449,14 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         shape_r = [int(x) for x in r.size]
         gs = [int(x) for x in r.start]
         if not ared:
-            fop = RT.launch(prog, shape_r, gs, bound, reds=gred_out, worker_num=w, num_workers=W)
-            if pkey is not None:
-                if single and not pending and not post_wait and not recv_bufs and len(ranges) == 1:
+            if single and not pending and not post_wait and not tape.buffers and not tape.actions and len(ranges) == 1 \
+                    and verify_script is None:
+                # the plain flush: one launch, everything local - kept as a single template (see _remember_plan)
+                fop = RT.launch(prog, shape_r, gs, bound, reds=gred_out, worker_num=w, num_workers=W)
+                if pkey is not None:
                     _remember_plan(pkey, fop, shards, bound, gred_out, gred_src)
-                else:
-                    _plan_cache[pkey] = _PLAN_GENERAL
-                pkey = None
+                return
+            tape.launch(prog, shape_r, gs, bound, reds=gred_out, worker_num=w, num_workers=W)
             continue
         # ---- axis reduction: stage 1 into per-split partials, then fold into the partial array
         shape_p = [shape_r[d] for d in order]
@@ -1300,34 +1473,31 @@ def run_deferred_ops(uuid, views, prog, exec_dist, gred, ared, red_axes):
         target = 148 * 2048
         nsplit = 1 if kept_work >= target else builtins.min(builtins.max(1, red_len // 8), -(-target // kept_work))
         nslots = len(prog.reds)
-        partials = torch.empty(nslots * nsplit * kept_elems + 1, dtype=torch.float64, device=RT.device)
+        partials = tape.empty(nslots * nsplit * kept_elems + 1, torch.float64)
         prog_p = _remap_iota(prog, order)
-        RT.launch(prog_p, shape_p, gs_p, bound_p, n_axis_red=nred, axis_nsplit=nsplit,
-                  axis_partials=partials.data_ptr(), worker_num=w, num_workers=W)
+        tape.launch(prog_p, shape_p, gs_p, bound_p, n_axis_red=nred, axis_nsplit=nsplit,
+                    axis_partials=partials.data_ptr(), worker_num=w, num_workers=W)
         for (slot, red_view, redop) in ared:
             rop, rct = prog.reds[slot]
             acc_code = cabi.F64 if rct == cabi.T_F64 else cabi.I64
             base = partials.data_ptr() + slot * nsplit * kept_elems * 8
             tot_ptr = base
             if nsplit > 1:
-                tot = torch.empty(kept_elems + 1, dtype=torch.float64, device=RT.device)
-                RT._reduce_partials(tot.data_ptr(), base, kept_elems, nsplit, kept_elems, acc_code, rop, RT.stream_handle())
+                tot = tape.empty(kept_elems + 1, torch.float64)
+                tape.reduce_partials(tot.data_ptr(), base, kept_elems, nsplit, kept_elems, acc_code, rop)
                 tot_ptr = tot.data_ptr()
-                recv_bufs.append(tot)
             i = [j for j, (g, det) in enumerate(views) if g == red_view.gid and shardview.dist_is_eq(det.distribution, red_view.distribution)][0]
             kept_shape = shape_p[nred:]
             cst, _ = _contig_strides(kept_shape, [False] * len(kept_shape))
             rb = bound_p[i]
-            RT.launch(_combine_program(vcode[i], acc_code, rop), kept_shape, gs_p[nred:],
-                      [(rb[0], rb[1][nred:], rb[2]), (tot_ptr, cst, acc_code)])
-        recv_bufs.append(partials)
-    for wk in pending:  # (nothing needed them, e.g. an empty boundary)
-        wk.wait()
+            tape.launch(_combine_program(vcode[i], acc_code, rop), kept_shape, gs_p[nred:],
+                        [(rb[0], rb[1][nred:], rb[2]), (tot_ptr, cst, acc_code)])
+    tape.wait(pending)  # (nothing needed them, e.g. an empty boundary)
     for (pp, pshape, pbound) in post_wait:
-        RT.launch(pp, pshape, [0] * len(pshape), pbound)
+        tape.launch(pp, pshape, [0] * len(pshape), pbound)
     # staging buffers are torch allocations consumed on the launching stream: the caching allocator reuses them in
-    # stream order, so no host synchronisation is needed here (the references are kept until the next flush anyway)
-    RT.keepalive = recv_bufs
+    # stream order, so no host synchronisation is needed here (the tape keeps the references until the next flush)
+    _done()
 
 
 def _remap_iota(prog, order):

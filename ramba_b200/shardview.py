@@ -356,7 +356,14 @@ def compatible_distributions(d1, d2):
 
 
 def dist_is_eq(d1, d2):
-    return d1 is d2 or (len(d1) == len(d2) and all(is_eq(a, b) for a, b in zip(d1, d2)))
+    if d1 is d2:
+        return True
+    if len(d1) != len(d2):
+        return False
+    for a, b in zip(d1, d2):
+        if a is not b and a.key() != b.key():
+            return False
+    return True
 
 
 def dist_has_neg_step(dist):

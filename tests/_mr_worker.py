@@ -70,6 +70,13 @@ def main():
             print("RANK %d failed in %s:\n%s" % (common.worker_num, prog.__name__, traceback.format_exc()), flush=True)
             os._exit(3)  # (the other ranks are released by their watchdogs)
         exp = prog(onp)
+        # a second run of the same program meets the memoised flush scripts (pack -> transfers -> ranges replayed from the
+        # tape of the first run): it must give the same values
+        again = prog(rb)
+        if len(again) != len(got) or not all(onp.array_equal(onp.asarray(a), onp.asarray(b), equal_nan=True)
+                                              if onp.asarray(a).dtype.kind in "fc" else onp.array_equal(onp.asarray(a), onp.asarray(b))
+                                              for a, b in zip(again, got)):
+            failures.append("%s (second run differs from the first)" % prog.__name__)
         for i, (g, e) in enumerate(zip(got, exp)):
             g, e = onp.asarray(g), onp.asarray(e)
             if prog in loose:

@@ -231,3 +231,18 @@ def test_fuzzed_programs_match_numpy(eng, chunk, monkeypatch):
     monkeypatch.setattr(ramba, "NO_DAG", True)
     for f in _dag_fuzz.CASES[chunk * 30:chunk * 30 + 6]:
         _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_programs_at_the_fusers_table_sizes(eng, chunk, monkeypatch):
+    """tests/_limit_fuzz.py: long same-shaped runs with many live arrays, dying temporaries and reductions of temporaries at
+    every distance from the 40-statement / 16-view limits - values as in NumPy, with the DAG and with RAMBA_NO_DAG."""
+    import _limit_fuzz
+
+    rb, ramba, RT = eng
+    cases = _limit_fuzz.CASES[chunk * 20:(chunk + 1) * 20]
+    for f in cases:
+        _same(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in cases:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")

@@ -27,3 +27,19 @@ def test_fuzzed_programs_cuda(gpu_engine, chunk):
     for f in _dag_fuzz.CASES[chunk * 15:(chunk + 1) * 15]:
         _close(f(rb), f(onp), f.__name__)
     assert RT.is_cuda and _cabi.launch_count() > before
+
+
+@pytest.mark.parametrize("chunk", range(2))
+def test_programs_at_the_fusers_table_sizes_cuda(gpu_engine, chunk):
+    """tests/_limit_fuzz.py through the CUDA library: includes op lists that load a view into a register, store to the same
+    view and use the OLD value afterwards (`t = a*2; a += 1; r = t - b` fused) - the pattern whose oracle evaluation was
+    wrong until this round (oracle/vm.py handed out an alias of the host buffer on loads)."""
+    import _limit_fuzz
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    for f in _limit_fuzz.CASES[chunk * 12:(chunk + 1) * 12]:
+        _close(f(rb), f(onp), f.__name__)
+    assert RT.is_cuda and _cabi.launch_count() > before

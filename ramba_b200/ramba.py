@@ -2532,6 +2532,31 @@ def fromarray_local(block, shape, dtype=None, **kwargs):
     return new
 
 
+def load(fname, dtype=None, local=False, ftype=None, **kwargs):
+    """Array from a file (ramba/ramba.py:8930-8945).  File types that can be read in parts are loaded DISTRIBUTED: every rank
+    reads only the block of the file its shard holds (the worker side of the reference, RemoteState.load 3929-3956) and
+    uploads it; the others (images) are read whole and distributed like `fromarray`.  `local=True` forces the second way.
+    Extra keyword arguments go to the handler (`arr_path` for HDF5, `var_select` for netCDF)."""
+    from . import fileio
+
+    fldr = fileio.get_load_handler(fname, ftype)
+    if local or not fldr.is_dist:
+        tmp = fldr.readall(fname, **kwargs)
+        return fromarray(tmp, dtype=tmp.dtype if dtype is None else dtype)
+    shp, dt = fldr.getinfo(fname, **kwargs)
+    shp = shapeToInt(shp)
+    if dtype is None:
+        dtype = dt
+    if shp == ():
+        return array(np.asarray(fldr.readall(fname, **kwargs)).astype(dtype))
+    sv = shardview.default_distribution(shp)[common.worker_num]
+    if shardview.is_empty(sv):
+        block = np.empty([0] * len(shp), dtype=dtype)
+    else:
+        block = fldr.read(fname, shardview.to_slice(sv), **kwargs)
+    return fromarray_local(block, shp, dtype=dtype)
+
+
 def local_block_to_host(nd, out=None, non_blocking=False):
     """SPMD extension: this rank's block of `nd` as a host array (no gather)."""
     DAG.instantiate(nd)

@@ -56,6 +56,14 @@ def main():
     def scan_small(np):
         return test_scan_kernel.scans(np, False)
 
+    if os.environ.get("RB200_MR_NPY"):
+        def load_npy(np):
+            # every rank reads only its own block of the file (ramba_b200.load); NumPy reads it whole
+            x = np.load(os.environ["RB200_MR_NPY"])
+            return [onp.asarray(x.asarray() if hasattr(x, "asarray") else x), onp.asarray(float((x * 2.0).sum()))]
+
+        progs.append(load_npy)
+
     loose.append(scan_small)
     for prog in progs + loose:
         if prog.__name__ not in names and names != ["all"]:

@@ -58,3 +58,18 @@ def test_local_border_halo_goes_into_the_ring():
     (getborder) and the stencil reads one buffer."""
     outs = _run(4, "sstencil_local_border")
     assert all("ring_receives=0 " not in o for _, o in outs), outs
+
+
+@pytest.mark.timeout(300)
+def test_distributed_file_load(tmp_path):
+    """`load` of a file type that can be read in parts: every rank reads its own block (ramba/ramba.py:8930-8945,
+    3929-3956); the values and a reduction over them match NumPy on every rank."""
+    import numpy as onp
+
+    path = str(tmp_path / "field.npy")
+    onp.save(path, (onp.arange(46 * 61, dtype=onp.float64).reshape(46, 61) % 13) - 5.0)
+    os.environ["RB200_MR_NPY"] = path
+    try:
+        _run(3, "load_npy")
+    finally:
+        del os.environ["RB200_MR_NPY"]

@@ -694,10 +694,13 @@ class DAG:
     # ---- pruning ---------------------------------------------------------------------------
     def _output_died(self, _ref=None):
         """Weakref callback: the last handle of this node's (out-of-place) destination is gone."""
-        if self.executed or DAG.in_evaluate:
-            return  # (during an evaluation the execution loop skips it)
-        if not self.forward_deps:
-            self._retire(False)
+        try:
+            if self.executed or DAG.in_evaluate:
+                return  # (during an evaluation the execution loop skips it)
+            if not self.forward_deps:
+                self._retire(False)
+        except Exception:  # (interpreter shutdown: module globals may be gone)
+            pass
 
     def _retire(self, ran):
         """Take the node out of the graph (executed or pruned) and let go of its operands."""

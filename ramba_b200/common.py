@@ -28,6 +28,7 @@ def _env_int(name, default=0):
 ndebug = _env_int("RAMBA_DEBUG", 0)
 ntiming = _env_int("RAMBA_TIMING", 0)
 debug_showcode = _env_int("RAMBA_SHOW_CODE", 0) != 0
+reshape_forwarding = _env_int("RAMBA_RESHAPE_COPY", 0) != 0  # reshape() calls forward to reshape_copy (ramba/common.py:141-146)
 ramba_big_data = True  # indices are always int64 here (RAMBA_BIG_DATA, ramba/shardview_array.py:24-28)
 
 # worker identity: torchrun exports RANK / WORLD_SIZE / LOCAL_RANK

@@ -1628,6 +1628,37 @@ def _slice_len(s):
     return builtins.max(0, -(-(s.start - s.stop) // (-s.step)))
 
 
+class ReshapeError(Exception):
+    """A reshape that would have to move data between shards (ramba/ramba.py: ReshapeError)."""
+
+
+class ndarray_flags:
+    __slots__ = ("arr",)
+
+    def __init__(self, arr):
+        self.arr = arr
+
+    def __getitem__(self, item):
+        if not isinstance(item, str):
+            assert len(item) == 1
+            item = item[0]
+        if item == "WRITEABLE":
+            return self.writeable
+        raise KeyError(item)
+
+    @property
+    def writeable(self):
+        return not self.arr.readonly
+
+    @writeable.setter
+    def writeable(self, val):
+        # read-only is checked when a statement is issued (in program order), so the flag changes at once; a view of a
+        # read-only base cannot be made writeable (NumPy's rule)
+        if val and self.arr.base is not None and self.arr.base.readonly:
+            raise ValueError("cannot set WRITEABLE flag to True of this array")
+        self.arr.readonly = not val
+
+
 class ndarray:
     __slots__ = ("base", "bdarray", "shape", "distribution", "local_border", "readonly", "maskarray", "_slices", "_ref", "__weakref__")
     __array_priority__ = 20.0
@@ -1690,6 +1721,11 @@ class ndarray:
     def instantiate(self):
         DAG.instantiate(self)
         return self
+
+    @property
+    def flags(self):
+        """`arr.flags.writeable` / `arr.flags["WRITEABLE"]` (ndarray_flags, ramba/ramba.py:5365-5385)."""
+        return ndarray_flags(self)
 
     # ---- host round trip (ramba/ramba.py:5735-5765)
     def asarray(self, out=None, non_blocking=False):
@@ -1987,18 +2023,26 @@ class ndarray:
         return self.remapped_axis([i for i in range(self.ndim) if i not in axes])
 
     def reshape(self, *shape):
-        """Only reshapes that insert or remove unit dims are views here; anything else is a redistribution
-        (the reference's reshape_copy, ramba/ramba.py:9241-9277) and outside this path."""
+        """Reshapes that insert or remove unit dims are views; anything else has to move data between shards and, like in the
+        reference (ramba/ramba.py:9178-9238), raises ReshapeError unless RAMBA_RESHAPE_COPY forwards it to reshape_copy."""
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
-        shape = shapeToInt(shape)
+        shape = _norm_newshape(self, shape)
         if shape == self.shape:
             return self
         if [s for s in shape if s != 1] != [s for s in self.shape if s != 1]:
-            raise NotImplementedError("reshape %s -> %s moves data between shards (reshape_copy): not on this path" % (self.shape, shape))
+            if common.reshape_forwarding:
+                return reshape_copy(self, shape)
+            raise ReshapeError(
+                "ramba.reshape not supported as distributed array reshape cannot be done inplace.  Use reshape_copy instead to "
+                "create a non-inplace reshape or set RAMBA_RESHAPE_COPY environment variable to convert all reshape calls to "
+                "reshape_copy.")
         flat = self.squeeze() if builtins.any(s == 1 for s in self.shape) else self
         axes = [i for i, s in enumerate(shape) if s == 1]
         return flat.expand_dims(axes) if axes else flat
+
+    def reshape_copy(self, newshape):
+        return reshape_copy(self, newshape)
 
     def transpose(self, *args):
         nd = self.ndim
@@ -2898,6 +2942,119 @@ def reshape(a, *shape):
     return _as_nd(a).reshape(*shape)
 
 
+def _norm_newshape(arr, newshape):
+    if isinstance(newshape, numbers.Integral):
+        newshape = (newshape,)
+    newshape = tuple(int(x) for x in newshape)
+    if builtins.any(x < -1 for x in newshape):
+        raise ValueError("Illegal dimension size in reshape.")
+    total = arr.size
+    if newshape.count(-1) > 1:
+        raise ValueError("Too many -1 dimensions given to reshape.")
+    if -1 in newshape:
+        rest = int(np.prod([x for x in newshape if x != -1], dtype=np.int64))
+        if rest == 0 or total % rest != 0:
+            raise ValueError("Incompatible shape given to reshape.")
+        newshape = tuple(total // rest if x == -1 else x for x in newshape)
+    if int(np.prod(newshape, dtype=np.int64)) != total:
+        raise ValueError("cannot reshape array of size %d into shape %s" % (total, newshape))
+    return newshape
+
+
+def reshape_copy(arr, newshape):
+    """A new array of shape `newshape` holding arr's elements in C order (ramba/ramba.py:9241-9277; worker side
+    RemoteState.reshape 2409-2499 moves one element at a time in Python).  Here: the blocks of both arrays are cut into
+    runs of consecutive linear indices, every (source rank, destination rank) pair exchanges the intersections of its runs
+    - packed into one buffer per peer, one grouped send / receive - and runs of equal length at constant steps are single
+    2-D strided copies on the GPU (ramba_b200/redistribute.py)."""
+    import torch
+
+    from . import redistribute as R
+
+    arr = _as_nd(arr)
+    newshape = _norm_newshape(arr, newshape)
+    if arr.shape == ():
+        return full(newshape, arr.distribution.item(), dtype=arr.dtype)
+    # the source as a whole array in its own buffer (views, masks and padded blocks are materialised by one fused copy)
+    src = arr
+    if arr.base is not None or arr.maskarray is not None or arr.local_border or \
+            not (arr.distribution is arr.bdarray.distribution or shardview.dist_is_eq(arr.distribution, arr.bdarray.distribution)):
+        src = copy(arr)
+    out = ndarray(newshape, dtype=arr.dtype, flex_dist=False)
+    DAG.instantiate(src)
+    W, w = common.num_workers, common.worker_num
+    sdist, ddist = src.bdarray.distribution, out.bdarray.distribution
+    sh_src = RT.shards.get(src.gid) or RT.create_array(src.gid, _local_shape(sdist, w), src.dtype, src.bdarray.pad)
+    sh_dst = RT.create_array(out.gid, _local_shape(ddist, w), out.dtype, out.bdarray.pad)
+    out.bdarray.remote_constructed = True
+    out.bdarray.flex_dist = False
+    if arr.size == 0:
+        return out
+    code = rb_dtype(arr.dtype)
+    isz = np.dtype(np.uint8 if arr.dtype == np.bool_ else arr.dtype).itemsize
+    prog = _pack_program(code, code)
+
+    def runs(shape, dist, r, shard):
+        sv = dist[r]
+        if shardview.is_empty(sv):
+            return np.zeros(0, dtype=np.int64), 0, None
+        st, ln, m = R.block_runs(shape, sv.start, sv.size, True)
+        loc = None
+        if shard is not None:
+            loc = R.run_local_offsets(sv.size, m, shard.strides, 0)
+        return st, ln, loc
+
+    my_s, my_sl, my_sloc = runs(src.shape, sdist, w, sh_src)
+    my_d, my_dl, my_dloc = runs(out.shape, ddist, w, sh_dst)
+
+    def copy_groups(length, so, do, sptr, dptr, sbounds, dbounds):
+        for (i0, cnt, ln, ds, dd) in R.strided_groups(length, so, do):
+            a = (sptr + int(so[i0]) * isz, [ds, 1], code) + ((sbounds,) if sbounds is not None else ())
+            b = (dptr + int(do[i0]) * isz, [dd, 1], code) + ((dbounds,) if dbounds is not None else ())
+            RT.launch(prog, [cnt, ln], [0, 0], [a, b])
+
+    # pieces that stay on this rank
+    ia, ib, ps, pl = R.intersect_runs(my_s, my_sl, my_d, my_dl)
+    if len(ps):
+        copy_groups(pl, my_sloc[ia] + (ps - my_s[ia]), my_dloc[ib] + (ps - my_d[ib]), sh_src.ptr(0), sh_dst.ptr(0), sh_src.bounds, sh_dst.bounds)
+    if W == 1:
+        return out
+    RT.ensure_process_group()
+    import torch.distributed as dist
+
+    ops, bufs, unpack = [], [], []
+    tdt = torch_dtype(arr.dtype)
+    for peer in range(W):
+        if peer == w:
+            continue
+        # what `peer` needs from my source block, in linear order
+        p_d, p_dl, _ = runs(out.shape, ddist, peer, None)
+        ia, ib, ps, pl = R.intersect_runs(my_s, my_sl, p_d, p_dl)
+        if len(ps):
+            n = int(pl.sum())
+            buf = torch.empty(n, dtype=tdt, device=RT.device)
+            copy_groups(pl, my_sloc[ia] + (ps - my_s[ia]), np.cumsum(pl) - pl, sh_src.ptr(0), buf.data_ptr(), sh_src.bounds, None)
+            ops.append(dist.P2POp(dist.isend, buf.view(torch.uint8), peer))
+            bufs.append(buf)
+            RT.bytes_sent += n * isz
+        # what I need from `peer`'s source block
+        p_s, p_sl, _ = runs(src.shape, sdist, peer, None)
+        ia, ib, ps, pl = R.intersect_runs(p_s, p_sl, my_d, my_dl)
+        if len(ps):
+            n = int(pl.sum())
+            buf = torch.empty(n, dtype=tdt, device=RT.device)
+            ops.append(dist.P2POp(dist.irecv, buf.view(torch.uint8), peer))
+            bufs.append(buf)
+            unpack.append((pl, np.cumsum(pl) - pl, my_dloc[ib] + (ps - my_d[ib]), buf))
+    if ops:
+        for wk in dist.batch_isend_irecv(ops):
+            wk.wait()  # (the launching stream waits; the host does not)
+    for (pl, so, do, buf) in unpack:
+        copy_groups(pl, so, do, buf.data_ptr(), sh_dst.ptr(0), None, sh_dst.bounds)
+    RT.keepalive = bufs
+    return out
+
+
 def ndim(a):
     return a.ndim if hasattr(a, "ndim") else np.ndim(a)
 
@@ -3466,6 +3623,13 @@ def cumsum(a, axis=None, dtype=None, out=None):
         cur = nxt
         d *= 2
     return cur
+
+
+def instantiate_all(*args, **kwargs):
+    """Make sure all arrays among the arguments have been computed (ramba/ramba.py:5318-5324)."""
+    for a in args:
+        if isinstance(a, ndarray):
+            a.instantiate()
 
 
 def sync():

@@ -41,11 +41,13 @@ def main():
 
     import _dag_fuzz
     import _limit_fuzz
+    import test_reshape_copy
 
     progs = (list(_programs.ALL) + list(test_api_parity.CASES) + [test_edges._ragged, test_edges._empty, test_edges._dtypes]
              + (_random_programs.CASES if os.environ.get("RB200_MR_ALL_RANDOM") else _random_programs.CASES[:12])
              + (_dag_fuzz.CASES[:60] if os.environ.get("RB200_MR_ALL_RANDOM") else _dag_fuzz.CASES[:10])
-             + (_limit_fuzz.CASES[:40] if os.environ.get("RB200_MR_ALL_RANDOM") else _limit_fuzz.CASES[:6]))
+             + (_limit_fuzz.CASES[:40] if os.environ.get("RB200_MR_ALL_RANDOM") else _limit_fuzz.CASES[:6])
+             + [test_reshape_copy.reshape_programs])
     # the stencil / streaming / scan kernel programs: float32 arrays with Python-float weights are computed in float64 by
     # the op list (Numba's typing) but in float32 by NumPy, so these compare with a dtype tolerance across ranks
     loose = []

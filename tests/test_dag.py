@@ -246,3 +246,25 @@ def test_programs_at_the_fusers_table_sizes(eng, chunk, monkeypatch):
     monkeypatch.setattr(ramba, "NO_DAG", True)
     for f in cases:
         _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+def test_instantiate_all_and_flags(eng):
+    rb, ramba, RT = eng
+    a = rb.arange(500) * 1.0
+    b = a + 1.0
+    c = rb.arange(200) * 3.0
+    rb.instantiate_all(a, b, 5, "x")
+    assert len(ramba.DAG.pending) == 2          # c's two statements are still waiting
+    assert b.flags.writeable and b.flags["WRITEABLE"]
+    b.flags.writeable = False
+    with pytest.raises(ValueError):
+        b += 1.0
+    with pytest.raises(ValueError):
+        b[3:9] = 0.0
+    v = b[10:20]
+    assert not v.flags.writeable
+    with pytest.raises(ValueError):
+        v.flags.writeable = True
+    b.flags.writeable = True
+    b += 1.0
+    assert onp.array_equal(b.asarray(), onp.arange(500) + 2.0) and onp.array_equal(c.asarray(), onp.arange(200) * 3.0)

@@ -43,3 +43,18 @@ def test_programs_at_the_fusers_table_sizes_cuda(gpu_engine, chunk):
     for f in _limit_fuzz.CASES[chunk * 12:(chunk + 1) * 12]:
         _close(f(rb), f(onp), f.__name__)
     assert RT.is_cuda and _cabi.launch_count() > before
+
+
+def test_reshape_copy_cuda(gpu_engine):
+    """tests/test_reshape_copy.py's programs through the CUDA library (strided copies on the op-list kernels)."""
+    import ramba_b200 as rb
+    import test_reshape_copy
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    got, exp = test_reshape_copy.reshape_programs(rb), test_reshape_copy.reshape_programs(onp)
+    assert len(got) == len(exp)
+    for i, (g, e) in enumerate(zip(got, exp)):
+        assert g.shape == e.shape and g.dtype == e.dtype and onp.array_equal(g, e), i
+    assert RT.is_cuda and _cabi.launch_count() > before

@@ -490,6 +490,20 @@ def ref_concatenate(np):
 
 
 @case
+def ref_reshape_copy(np):
+    """reshape_copy (ramba/ramba.py:9241-9277): merges, splits, an unrelated factorization, a sliced source; small sizes
+    (the reference moves one element at a time in Python)."""
+    def rc(a, shp):
+        return a.reshape_copy(shp) if np is not onp else onp.reshape(a, shp).copy()
+
+    a = np.fromfunction(lambda i, j: i * 15 + j, (24, 15), dtype=int)
+    v = np.arange(360) * 2
+    out = [_h(rc(a, (360,))), _h(rc(v, (24, 15))), _h(rc(a, (15, 24))), _h(rc(a, (4, 6, 15))), _h(rc(a, (20, 18)))]
+    out.append(_h(rc(v[20:320], (30, 10)) + 1))
+    return out
+
+
+@case
 def nan_reductions(np):  # the reference's nansum / nanmean give NaN here (its masked sum does not keep the NaNs out)
     v = onp.arange(240) * 0.5
     v[::7] = onp.nan

@@ -117,7 +117,8 @@ def test_api_golden_covers_the_cases(golden_api):
     not_run = sorted(n for n in names if status[n] != "ok")
     assert not_run == sorted(["reductions_full", "reductions_axis", "sstencil_skeleton", "random_generic", "zero_d", "tril_family",
                               "mgrid_offsets", "sreduce_forms", "ref_reduction_min_max", "stack_family",
-                              "scumulative_forms", "numpy_protocol_more"]), not_run
+                              "scumulative_forms", "numpy_protocol_more",
+                              "ref_reshape_copy"]), not_run  # (ref_reshape_copy: KeyError in the reference's single-worker RemoteState.reshape)
     # ran in the reference but is knowingly not followed (see the case): excluded from the comparisons below
     assert status["nan_reductions"] == "ok"
 

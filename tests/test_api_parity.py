@@ -7,6 +7,7 @@ import numpy as onp
 import pytest
 
 CASES = []
+FIRST_GPU_RUN_IS_THE_DRIVERS = {"ref_reshape_copy"}  # -m gpu legs of these cases live in tests/test_zz_dag_fuzz_gpu.py
 
 
 def case(f):
@@ -937,6 +938,8 @@ def test_run_both_cuda(gpu_engine, f):
     from ramba_b200 import _cabi
     from ramba_b200.runtime import RT
 
+    if f.__name__ in FIRST_GPU_RUN_IS_THE_DRIVERS:
+        pytest.skip("runs in tests/test_zz_dag_fuzz_gpu.py (written after the round's GPU budget was spent: collected last)")
     before = _cabi.launch_count()
     got = f(rb)
     assert RT.is_cuda and _cabi.launch_count() > before

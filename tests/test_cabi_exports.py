@@ -131,3 +131,27 @@ def test_malformed_op_lists_are_rejected_with_a_reason():
         bad = _one_insn_op()
         bad.insns[0].op = 200
         _cabi.run_deferred_ops(bad)
+
+
+def test_cuda_backend_wiring(monkeypatch):
+    """The one backend of the package (ramba_b200.runtime.CudaBackend) with the torch.cuda calls it makes replaced by fakes:
+    the library is loaded, op lists go to rb200_run_deferred_ops, partial folds to rb200_reduce_partials, ranks talk NCCL."""
+    import torch
+
+    from ramba_b200 import _cabi, runtime
+
+    class FakeStream:
+        cuda_stream = 1234
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: FakeStream())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda d=None: None)
+    be = runtime.CudaBackend()
+    assert be.device.type == "cuda" and be.stream_handle() == 1234 and be.dist_backend == "nccl" and be.timing
+    assert be.run is _cabi.run_deferred_ops and be.reduce_partials is _cabi.reduce_partials
+    assert be.red_scratch_bytes() == _cabi.red_scratch_bytes() > 0
+    be.synchronize()
+    rt = runtime.Runtime()
+    rt.backend = be
+    assert rt.is_cuda and rt.device == be.device and rt.executor() is _cabi.run_deferred_ops

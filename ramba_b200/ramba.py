@@ -59,7 +59,7 @@ def shapeToInt(shape):
 # =============================================================================================
 class bdarray:
     gid_map = weakref.WeakValueDictionary()
-    __slots__ = ("shape", "gid", "pad", "distribution", "nrefs", "remote_constructed", "flex_dist", "dtype", "__weakref__")
+    __slots__ = ("shape", "gid", "pad", "distribution", "nrefs", "remote_constructed", "flex_dist", "dtype", "failed", "__weakref__")
 
     def __init__(self, shape, distribution, gid, pad, fdist, dtype):
         self.shape = shape
@@ -70,6 +70,7 @@ class bdarray:
         self.remote_constructed = False
         self.flex_dist = fdist
         self.dtype = np.dtype(dtype)
+        self.failed = None  # why the last fused op that wrote this array did not run (its contents are undefined then)
         bdarray.gid_map[gid] = self
 
     def ndarray_del_callback(self):
@@ -133,6 +134,10 @@ class ArrRef:
         self.local_border = nd.local_border
         self.bd = nd.bdarray
         self.value = nd.distribution.item() if nd.shape == () else None
+
+
+def _raise_failed(bd):
+    raise RuntimeError("this array was to be written by a fused op that failed (%s): its contents are undefined" % (bd.failed,))
 
 
 def _ref_of(nd):
@@ -328,6 +333,8 @@ class deferred_op:
         read_arrs, read_gids = cur.read_arrs, cur.read_gids
         for x in operands:
             xbd = x.bdarray
+            if xbd.failed is not None:
+                _raise_failed(xbd)
             read_arrs.append((xbd.gid, None if xbd.flex_dist else x.distribution))
             read_gids.add(xbd.gid)
             cur.add_gid(x)
@@ -369,6 +376,16 @@ class deferred_op:
         self._pin(live_gids)
         try:
             self._run_statements(self.statements, live_gids)
+        except BaseException as ex:
+            # the statements of this op are gone: what they were to write is undefined from here on.  Reading it later must
+            # fail loudly, not return whatever the shard holds (the reference re-raises on the driver and stops there,
+            # ramba/ramba.py:3875-3881, 4053-4054)
+            why = "%s: %s" % (type(ex).__name__, str(ex)[:300])
+            for g in self.write_gids:
+                bd = bdarray.gid_map.get(g)
+                if bd is not None:
+                    bd.failed = why
+            raise
         finally:
             self._finish(live_gids)
         add_time("driver_deferred_op", timer() - t0)
@@ -2431,6 +2448,8 @@ def _part_to_host(nd, w, out=None, non_blocking=False):
     """This worker's part of view `nd` as a contiguous host array (get_view, ramba/ramba.py:2160-2176)."""
     import torch
 
+    if nd.bdarray.failed is not None:
+        _raise_failed(nd.bdarray)
     sv = nd.distribution[w]
     if shardview.is_empty(sv):
         return np.zeros([0] * nd.ndim, dtype=nd.dtype)

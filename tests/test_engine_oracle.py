@@ -107,3 +107,37 @@ def test_dead_store_elimination_respects_masks_and_aliases(oracle_engine, monkey
     de[de > 1.0] = 2.0
     de[onp.arange(150) % 2 == 0] = 7.0
     assert onp.array_equal(d.asarray(), de)
+
+
+def test_a_failed_flush_poisons_what_it_was_to_write(oracle_engine, monkeypatch):
+    """A fused op that fails takes its statements with it: the arrays they were to write must raise when read, not return
+    whatever their shards hold; arrays of other ops are unaffected."""
+    import ramba_b200 as rb
+    from ramba_b200 import ramba
+
+    a = rb.fromarray(onp.arange(300, dtype=onp.float64))
+    other = rb.fromarray(onp.arange(50, dtype=onp.float64)) + 1.0
+    assert onp.array_equal(other.asarray(), onp.arange(50) + 1.0)
+    good = a * 2.0
+    bad = a + 1.0
+    orig = ramba.run_deferred_ops
+    calls = []
+
+    def failing(*args, **kw):
+        calls.append(1)
+        raise ramba.ProgramError("injected failure")
+
+    monkeypatch.setattr(ramba, "run_deferred_ops", failing)
+    with pytest.raises(ramba.ProgramError):
+        rb.sync()
+    monkeypatch.setattr(ramba, "run_deferred_ops", orig)
+    assert calls
+    for x in (good, bad):
+        with pytest.raises(RuntimeError, match="fused op that failed"):
+            x.asarray()
+        with pytest.raises(RuntimeError, match="fused op that failed"):
+            (x + 1.0).asarray()
+    # the source and unrelated arrays are intact, and new work runs
+    assert onp.array_equal(a.asarray(), onp.arange(300))
+    assert onp.array_equal((a * 3.0).asarray(), onp.arange(300) * 3.0)
+    assert onp.array_equal((other * 2.0).asarray(), (onp.arange(50) + 1.0) * 2.0)

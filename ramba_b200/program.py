@@ -358,10 +358,34 @@ class Lowering:
             tv = self._node("mov", tv.cls, tv.cls, tv.is_bool, [tv])
         return tv
 
+    def _same_array(self, a, b):
+        gids = getattr(self, "view_gids", None)
+        return a == b or gids is None or gids[a] == gids[b]
+
+    def _touched(self, nodes, vidx):
+        """Does any of `nodes` read or write the array behind view `vidx`?"""
+        for m in nodes:
+            for a in m.args:
+                if a.kind == "view" and self._same_array(a.ref, vidx):
+                    return True
+            if (m.store is not None and self._same_array(m.store, vidx)) or (m.store2 is not None and self._same_array(m.store2, vidx)):
+                return True
+        return False
+
     def store(self, vidx, tv, mask=None):
         code = self.view_dtypes[vidx]
         tv = self._materialise(tv)
         node = tv.ref
+        if node is not self.nodes[-1]:
+            # Instructions run in node order and a store runs where its node sits.  A value built by an EARLIER statement
+            # (`t = a*2; b -= a; b[:] = t` with t never stored) must not carry this store back in front of statements that
+            # read or write the array in between: the value is moved at THIS statement's position instead.
+            i = len(self.nodes) - 1
+            while self.nodes[i] is not node:
+                i -= 1
+            if self._touched(self.nodes[i + 1:], vidx):
+                tv = self._node("mov", tv.cls, tv.cls, tv.is_bool, [tv])
+                node = tv.ref
         node.store = vidx
         if mask is not None:
             m = self._materialise(mask) if mask.kind != "node" else mask
@@ -445,7 +469,11 @@ class Lowering:
             # ... unless all it does is store the value in its own dtype: then SINCOS stores the parked
             # half itself and every later use reads the parked register directly
             own = {T_F64: cabi.F64, T_F32: cabi.F32}[f.rcls]
-            if n.mask is None and not n.mask_use and (n.store is None or self.view_dtypes[n.store] == own):
+            between = self.nodes[self.nodes.index(p) + 1:self.nodes.index(n)]
+            if n.mask is None and not n.mask_use and (n.store is None or (self.view_dtypes[n.store] == own
+                                                                          and not self._touched(between, n.store))):
+                # (moving the store of the second half up to the SINCOS is only right if nothing in between reads or writes
+                # that array)
                 f.store2 = n.store
                 n.store = None
                 for m in self.nodes:

@@ -141,3 +141,37 @@ def test_a_failed_flush_poisons_what_it_was_to_write(oracle_engine, monkeypatch)
     assert onp.array_equal(a.asarray(), onp.arange(300))
     assert onp.array_equal((a * 3.0).asarray(), onp.arange(300) * 3.0)
     assert onp.array_equal((other * 2.0).asarray(), (onp.arange(50) + 1.0) * 2.0)
+
+
+@pytest.mark.parametrize("nodag", [False, True])
+def test_a_forwarded_value_does_not_carry_its_store_back_in_time(oracle_engine, nodag, monkeypatch):
+    """Lowering: instructions run in node order and a store runs where its node sits.  `t = a*2; b -= a; b[:] = t` with t
+    never stored used to attach the last store to the multiplication - in FRONT of the in-place update, which then read the
+    new b (found by the DAG fuzzer, seeds 592 / 1660; the statement order alone triggers it, with or without the DAG)."""
+    import ramba_b200 as rb
+    from ramba_b200 import ramba
+
+    monkeypatch.setattr(ramba, "NO_DAG", nodag)
+    xa, xb = onp.arange(204, dtype=onp.float64).reshape(12, 17), onp.ones((12, 17))
+    a, b = rb.fromarray(xa), rb.fromarray(xb)
+    rb.sync()
+    t = a * 2.0
+    b -= a
+    b[0:12, 0:17] = t
+    del t
+    assert onp.array_equal(b.asarray(), xa * 2.0)
+    # the same with a reader of the old value in between, and with the sin / cos pairing moving a store up
+    a, b = rb.fromarray(xa), rb.fromarray(xb)
+    c = rb.fromarray(xb * 3.0)
+    rb.sync()
+    t = a * 2.0
+    u = b + 1.0          # reads the old b
+    b[:, :] = t
+    del t
+    assert onp.array_equal(u.asarray(), xb + 1.0) and onp.array_equal(b.asarray(), xa * 2.0)
+    s = rb.sin(a)
+    y = c * 2.0          # reads the old c ...
+    c[:, :] = rb.cos(a)  # ... before its overwrite by the half SINCOS would like to store early
+    rb.sync()
+    assert onp.array_equal(y.asarray(), xb * 6.0)
+    assert onp.allclose(c.asarray(), onp.cos(xa), rtol=1e-13, atol=1e-15) and onp.allclose(s.asarray(), onp.sin(xa), rtol=1e-13, atol=1e-15)

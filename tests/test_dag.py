@@ -268,3 +268,30 @@ def test_instantiate_all_and_flags(eng):
     b.flags.writeable = True
     b += 1.0
     assert onp.array_equal(b.asarray(), onp.arange(500) + 2.0) and onp.array_equal(c.asarray(), onp.arange(200) * 3.0)
+
+
+@pytest.mark.parametrize("chunk", range(5))
+def test_mixed_statement_forms_match_numpy(eng, chunk, monkeypatch):
+    """tests/_expr_fuzz.py: integer / float / bool arrays, where, comparisons, floor division, astype, in-place updates, strided /
+    reversed / transposed / broadcast operands, sliced assignments (possibly overlapping), temporaries consumed statements
+    later, reductions - exact against NumPy, with the DAG and without."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+    cases = _expr_fuzz.CASES[chunk * 40:(chunk + 1) * 40]
+    for f in cases:
+        got, exp = f(rb), f(onp)
+        _same(got, exp, f.__name__)
+        assert all(onp.asarray(g).dtype == onp.asarray(e).dtype for g, e in zip(got, exp)), f.__name__
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in cases[:10]:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+def test_fuzzer_finds_of_this_round_stay_fixed(eng):
+    """Seeds beyond the committed ranges that exposed the lowering's store-order bugs."""
+    import _dag_fuzz
+
+    rb, ramba, RT = eng
+    for seed in (592, 1660):
+        _same(_dag_fuzz.dag_program(rb, seed), _dag_fuzz.dag_program(onp, seed), "dag_program_%d" % seed)

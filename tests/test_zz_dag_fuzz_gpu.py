@@ -73,3 +73,18 @@ def test_late_api_cases_cuda(gpu_engine):
             got = f(rb)
             assert RT.is_cuda and _cabi.launch_count() > before
             test_api_parity._compare(got, f(onp), f.__name__)
+
+
+@pytest.mark.parametrize("chunk", range(2))
+def test_mixed_statement_forms_cuda(gpu_engine, chunk):
+    """tests/_expr_fuzz.py through the CUDA library (integer-valued data: results are exact; compared with the file's
+    tolerance all the same)."""
+    import _expr_fuzz
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    for f in _expr_fuzz.CASES[chunk * 15:(chunk + 1) * 15]:
+        _close(f(rb), f(onp), f.__name__)
+    assert RT.is_cuda and _cabi.launch_count() > before

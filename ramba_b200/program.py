@@ -386,9 +386,15 @@ class Lowering:
             if self._touched(self.nodes[i + 1:], vidx):
                 tv = self._node("mov", tv.cls, tv.cls, tv.is_bool, [tv])
                 node = tv.ref
-        node.store = vidx
         if mask is not None:
             m = self._materialise(mask) if mask.kind != "node" else mask
+            if self.nodes.index(m.ref) > self.nodes.index(node):
+                # the mask has to be in a register when the storing node runs: a mask that is a stored array is loaded HERE,
+                # after the value's node - the value is moved behind it (`x[m] = 0.5` with m materialised by an earlier flush)
+                tv = self._node("mov", tv.cls, tv.cls, tv.is_bool, [tv])
+                node = tv.ref
+        node.store = vidx
+        if mask is not None:
             node.mask = m.ref
             m.ref.mask_use = True
             # masked store: elements where the mask is false keep their old value -> no forwarding

@@ -572,6 +572,11 @@ class deferred_op:
                     # materialises it: ramba_b200 only skips the memory traffic, not the rounding)
                     dead_values[dst.gid] = lw.astype(tv, rb_dtype(dst.dtype))
                 else:
+                    if mask is not None and dst.gid in dead_values:
+                        # a masked assignment to an array that lives in a register: elements where the mask is false keep
+                        # the value the array had (`t = a + b; t[m] = 0.5; r = cos(t)` with t never stored)
+                        old = dead_values[dst.gid]
+                        tv = lw.build(E("where", mask, lw.coerce(tv, old.cls), old), resolve)
                     dead_values[dst.gid] = tv
             elif st[0] == "gred":
                 gslots.append((lw.reduce(st[1], lw.build(st[2], resolve)), si))

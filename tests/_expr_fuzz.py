@@ -114,3 +114,80 @@ def _case(seed):
 
 
 CASES = [_case(s) for s in range(200)]
+
+
+def trig_mask_program(np, seed, n_actions=36):
+    """sin / cos of shared operands (the SINCOS pairing and the store it moves), sqrt / exp, boolean-mask assignment and
+    masked sums, float32 arrays next to float64 ones - around in-place updates and held temporaries.  Compared with a
+    tolerance (transcendentals) by the caller."""
+    rng = onp.random.RandomState(12000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    F = [fa(rng.randint(-6, 7, size=(R, C)).astype(onp.float64) * 0.25) for _ in range(3)]
+    G = [fa(rng.randint(-6, 7, size=(R, C)).astype(onp.float32)) for _ in range(2)]      # float32 pool (array-with-array ops only)
+    out = []
+    held = []
+
+    def f():
+        return F[int(rng.randint(len(F)))]
+
+    def g():
+        return G[int(rng.randint(len(G)))]
+
+    def put(pool, v):
+        if len(pool) >= 5:
+            del pool[int(rng.randint(len(pool)))]
+        pool.append(v)
+
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 18))
+        if k == 0:
+            x = f(); put(F, np.sin(x) * np.sin(x) + np.cos(x) * np.cos(x))
+        elif k == 1:
+            x = f(); s = np.sin(x); y = f(); y += 1.0; c = np.cos(x); put(F, s - c)       # an in-place update between the pair
+        elif k == 2:
+            x = f(); s = np.sin(x); y = f(); u = y * 2.0; y[:, :] = np.cos(x); put(F, u + s)   # the pair's second half overwrites y
+        elif k == 3:
+            put(F, np.sqrt(abs(f())) + np.exp(np.minimum(f(), 2.0)))
+        elif k == 4:
+            x = f(); m = f() > 0.0; x[m] = 0.5                                             # boolean-mask assignment
+        elif k == 5:
+            x = f(); m = x > f(); out.append(onp.asarray(float(x[m].sum())))              # masked sum
+        elif k == 6:
+            put(G, np.minimum(np.maximum(g() + g(), -8.0), 8.0))      # (kept small: float32 results stay exact, so NumPy's
+        elif k == 7:                                                   # rounding of every temporary cannot differ)
+            put(G, np.minimum(np.maximum(g() * g() - g(), -8.0), 8.0))
+        elif k == 8:
+            put(F, g().astype(onp.float64) * 0.5 + f())
+        elif k == 9:
+            put(G, np.minimum(np.maximum((g().astype(onp.float64) * 2.0).astype(onp.float32) - g(), -8.0), 8.0))
+        elif k == 10:
+            x = g(); x += g()
+        elif k in (11, 12):
+            if len(held) < 2:
+                x = f(); held.append(np.cos(x) if k == 11 else np.sin(x) + 1.0)
+        elif k == 13:
+            if held:
+                x = f(); x[:, :] = held.pop(0)
+        elif k == 14:
+            if held:
+                put(F, held.pop() * 2.0)
+        elif k == 15:
+            out.append(_h(f()))
+        elif k == 16:
+            out.append(onp.asarray(float((np.sin(f()) + np.cos(f())).sum())))
+        else:
+            x = f(); x -= f()
+    for x in F + G:
+        out.append(_h(x))
+    return out
+
+
+def _tcase(seed):
+    def f(np):
+        return trig_mask_program(np, seed)
+
+    f.__name__ = "trig_mask_program_%d" % seed
+    return f
+
+
+TRIG_CASES = [_tcase(s) for s in range(120)]

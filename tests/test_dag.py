@@ -295,3 +295,50 @@ def test_fuzzer_finds_of_this_round_stay_fixed(eng):
     rb, ramba, RT = eng
     for seed in (592, 1660):
         _same(_dag_fuzz.dag_program(rb, seed), _dag_fuzz.dag_program(onp, seed), "dag_program_%d" % seed)
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_trig_mask_and_float32_programs(eng, chunk, monkeypatch):
+    """tests/_expr_fuzz.py::trig_mask_program: sin / cos pairs around in-place updates, boolean-mask assignment (also into
+    arrays that live in registers, with masks materialised by an earlier flush), masked sums, float32 next to float64."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+
+    def close(got, exp, name):
+        assert len(got) == len(exp), name
+        for i, (g, e) in enumerate(zip(got, exp)):
+            assert g.shape == e.shape and g.dtype == e.dtype and onp.allclose(g, e, rtol=1e-12, atol=1e-12), "%s[%d]" % (name, i)
+
+    cases = _expr_fuzz.TRIG_CASES[chunk * 30:(chunk + 1) * 30]
+    for f in cases:
+        close(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in cases[:8]:
+        close(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+@pytest.mark.parametrize("nodag", [False, True])
+def test_masked_assignment_corner_cases(eng, nodag, monkeypatch):
+    """Found by the trig / mask fuzzer: (1) a mask that is a STORED bool array (materialised by an earlier flush) used to fail
+    in the lowering ('mask not in a register'); (2) a masked assignment into an array that never leaves the registers
+    overwrote it whole (`t = a + b; t[m] = 0.5; r = cos(t)` with t dead gave cos(0.5) everywhere)."""
+    rb, ramba, RT = eng
+    monkeypatch.setattr(ramba, "NO_DAG", nodag)
+    a = onp.arange(300.0) - 150.0
+    x = rb.fromarray(a)
+    m = x > 0.0
+    rb.sync()
+    x[m] = 0.5
+    e = a.copy()
+    e[a > 0] = 0.5
+    assert onp.array_equal(x.asarray(), e)
+    x, y = rb.fromarray(a), rb.fromarray(a * 0.5)
+    rb.sync()
+    t = x + y
+    t[t > 30.0] = 0.5
+    r = rb.cos(t)
+    del t
+    et = a + a * 0.5
+    et[et > 30.0] = 0.5
+    assert onp.allclose(r.asarray(), onp.cos(et), rtol=1e-13, atol=1e-15)

@@ -191,3 +191,77 @@ def _tcase(seed):
 
 
 TRIG_CASES = [_tcase(s) for s in range(120)]
+
+
+def view_program(np, seed, n_actions=34):
+    """Writes THROUGH views: strided, reversed and transposed targets, row / column broadcast assignment, windows of one array
+    combined with shifted windows of the same or another array (the stencil form, also in place), slices of slices,
+    axis sums fed back as broadcast operands.  Integer-valued float64 / int64 data (weights 2, 0.5, -1): exact."""
+    rng = onp.random.RandomState(15000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    A = [fa(rng.randint(-4, 5, size=(R, C)).astype(onp.float64) * 2.0) for _ in range(3)]
+    T = [fa(rng.randint(-4, 5, size=(C, R)).astype(onp.float64) * 2.0)]                    # transposed shape
+    out = []
+
+    def a():
+        return A[int(rng.randint(len(A)))]
+
+    def put(v):
+        if len(A) >= 5:
+            del A[int(rng.randint(len(A)))]
+        A.append(v)
+
+    def win(h, w):
+        i = int(rng.randint(0, R - h + 1)); j = int(rng.randint(0, C - w + 1))
+        return (slice(i, i + h), slice(j, j + w))
+
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 16))
+        if k == 0:
+            x = a(); x[::2, :] = a()[1::2, :][:x[::2, :].shape[0], :] if R % 2 == 0 else a()[::2, :] * 0.5     # strided target
+        elif k == 1:
+            x = a(); x[:, ::-1] = a() - 1.0                                          # reversed target
+        elif k == 2:
+            x = a(); x[::-1, ::3] = a()[:, ::3] * 2.0                                # reversed + strided target
+        elif k == 3:
+            t = T[0]; t.T[:, :] = a() + 1.0                                          # transposed target
+        elif k == 4:
+            put(T[0].T * 0.5 + a())                                                  # transposed operand
+        elif k == 5:
+            x = a(); x[2:5, :] = a()[0, :]                                           # row broadcast into a window
+        elif k == 6:
+            x = a(); x[:, 3:7] = a()[:, 5:6]                                         # column broadcast into a window
+        elif k == 7:
+            x = a(); h, w = 6, 9; w1, w2, w3 = win(h, w), win(h, w), win(h, w)
+            x[w1] = x[w2] * 0.5 + a()[w3]                                            # shifted windows, possibly of the same array
+        elif k == 8:
+            x, y = a(), a()
+            y[1:-1, 1:-1] = x[:-2, 1:-1] + x[2:, 1:-1] + x[1:-1, :-2] + x[1:-1, 2:] - 4.0 * x[1:-1, 1:-1]   # 5-point stencil, maybe in place
+        elif k == 9:
+            x = a(); v = x[2:11, 4:20]; v[1:4, ::2] = 7.0; out.append(_h(v[::2, 1:5] * 2.0))   # slices of slices
+        elif k == 10:
+            x = a(); put(x - x.sum(axis=0) * 0.5)                                    # axis sum fed back as a row operand
+        elif k == 11:
+            x = a(); s = x.sum(axis=1); out.append(_h(s)); put(x * 2.0 - a())
+        elif k == 12:
+            x = a(); x += a()[::-1, ::-1]                                            # in place from a reversed view
+        elif k == 13:
+            x = a(); x[win(4, 5)] *= 2.0                                             # in place on a window
+        elif k == 14:
+            out.append(_h(a()))
+        else:
+            out.append(onp.asarray(float((a()[1:, :] - a()[:-1, :]).sum())))
+    for x in A + T:
+        out.append(_h(x))
+    return out
+
+
+def _vcase(seed):
+    def f(np):
+        return view_program(np, seed)
+
+    f.__name__ = "view_program_%d" % seed
+    return f
+
+
+VIEW_CASES = [_vcase(s) for s in range(120)]

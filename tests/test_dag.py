@@ -342,3 +342,18 @@ def test_masked_assignment_corner_cases(eng, nodag, monkeypatch):
     et = a + a * 0.5
     et[et > 30.0] = 0.5
     assert onp.allclose(r.asarray(), onp.cos(et), rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("chunk", range(3))
+def test_writes_through_views_match_numpy(eng, chunk, monkeypatch):
+    """tests/_expr_fuzz.py::view_program: strided / reversed / transposed targets, row and column broadcast assignment,
+    shifted windows of one array (stencil form, also in place), slices of slices, axis sums fed back - exact."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+    cases = _expr_fuzz.VIEW_CASES[chunk * 40:(chunk + 1) * 40]
+    for f in cases:
+        _same(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in cases[:8]:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")

@@ -164,8 +164,21 @@ def _array_operands(x, out):
     if isinstance(x, E):
         for a in x.args:
             _array_operands(a, out)
-    elif isinstance(x, ndarray) and x.shape != ():
-        out.append(x)
+    elif isinstance(x, ndarray):
+        if x.shape != ():
+            out.append(x)
+        else:
+            out.append(None)  # (marks a 0-d array leaf: DAG.add replaces those by their current values)
+
+
+def _snapshot_0d(x):
+    """The expression with every 0-d array leaf replaced by the value it holds NOW (0-d arrays keep their value on the host
+    and can be assigned to before a deferred statement runs)."""
+    if isinstance(x, E):
+        return E(x.op, *[_snapshot_0d(a) for a in x.args], imm=x.imm)
+    if isinstance(x, ndarray) and x.shape == ():
+        return x.distribution[()]
+    return x
 
 
 def _walk_operands(x, out):
@@ -256,6 +269,8 @@ class deferred_op:
         if _reads is None:
             _reads = []
             _array_operands(expr, _reads)
+            if None in _reads:
+                _reads = [o for o in _reads if o is not None]
         operands = [dst] + _reads if dst_nd and dst.shape != () else _reads
         arr = write_array
         if arr is None:
@@ -641,6 +656,9 @@ class DAG:
         dst, expr = oplist[0], oplist[1]
         reads = []
         _array_operands(expr, reads)
+        if None in reads:
+            expr = _snapshot_0d(expr)
+            reads = [o for o in reads if o is not None]
         node = object.__new__(cls)
         seq = node.seq_no = cls.dag_count
         cls.dag_count = seq + 1
@@ -1793,7 +1811,7 @@ class ndarray:
 
         def view(x):
             if isinstance(x, ndarray) and x.shape == ():
-                return x.distribution
+                return x.distribution[()]  # (the VALUE, now: a 0-d array may be assigned to before the statement runs)
             if not isinstance(x, ndarray) or new_shape == x.shape:
                 return x
             return x.broadcast_to(new_shape)

@@ -357,3 +357,19 @@ def test_writes_through_views_match_numpy(eng, chunk, monkeypatch):
     monkeypatch.setattr(ramba, "NO_DAG", True)
     for f in cases[:8]:
         _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+@pytest.mark.parametrize("nodag", [False, True])
+def test_zero_d_operands_are_read_when_the_statement_is_written(eng, nodag, monkeypatch):
+    """0-d arrays keep their value on the host: a statement uses the value the array has when the statement is WRITTEN,
+    not the one it has when the fused op finally runs."""
+    rb, ramba, RT = eng
+    monkeypatch.setattr(ramba, "NO_DAG", nodag)
+    x = rb.fromarray(onp.arange(200.0))
+    z = rb.array(3.0)
+    y = x * z
+    w = rb.where(x > 100.0, x, x) + z
+    z[()] = 5.0
+    v = x - z
+    assert onp.array_equal(y.asarray(), onp.arange(200.0) * 3.0) and onp.array_equal(w.asarray(), onp.arange(200.0) + 3.0)
+    assert onp.array_equal(v.asarray(), onp.arange(200.0) - 5.0)

@@ -265,3 +265,73 @@ def _vcase(seed):
 
 
 VIEW_CASES = [_vcase(s) for s in range(120)]
+
+
+def api_program(np, seed, n_actions=30):
+    """Library-level calls inside pending stretches, with the sources updated in place AFTER the call and before anything is
+    read: cumsum (a direct scan at call time), concatenate / stack / pad (slice assignments into a new array), reshape_copy
+    (a direct redistribution at call time), clip, where, axis sums, transposes, unit-dim reshapes, broadcast_to, astype."""
+    rng = onp.random.RandomState(18000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    A = [fa(rng.randint(-4, 5, size=(R, C)).astype(onp.float64)) for _ in range(3)]
+    V = [fa(rng.randint(-4, 5, size=(150,)).astype(onp.float64)) for _ in range(2)]
+    out = []
+
+    def a():
+        return A[int(rng.randint(len(A)))]
+
+    def v():
+        return V[int(rng.randint(len(V)))]
+
+    def bump(x):
+        if rng.rand() < 0.6:
+            x += 1.0            # the source changes right after the call: the result must not see it
+
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 16))
+        if k == 0:
+            x = v(); c = np.cumsum(x); bump(x); out.append(_h(c))
+        elif k == 1:
+            x = a(); ax = int(rng.randint(0, 2)); c = np.cumsum(x * 2.0, axis=ax); bump(x); out.append(_h(c))
+        elif k == 2:
+            x, y = a(), a(); c = np.concatenate([x, y * 2.0], axis=int(rng.randint(0, 2))); bump(x); bump(y); out.append(_h(c + 1.0))
+        elif k == 3:
+            x, y = v(), v(); c = np.stack([x, y - 1.0]); bump(y); out.append(_h(c))
+        elif k == 4:
+            x = a(); c = np.pad(x, ((1, 2), (0, 3)), mode="constant", constant_values=7); bump(x); out.append(_h(c))
+        elif k == 5:
+            x = a(); c = (x.reshape_copy((C, R)) if np is not onp else onp.reshape(x, (C, R)).copy()); bump(x); out.append(_h(c * 2.0))
+        elif k == 6:
+            x = a(); c = np.clip(x, -2.0, 3.0); bump(x); A.append(c); del A[0]
+        elif k == 7:
+            x = a(); c = np.where(x > 0.0, x, -x); bump(x); out.append(_h(c))
+        elif k == 8:
+            x = a(); m = x.sum(axis=0) * 0.5; bump(x); out.append(_h(m))   # (mean is sum * (1/n) here, like the reference: not bit-equal to NumPy's)
+        elif k == 9:
+            x = a(); t = x.T; y = t * 2.0; bump(x); out.append(_h(y))
+        elif k == 10:
+            x = v(); e = np.expand_dims(x, 0); y = e + 1.0; bump(x); out.append(_h(y))
+        elif k == 11:
+            x = v(); b = np.broadcast_to(x, (4, 150)); y = b * 2.0; bump(x); out.append(_h(y))
+        elif k == 12:
+            x = a(); i = (x * 2.0).astype(onp.int64); bump(x); out.append(_h(i // 3))
+        elif k == 13:
+            x = a(); x[2:9, 3:12] = x[3:10, 4:13] + 1.0
+        elif k == 14:
+            x = a(); s = float(x.sum()); x -= 1.0; out.append(onp.asarray(s + float(x.sum())))
+        else:
+            x = v(); V.append(x[::-1] * 1.0 + v()); del V[0]
+    for x in A + V:
+        out.append(_h(x))
+    return out
+
+
+def _acase(seed):
+    def f(np):
+        return api_program(np, seed)
+
+    f.__name__ = "api_program_%d" % seed
+    return f
+
+
+API_CASES = [_acase(s) for s in range(100)]

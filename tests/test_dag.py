@@ -373,3 +373,18 @@ def test_zero_d_operands_are_read_when_the_statement_is_written(eng, nodag, monk
     v = x - z
     assert onp.array_equal(y.asarray(), onp.arange(200.0) * 3.0) and onp.array_equal(w.asarray(), onp.arange(200.0) + 3.0)
     assert onp.array_equal(v.asarray(), onp.arange(200.0) - 5.0)
+
+
+@pytest.mark.parametrize("chunk", range(2))
+def test_library_calls_inside_pending_stretches(eng, chunk, monkeypatch):
+    """tests/_expr_fuzz.py::api_program: cumsum / concatenate / stack / pad / reshape_copy / clip / where / transposes /
+    unit-dim reshapes / broadcast_to / astype with the source updated in place right after the call - exact."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+    cases = _expr_fuzz.API_CASES[chunk * 50:(chunk + 1) * 50]
+    for f in cases:
+        _same(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in cases[:8]:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")

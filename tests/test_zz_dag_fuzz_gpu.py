@@ -88,3 +88,23 @@ def test_mixed_statement_forms_cuda(gpu_engine, chunk):
     for f in _expr_fuzz.CASES[chunk * 15:(chunk + 1) * 15]:
         _close(f(rb), f(onp), f.__name__)
     assert RT.is_cuda and _cabi.launch_count() > before
+
+
+@pytest.mark.parametrize("which", ["VIEW_CASES", "API_CASES", "TRIG_CASES"])
+def test_more_fuzzed_families_cuda(gpu_engine, which):
+    """The view / library-call / trig-and-mask programs of tests/_expr_fuzz.py through the CUDA library (15 seeds each; the
+    trig family with a tolerance for libdevice vs NumPy transcendentals and the summation order of their sums)."""
+    import _expr_fuzz
+    import ramba_b200 as rb
+    from ramba_b200 import _cabi
+    from ramba_b200.runtime import RT
+
+    before = _cabi.launch_count()
+    for f in getattr(_expr_fuzz, which)[:15]:
+        got, exp = f(rb), f(onp)
+        assert len(got) == len(exp), f.__name__
+        for i, (g, e) in enumerate(zip(got, exp)):
+            g, e = onp.asarray(g), onp.asarray(e)
+            tol = 1e-10 if which == "TRIG_CASES" else 1e-12
+            assert g.shape == e.shape and g.dtype == e.dtype and onp.allclose(g, e, rtol=tol, atol=tol), "%s[%d]" % (f.__name__, i)
+    assert RT.is_cuda and _cabi.launch_count() > before

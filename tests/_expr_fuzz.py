@@ -335,3 +335,66 @@ def _acase(seed):
 
 
 API_CASES = [_acase(s) for s in range(100)]
+
+
+SHAPES = [(7,), (3, 5), (1,), (0,), (4, 0), (200,), (101,), (6, 7, 8), (2, 3, 4, 5), (1, 150), (150, 1), (99,), (100,)]
+
+
+def shape_program(np, seed, n_actions=26):
+    """Shapes around the distribution threshold (arrays under 100 elements live on one rank), single elements, empty arrays,
+    3-D and 4-D arrays, unit dims - int64 / float64 / bool / int32 data, elementwise ops, comparisons, where, reductions
+    over all axes and over one, in-place updates, slices, transposes, scalar reads."""
+    rng = onp.random.RandomState(21000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    out = []
+    for _round in range(3):
+        shp = SHAPES[int(rng.randint(len(SHAPES)))]
+        P = [fa(rng.randint(-5, 6, size=shp).astype(onp.float64)) for _ in range(2)]
+        Q = [fa(rng.randint(-5, 6, size=shp).astype(onp.int64)), fa(rng.randint(0, 5, size=shp).astype(onp.int32))]
+        nd = len(shp)
+        for _ in range(n_actions // 3):
+            k = int(rng.randint(0, 14))
+            p, q = P[int(rng.randint(2))], Q[0]
+            if k == 0:
+                P[int(rng.randint(2))] = p * 2.0 - P[int(rng.randint(2))]
+            elif k == 1:
+                P[int(rng.randint(2))] = np.where(p > 0.0, p, p * -1.0) + q.astype(onp.float64)
+            elif k == 2:
+                Q[0] = q * 2 - Q[0] // 3
+            elif k == 3:
+                Q[1] = Q[1] + Q[1] % 3              # int32 with int32
+            elif k == 4:
+                p += 1.0
+            elif k == 5:
+                q -= 2
+            elif k == 6:
+                out.append(onp.asarray(float(p.sum())))
+            elif k == 7:
+                out.append(onp.asarray(int(q.sum())))
+            elif k == 8 and nd >= 2 and 0 not in shp:
+                out.append(_h(p.sum(axis=int(rng.randint(nd)))))
+            elif k == 9 and nd >= 2:
+                out.append(_h(np.transpose(p) * 2.0))
+            elif k == 10 and shp[0] >= 3:
+                s = (slice(1, shp[0] - 1),) + (slice(None),) * (nd - 1)
+                p[s] = p[s] * 0.5
+            elif k == 11 and 0 not in shp:
+                idx = tuple(int(rng.randint(n)) for n in shp)
+                out.append(onp.asarray(float(p[idx])))          # a single element, read back as a scalar
+            elif k == 12:
+                out.append(_h((p > 0.0) & (q < 2) if np is onp else np.logical_and(p > 0.0, q < 2)))
+            else:
+                out.append(_h(Q[1] * 2))
+        out += [_h(x) for x in P + Q]
+    return out
+
+
+def _scase(seed):
+    def f(np):
+        return shape_program(np, seed)
+
+    f.__name__ = "shape_program_%d" % seed
+    return f
+
+
+SHAPE_CASES = [_scase(s) for s in range(100)]

@@ -388,3 +388,16 @@ def test_library_calls_inside_pending_stretches(eng, chunk, monkeypatch):
     monkeypatch.setattr(ramba, "NO_DAG", True)
     for f in cases[:8]:
         _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+def test_shapes_around_the_distribution_threshold(eng, monkeypatch):
+    """tests/_expr_fuzz.py::shape_program: single-owner arrays (< 100 elements), single elements, empty arrays, 3-D / 4-D,
+    unit dims; int64 / float64 / bool / int32 - exact."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+    for f in _expr_fuzz.SHAPE_CASES[:60]:
+        _same(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in _expr_fuzz.SHAPE_CASES[60:70]:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")

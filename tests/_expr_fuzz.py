@@ -398,3 +398,99 @@ def _scase(seed):
 
 
 SHAPE_CASES = [_scase(s) for s in range(100)]
+
+
+def _st_cross(a):
+    return a[-1, 0] + a[1, 0] + a[0, -1] + a[0, 1] - 4.0 * a[0, 0]
+
+
+def _st_row(a, b):
+    return a[0, -2] + a[0, 2] - 2.0 * b[0, 0]
+
+
+def skeleton_program(np, seed, n_actions=24):
+    """The skeletons (functions traced into the op list) inside pending stretches, their sources updated right after the
+    call: smap / smap_index with Python and string lambdas, sreduce with +, max, sstencil / stencil with relative indices,
+    scumulative with + and max, fromfunction, triu."""
+    rng = onp.random.RandomState(24000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    A = [fa(rng.randint(-4, 5, size=(R, C)).astype(onp.float64)) for _ in range(3)]
+    V = [fa(rng.randint(-4, 5, size=(160,)).astype(onp.int64)) for _ in range(2)]
+    out = []
+    is_np = np is onp
+
+    def a():
+        return A[int(rng.randint(len(A)))]
+
+    def v():
+        return V[int(rng.randint(len(V)))]
+
+    def bump(x, by):
+        if rng.rand() < 0.6:
+            x += by
+
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 12))
+        if k == 0:
+            x, y = v(), v()
+            r = 3 * x - 7 * y if is_np else np.smap(lambda p, q: 3 * p - 7 * q, x, y)
+            bump(x, 1); out.append(_h(r))
+        elif k == 1:
+            x = v()
+            r = 3 * x - 7 if is_np else np.smap("lambda x: 3*x-7", x)
+            bump(x, 2); out.append(_h(r))
+        elif k == 2:
+            x = v()
+            r = 7 * onp.arange(160) + x if is_np else np.smap_index(lambda i, p: 7 * i + p, x)
+            bump(x, 1); out.append(_h(r))
+        elif k == 3:
+            x = v()
+            r = (x * x).sum() if is_np else np.sreduce(lambda p: p * p, lambda s, t: s + t, 0, x)
+            x -= 1; out.append(onp.asarray(int(r)))
+        elif k == 4:
+            x = v()
+            r = onp.max(2 * x + 1) if is_np else np.sreduce(lambda p: 2 * p + 1, lambda s, t: max(s, t), -10**9, x)
+            x += 1; out.append(onp.asarray(int(r)))
+        elif k == 5:
+            x = a()
+            if is_np:
+                r = onp.zeros((R, C)); r[1:-1, 1:-1] = x[:-2, 1:-1] + x[2:, 1:-1] + x[1:-1, :-2] + x[1:-1, 2:] - 4.0 * x[1:-1, 1:-1]
+            else:
+                r = np.sstencil(np.stencil(_st_cross), x)
+            bump(x, 1.0); out.append(_h(r))
+        elif k == 6:
+            x, y = a(), a()
+            if is_np:
+                r = onp.zeros((R, C)); r[:, 2:-2] = x[:, :-4] + x[:, 4:] - 2.0 * y[:, 2:-2]
+            else:
+                r = np.stencil(_st_row)(x, y)
+            bump(y, 1.0); out.append(_h(r))
+        elif k == 7:
+            x = v()
+            r = onp.cumsum(x) if is_np else np.scumulative(lambda p, q: p + q, lambda p, q: p + q, x)
+            bump(x, 1); out.append(_h(r))
+        elif k == 8:
+            x = v()
+            r = onp.maximum.accumulate(x) if is_np else np.scumulative(lambda p, q: np.maximum(p, q), lambda p, q: np.maximum(p, q), x)
+            bump(x, 3); out.append(_h(r))
+        elif k == 9:
+            r = np.fromfunction(lambda i, j: (i * 3 + j) % 7, (R, C)) + a()
+            A.append(r); del A[0]
+        elif k == 10:
+            x = a(); r = np.triu(x, 1) * 2.0; bump(x, 1.0); out.append(_h(r))
+        else:
+            x = a(); x[1:-1, :] = x[:-2, :] + x[2:, :]
+    for x in A + V:
+        out.append(_h(x))
+    return out
+
+
+def _kcase(seed):
+    def f(np):
+        return skeleton_program(np, seed)
+
+    f.__name__ = "skeleton_program_%d" % seed
+    return f
+
+
+SKELETON_CASES = [_kcase(s) for s in range(80)]

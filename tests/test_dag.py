@@ -401,3 +401,16 @@ def test_shapes_around_the_distribution_threshold(eng, monkeypatch):
     monkeypatch.setattr(ramba, "NO_DAG", True)
     for f in _expr_fuzz.SHAPE_CASES[60:70]:
         _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+def test_skeletons_inside_pending_stretches(eng, monkeypatch):
+    """tests/_expr_fuzz.py::skeleton_program: smap / smap_index / sreduce / sstencil / stencil / scumulative / fromfunction /
+    triu with their sources updated right after the call - exact."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+    for f in _expr_fuzz.SKELETON_CASES[:50]:
+        _same(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in _expr_fuzz.SKELETON_CASES[50:58]:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")

@@ -416,6 +416,9 @@ def skeleton_program(np, seed, n_actions=24):
     fa = (lambda x: x.copy()) if np is onp else np.fromarray
     A = [fa(rng.randint(-4, 5, size=(R, C)).astype(onp.float64)) for _ in range(3)]
     V = [fa(rng.randint(-4, 5, size=(160,)).astype(onp.int64)) for _ in range(2)]
+    # two arrays with padded shards (local_border: the neighbours' edges are received into the ring of the block)
+    fb = (lambda x: x.copy()) if np is onp else (lambda x: np.fromarray(x, local_border=2))
+    B = [fb(rng.randint(-4, 5, size=(R, C)).astype(onp.float64)) for _ in range(2)]
     out = []
     is_np = np is onp
 
@@ -430,8 +433,26 @@ def skeleton_program(np, seed, n_actions=24):
             x += by
 
     for _ in range(n_actions):
-        k = int(rng.randint(0, 12))
-        if k == 0:
+        k = int(rng.randint(0, 16))
+        if k == 12:
+            x = B[int(rng.randint(2))]
+            if is_np:
+                r = onp.zeros((R, C)); r[1:-1, 1:-1] = x[:-2, 1:-1] + x[2:, 1:-1] + x[1:-1, :-2] + x[1:-1, 2:] - 4.0 * x[1:-1, 1:-1]
+            else:
+                r = np.sstencil(np.stencil(_st_cross), x)
+            bump(x, 1.0); out.append(_h(r))
+        elif k == 13:
+            x, y = B[0], B[1]
+            if is_np:
+                r = onp.zeros((R, C)); r[:, 2:-2] = x[:, :-4] + x[:, 4:] - 2.0 * y[:, 2:-2]
+            else:
+                r = np.stencil(_st_row)(x, y)
+            bump(x, 2.0); out.append(_h(r))
+        elif k == 14:
+            x = B[int(rng.randint(2))]; x += a() * 0.5                     # padded and plain arrays in one statement
+        elif k == 15:
+            x = B[int(rng.randint(2))]; x[1:-1, 1:-1] = x[:-2, 1:-1] * 0.5 + x[1:-1, 2:]   # in place through shifted views of a padded array
+        elif k == 0:
             x, y = v(), v()
             r = 3 * x - 7 * y if is_np else np.smap(lambda p, q: 3 * p - 7 * q, x, y)
             bump(x, 1); out.append(_h(r))
@@ -480,7 +501,7 @@ def skeleton_program(np, seed, n_actions=24):
             x = a(); r = np.triu(x, 1) * 2.0; bump(x, 1.0); out.append(_h(r))
         else:
             x = a(); x[1:-1, :] = x[:-2, :] + x[2:, :]
-    for x in A + V:
+    for x in A + V + B:
         out.append(_h(x))
     return out
 

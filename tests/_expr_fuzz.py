@@ -515,3 +515,79 @@ def _kcase(seed):
 
 
 SKELETON_CASES = [_kcase(s) for s in range(80)]
+
+
+def partition_program(np, seed, n_actions=26):
+    """Operands with DIFFERENT partitions in one statement (multi-rank: pieces exchanged, operands all-gathered, boxes cut
+    into ranges): arrays split by rows, by columns and by the default rule; misaligned windows; transposes (a row-split
+    array read as a column-split one); vectors with their own 1-D partition broadcast along either axis; axis sums over the
+    split and the unsplit axis; in-place updates whose operand lives elsewhere."""
+    rng = onp.random.RandomState(27000 + seed)
+    H, W_ = 24, 36
+    is_np = np is onp
+
+    def mk(kw):
+        x = rng.randint(-4, 5, size=(H, W_)).astype(onp.float64)
+        return x.copy() if is_np else np.fromarray(x, **kw)
+
+    layouts = [{}, {"dist_dims": 0}, {"dist_dims": 1}]
+    A = [mk(layouts[i % 3]) for i in range(4)]
+    S = [(lambda x: x.copy() if is_np else np.fromarray(x, dist_dims=d))(rng.randint(-4, 5, size=(W_, H)).astype(onp.float64)) for d in (0, 1)]
+    row = (lambda x: x.copy() if is_np else np.fromarray(x))(rng.randint(-3, 4, size=(W_,)).astype(onp.float64))
+    col = (lambda x: x.copy() if is_np else np.fromarray(x))(rng.randint(-3, 4, size=(H,)).astype(onp.float64))
+    out = []
+
+    def a():
+        return A[int(rng.randint(len(A)))]
+
+    def put(v):
+        del A[int(rng.randint(len(A)))]
+        A.append(v)
+
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 14))
+        if k == 0:
+            put(a() + a() * 2.0 - a())                                    # three partitions in one statement
+        elif k == 1:
+            put(a() + S[int(rng.randint(2))].T)                           # transposed operand with its own split
+        elif k == 2:
+            put(a() * row + col.reshape(H, 1) if is_np else a() * row + np.expand_dims(col, 1))
+        elif k == 3:
+            x = a(); x += a()                                             # in place, operand elsewhere
+        elif k == 4:
+            x = a(); out.append(_h(x.sum(axis=0))); out.append(_h(x.sum(axis=1)))
+        elif k == 5:
+            x, y = a(), a(); i, j = int(rng.randint(0, 6)), int(rng.randint(0, 9))
+            put(np.concatenate([x[i:i + 12, :], y[i + 3:i + 15, :]], axis=0) if rng.rand() < 0.5 else x * 1.0)
+        elif k == 6:
+            x, y = a(), a(); i, j = int(rng.randint(0, 8)), int(rng.randint(0, 12))
+            x[2:18, 3:27] = y[i:i + 16, j:j + 24] * 0.5                   # misaligned window of another layout
+        elif k == 7:
+            x = a(); y = a()
+            x[1:-1, 1:-1] = y[:-2, 1:-1] + y[2:, 1:-1] + y[1:-1, :-2] + y[1:-1, 2:]
+        elif k == 8:
+            out.append(onp.asarray(float((a() * S[0].T).sum())))
+        elif k == 9:
+            s = S[int(rng.randint(2))]; s += a().T
+        elif k == 10:
+            put(np.where(a() > a(), a(), S[1].T))
+        elif k == 11:
+            out.append(_h(a()[::2, ::3] - a()[1::2, 1::3]))
+        elif k == 12:
+            out.append(_h(a()))
+        else:
+            x = a(); x[:, :] = x.sum(axis=0) * 0.25 + x                  # a reduction over the (maybe split) axis fed back
+    for x in A + S:
+        out.append(_h(x))
+    return out
+
+
+def _pcase(seed):
+    def f(np):
+        return partition_program(np, seed)
+
+    f.__name__ = "partition_program_%d" % seed
+    return f
+
+
+PARTITION_CASES = [_pcase(s) for s in range(80)]

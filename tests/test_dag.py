@@ -414,3 +414,13 @@ def test_skeletons_inside_pending_stretches(eng, monkeypatch):
     monkeypatch.setattr(ramba, "NO_DAG", True)
     for f in _expr_fuzz.SKELETON_CASES[50:58]:
         _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+def test_operands_with_different_partitions(eng):
+    """tests/_expr_fuzz.py::partition_program on one rank (its point is the multi-rank worker: row-split, column-split and
+    default-split operands in one statement; tests/test_multirank_gloo.py runs it on worlds 2, 3, 4 and 8)."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+    for f in _expr_fuzz.PARTITION_CASES[:20]:
+        _same(f(rb), f(onp), f.__name__)

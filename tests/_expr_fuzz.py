@@ -149,9 +149,10 @@ def trig_mask_program(np, seed, n_actions=36):
         elif k == 3:
             put(F, np.sqrt(abs(f())) + np.exp(np.minimum(f(), 2.0)))
         elif k == 4:
-            x = f(); m = f() > 0.0; x[m] = 0.5                                             # boolean-mask assignment
+            x = f(); m = g() > 0.0; x[m] = 0.5                 # boolean-mask assignment (mask from exact data: no comparison
+                                                               # can fall differently on another sin / cos implementation)
         elif k == 5:
-            x = f(); m = x > f(); out.append(onp.asarray(float(x[m].sum())))              # masked sum
+            x = f(); m = g() > g(); out.append(onp.asarray(float(x[m].sum())))            # masked sum
         elif k == 6:
             put(G, np.minimum(np.maximum(g() + g(), -8.0), 8.0))      # (kept small: float32 results stay exact, so NumPy's
         elif k == 7:                                                   # rounding of every temporary cannot differ)

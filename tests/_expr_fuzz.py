@@ -592,3 +592,66 @@ def _pcase(seed):
 
 
 PARTITION_CASES = [_pcase(s) for s in range(80)]
+
+
+def reduction_program(np, seed, n_actions=22):
+    """Reductions in every form: sum / min / max / prod / all / any, over all axes, one axis and several, keepdims, of
+    views (strided, reversed, transposed, windows), of expressions whose temporary dies, chained (a reduction of a
+    reduction), next to in-place updates of the source.  2-D and 3-D integer-valued arrays."""
+    rng = onp.random.RandomState(30000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    A2 = [fa(rng.randint(-4, 5, size=(R, C)).astype(onp.float64)) for _ in range(2)]
+    A3 = [fa(rng.randint(-3, 4, size=(6, 9, 11)).astype(onp.int64)) for _ in range(2)]
+    out = []
+
+    def red(x, name, **kw):
+        return getattr(x, name)(**kw)
+
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 14))
+        x2, x3 = A2[int(rng.randint(2))], A3[int(rng.randint(2))]
+        name = ["sum", "min", "max"][int(rng.randint(3))]
+        if k == 0:
+            out.append(_h(red(x2, name, axis=int(rng.randint(2)))))
+        elif k == 1:
+            out.append(_h(red(x3, name, axis=int(rng.randint(3)))))
+        elif k == 2:
+            ax = [(0, 1), (0, 2), (1, 2)][int(rng.randint(3))]
+            out.append(_h(x3.sum(axis=ax)))
+        elif k == 3:
+            out.append(_h(x2.sum(axis=int(rng.randint(2)), keepdims=True)))
+        elif k == 4:
+            out.append(onp.asarray(float(red(x2 * 2.0 + 1.0, name))))                    # temporary dies in the reduction
+        elif k == 5:
+            out.append(_h(red(x2[1::2, ::-1], name, axis=int(rng.randint(2)))))          # strided + reversed view
+        elif k == 6:
+            out.append(_h(red(x2.T, name, axis=int(rng.randint(2)))))                    # transposed view
+        elif k == 7:
+            out.append(_h(x3[1:5, :, 2:9].sum(axis=1)))                                  # window of a 3-D array
+        elif k == 8:
+            out.append(onp.asarray(float(x2.sum(axis=0).sum())))                         # a reduction of a reduction
+            out.append(onp.asarray(float(x2.sum(axis=1).max())))
+        elif k == 9:
+            s = x2.sum(axis=1); x2 += 1.0; out.append(_h(s))                             # source updated after the call
+        elif k == 10:
+            out.append(onp.asarray(bool((x3 > -4).all()))); out.append(onp.asarray(bool((x3 > 2).any())))
+        elif k == 11:
+            out.append(onp.asarray(int((abs(x3) % 2 + 1)[0:2, 0:3, 0:4].prod())))
+        elif k == 12:
+            x3 -= A3[int(rng.randint(2))] // 2
+        else:
+            A2[int(rng.randint(2))] = x2 - x2.sum(axis=0) * 0.125
+    for x in A2 + A3:
+        out.append(_h(x))
+    return out
+
+
+def _rcase(seed):
+    def f(np):
+        return reduction_program(np, seed)
+
+    f.__name__ = "reduction_program_%d" % seed
+    return f
+
+
+REDUCTION_CASES = [_rcase(s) for s in range(80)]

@@ -424,3 +424,16 @@ def test_operands_with_different_partitions(eng):
     rb, ramba, RT = eng
     for f in _expr_fuzz.PARTITION_CASES[:20]:
         _same(f(rb), f(onp), f.__name__)
+
+
+def test_reductions_in_every_form(eng, monkeypatch):
+    """tests/_expr_fuzz.py::reduction_program: sum / min / max / prod / all / any over all axes, one, several, keepdims, of
+    strided / reversed / transposed views and windows, of dying temporaries, chained, next to in-place updates - exact."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+    for f in _expr_fuzz.REDUCTION_CASES[:50]:
+        _same(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in _expr_fuzz.REDUCTION_CASES[50:58]:
+        _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")

@@ -90,9 +90,9 @@ def test_mixed_statement_forms_cuda(gpu_engine, chunk):
     assert RT.is_cuda and _cabi.launch_count() > before
 
 
-@pytest.mark.parametrize("which", ["VIEW_CASES", "API_CASES", "TRIG_CASES"])
+@pytest.mark.parametrize("which", ["VIEW_CASES", "API_CASES", "TRIG_CASES", "SHAPE_CASES", "SKELETON_CASES", "REDUCTION_CASES"])
 def test_more_fuzzed_families_cuda(gpu_engine, which):
-    """The view / library-call / trig-and-mask programs of tests/_expr_fuzz.py through the CUDA library (15 seeds each; the
+    """The view / library-call / trig-and-mask / odd-shape / skeleton / reduction programs of tests/_expr_fuzz.py through the CUDA library (15 seeds each; the
     trig family with a tolerance for libdevice vs NumPy transcendentals and the summation order of their sums)."""
     import _expr_fuzz
     import ramba_b200 as rb

@@ -655,3 +655,119 @@ def _rcase(seed):
 
 
 REDUCTION_CASES = [_rcase(s) for s in range(80)]
+
+
+def mixed_program(np, seed, n_actions=40):
+    """Everything on ONE pool: arrays with three partitions (default, row-split, column-split) and one with padded shards;
+    arithmetic / where / in-place / overlapping windows / strided, reversed and transposed targets / boolean masks (from
+    exact data) / sin-cos pairs / temporaries held across statements / cumsum, concatenate, pad, reshape_copy, smap,
+    sstencil / reductions fed back / rebinding, del, sync, partial reads.  Compared with a tolerance (transcendentals)."""
+    rng = onp.random.RandomState(33000 + seed)
+    is_np = np is onp
+    kws = [{}, {"dist_dims": 0}, {"dist_dims": 1}]
+
+    def mk(i):
+        x = rng.randint(-4, 5, size=(R, C)).astype(onp.float64)
+        return x.copy() if is_np else np.fromarray(x, **kws[i % 3])
+
+    P = [mk(i) for i in range(4)]
+    K = (lambda x: x.copy() if is_np else np.fromarray(x))(rng.randint(-4, 5, size=(R, C)).astype(onp.int64))     # exact data for masks
+    B = (lambda x: x.copy() if is_np else np.fromarray(x, local_border=2))(rng.randint(-4, 5, size=(R, C)).astype(onp.float64))
+    held = []
+    out = []
+
+    def p():
+        return P[int(rng.randint(len(P)))]
+
+    def put(v):
+        if len(P) >= 6:
+            del P[int(rng.randint(len(P)))]
+        P.append(v)
+
+    def win(h, w):
+        i = int(rng.randint(0, R - h + 1)); j = int(rng.randint(0, C - w + 1))
+        return (slice(i, i + h), slice(j, j + w))
+
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 30))
+        if k == 0:
+            put(p() * 2.0 - p() + np.where(p() > 0.0, p(), 1.0 - p()))
+        elif k == 1:
+            x = p(); x += p() * 0.5
+        elif k == 2:
+            x = p(); w1, w2 = win(5, 8), win(5, 8); x[w1] = x[w2] - p()[w1]
+        elif k == 3:
+            x = p(); x[::2, ::-1] = p()[::2, :] + 1.0
+        elif k == 4:
+            x = p(); x.T[:, :] = p().T * 2.0
+        elif k == 5:
+            x = p(); m = K > int(rng.randint(-3, 3)); x[m] = -1.0
+        elif k == 6:
+            x = p(); m = K < 0; out.append(onp.asarray(float(x[m].sum())))
+        elif k == 7:
+            x = p(); put(np.sin(x) * np.cos(x))
+        elif k == 8:
+            x = p(); s = np.sin(x); y = p(); y -= 1.0; put(s + np.cos(x))
+        elif k in (9, 10):
+            if len(held) < 2:
+                held.append(p() * 2.0 + 1.0 if k == 9 else np.cos(p()))
+        elif k == 11:
+            if held:
+                x = p(); x[:, :] = held.pop(0)
+        elif k == 12:
+            if held:
+                put(held.pop() - p())
+        elif k == 13:
+            x = p(); c = np.cumsum(x, axis=int(rng.randint(2))); x += 1.0; put(c * 0.125)
+        elif k == 14:
+            x, y = p(), p(); c = np.concatenate([x[:6, :], y[6:, :]], axis=0); y -= 1.0; put(c)
+        elif k == 15:
+            x = p(); c = np.pad(x[1:-1, 2:-2], ((1, 1), (2, 2)), mode="edge"); x += 1.0; put(c)
+        elif k == 16:
+            x = p(); c = x.reshape_copy((C, R)) if not is_np else onp.reshape(x, (C, R)).copy(); x -= 1.0; out.append(_h(c))
+        elif k == 17:
+            x = p(); r = 3 * x - 7 if is_np else np.smap("lambda x: 3*x-7", x); x += 1.0; put(np.minimum(np.maximum(r, -50.0), 50.0))
+        elif k == 18:
+            if is_np:
+                r = onp.zeros((R, C)); r[1:-1, 1:-1] = B[:-2, 1:-1] + B[2:, 1:-1] + B[1:-1, :-2] + B[1:-1, 2:] - 4.0 * B[1:-1, 1:-1]
+            else:
+                r = np.sstencil(np.stencil(_st_cross), B)
+            B += p() * 0.5; put(r * 0.25)
+        elif k == 19:
+            x = p(); put(x - x.sum(axis=0) * 0.0625)
+        elif k == 20:
+            x = p(); out.append(_h(x.max(axis=1))); out.append(onp.asarray(float((x * 0.5 + p()).sum())))
+        elif k == 21:
+            x = p(); y = p(); y[1:-1, 1:-1] = x[:-2, 1:-1] + x[2:, 1:-1] - 2.0 * x[1:-1, 1:-1]
+        elif k == 22:
+            i = int(rng.randint(len(P))); P[i] = np.minimum(np.maximum(P[i], -30.0), 30.0)      # rebinding keeps values small
+        elif k == 23:
+            if len(P) > 3:
+                del P[int(rng.randint(len(P)))]
+        elif k == 24:
+            if not is_np:
+                np.sync()
+        elif k == 25:
+            out.append(_h(p()))
+        elif k == 26:
+            x = p(); _ = np.cos(x) * 3.0; del _                                          # never observed
+        elif k == 27:
+            K += 1; K[K > 4] = -4                                                        # the mask source itself changes
+        elif k == 28:
+            x = p(); v = x[2:11, 3:19]; v *= 0.5; out.append(_h(v[::2, ::3]))
+        else:
+            x = p(); put((x > p()).astype(onp.float64) + (K % 3).astype(onp.float64))
+    for x in P + [K, B]:
+        out.append(_h(x))
+    return out
+
+
+def _mcase(seed):
+    def f(np):
+        return mixed_program(np, seed)
+
+    f.__name__ = "mixed_program_%d" % seed
+    return f
+
+
+MIXED_CASES = [_mcase(s) for s in range(120)]

@@ -56,6 +56,7 @@ def main():
              + (_expr_fuzz.SKELETON_CASES[:50] if os.environ.get("RB200_MR_ALL_RANDOM") else _expr_fuzz.SKELETON_CASES[:6])
              + (_expr_fuzz.PARTITION_CASES[:60] if os.environ.get("RB200_MR_ALL_RANDOM") else _expr_fuzz.PARTITION_CASES[:10])
              + (_expr_fuzz.REDUCTION_CASES[:50] if os.environ.get("RB200_MR_ALL_RANDOM") else _expr_fuzz.REDUCTION_CASES[:8])
+             + (_expr_fuzz.MIXED_CASES[:60] if os.environ.get("RB200_MR_ALL_RANDOM") else _expr_fuzz.MIXED_CASES[:10])
              + [test_reshape_copy.reshape_programs])
     # the stencil / streaming / scan kernel programs: float32 arrays with Python-float weights are computed in float64 by
     # the op list (Numba's typing) but in float32 by NumPy, so these compare with a dtype tolerance across ranks
@@ -104,7 +105,7 @@ def main():
                 tol = 1e-5 if e.dtype == onp.float32 else 1e-12
                 ok = g.shape == e.shape and g.dtype == e.dtype and (onp.allclose(g, e, rtol=tol, atol=tol) if e.dtype.kind == "f" else onp.array_equal(g, e))
             else:
-                ok = g.shape == e.shape and (onp.allclose(g, e, rtol=1e-13, atol=1e-12 if prog.__name__.startswith(("random_program", "dag_program", "limit_program", "expr_program", "trig_mask_program", "view_program", "api_program", "shape_program", "skeleton_program", "partition_program", "reduction_program")) else 1e-15) if e.dtype.kind == "f" else onp.array_equal(g, e))
+                ok = g.shape == e.shape and (onp.allclose(g, e, rtol=1e-13, atol=1e-12 if prog.__name__.startswith(("random_program", "dag_program", "limit_program", "expr_program", "trig_mask_program", "view_program", "api_program", "shape_program", "skeleton_program", "partition_program", "reduction_program", "mixed_program")) else 1e-15) if e.dtype.kind == "f" else onp.array_equal(g, e))
             if not ok:
                 failures.append("%s[%d]" % (prog.__name__, i))
     if MODE == "cuda":

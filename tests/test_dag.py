@@ -437,3 +437,25 @@ def test_reductions_in_every_form(eng, monkeypatch):
     monkeypatch.setattr(ramba, "NO_DAG", True)
     for f in _expr_fuzz.REDUCTION_CASES[50:58]:
         _same(f(rb), f(onp), f.__name__ + " (NO_DAG)")
+
+
+@pytest.mark.parametrize("chunk", range(2))
+def test_everything_on_one_pool(eng, chunk, monkeypatch):
+    """tests/_expr_fuzz.py::mixed_program: three partitions + padded shards, arithmetic / in-place / windows / view targets /
+    masks / sin-cos / held temporaries / library calls / skeletons / reductions fed back / rebinding, del, sync, partial
+    reads - all on shared arrays."""
+    import _expr_fuzz
+
+    rb, ramba, RT = eng
+
+    def close(got, exp, name):
+        assert len(got) == len(exp), name
+        for i, (g, e) in enumerate(zip(got, exp)):
+            assert g.shape == e.shape and g.dtype == e.dtype and onp.allclose(g, e, rtol=1e-11, atol=1e-11), "%s[%d]" % (name, i)
+
+    cases = _expr_fuzz.MIXED_CASES[chunk * 40:(chunk + 1) * 40]
+    for f in cases:
+        close(f(rb), f(onp), f.__name__)
+    monkeypatch.setattr(ramba, "NO_DAG", True)
+    for f in cases[:6]:
+        close(f(rb), f(onp), f.__name__ + " (NO_DAG)")

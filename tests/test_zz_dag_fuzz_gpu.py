@@ -90,7 +90,7 @@ def test_mixed_statement_forms_cuda(gpu_engine, chunk):
     assert RT.is_cuda and _cabi.launch_count() > before
 
 
-@pytest.mark.parametrize("which", ["VIEW_CASES", "API_CASES", "TRIG_CASES", "SHAPE_CASES", "SKELETON_CASES", "REDUCTION_CASES"])
+@pytest.mark.parametrize("which", ["VIEW_CASES", "API_CASES", "TRIG_CASES", "SHAPE_CASES", "SKELETON_CASES", "REDUCTION_CASES", "MIXED_CASES"])
 def test_more_fuzzed_families_cuda(gpu_engine, which):
     """The view / library-call / trig-and-mask / odd-shape / skeleton / reduction programs of tests/_expr_fuzz.py through the CUDA library (15 seeds each; the
     trig family with a tolerance for libdevice vs NumPy transcendentals and the summation order of their sums)."""
@@ -105,6 +105,6 @@ def test_more_fuzzed_families_cuda(gpu_engine, which):
         assert len(got) == len(exp), f.__name__
         for i, (g, e) in enumerate(zip(got, exp)):
             g, e = onp.asarray(g), onp.asarray(e)
-            tol = 1e-10 if which == "TRIG_CASES" else 1e-12
+            tol = 1e-10 if which in ("TRIG_CASES", "MIXED_CASES") else 1e-12
             assert g.shape == e.shape and g.dtype == e.dtype and onp.allclose(g, e, rtol=tol, atol=tol), "%s[%d]" % (f.__name__, i)
     assert RT.is_cuda and _cabi.launch_count() > before

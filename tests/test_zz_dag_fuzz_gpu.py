@@ -108,3 +108,28 @@ def test_more_fuzzed_families_cuda(gpu_engine, which):
             tol = 1e-10 if which in ("TRIG_CASES", "MIXED_CASES") else 1e-12
             assert g.shape == e.shape and g.dtype == e.dtype and onp.allclose(g, e, rtol=tol, atol=tol), "%s[%d]" % (f.__name__, i)
     assert RT.is_cuda and _cabi.launch_count() > before
+
+
+def test_fuzz_programs_match_the_real_reference_cuda(gpu_engine):
+    """The fuzz programs the real reference runs correctly (tests/golden/fuzz_golden.npz, 70 programs), through the CUDA library
+    against the reference's own outputs."""
+    import json
+    import os
+
+    import ramba_b200 as rb
+    import test_golden
+
+    z = onp.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_golden.npz"))
+    status = json.loads(str(z["__status__"]))
+    n = 0
+    for name, st in status.items():
+        if st == "ok":
+            fn, seed = test_golden._fuzz_fn(name)
+            got = fn(rb, seed)
+            keys = sorted((k for k in z.files if k.startswith(name + "__")), key=lambda k: int(k.rsplit("o", 1)[1]))
+            assert len(keys) == len(got), name
+            for i, k in enumerate(keys):
+                g, e = onp.asarray(got[i]), z[k]
+                assert g.shape == e.shape and onp.allclose(g, e, rtol=1e-12, atol=1e-9), "%s[%d]" % (name, i)
+            n += 1
+    assert n >= 60

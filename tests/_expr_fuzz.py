@@ -819,3 +819,53 @@ def typing_program(np, seed, n_actions=16):
         out.append(_h(r))
     out.append(_h(A)); out.append(_h(D))
     return out
+
+
+def typing2_program(np, seed, n_actions=14):
+    """More statement forms for the typing rules (see typing_program): integer arrays with float scalars, floor division and
+    modulo on inexact floats, abs / negation, minimum / maximum with scalars, comparisons stored as float32, truncating
+    casts, exp.  Pinned by the real reference where it can run them."""
+    rng = onp.random.RandomState(39000 + seed)
+    fa = (lambda x: x.copy()) if np is onp else np.fromarray
+    A = fa((rng.randint(-40, 41, size=(120,)) * 0.1).astype(onp.float32))
+    B = fa((rng.randint(1, 41, size=(120,)) * 0.3).astype(onp.float32))
+    D = fa(rng.randint(-40, 41, size=(120,)) * 0.1)
+    I = fa(rng.randint(-9, 10, size=(120,)).astype(onp.int64))
+    out = []
+    for _ in range(n_actions):
+        k = int(rng.randint(0, 16))
+        if k == 0:
+            r = I * 0.5 + A
+        elif k == 1:
+            r = I / 3
+        elif k == 2:
+            r = I // 2 + I % 3
+        elif k == 3:
+            r = A // 0.3
+        elif k == 4:
+            r = D % 0.7
+        elif k == 5:
+            r = abs(A) - (-B)
+        elif k == 6:
+            r = np.minimum(A, 0.5) + np.maximum(B, 2.25)
+        elif k == 7:
+            r = np.maximum(A, B) * D
+        elif k == 8:
+            r = (A > 0.3).astype(onp.float32) * B
+        elif k == 9:
+            r = (A * 10.0).astype(onp.int64) + I
+        elif k == 10:
+            r = (D * 7.0).astype(onp.int32)
+        elif k == 11:
+            r = I.astype(onp.float32) * 0.1
+        elif k == 12:
+            r = np.exp(A * 0.1) * B
+        elif k == 13:
+            r = A * A * A - B * 0.5
+        elif k == 14:
+            r = (A + B) * (A - B)
+        else:
+            B *= 1.1; r = B
+        out.append(_h(r))
+    out.append(_h(B))
+    return out

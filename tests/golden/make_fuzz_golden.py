@@ -18,8 +18,8 @@ ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 FAMILIES = {"dag_program": ("_dag_fuzz", 24), "limit_program": ("_limit_fuzz", 24), "view_program": ("_expr_fuzz", 30),
             "shape_program": ("_expr_fuzz", 24), "partition_program": ("_expr_fuzz", 16),
             # not comparable with NumPy by design (the reference's typing / rounding rules): kept whenever the reference runs it
-            "typing_program": ("_expr_fuzz", 40)}
-NOT_NUMPY = {"typing_program"}
+            "typing_program": ("_expr_fuzz", 40), "typing2_program": ("_expr_fuzz", 40)}
+NOT_NUMPY = {"typing_program", "typing2_program"}
 
 CHILD = r'''
 import sys, warnings, json

@@ -168,7 +168,7 @@ def _fuzz_fn(name):
     return getattr(mod, fam), int(seed)
 
 
-def _compare_fuzz(name, got, z, one_ulp_f64=False):
+def _compare_fuzz(name, got, z, one_ulp_f64=False, f32_ulps=0):
     keys = sorted((k for k in z.files if k.startswith(name + "__")), key=lambda k: int(k.rsplit("o", 1)[1]))
     assert len(keys) == len(got), name
     n_inexact = 0
@@ -176,6 +176,9 @@ def _compare_fuzz(name, got, z, one_ulp_f64=False):
         g, e = onp.asarray(got[i]), z[k]
         assert g.shape == e.shape and g.dtype == e.dtype, "%s[%d]" % (name, i)
         if onp.array_equal(g, e):
+            continue
+        if f32_ulps and g.dtype == onp.float32 and bool(onp.all(onp.abs(g - e) <= f32_ulps * onp.spacing(onp.abs(e)))):
+            n_inexact += 1  # (CUDA legs: libdevice exp / pow vs libm, seen through one float32 rounding)
             continue
         # the reference compiles its kernels with fastmath on an FMA-capable host: a float64 `x*y + z` inside one statement may
         # be contracted into one fused multiply-add there; the kernels here round the product and the sum separately
@@ -202,8 +205,8 @@ def test_fuzz_programs_match_the_real_reference(oracle_engine, golden_fuzz):
     n = m = 0
     for name, st in status.items():
         fn, seed = _fuzz_fn(name)
-        if st == "ok" and name.startswith("typing_program"):
-            continue  # (its own test below)
+        if st == "ok" and name.startswith("typing"):
+            continue  # (their own test below)
         if st == "ok":
             _compare_fuzz(name, fn(rb, seed), z)
             n += 1
@@ -215,8 +218,9 @@ def test_fuzz_programs_match_the_real_reference(oracle_engine, golden_fuzz):
 
 
 def test_typing_and_rounding_follow_the_real_reference(oracle_engine, golden_fuzz):
-    """tests/_expr_fuzz.py::typing_program (float32 / float64 / int64 arrays with Python and NumPy scalars on values that are not
-    exactly representable - NOT NumPy's results): the programs the real reference can run give here the SAME BITS for every
+    """tests/_expr_fuzz.py::typing_program / typing2_program (float32 / float64 / int64 arrays with Python and NumPy scalars on
+    values that are not exactly representable, integer arrays with float scalars, floor division / modulo on inexact floats,
+    truncating casts, exp - NOT NumPy's results): the programs the real reference can run give here the SAME BITS for every
     float32 result and for every float64 result except `x*y + z` in one statement, where the reference's fastmath kernel may
     use one fused multiply-add (a difference of one rounding of the product)."""
     import ramba_b200 as rb
@@ -224,10 +228,10 @@ def test_typing_and_rounding_follow_the_real_reference(oracle_engine, golden_fuz
     z, status = golden_fuzz
     n = outputs = inexact = 0
     for name, st in status.items():
-        if st == "ok" and name.startswith("typing_program"):
+        if st == "ok" and name.startswith("typing"):
             fn, seed = _fuzz_fn(name)
             got = fn(rb, seed)
             inexact += _compare_fuzz(name, got, z, one_ulp_f64=True)
             outputs += len(got)
             n += 1
-    assert n >= 15 and inexact <= 0.1 * outputs
+    assert n >= 30 and inexact <= 0.1 * outputs
